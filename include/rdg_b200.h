@@ -1,0 +1,128 @@
+/* rdg_b200.h -- C ABI of the B200-native RainDisaggGAN hot path.
+ *
+ * Drop-in boundary for the ONE call boundary the reference has on this path: the Keras
+ * model calls it makes into TensorFlow.  Every entry point cites the reference interface
+ * it replaces (file:line under the reference repo).  Plain pointers and sizes only; no
+ * torch / Python types.  All "dev" pointers are CUDA device pointers on the context's
+ * device, "host" pointers are ordinary host memory.  Calls taking a stream are
+ * stream-ordered and non-blocking unless stated otherwise; stream is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).
+ *
+ * Return value: 0 = ok, >0 = cudaError_t, <0 = RDG_E_* below.  rdg_last_error() returns a
+ * thread-local message for the last non-zero return.
+ *
+ * Layouts (Keras channels-last, row-major):
+ *   latent  [B,100] f32          cond   [Bc,nd,nd,ncond] f32 (already / norm_scale)
+ *   sample  [B,24,nd,nd,1] f32   scores [B] f32
+ *   Keras weights: Dense kernel (in,out); Conv3D kernel (kt,kh,kw,Cin,Cout); bias (Cout)
+ */
+#ifndef RDG_B200_H
+#define RDG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDG_E_BADARG   (-1)
+#define RDG_E_NOWEIGHT (-2)
+#define RDG_E_NONFINITE (-3)  /* mirrors tf.debugging.check_numerics, gan_train_cwgangp_pixelnorm.py:349-350 */
+#define RDG_E_NODEVICE (-4)
+#define RDG_E_NOMEM    (-5)
+
+/* arithmetic modes of the generator forward */
+#define RDG_MODE_FP32 0   /* FP32 SIMT path: <=1e-5 relative vs the FP64 oracle              */
+#define RDG_MODE_BF16 1   /* tcgen05 kind::f16, bf16 operands, f32 accumulate in TMEM        */
+#define RDG_MODE_FP16 2   /* tcgen05 kind::f16, fp16 operands, f32 accumulate in TMEM        */
+
+/* output scaling of the generator forward */
+#define RDG_OUT_FRACTION 0  /* gen.predict: fractions, sum over the 24 hours == 1 (gan_train...py:347)      */
+#define RDG_OUT_MM       1  /* fraction * cond * norm_scale, raindisagg_gan_pretrained.py:62-64 fused on-chip */
+
+typedef struct rdg_ctx rdg_ctx;
+
+const char* rdg_last_error(void);
+int  rdg_version(void);
+
+/* One context per (device, domain size). nd: 16 (gan_train_cwgangp_pixelnorm.py:51) or 64
+ * (alternative_domains/...largedomain.py:59); ncond: condition channels (1; 2/3 for the
+ * revision1 variants).  max_chunk = largest number of samples processed per internal pass
+ * (workspace is sized from it; 0 = default). */
+int  rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int max_chunk);
+void rdg_ctx_destroy(rdg_ctx* ctx);
+int  rdg_ctx_info(const rdg_ctx* ctx, int* nd, int* ncond, int* max_chunk, int* sm_count);
+size_t rdg_ctx_workspace_bytes(const rdg_ctx* ctx);
+
+/* Replaces tf.keras.models.load_model(...).get_weights() -> device
+ * (raindisagg_gan_pretrained.py:43-45; gan_train_cwgangp_pixelnorm.py:361).  `tensors` are the
+ * 10 generator arrays in Keras order (Dense k,b; Conv3D k,b x4), host f32.  Packs the FP32
+ * copies, and the upsample-folded + swizzled 16-bit operand tiles for both tensor modes. */
+int  rdg_generator_set_weights(rdg_ctx* ctx, const float* const* tensors, const size_t* sizes, int n);
+int  rdg_generator_get_weights(rdg_ctx* ctx, float* const* tensors, const size_t* sizes, int n);
+
+/* Replaces gen.predict([latent, cond_batch]) (raindisagg_gan_pretrained.py:60;
+ * generate_and_evaluate_crps.py:185).  latent_dev [B,100]; cond_dev [ceil(B/scen_per_cond),
+ * nd,nd,ncond] -- sample b uses condition b / scen_per_cond (scen_per_cond=1: one condition
+ * per sample, as Keras).  out_dev [B,24,nd,nd] f32.  nonfinite_flag_dev (optional, int32)
+ * is set !=0 if any output is NaN/Inf (check_numerics). */
+int  rdg_generator_forward(rdg_ctx* ctx, const float* latent_dev, const float* cond_dev,
+                           int scen_per_cond, float* out_dev, int B, int mode, int out_kind,
+                           float norm_scale, int* nonfinite_flag_dev, void* stream);
+
+/* Host-buffer end-to-end variant of the same call: chunks the batch, overlaps H2D of the
+ * next chunk / compute / D2H of the previous one on three streams with pinned staging.
+ * Blocking.  Returns RDG_E_NONFINITE like check_numerics would raise. */
+int  rdg_generate_host(rdg_ctx* ctx, const float* latent_host, const float* cond_host,
+                       int scen_per_cond, float* out_host, long long B, int mode, int out_kind,
+                       float norm_scale);
+
+/* Device-side N(0,1) latent (counter-based Philox4x32-10 + Box-Muller), for throughput runs
+ * where the reference would call np.random.normal (raindisagg_gan_pretrained.py:56). */
+int  rdg_fill_normal(float* dst_dev, long long n, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- critic (create_discriminator, gan_train_cwgangp_pixelnorm.py:272-309) ---- */
+int  rdg_critic_set_weights(rdg_ctx* ctx, const float* const* tensors, const size_t* sizes, int n);
+int  rdg_critic_get_weights(rdg_ctx* ctx, float* const* tensors, const size_t* sizes, int n);
+/* critic([sample, cond]) -> score[B].  masks_dev: NULL (inference) or 4 device pointers to
+ * {0,1} f32 dropout keep-masks shaped like each conv output (training mode, A9). */
+int  rdg_critic_forward(rdg_ctx* ctx, const float* sample_dev, const float* cond_dev,
+                        const float* const* masks_dev, float* score_dev, int B, void* stream);
+
+/* ---- training steps (gan_train_cwgangp_pixelnorm.py:365-408, 468-482) ----
+ * Evaluate the losses and the gradient of the step's loss w.r.t. the trainable net, leaving
+ * the gradients in the context's gradient buffers (for an allreduce between ranks), then
+ * rdg_adam_apply() performs the Keras-Adam update (:385) with the shared step counter. */
+int  rdg_critic_step_grads(rdg_ctx* ctx, const float* x_real_dev, const float* cond_dev,
+                           const float* latent_dev, const float* alpha_dev,
+                           const float* const* masks_fake, const float* const* masks_real,
+                           const float* const* masks_hat, int B, int gen_mode,
+                           float* losses4_dev, void* stream);
+int  rdg_generator_step_grads(rdg_ctx* ctx, const float* latent_dev, const float* cond_dev,
+                              const float* const* masks, int B, float* loss_dev, void* stream);
+/* which: 0 = generator, 1 = critic.  Returns device pointer + element count of the flat
+ * FP32 gradient / parameter buffers (Keras tensor order, concatenated). */
+int  rdg_grad_buffer(rdg_ctx* ctx, int which, float** grads_dev, size_t* n);
+int  rdg_param_buffer(rdg_ctx* ctx, int which, float** params_dev, size_t* n);
+/* tf.optimizers.Adam(lr, beta_1, beta_2) OptimizerV2 semantics; step_t is the
+ * already-incremented shared counter; grad_scale multiplies the gradient first (1/world). */
+int  rdg_adam_apply(rdg_ctx* ctx, int which, float lr, float beta1, float beta2, float eps,
+                    long long step_t, float grad_scale, void* stream);
+int  rdg_adam_reset(rdg_ctx* ctx, int which);
+
+/* ---- building blocks exposed for tests (same kernels the calls above use) ---- */
+/* y = x / sqrt(mean_c(x^2) + 1e-8), optional LeakyReLU(0.2) (gan_train...py:255-266, :333) */
+int  rdg_pixelnorm(const float* x_dev, float* y_dev, long long rows, int C, int lrelu, void* stream);
+/* softmax over the hour axis of logits [B,24,P] (gan_train...py:347) */
+int  rdg_softmax_hours(const float* logits_dev, float* out_dev, long long B, int P, void* stream);
+
+/* one tensor-core generator layer (0..2) in isolation: UpSampling3D + Conv3D + PixelNorm + LeakyReLU
+ * (gan_train_cwgangp_pixelnorm.py:330-343); x f32 [B,T,H,W,Cin] is rounded to the mode's 16-bit type,
+ * y f32 [B,2T,2H,2W,Cout] is the widened 16-bit result. */
+int  rdg_tc_layer(rdg_ctx* ctx, int layer, int mode, const float* x_dev, float* y_dev, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDG_B200_H */

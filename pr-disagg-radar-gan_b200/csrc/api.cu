@@ -1,0 +1,458 @@
+// C ABI (include/rdg_b200.h): context, weight packing, generator / critic forward orchestration
+// and the host-buffer end-to-end pipeline.  Training steps live in train.cu.
+#include "rdg_common.cuh"
+#include "gen_tc.h"
+#include "ctx.h"
+#include "../../include/rdg_b200.h"
+
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void rdg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* rdg_last_error(void) { return g_err; }
+extern "C" int rdg_version(void) { return 100; }
+
+// ------------------------------------------------------------------ geometry helpers
+static void tf_same(int i, int k, int s, int* o, int* before) {
+    *o = (i + s - 1) / s;
+    int p = std::max((*o - 1) * s + k - i, 0);
+    *before = p / 2;
+}
+
+ConvGeom rdg_gen_conv_geom(const rdg_ctx* c, int layer, int B) {   // layer 0..2 upsampled convs, 3 = output conv
+    const int s = c->nd / 8;
+    static const int cin[4] = {256, 256, 128, 64}, cout[4] = {256, 128, 64, 1};
+    ConvGeom g{};
+    g.B = B;
+    const int f = 1 << layer;
+    if (layer < 3) { g.Ti = 3 * f; g.Hi = s * f; g.Wi = s * f; g.up = 1; }
+    else { g.Ti = 24; g.Hi = c->nd; g.Wi = c->nd; g.up = 0; }
+    g.Ci = cin[layer]; g.Co = cout[layer];
+    g.To = layer < 3 ? g.Ti * 2 : g.Ti; g.Ho = layer < 3 ? g.Hi * 2 : g.Hi; g.Wo = layer < 3 ? g.Wi * 2 : g.Wi;
+    g.KT = g.KH = g.KW = 3; g.stride = 1; g.pt = g.ph = g.pw = 1;
+    return g;
+}
+
+ConvGeom rdg_gen_dense_geom(const rdg_ctx* c, int B) {
+    ConvGeom g{};
+    g.B = B; g.Ti = g.Hi = g.Wi = 1; g.To = g.Ho = g.Wo = 1;
+    g.Ci = RDG_LATENT + c->nd * c->nd * c->ncond; g.Co = 256 * (c->nd / 8) * (c->nd / 8) * 3;
+    g.KT = g.KH = g.KW = 1; g.stride = 1;
+    return g;
+}
+
+ConvGeom rdg_critic_conv_geom(const rdg_ctx* c, int layer, int B) {   // layer 0..3
+    static const int cout[4] = {64, 128, 256, 256};
+    int dims[3] = {RDG_NHOURS, c->nd, c->nd};
+    int cin = 1 + c->ncond;
+    ConvGeom g{};
+    for (int l = 0; l <= layer; ++l) {
+        g = ConvGeom{};
+        g.B = B; g.Ti = dims[0]; g.Hi = dims[1]; g.Wi = dims[2]; g.Ci = cin; g.Co = cout[l];
+        g.KT = g.KH = g.KW = 3; g.stride = 2;
+        if (l == 0) {   // padding='valid'  gan_train_cwgangp_pixelnorm.py:286-287
+            g.To = (dims[0] - 3) / 2 + 1; g.Ho = (dims[1] - 3) / 2 + 1; g.Wo = (dims[2] - 3) / 2 + 1;
+        } else {        // TF 'same', asymmetric for even inputs
+            tf_same(dims[0], 3, 2, &g.To, &g.pt); tf_same(dims[1], 3, 2, &g.Ho, &g.ph); tf_same(dims[2], 3, 2, &g.Wo, &g.pw);
+        }
+        dims[0] = g.To; dims[1] = g.Ho; dims[2] = g.Wo; cin = g.Co;
+    }
+    return g;
+}
+
+ConvGeom rdg_critic_dense_geom(const rdg_ctx* c, int B) {
+    ConvGeom l3 = rdg_critic_conv_geom(c, 3, B);
+    ConvGeom g{};
+    g.B = B; g.Ti = g.Hi = g.Wi = 1; g.To = g.Ho = g.Wo = 1;
+    g.Ci = l3.To * l3.Ho * l3.Wo * 256; g.Co = 1; g.KT = g.KH = g.KW = 1; g.stride = 1;
+    return g;
+}
+
+static void gen_shapes(const rdg_ctx* c, size_t* sz) {
+    ConvGeom d = rdg_gen_dense_geom(c, 1);
+    sz[0] = (size_t)d.Ci * d.Co; sz[1] = d.Co;
+    static const int cin[4] = {256, 256, 128, 64}, cout[4] = {256, 128, 64, 1};
+    for (int l = 0; l < 4; ++l) { sz[2 + 2 * l] = (size_t)27 * cin[l] * cout[l]; sz[3 + 2 * l] = cout[l]; }
+}
+static void critic_shapes(const rdg_ctx* c, size_t* sz) {
+    for (int l = 0; l < 4; ++l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l, 1);
+        sz[2 * l] = (size_t)27 * g.Ci * g.Co; sz[2 * l + 1] = g.Co;
+    }
+    ConvGeom d = rdg_critic_dense_geom(c, 1);
+    sz[8] = d.Ci; sz[9] = 1;
+}
+
+// per-sample element counts of the generator activations
+static size_t gen_act_elems(const rdg_ctx* c, int layer) {   // 0 = dense out, 1..3 conv outs
+    const int s = c->nd / 8;
+    static const int ch[4] = {256, 256, 128, 64};
+    const int f = 1 << layer;
+    return (size_t)3 * f * s * f * s * f * ch[layer];
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int max_chunk) {
+    if (!out || nd < 16 || (nd & (nd - 1)) || nd > 256 || ncond < 1) { rdg_set_error("rdg_ctx_create: bad arguments"); return RDG_E_BADARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) { rdg_set_error("no CUDA device %d", device); return RDG_E_NODEVICE; }
+    RDG_CUDA(cudaSetDevice(device));
+    rdg_ctx* c = new rdg_ctx();
+    c->device = device; c->nd = nd; c->ncond = ncond;
+    cudaDeviceProp prop;
+    RDG_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) { rdg_set_error("device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); delete c; return RDG_E_NODEVICE; }
+    if (max_chunk <= 0) max_chunk = nd == 16 ? 32 * c->sm_count : std::max(32, 2 * c->sm_count);
+    c->max_chunk = max_chunk;
+    gen_shapes(c, c->g_size);
+    critic_shapes(c, c->c_size);
+    c->g_total = c->c_total = 0;
+    for (int i = 0; i < 10; ++i) { c->g_off[i] = c->g_total; c->g_total += (c->g_size[i] + 3) / 4 * 4; }
+    for (int i = 0; i < 10; ++i) { c->c_off[i] = c->c_total; c->c_total += (c->c_size[i] + 3) / 4 * 4; }
+    RDG_CUDA(cudaMalloc(&c->g_params, c->g_total * 4));
+    RDG_CUDA(cudaMalloc(&c->c_params, c->c_total * 4));
+    RDG_CUDA(cudaMemset(c->g_params, 0, c->g_total * 4));
+    RDG_CUDA(cudaMemset(c->c_params, 0, c->c_total * 4));
+    // workspace: sized for the 16-bit path at max_chunk samples
+    size_t per16 = 0, per32 = 0;
+    ConvGeom d = rdg_gen_dense_geom(c, 1);
+    per16 += (size_t)(d.Ci + d.Co) * 4;
+    per32 += (size_t)(d.Ci + d.Co) * 4;
+    for (int l = 0; l < 4; ++l) { per16 += gen_act_elems(c, l) * 2; per32 += (l ? gen_act_elems(c, l) * 4 : 0); }
+    c->per_sample16 = per16; c->per_sample32 = per32;
+    c->ws_bytes = per16 * (size_t)max_chunk + 4096 * 8;
+    RDG_CUDA(cudaMalloc(&c->ws, c->ws_bytes));
+    RDG_CUDA(cudaMalloc(&c->flag_dev, sizeof(int)));
+    RDG_CUDA(cudaMemset(c->flag_dev, 0, sizeof(int)));
+    RDG_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    RDG_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    RDG_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        RDG_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        RDG_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+        RDG_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->g_params); cudaFree(c->c_params); cudaFree(c->ws); cudaFree(c->flag_dev);
+    cudaFree(c->g_grads); cudaFree(c->g_m); cudaFree(c->g_v);
+    cudaFree(c->c_grads); cudaFree(c->c_m); cudaFree(c->c_v);
+    for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) cudaFree(c->g_wpack[k][l]);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->e2e_lat[i]); cudaFree(c->e2e_out[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
+    cudaFree(c->e2e_cond);
+    cudaFree(c->train_ws);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+extern "C" int rdg_ctx_info(const rdg_ctx* c, int* nd, int* ncond, int* max_chunk, int* sm_count) {
+    if (!c) return RDG_E_BADARG;
+    if (nd) *nd = c->nd;
+    if (ncond) *ncond = c->ncond;
+    if (max_chunk) *max_chunk = c->max_chunk;
+    if (sm_count) *sm_count = c->sm_count;
+    return 0;
+}
+extern "C" size_t rdg_ctx_workspace_bytes(const rdg_ctx* c) { return c ? c->ws_bytes : 0; }
+
+// ------------------------------------------------------------------ weight packing
+// Fold nearest-x2 upsample + 3^3 conv into 8 phases x 8 taps and lay each
+// (phase, tap, 64-channel chunk) out as a [Cout rows x 64 k] K-major tile whose 16-byte chunks are
+// XOR-swizzled by (row & 7): the exact shared-memory image tcgen05.mma reads with SWIZZLE_128B.
+template <typename HT, typename CVT>
+static void pack_folded(const float* k, int Cin, int Cout, std::vector<HT>& dst, CVT cvt) {
+    const int nchunk = Cin / 64;
+    dst.assign((size_t)64 * nchunk * Cout * 64, cvt(0.f));
+    std::vector<float> wf((size_t)Cin * Cout);
+    // per-axis tap sets: phase 0: tap0 <- {0}, tap1 <- {1,2}; phase 1: tap0 <- {0,1}, tap1 <- {2}
+    auto lo = [](int ph, int a) { return ph == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2); };
+    auto hi = [](int ph, int a) { return ph == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2); };
+    for (int p = 0; p < 8; ++p)
+        for (int a = 0; a < 8; ++a) {
+            const int pt = p >> 2, ph = (p >> 1) & 1, pw = p & 1, at = a >> 2, ah = (a >> 1) & 1, aw = a & 1;
+            std::fill(wf.begin(), wf.end(), 0.f);
+            for (int kt = lo(pt, at); kt <= hi(pt, at); ++kt)
+                for (int kh = lo(ph, ah); kh <= hi(ph, ah); ++kh)
+                    for (int kw = lo(pw, aw); kw <= hi(pw, aw); ++kw) {
+                        const float* src = k + (size_t)((kt * 3 + kh) * 3 + kw) * Cin * Cout;
+                        for (size_t i = 0; i < (size_t)Cin * Cout; ++i) wf[i] += src[i];
+                    }
+            for (int c = 0; c < nchunk; ++c) {
+                HT* tile = dst.data() + ((size_t)(p * 8 + a) * nchunk + c) * Cout * 64;
+                for (int n = 0; n < Cout; ++n)
+                    for (int j = 0; j < 8; ++j)
+                        for (int e = 0; e < 8; ++e)
+                            tile[(size_t)n * 64 + ((j ^ (n & 7)) * 8) + e] = cvt(wf[(size_t)(c * 64 + j * 8 + e) * Cout + n]);
+            }
+        }
+}
+
+static int upload_params(float* dev, const size_t* off, const size_t* size, const float* const* tensors,
+                         const size_t* sizes, int n, const char* what) {
+    if (n != 10) { rdg_set_error("%s: expected 10 tensors, got %d", what, n); return RDG_E_BADARG; }
+    for (int i = 0; i < 10; ++i)
+        if (sizes[i] != size[i]) { rdg_set_error("%s: tensor %d has %zu elements, expected %zu", what, i, sizes[i], size[i]); return RDG_E_BADARG; }
+    for (int i = 0; i < 10; ++i) RDG_CUDA(cudaMemcpy(dev + off[i], tensors[i], size[i] * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int rdg_repack_generator(rdg_ctx* c, const float* const* host_tensors) {
+    static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
+    for (int l = 0; l < 3; ++l) {
+        std::vector<__nv_bfloat16> pb;
+        std::vector<__half> ph;
+        pack_folded<__nv_bfloat16>(host_tensors[2 + 2 * l], cin[l], cout[l], pb, [](float f) { return __float2bfloat16_rn(f); });
+        pack_folded<__half>(host_tensors[2 + 2 * l], cin[l], cout[l], ph, [](float f) { return __float2half_rn(f); });
+        for (int k = 0; k < 2; ++k) {
+            if (!c->g_wpack[k][l]) RDG_CUDA(cudaMalloc(&c->g_wpack[k][l], pb.size() * 2));
+        }
+        RDG_CUDA(cudaMemcpy(c->g_wpack[0][l], pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
+        RDG_CUDA(cudaMemcpy(c->g_wpack[1][l], ph.data(), ph.size() * 2, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+extern "C" int rdg_generator_set_weights(rdg_ctx* c, const float* const* tensors, const size_t* sizes, int n) {
+    if (!c || !tensors || !sizes) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
+    int r = upload_params(c->g_params, c->g_off, c->g_size, tensors, sizes, n, "generator weights");
+    if (r) return r;
+    r = rdg_repack_generator(c, tensors);
+    if (r) return r;
+    c->gen_ready = true;
+    return 0;
+}
+
+static int download_params(const float* dev, const size_t* off, const size_t* size, float* const* tensors,
+                           const size_t* sizes, int n, const char* what) {
+    if (n != 10) { rdg_set_error("%s: expected 10 tensors", what); return RDG_E_BADARG; }
+    for (int i = 0; i < 10; ++i)
+        if (sizes[i] != size[i]) { rdg_set_error("%s: tensor %d size mismatch", what, i); return RDG_E_BADARG; }
+    RDG_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 10; ++i) RDG_CUDA(cudaMemcpy(tensors[i], dev + off[i], size[i] * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int rdg_generator_get_weights(rdg_ctx* c, float* const* tensors, const size_t* sizes, int n) {
+    if (!c) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
+    return download_params(c->g_params, c->g_off, c->g_size, tensors, sizes, n, "generator weights");
+}
+extern "C" int rdg_critic_set_weights(rdg_ctx* c, const float* const* tensors, const size_t* sizes, int n) {
+    if (!c || !tensors || !sizes) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
+    int r = upload_params(c->c_params, c->c_off, c->c_size, tensors, sizes, n, "critic weights");
+    if (r) return r;
+    c->critic_ready = true;
+    return 0;
+}
+extern "C" int rdg_critic_get_weights(rdg_ctx* c, float* const* tensors, const size_t* sizes, int n) {
+    if (!c) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
+    return download_params(c->c_params, c->c_off, c->c_size, tensors, sizes, n, "critic weights");
+}
+
+// ------------------------------------------------------------------ generator forward
+// One chunk of n samples starting at global sample index b_off (for the cond lookup).
+static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond, int spc, int b_off, float* out, int n,
+                             int mode, int out_kind, float norm_scale, int* flag, cudaStream_t st) {
+    const int nd = c->nd, s = nd / 8;
+    const ConvGeom dg = rdg_gen_dense_geom(c, n);
+    uint8_t* p = reinterpret_cast<uint8_t*>(c->ws);
+    auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) / 256 * 256; return r; };
+    float* x0 = (float*)take((size_t)n * dg.Ci * 4);
+    float* d0 = (float*)take((size_t)n * dg.Co * 4);
+    int r;
+    if ((r = ew_assemble_gen_input(latent, cond, spc, b_off, x0, n, nd * nd * c->ncond, st))) return r;
+    if ((r = simt_conv_fwd(x0, c->g_params + c->g_off[0], c->g_params + c->g_off[1], d0, dg, ACT_LRELU, nullptr, 1.f, st))) return r;
+    const float* w4 = c->g_params + c->g_off[8];
+    const float* b4 = c->g_params + c->g_off[9];
+    if (mode == RDG_MODE_FP32) {
+        const float* cur = d0;
+        for (int l = 0; l < 3; ++l) {
+            ConvGeom g = rdg_gen_conv_geom(c, l, n);
+            float* y = (float*)take((size_t)n * gen_act_elems(c, l + 1) * 4);
+            if ((r = simt_conv_fwd(cur, c->g_params + c->g_off[2 + 2 * l], c->g_params + c->g_off[3 + 2 * l], y, g, ACT_NONE, nullptr, 1.f, st))) return r;
+            if ((r = ew_pixelnorm(y, y, (long long)n * g.To * g.Ho * g.Wo, g.Co, 1, st))) return r;
+            cur = y;
+        }
+        return conv_out_softmax(RDG_HALF_F32, cur, w4, b4, out, cond, n, nd, spc, b_off, c->ncond, norm_scale,
+                                out_kind == RDG_OUT_MM, flag, st);
+    }
+    const int hk = mode == RDG_MODE_BF16 ? RDG_HALF_BF16 : RDG_HALF_FP16;
+    void* h = take((size_t)n * gen_act_elems(c, 0) * 2);
+    if ((r = f32_to_half(hk, d0, h, (long long)n * dg.Co, st))) return r;
+    static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
+    for (int l = 0; l < 3; ++l) {
+        const int f = 1 << l;
+        void* y = take((size_t)n * gen_act_elems(c, l + 1) * 2);
+        if ((r = tc_upconv_pixelnorm(hk, h, c->g_wpack[hk == RDG_HALF_BF16 ? 0 : 1][l], c->g_params + c->g_off[3 + 2 * l], y, n,
+                                     3 * f, s * f, s * f, cin[l], cout[l], c->sm_count, st))) return r;
+        h = y;
+    }
+    return conv_out_softmax(hk, h, w4, b4, out, cond, n, nd, spc, b_off, c->ncond, norm_scale, out_kind == RDG_OUT_MM, flag, st);
+}
+
+static int chunk_for_mode(const rdg_ctx* c, int mode) {
+    if (mode != RDG_MODE_FP32) return c->max_chunk;
+    size_t n = (c->ws_bytes - 4096 * 8) / c->per_sample32;
+    return (int)std::max<size_t>(1, std::min<size_t>(n, (size_t)c->max_chunk));
+}
+
+extern "C" int rdg_generator_forward(rdg_ctx* c, const float* latent_dev, const float* cond_dev, int spc, float* out_dev,
+                                     int B, int mode, int out_kind, float norm_scale, int* flag_dev, void* stream) {
+    if (!c || B < 0 || spc < 1 || mode < 0 || mode > 2) { rdg_set_error("rdg_generator_forward: bad arguments"); return RDG_E_BADARG; }
+    if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
+    RDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunk = chunk_for_mode(c, mode);
+    const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        int n = std::min(chunk, B - b0);
+        int r = gen_forward_chunk(c, latent_dev + (size_t)b0 * RDG_LATENT, cond_dev, spc, b0, out_dev + (size_t)b0 * plane, n,
+                                  mode, out_kind, norm_scale, flag_dev, st);
+        if (r) return r;
+    }
+    return 0;
+}
+
+extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const float* cond_host, int spc, float* out_host,
+                                 long long B, int mode, int out_kind, float norm_scale) {
+    if (!c || B < 0 || spc < 1 || mode < 0 || mode > 2) { rdg_set_error("rdg_generate_host: bad arguments"); return RDG_E_BADARG; }
+    if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
+    if (B == 0) return 0;
+    RDG_CUDA(cudaSetDevice(c->device));
+    const int chunk = chunk_for_mode(c, mode);
+    const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
+    const size_t ncf = (size_t)c->nd * c->nd * c->ncond;
+    const long long n_cond = (B + spc - 1) / spc;
+    for (int i = 0; i < 2; ++i) {
+        if (!c->e2e_lat[i]) RDG_CUDA(cudaMalloc(&c->e2e_lat[i], (size_t)c->max_chunk * RDG_LATENT * 4));
+        if (!c->e2e_out[i]) RDG_CUDA(cudaMalloc(&c->e2e_out[i], (size_t)c->max_chunk * plane * 4));
+    }
+    if (c->e2e_cond_cap < (size_t)n_cond * ncf) {
+        cudaFree(c->e2e_cond);
+        c->e2e_cond = nullptr;
+        RDG_CUDA(cudaMalloc(&c->e2e_cond, (size_t)n_cond * ncf * 4));
+        c->e2e_cond_cap = (size_t)n_cond * ncf;
+    }
+    RDG_CUDA(cudaMemsetAsync(c->flag_dev, 0, sizeof(int), c->s_comp));
+    RDG_CUDA(cudaMemcpyAsync(c->e2e_cond, cond_host, (size_t)n_cond * ncf * 4, cudaMemcpyHostToDevice, c->s_comp));
+    long long it = 0;
+    for (long long b0 = 0; b0 < B; b0 += chunk, ++it) {
+        const int n = (int)std::min<long long>(chunk, B - b0);
+        const int k = (int)(it & 1);
+        // the latent buffer k is free once the compute of chunk it-2 finished
+        if (it >= 2) RDG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[k], 0));
+        RDG_CUDA(cudaMemcpyAsync(c->e2e_lat[k], latent_host + b0 * RDG_LATENT, (size_t)n * RDG_LATENT * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        RDG_CUDA(cudaEventRecord(c->ev_in[k], c->s_h2d));
+        RDG_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_in[k], 0));
+        // the output buffer k is free once the D2H of chunk it-2 finished
+        if (it >= 2) RDG_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_out[k], 0));
+        int r = gen_forward_chunk(c, c->e2e_lat[k], c->e2e_cond, spc, (int)b0, c->e2e_out[k], n, mode, out_kind, norm_scale,
+                                  c->flag_dev, c->s_comp);
+        if (r) return r;
+        RDG_CUDA(cudaEventRecord(c->ev_comp[k], c->s_comp));
+        RDG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[k], 0));
+        RDG_CUDA(cudaMemcpyAsync(out_host + b0 * plane, c->e2e_out[k], (size_t)n * plane * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        RDG_CUDA(cudaEventRecord(c->ev_out[k], c->s_d2h));
+    }
+    int flag = 0;
+    RDG_CUDA(cudaStreamSynchronize(c->s_d2h));
+    RDG_CUDA(cudaMemcpyAsync(&flag, c->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, c->s_comp));
+    RDG_CUDA(cudaStreamSynchronize(c->s_comp));
+    RDG_CUDA(cudaStreamSynchronize(c->s_h2d));
+    if (flag) { rdg_set_error("found nan in output of per_gridpoint_softmax"); return RDG_E_NONFINITE; }
+    return 0;
+}
+
+extern "C" int rdg_fill_normal(float* dst_dev, long long n, uint64_t seed, uint64_t offset, void* stream) {
+    if (!dst_dev || n < 0 || (offset & 3)) { rdg_set_error("rdg_fill_normal: bad arguments (offset must be a multiple of 4)"); return RDG_E_BADARG; }
+    return ew_fill_normal(dst_dev, n, seed, offset, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ critic forward
+extern "C" int rdg_critic_forward(rdg_ctx* c, const float* sample_dev, const float* cond_dev, const float* const* masks_dev,
+                                  float* score_dev, int B, void* stream) {
+    if (!c || B < 0) return RDG_E_BADARG;
+    if (!c->critic_ready) { rdg_set_error("critic weights not set"); return RDG_E_NOWEIGHT; }
+    RDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // per-sample workspace of the critic
+    size_t per = (size_t)RDG_NHOURS * c->nd * c->nd * (1 + c->ncond);
+    for (int l = 0; l < 4; ++l) { ConvGeom g = rdg_critic_conv_geom(c, l, 1); per += (size_t)g.To * g.Ho * g.Wo * g.Co; }
+    per = per * 4 + 4 * 256;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((c->ws_bytes - 4096) / per, 1 << 20));
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int n = std::min(chunk, B - b0);
+        uint8_t* p = reinterpret_cast<uint8_t*>(c->ws);
+        auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) / 256 * 256; return r; };
+        float* x = (float*)take((size_t)n * RDG_NHOURS * c->nd * c->nd * (1 + c->ncond) * 4);
+        int r;
+        if ((r = ew_critic_input(sample_dev + (size_t)b0 * RDG_NHOURS * c->nd * c->nd, cond_dev + (size_t)b0 * c->nd * c->nd * c->ncond, x, n, c->nd, c->ncond, st))) return r;
+        const float* cur = x;
+        for (int l = 0; l < 4; ++l) {
+            ConvGeom g = rdg_critic_conv_geom(c, l, n);
+            const size_t per_l = (size_t)g.To * g.Ho * g.Wo * g.Co;
+            float* y = (float*)take((size_t)n * per_l * 4);
+            const float* m = masks_dev ? masks_dev[l] + (size_t)b0 * per_l : nullptr;
+            if ((r = simt_conv_fwd(cur, c->c_params + c->c_off[2 * l], c->c_params + c->c_off[2 * l + 1], y, g, ACT_LRELU, m, 1.f / 0.75f, st))) return r;
+            cur = y;
+        }
+        ConvGeom d = rdg_critic_dense_geom(c, n);
+        if ((r = simt_conv_fwd(cur, c->c_params + c->c_off[8], c->c_params + c->c_off[9], score_dev + b0, d, ACT_NONE, nullptr, 1.f, st))) return r;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ building blocks for tests
+// One tensor-core layer in isolation: x f32 [B,T,H,W,Cin] -> rounded to 16 bit -> layer -> y f32 [B,2T,2H,2W,Cout]
+extern "C" int rdg_tc_layer(rdg_ctx* c, int layer, int mode, const float* x_dev, float* y_dev, int B, void* stream) {
+    if (!c || layer < 0 || layer > 2 || (mode != RDG_MODE_BF16 && mode != RDG_MODE_FP16)) return RDG_E_BADARG;
+    if (!c->gen_ready) return RDG_E_NOWEIGHT;
+    RDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
+    const int hk = mode == RDG_MODE_BF16 ? RDG_HALF_BF16 : RDG_HALF_FP16;
+    const int s = c->nd / 8, f = 1 << layer;
+    const size_t n_in = (size_t)B * 3 * f * s * f * s * f * cin[layer];
+    const size_t n_out = (size_t)B * 24 * f * s * f * s * f * cout[layer];
+    if ((n_in + n_out) * 2 + 1024 > c->ws_bytes) { rdg_set_error("rdg_tc_layer: batch too large for workspace"); return RDG_E_BADARG; }
+    uint8_t* xin = reinterpret_cast<uint8_t*>(c->ws);
+    uint8_t* yout = xin + (n_in * 2 + 255) / 256 * 256;
+    int r;
+    if ((r = f32_to_half(hk, x_dev, xin, (long long)n_in, st))) return r;
+    if ((r = tc_upconv_pixelnorm(hk, xin, c->g_wpack[hk == RDG_HALF_BF16 ? 0 : 1][layer], c->g_params + c->g_off[3 + 2 * layer], yout, B,
+                                 3 * f, s * f, s * f, cin[layer], cout[layer], c->sm_count, st))) return r;
+    return half_to_f32(hk, yout, y_dev, (long long)n_out, st);
+}
+
+extern "C" int rdg_pixelnorm(const float* x_dev, float* y_dev, long long rows, int C, int lrelu, void* stream) {
+    return ew_pixelnorm(x_dev, y_dev, rows, C, lrelu, (cudaStream_t)stream);
+}
+extern "C" int rdg_softmax_hours(const float* logits_dev, float* out_dev, long long B, int P, void* stream) {
+    return ew_softmax_hours(logits_dev, out_dev, B, P, nullptr, 1, 1, 1.f, 0, nullptr, (cudaStream_t)stream);
+}

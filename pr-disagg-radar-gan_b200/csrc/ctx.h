@@ -1,0 +1,32 @@
+// Context object behind the opaque rdg_ctx handle of include/rdg_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "rdg_common.cuh"
+
+struct rdg_ctx {
+    int device = 0, nd = 16, ncond = 1, max_chunk = 0, sm_count = 0;
+    // FP32 master parameters, Keras tensor order, concatenated (each tensor 16-byte aligned)
+    float* g_params = nullptr; size_t g_off[10] = {}, g_size[10] = {}, g_total = 0;
+    float* c_params = nullptr; size_t c_off[10] = {}, c_size[10] = {}, c_total = 0;
+    bool gen_ready = false, critic_ready = false, gen_packed_stale = false;
+    // folded + swizzled 16-bit operand tiles of the three upsampled convs: [0]=bf16, [1]=fp16
+    void* g_wpack[2][3] = {};
+    // training state (allocated on first use)
+    float* g_grads = nullptr; float* g_m = nullptr; float* g_v = nullptr;
+    float* c_grads = nullptr; float* c_m = nullptr; float* c_v = nullptr;
+    void* train_ws = nullptr; size_t train_ws_bytes = 0;
+    // forward workspace
+    void* ws = nullptr; size_t ws_bytes = 0; size_t per_sample16 = 0, per_sample32 = 0;
+    int* flag_dev = nullptr;
+    // host-buffer pipeline
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
+    float* e2e_lat[2] = {}; float* e2e_out[2] = {}; float* e2e_cond = nullptr; size_t e2e_cond_cap = 0;
+};
+
+ConvGeom rdg_gen_conv_geom(const rdg_ctx* c, int layer, int B);
+ConvGeom rdg_gen_dense_geom(const rdg_ctx* c, int B);
+ConvGeom rdg_critic_conv_geom(const rdg_ctx* c, int layer, int B);
+ConvGeom rdg_critic_dense_geom(const rdg_ctx* c, int B);
+int rdg_repack_generator(rdg_ctx* c, const float* const* host_tensors);

@@ -1,0 +1,263 @@
+// Elementwise / reduction kernels of the RainDisaggGAN hot path (FP32).
+//   PixelNormalization   gan_train_cwgangp_pixelnorm.py:249-270
+//   LeakyReLU(0.2)       :327,333,338,343 / :288-300
+//   Softmax(axis=1)      :347  (+ check_numerics :349-350, + mm rescale raindisagg_gan_pretrained.py:62-64)
+//   cond tiling/concat   :275-282 ; latent/cond concat :319-323
+//   Adam                 :385 (Keras OptimizerV2 form)
+#include "rdg_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void assemble_gen_input_kernel(const float* __restrict__ latent, const float* __restrict__ cond,
+                                          int spc, int b_off, float* __restrict__ x0, int B, int ncf) {
+    const int K = RDG_LATENT + ncf;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * K) return;
+    int b = (int)(i / K), k = (int)(i % K);
+    x0[i] = k < RDG_LATENT ? latent[(long long)b * RDG_LATENT + k]
+                           : cond[(long long)((b_off + b) / spc) * ncf + (k - RDG_LATENT)];
+}
+
+// one warp per row of C channels
+__global__ void pixelnorm_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int C,
+                                 int lrelu) {
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) { float v = xr[c]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    const float l2 = sqrtf(s / (float)C + 1.0e-8f);
+    for (int c = lane; c < C; c += 32) {
+        float v = xr[c] / l2;
+        if (lrelu) v = v > 0.f ? v : 0.2f * v;
+        y[row * C + c] = v;
+    }
+}
+
+// backward of LeakyReLU(PixelNorm(x)) given the conv output x (pre-norm) -- SURVEY A4
+__global__ void pixelnorm_lrelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                           float* __restrict__ dx, long long rows, int C) {
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + row * C;
+    const float* gr = dy + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) { float v = xr[c]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    const float l2 = sqrtf(s / (float)C + 1.0e-8f);
+    float dot = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float yn = xr[c] / l2;
+        float g = gr[c] * (yn > 0.f ? 1.f : 0.2f);
+        dot = fmaf(g, yn, dot);
+    }
+    dot = warp_sum(dot) / (float)C;
+    for (int c = lane; c < C; c += 32) {
+        float yn = xr[c] / l2;
+        float g = gr[c] * (yn > 0.f ? 1.f : 0.2f);
+        dx[row * C + c] = (g - yn * dot) / l2;
+    }
+}
+
+// logits [B,24,P] -> fractions (or mm) [B,24,P]; thread per (b,p)
+__global__ void softmax_hours_kernel(const float* __restrict__ logits, float* __restrict__ out, long long B, int P,
+                                     const float* __restrict__ cond, int spc, int ncond, float scale, int out_mm,
+                                     int* __restrict__ nonfinite) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * P) return;
+    long long b = i / P; int p = (int)(i % P);
+    const float* l = logits + b * RDG_NHOURS * P + p;
+    float v[RDG_NHOURS], mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) { v[t] = l[(long long)t * P]; mx = fmaxf(mx, v[t]); }
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) { v[t] = expf(v[t] - mx); s += v[t]; }
+    float mul = 1.f;
+    if (out_mm) mul = cond[((b / spc) * P + p) * ncond] * scale;
+    bool bad = false;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) {
+        float f = v[t] / s;
+        bad |= !isfinite(f);
+        out[b * RDG_NHOURS * P + (long long)t * P + p] = f * mul;
+    }
+    if (bad && nonfinite) atomicOr(nonfinite, 1);
+}
+
+__global__ void softmax_hours_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                         float* __restrict__ dl, long long B, int P) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * P) return;
+    long long b = i / P; int p = (int)(i % P);
+    long long base = b * RDG_NHOURS * P + p;
+    float dot = 0.f;
+    for (int t = 0; t < RDG_NHOURS; ++t) dot = fmaf(y[base + (long long)t * P], dy[base + (long long)t * P], dot);
+    for (int t = 0; t < RDG_NHOURS; ++t) {
+        long long k = base + (long long)t * P;
+        dl[k] = y[k] * (dy[k] - dot);
+    }
+}
+
+__global__ void lrelu_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dy, float* __restrict__ dx,
+                                 long long n, const float* __restrict__ mask, float mask_scale) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g = dy[i] * (pre[i] > 0.f ? 1.f : 0.2f);
+    if (mask) g *= mask[i] * mask_scale;
+    dx[i] = g;
+}
+
+// gradient of nearest x2 upsample: 2x2x2 sum-pool
+__global__ void upsample_pool_kernel(const float* __restrict__ du, float* __restrict__ dl, int B, int T, int H, int W,
+                                     int C) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)B * T * H * W * C;
+    if (i >= n) return;
+    int c = (int)(i % C); long long r = i / C;
+    int w = (int)(r % W); r /= W;
+    int h = (int)(r % H); r /= H;
+    int t = (int)(r % T); int b = (int)(r / T);
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        int tt = 2 * t + (a >> 2), hh = 2 * h + ((a >> 1) & 1), ww = 2 * w + (a & 1);
+        s += du[((((long long)b * 2 * T + tt) * 2 * H + hh) * 2 * W + ww) * C + c];
+    }
+    dl[i] = s;
+}
+
+__global__ void critic_input_kernel(const float* __restrict__ sample, const float* __restrict__ cond,
+                                    float* __restrict__ x, int B, int nd, int ncond) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = 1 + ncond;
+    long long n = (long long)B * RDG_NHOURS * nd * nd * C;
+    if (i >= n) return;
+    int c = (int)(i % C); long long r = i / C;
+    int p = (int)(r % (nd * nd)); r /= (nd * nd);
+    long long b = r / RDG_NHOURS;
+    x[i] = c == 0 ? sample[i / C] : cond[(b * nd * nd + p) * ncond + (c - 1)];
+}
+
+// Philox4x32-10 counter-based generator + Box-Muller; element i uses counter (offset+i)/4.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+
+__global__ void fill_normal_kernel(float* __restrict__ dst, long long n, uint64_t seed, uint64_t offset) {
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // quad index
+    if (q * 4 >= n) return;
+    uint64_t ctr = offset / 4 + (uint64_t)q;
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    float u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = ((float)c[j] + 0.5f) * 2.3283064365386963e-10f;   // (0,1)
+    float r0 = sqrtf(-2.f * logf(u[0])), r1 = sqrtf(-2.f * logf(u[2]));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u[1], &s0, &c0);
+    sincospif(2.f * u[3], &s1, &c1);
+    float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (q * 4 + j < n) dst[q * 4 + j] = z[j];
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
+                            float gs) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i] * gs;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+}
+
+}  // namespace
+
+#define EW_GRID(n) ceil_div((n), 256), 256, 0, st
+
+int ew_assemble_gen_input(const float* latent, const float* cond, int spc, int b_off, float* x0, int B, int ncf,
+                          cudaStream_t st) {
+    long long n = (long long)B * (RDG_LATENT + ncf);
+    if (!n) return 0;
+    assemble_gen_input_kernel<<<EW_GRID(n)>>>(latent, cond, spc, b_off, x0, B, ncf);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_pixelnorm(const float* x, float* y, long long rows, int C, int lrelu, cudaStream_t st) {
+    if (!rows) return 0;
+    pixelnorm_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, y, rows, C, lrelu);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_pixelnorm_lrelu_bwd(const float* x_pre, const float* dy, float* dx, long long rows, int C, cudaStream_t st) {
+    if (!rows) return 0;
+    pixelnorm_lrelu_bwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x_pre, dy, dx, rows, C);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_softmax_hours(const float* logits, float* out, long long B, int P, const float* cond, int spc, int ncond,
+                     float scale, int out_mm, int* nonfinite, cudaStream_t st) {
+    if (!B) return 0;
+    softmax_hours_kernel<<<EW_GRID(B * P)>>>(logits, out, B, P, cond, spc, ncond, scale, out_mm, nonfinite);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_softmax_hours_bwd(const float* y, const float* dy, float* dl, long long B, int P, cudaStream_t st) {
+    if (!B) return 0;
+    softmax_hours_bwd_kernel<<<EW_GRID(B * P)>>>(y, dy, dl, B, P);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_lrelu_bwd(const float* pre, const float* dy, float* dx, long long n, const float* mask, float mask_scale,
+                 cudaStream_t st) {
+    if (!n) return 0;
+    lrelu_bwd_kernel<<<EW_GRID(n)>>>(pre, dy, dx, n, mask, mask_scale);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_upsample_pool(const float* d_up, float* d_lo, int B, int T, int H, int W, int C, cudaStream_t st) {
+    long long n = (long long)B * T * H * W * C;
+    if (!n) return 0;
+    upsample_pool_kernel<<<EW_GRID(n)>>>(d_up, d_lo, B, T, H, W, C);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_critic_input(const float* sample, const float* cond, float* x, int B, int nd, int ncond, cudaStream_t st) {
+    long long n = (long long)B * RDG_NHOURS * nd * nd * (1 + ncond);
+    if (!n) return 0;
+    critic_input_kernel<<<EW_GRID(n)>>>(sample, cond, x, B, nd, ncond);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_fill_normal(float* dst, long long n, uint64_t seed, uint64_t offset, cudaStream_t st) {
+    if (!n) return 0;
+    fill_normal_kernel<<<EW_GRID((n + 3) / 4)>>>(dst, n, seed, offset);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+            float eps, float grad_scale, cudaStream_t st) {
+    if (!n) return 0;
+    adam_kernel<<<EW_GRID(n)>>>(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}

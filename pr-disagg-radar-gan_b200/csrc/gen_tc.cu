@@ -1,0 +1,626 @@
+// Tensor-core generator layers for sm_100a: UpSampling3D(2) + Conv3D(3^3,'same') + bias +
+// PixelNormalization + LeakyReLU(0.2) (gan_train_cwgangp_pixelnorm.py:330-343) as ONE kernel.
+//
+// Algorithm: the nearest x2 upsample is folded into the weights: each of the 8
+// output phases (pt,ph,pw) is a 2x2x2 convolution on the LOW-RES grid.  Per phase and tap the
+// contribution is a plain GEMM  D[128 positions, Cout] += A[128, Cin] * Wf[phase][tap][Cin, Cout]
+// where A is the input activation tile shifted by the tap offset.  A tiles are fetched with 5-D
+// TMA box loads straight from the channels-last activation tensor (zero fill outside the grid
+// implements the conv padding), weight tiles with 1-D bulk copies of host-pre-swizzled images;
+// both land in 128B-swizzled K-major shared memory and feed tcgen05.mma (kind::f16, M=128,
+// N=Cout, K=16) accumulating in TMEM.  NPH phases share one pass so that an A tile is reused by
+// every phase that needs that offset.  The epilogue warps read the accumulators back with
+// tcgen05.ld, apply bias + PixelNorm + LeakyReLU in FP32 and store 16-bit channels-last output.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each).
+#include "rdg_common.cuh"
+#include "gen_tc.h"
+#include <cuda.h>
+
+namespace {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 64 16-bit elements (128 B), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset (between 8-row groups)
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+template <typename HT> struct HalfOps;
+template <> struct HalfOps<__nv_bfloat16> {
+    static constexpr uint32_t kFmt = 1;
+    static __device__ __forceinline__ uint32_t pack(float a, float b) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ float2 unpack(uint32_t u) {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    }
+    static __device__ __forceinline__ __nv_bfloat16 from_float(float a) { return __float2bfloat16_rn(a); }
+};
+template <> struct HalfOps<__half> {
+    static constexpr uint32_t kFmt = 0;
+    static __device__ __forceinline__ uint32_t pack(float a, float b) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+    static __device__ __forceinline__ __half from_float(float a) { return __float2half_rn(a); }
+};
+
+// ------------------------------------------------------------------ step enumeration
+// One source of truth for the K-loop order, shared by the producer and the MMA issuer.
+// For pass `pass` (phases pass*NPH .. pass*NPH+NPH-1) walk the 27 low-res offsets; an offset
+// (dt,dh,dw) serves phase p=(pt,ph,pw) with tap a=(dt+1-pt, dh+1-ph, dw+1-pw) if all in {0,1}.
+template <int NPH, typename FA, typename FB>
+__device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk, FA&& on_a, FB&& on_b) {
+    for (int o = 0; o < 27; ++o) {
+        const int dt = o / 9 - 1, dh = (o / 3) % 3 - 1, dw = o % 3 - 1;
+        if (t + dt < 0 || t + dt >= T) continue;   // whole tile in the zero padding
+        uint32_t mask = 0;
+#pragma unroll
+        for (int s = 0; s < NPH; ++s) {
+            const int p = pass * NPH + s;
+            const int at = dt + 1 - (p >> 2), ah = dh + 1 - ((p >> 1) & 1), aw = dw + 1 - (p & 1);
+            if ((unsigned)at < 2u && (unsigned)ah < 2u && (unsigned)aw < 2u) mask |= 1u << s;
+        }
+        if (!mask) continue;
+        for (int c = 0; c < nchunk; ++c) {
+            on_a(dt, dh, dw, c);
+#pragma unroll
+            for (int s = 0; s < NPH; ++s) {
+                if (!(mask & (1u << s))) continue;
+                const int p = pass * NPH + s;
+                const int a = ((dt + 1 - (p >> 2)) << 2) | ((dh + 1 - ((p >> 1) & 1)) << 1) | (dw + 1 - (p & 1));
+                on_b(s, (p * 8 + a) * nchunk + c);
+            }
+        }
+    }
+}
+
+constexpr int kThreads = 192;
+constexpr int kATile = 128 * 128;   // 128 rows x 64 x 2 B
+
+template <int COUT, int NPH> struct TcCfg {
+    static constexpr int kBTile = COUT * 128;
+    static constexpr int kAccCols = NPH * COUT;
+    static constexpr int kAccStages = (kAccCols * 2 <= 512) ? 2 : 1;
+    static constexpr int kAStages = 4;
+    static constexpr int kBStages = (200 * 1024 - kAStages * kATile) / kBTile > 12
+                                        ? 12 : (200 * 1024 - kAStages * kATile) / kBTile;
+    static constexpr int kSmem = 1024 + kAStages * kATile + kBStages * kBTile + COUT * 4 + 512;
+    static_assert(kAccCols * kAccStages <= 512, "TMEM overflow");
+    static_assert(kBStages >= 2, "need at least 2 weight stages");
+};
+
+template <typename HT, int COUT, int NPH>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs args) {
+    using Cfg = TcCfg<COUT, NPH>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_buf = smem;
+    uint8_t* b_buf = a_buf + Cfg::kAStages * kATile;
+    float* s_bias = reinterpret_cast<float*>(b_buf + Cfg::kBStages * Cfg::kBTile);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + COUT);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + Cfg::kAStages;
+    uint64_t* b_full = a_empty + Cfg::kAStages;
+    uint64_t* b_empty = b_full + Cfg::kBStages;
+    uint64_t* acc_full = b_empty + Cfg::kBStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunk = args.Cin / 64;
+    const int n_hblk = args.H / args.Hb;
+
+    for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = args.bias[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::kAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t ai = 0, bi = 0;   // running slot counters
+            for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+                const int hblk = tile % n_hblk, t = (tile / n_hblk) % args.T, bblk = tile / (n_hblk * args.T);
+                const int h0 = hblk * args.Hb, b0 = bblk * args.Bt;
+                for (int pass = 0; pass < 8 / NPH; ++pass) {
+                    for_each_step<NPH>(
+                        pass, t, args.T, nchunk,
+                        [&](int dt, int dh, int dw, int c) {
+                            const uint32_t s = ai % Cfg::kAStages, ph = (ai / Cfg::kAStages) & 1;
+                            mbar_wait(&a_empty[s], ph ^ 1);
+                            mbar_expect_tx(&a_full[s], kATile);
+                            tma_load_5d(a_buf + s * kATile, &tmap, &a_full[s], c * 64, dw, h0 + dh, t + dt, b0);
+                            ++ai;
+                        },
+                        [&](int, int wtile) {
+                            const uint32_t s = bi % Cfg::kBStages, ph = (bi / Cfg::kBStages) & 1;
+                            mbar_wait(&b_empty[s], ph ^ 1);
+                            mbar_expect_tx(&b_full[s], Cfg::kBTile);
+                            bulk_load_1d(b_buf + s * Cfg::kBTile,
+                                         reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile,
+                                         Cfg::kBTile, &b_full[s]);
+                            ++bi;
+                        });
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
+                                       ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint32_t ai = 0, bi = 0, acc_it = 0;
+            for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+                const int t = (tile / n_hblk) % args.T;
+                for (int pass = 0; pass < 8 / NPH; ++pass, ++acc_it) {
+                    const uint32_t as = acc_it % Cfg::kAccStages, aph = (acc_it / Cfg::kAccStages) & 1;
+                    mbar_wait(&acc_empty[as], aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
+                    uint32_t started = 0;
+                    uint32_t cur_a = 0;
+                    bool have_a = false;
+                    uint32_t prev_a_slot = 0;
+                    for_each_step<NPH>(
+                        pass, t, args.T, nchunk,
+                        [&](int, int, int, int) {
+                            if (have_a) tc_commit(&a_empty[prev_a_slot]);   // all MMAs reading the previous A tile issued
+                            const uint32_t s = ai % Cfg::kAStages, ph = (ai / Cfg::kAStages) & 1;
+                            mbar_wait(&a_full[s], ph);
+                            tc_fence_after();
+                            cur_a = smem_u32(a_buf + s * kATile);
+                            prev_a_slot = s;
+                            have_a = true;
+                            ++ai;
+                        },
+                        [&](int slot, int) {
+                            const uint32_t s = bi % Cfg::kBStages, ph = (bi / Cfg::kBStages) & 1;
+                            mbar_wait(&b_full[s], ph);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(b_buf + s * Cfg::kBTile);
+                            const uint64_t ad = make_sdesc(cur_a), bd = make_sdesc(b_addr);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                // +32 B per K=16 step inside the 128 B swizzle atom (encoded >>4)
+                                tc_mma_f16(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc,
+                                           ((started >> slot) & 1u) | (k > 0 ? 1u : 0u));
+                            }
+                            started |= 1u << slot;
+                            tc_commit(&b_empty[s]);
+                            ++bi;
+                        });
+                    if (have_a) tc_commit(&a_empty[prev_a_slot]);
+                    tc_commit(&acc_full[as]);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int r = q * 32 + lane;            // accumulator row = position within the tile
+        const int bl = r / (args.Hb * args.W), hl = (r / args.W) % args.Hb, w = r % args.W;
+        HT* out = reinterpret_cast<HT*>(args.out);
+        uint32_t acc_it = 0;
+        for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+            const int hblk = tile % n_hblk, t = (tile / n_hblk) % args.T, bblk = tile / (n_hblk * args.T);
+            const int b = bblk * args.Bt + bl, h = hblk * args.Hb + hl;
+            const bool valid = b < args.B;
+            for (int pass = 0; pass < 8 / NPH; ++pass, ++acc_it) {
+                const uint32_t as = acc_it % Cfg::kAccStages, aph = (acc_it / Cfg::kAccStages) & 1;
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+#pragma unroll 1
+                for (int s = 0; s < NPH; ++s) {
+                    const int p = pass * NPH + s;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::kAccCols + s * COUT;
+                    float ss = 0.f;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < COUT; c0 += 32) {
+                        uint32_t v[32];
+                        tc_ld32(taddr + c0, v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = __uint_as_float(v[j]) + s_bias[c0 + j];
+                            ss = fmaf(x, x, ss);
+                        }
+                    }
+                    const float inv = 1.0f / sqrtf(ss * (1.0f / COUT) + 1.0e-8f);
+                    const size_t o_row = ((((size_t)b * (2 * args.T) + (2 * t + (p >> 2))) * (2 * args.H) +
+                                           (2 * h + ((p >> 1) & 1))) * (2 * args.W) + (2 * w + (p & 1))) * COUT;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < COUT; c0 += 32) {
+                        uint32_t v[32];
+                        tc_ld32(taddr + c0, v);
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float x0 = (__uint_as_float(v[2 * j]) + s_bias[c0 + 2 * j]) * inv;
+                            float x1 = (__uint_as_float(v[2 * j + 1]) + s_bias[c0 + 2 * j + 1]) * inv;
+                            x0 = x0 > 0.f ? x0 : 0.2f * x0;
+                            x1 = x1 > 0.f ? x1 : 0.2f * x1;
+                            pk[j] = HalfOps<HT>::pack(x0, x1);
+                        }
+                        if (valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(out + o_row + c0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[as]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ last conv + softmax
+// Conv3D(1,(3,3,3),'same') + Softmax over the 24 hours (+ optional mm rescale) fused:
+// gan_train_cwgangp_pixelnorm.py:345-350, raindisagg_gan_pretrained.py:62-64.
+// One CTA = one sample x 256 pixels (HB rows x W).  The 24 input hour-planes are streamed through a
+// shared-memory slab with a 1-pixel zero halo; lane l of a warp owns channels (2l, 2l+1), 54 weights
+// stay in registers; each input plane t contributes to logits t-1, t, t+1 of the warp's 32 pixels,
+// kept as rolling per-lane partials; completed logits are transpose-reduced across the warp so that
+// lane i ends up owning pixel i's 24 logits, does the softmax in registers and stores coalesced.
+template <typename TI> struct In2;
+template <> struct In2<float> {
+    static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+};
+template <> struct In2<__half> {
+    static __device__ __forceinline__ float2 ld(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+};
+template <> struct In2<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
+        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    }
+};
+
+// reduce 32 per-lane partials (one per pixel) so that lane i returns the warp-wide sum of v[i]
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            float send = upper ? v[i] : v[i + half];
+            float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(256, 1)
+conv_out_softmax_kernel(const TI* __restrict__ x, const float* __restrict__ w4, const float* __restrict__ b4,
+                        float* __restrict__ out, const float* __restrict__ cond, int B, int lognd, int HB, int spc,
+                        int b_off, int ncond, float scale, int out_mm, int* __restrict__ nonfinite) {
+    extern __shared__ __align__(16) uint8_t smem_raw2[];
+    float* logit_s = reinterpret_cast<float*>(smem_raw2);                       // [24][256]
+    TI* slab = reinterpret_cast<TI*>(smem_raw2 + RDG_NHOURS * 256 * 4);         // [(HB+2)][(nd+2)][64]
+    const int nd = 1 << lognd;
+    const int W2 = nd + 2;
+    const int n_hblk = nd / HB;
+    const int b = blockIdx.x / n_hblk, h0 = (blockIdx.x % n_hblk) * HB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // pixel i of this warp: index warp*32+i within the HB x nd tile
+    float wreg[27][2];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) { wreg[k][0] = w4[k * 64 + 2 * lane]; wreg[k][1] = w4[k * 64 + 2 * lane + 1]; }
+
+    // zero the slab once (halo stays zero; interior is overwritten per plane)
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(slab);
+        const int nwords = (HB + 2) * W2 * 64 * (int)sizeof(TI) / 4;
+        for (int i = threadIdx.x; i < nwords; i += 256) z[i] = 0u;
+    }
+    float accA[32], accB[32], accC[32];   // partial logits for hours t-1, t, t+1 (relative to current plane)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { accA[i] = 0.f; accB[i] = 0.f; accC[i] = 0.f; }
+    const TI* xb = x + (size_t)b * RDG_NHOURS * nd * nd * 64;
+    constexpr int VEC = 16 / (int)sizeof(TI);            // elements per 16-byte vector
+    const int vec_per_row = nd * 64 / VEC;               // contiguous (w,c) run of one h row
+
+#pragma unroll 1
+    for (int t = 0; t < RDG_NHOURS; ++t) {
+        __syncthreads();
+        // load rows h0-1 .. h0+HB of plane t (rows outside the domain stay/are zero)
+        for (int rr = 0; rr < HB + 2; ++rr) {
+            const int h = h0 + rr - 1;
+            uint4* drow = reinterpret_cast<uint4*>(slab + ((size_t)rr * W2 + 1) * 64);
+            if (h >= 0 && h < nd) {
+                const uint4* srow = reinterpret_cast<const uint4*>(xb + ((size_t)t * nd + h) * nd * 64);
+                for (int i = threadIdx.x; i < vec_per_row; i += 256) drow[i] = srow[i];
+            } else if (t == 0 || n_hblk > 1) {
+                for (int i = threadIdx.x; i < vec_per_row; i += 256) drow[i] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int pix = warp * 32 + i;
+            const int ph = pix >> lognd, pw = pix & (nd - 1);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float2 v = In2<TI>::ld(slab + ((size_t)(ph + kh) * W2 + (pw + kw)) * 64 + 2 * lane);
+                    // plane t feeds output hour (t - kt + 1) with tap kt
+                    a0 = fmaf(v.x, wreg[(2 * 3 + kh) * 3 + kw][0], fmaf(v.y, wreg[(2 * 3 + kh) * 3 + kw][1], a0));  // hour t-1
+                    a1 = fmaf(v.x, wreg[(1 * 3 + kh) * 3 + kw][0], fmaf(v.y, wreg[(1 * 3 + kh) * 3 + kw][1], a1));  // hour t
+                    a2 = fmaf(v.x, wreg[(0 * 3 + kh) * 3 + kw][0], fmaf(v.y, wreg[(0 * 3 + kh) * 3 + kw][1], a2));  // hour t+1
+                }
+            accA[i] += a0; accB[i] += a1; accC[i] += a2;
+        }
+        // hour t-1 is complete now
+        if (t >= 1) logit_s[(t - 1) * 256 + warp * 32 + lane] = transpose_reduce32(accA, lane);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { accA[i] = accB[i]; accB[i] = accC[i]; accC[i] = 0.f; }
+    }
+    logit_s[(RDG_NHOURS - 1) * 256 + warp * 32 + lane] = transpose_reduce32(accA, lane);
+
+    // softmax over hours for pixel `lane` of this warp (each lane re-reads only what it wrote)
+    const int pix = warp * 32 + lane;
+    const int h = h0 + (pix >> lognd), wq = pix & (nd - 1);
+    const float bias = b4[0];
+    float logit[RDG_NHOURS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) { logit[t] = logit_s[t * 256 + pix] + bias; mx = fmaxf(mx, logit[t]); }
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) { logit[t] = expf(logit[t] - mx); s += logit[t]; }
+    float mul = 1.f;
+    if (out_mm) mul = cond[(((size_t)((b_off + b) / spc) * nd + h) * nd + wq) * ncond] * scale;
+    bool bad = false;
+    float* ob = out + (size_t)b * RDG_NHOURS * nd * nd + (size_t)h * nd + wq;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) {
+        const float f = logit[t] / s;
+        bad |= !isfinite(f);
+        ob[(size_t)t * nd * nd] = f * mul;
+    }
+    if (bad && nonfinite) atomicOr(nonfinite, 1);
+}
+
+template <typename HT>
+__global__ void f32_to_half_kernel(const float* __restrict__ src, HT* __restrict__ dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = HalfOps<HT>::from_float(src[i]);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <typename HT, int COUT, int NPH>
+int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, int B, int T, int H, int W, int Cin,
+                  int sm_count, cudaStream_t st) {
+    using Cfg = TcCfg<COUT, NPH>;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { rdg_set_error("cuTensorMapEncodeTiled entry point not available"); return RDG_TC_E_DRIVER; }
+    if (Cin % 64 || W > 128 || (128 % W) != 0) { rdg_set_error("tc upconv: unsupported shape"); return RDG_TC_E_SHAPE; }
+    TcConvArgs a;
+    a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin;
+    int rows_per_sample_plane = H * W;
+    if (rows_per_sample_plane >= 128) { a.Hb = 128 / W; a.Bt = 1; }
+    else { a.Hb = H; a.Bt = 128 / rows_per_sample_plane; }
+    if (a.Hb < 1 || H % a.Hb) { rdg_set_error("tc upconv: H not divisible by tile rows"); return RDG_TC_E_SHAPE; }
+    a.n_tiles = ceil_div(B, a.Bt) * T * (H / a.Hb);
+    a.wpack = wpack; a.bias = bias; a.out = y;
+
+    CUtensorMap tmap;
+    cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                          (cuuint64_t)T * H * W * Cin * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)W, (cuuint32_t)a.Hb, 1, (cuuint32_t)a.Bt};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMapDataType dt = sizeof(HT) == 2 && HalfOps<HT>::kFmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = enc(&tmap, dt, 5, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return RDG_TC_E_DRIVER; }
+
+    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+        attr_set = true;
+    }
+    int grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
+    kern<<<grid, kThreads, Cfg::kSmem, st>>>(tmap, a);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename HT>
+int tc_upconv_dispatch(const void* x, const void* wpack, const float* bias, void* y, int B, int T, int H, int W,
+                       int Cin, int Cout, int sm_count, cudaStream_t st) {
+    if (Cout == 256) return launch_upconv<HT, 256, 1>(x, wpack, bias, y, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 128) return launch_upconv<HT, 128, 2>(x, wpack, bias, y, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 64) return launch_upconv<HT, 64, 4>(x, wpack, bias, y, B, T, H, W, Cin, sm_count, st);
+    rdg_set_error("tc upconv: unsupported Cout %d", Cout);
+    return RDG_TC_E_SHAPE;
+}
+
+template <typename TI>
+int launch_conv_out(const void* x, const float* w4, const float* b4, float* out, const float* cond, int B, int nd,
+                    int spc, int b_off, int ncond, float scale, int out_mm, int* nonfinite, cudaStream_t st) {
+    int lognd = 0;
+    while ((1 << lognd) < nd) ++lognd;
+    if ((1 << lognd) != nd || nd > 256) { rdg_set_error("conv_out: nd must be a power of two <= 256"); return RDG_TC_E_SHAPE; }
+    int HB = 256 / nd;
+    if (HB > nd) { rdg_set_error("conv_out: nd too small"); return RDG_TC_E_SHAPE; }
+    size_t smem = (size_t)(HB + 2) * (nd + 2) * 64 * sizeof(TI) + RDG_NHOURS * 256 * 4;
+    auto kern = conv_out_softmax_kernel<TI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) { rdg_set_error("conv_out: slab too large"); return RDG_TC_E_SHAPE; }
+    int grid = B * (nd / HB);
+    kern<<<grid, 256, smem, st>>>(reinterpret_cast<const TI*>(x), w4, b4, out, cond, B, lognd, HB, spc, b_off, ncond, scale,
+                                  out_mm, nonfinite);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int tc_upconv_pixelnorm(int half_kind, const void* x, const void* wpack, const float* bias, void* y, int B, int T,
+                        int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st) {
+    if (B <= 0) return 0;
+    if (half_kind == RDG_HALF_BF16)
+        return tc_upconv_dispatch<__nv_bfloat16>(x, wpack, bias, y, B, T, H, W, Cin, Cout, sm_count, st);
+    return tc_upconv_dispatch<__half>(x, wpack, bias, y, B, T, H, W, Cin, Cout, sm_count, st);
+}
+
+int conv_out_softmax(int in_kind, const void* x, const float* w4, const float* b4, float* out, const float* cond,
+                     int B, int nd, int spc, int b_off, int ncond, float scale, int out_mm, int* nonfinite, cudaStream_t st) {
+    if (B <= 0) return 0;
+    if (in_kind == RDG_HALF_BF16)
+        return launch_conv_out<__nv_bfloat16>(x, w4, b4, out, cond, B, nd, spc, b_off, ncond, scale, out_mm, nonfinite, st);
+    if (in_kind == RDG_HALF_FP16)
+        return launch_conv_out<__half>(x, w4, b4, out, cond, B, nd, spc, b_off, ncond, scale, out_mm, nonfinite, st);
+    return launch_conv_out<float>(x, w4, b4, out, cond, B, nd, spc, b_off, ncond, scale, out_mm, nonfinite, st);
+}
+
+namespace {
+template <typename HT>
+__global__ void half_to_f32_kernel(const HT* __restrict__ src, float* __restrict__ dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+}  // namespace
+
+int half_to_f32(int half_kind, const void* src, float* dst, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (half_kind == RDG_HALF_BF16)
+        half_to_f32_kernel<__nv_bfloat16><<<ceil_div(n, 256), 256, 0, st>>>((const __nv_bfloat16*)src, dst, n);
+    else
+        half_to_f32_kernel<__half><<<ceil_div(n, 256), 256, 0, st>>>((const __half*)src, dst, n);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int f32_to_half(int half_kind, const float* src, void* dst, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (half_kind == RDG_HALF_BF16)
+        f32_to_half_kernel<__nv_bfloat16><<<ceil_div(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, n);
+    else
+        f32_to_half_kernel<__half><<<ceil_div(n, 256), 256, 0, st>>>(src, (__half*)dst, n);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,30 @@
+// Host entry points of the tensor-core generator kernels (gen_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#define RDG_HALF_F32  0
+#define RDG_HALF_BF16 1
+#define RDG_HALF_FP16 2
+
+#define RDG_TC_E_DRIVER (-10)
+#define RDG_TC_E_SHAPE  (-11)
+
+struct TcConvArgs {
+    int B;              // samples in this launch
+    int T, H, W;        // low-res input grid
+    int Cin;
+    int Hb, Bt;         // TMA box: Bt samples x Hb rows x W columns = 128 accumulator rows
+    int n_tiles;
+    const void* wpack;  // [8 phases][8 taps][Cin/64][Cout rows x 64 k] 16-bit, rows pre-swizzled (128B)
+    const float* bias;
+    void* out;          // [B,2T,2H,2W,Cout] 16-bit
+};
+
+// y[B,2T,2H,2W,Cout] = LeakyReLU(PixelNorm(conv3x3x3(upsample2(x[B,T,H,W,Cin])) + bias))
+int tc_upconv_pixelnorm(int half_kind, const void* x, const void* wpack, const float* bias, void* y, int B, int T,
+                        int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st);
+// out[B,24,nd,nd] = softmax_hours(conv3x3x3(x[B,24,nd,nd,64]) + b) (* cond * scale)
+int conv_out_softmax(int in_kind, const void* x, const float* w4, const float* b4, float* out, const float* cond,
+                     int B, int nd, int spc, int b_off, int ncond, float scale, int out_mm, int* nonfinite, cudaStream_t st);
+int f32_to_half(int half_kind, const float* src, void* dst, long long n, cudaStream_t st);
+int half_to_f32(int half_kind, const void* src, float* dst, long long n, cudaStream_t st);

@@ -1,0 +1,80 @@
+// Shared declarations for the RainDisaggGAN sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define RDG_NHOURS 24
+#define RDG_LATENT 100
+
+// Geometry of one 3-D convolution over channels-last tensors (B,T,H,W,C).
+// Physical input dims (Ti,Hi,Wi); when `up` is set the kernel reads the input through a
+// nearest x2 upsample (logical dims 2Ti,2Hi,2Wi) -- UpSampling3D fused into the gather.
+struct ConvGeom {
+    int B;
+    int Ti, Hi, Wi, Ci;
+    int To, Ho, Wo, Co;
+    int KT, KH, KW;
+    int stride;
+    int pt, ph, pw;   // zero padding BEFORE (TF 'same' puts the odd one after)
+    int up;
+};
+
+enum { ACT_NONE = 0, ACT_LRELU = 1 };
+
+void rdg_set_error(const char* fmt, ...);
+
+#define RDG_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            rdg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return (int)e_;                                                                \
+        }                                                                                  \
+    } while (0)
+
+#define RDG_LAUNCH_CHECK()                                                                 \
+    do {                                                                                   \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess) {                                                           \
+            rdg_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return (int)e_;                                                                \
+        }                                                                                  \
+    } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- SIMT FP32 primitives (simt_conv.cu) ----
+// y = act(conv(x, w) + bias) [* mask * mask_scale]; w is Keras (KT,KH,KW,Ci,Co) f32.
+int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g,
+                  int act, const float* mask, float mask_scale, cudaStream_t st);
+// dx = conv_transpose(dy, w): gradient w.r.t. the (logical, i.e. upsampled if g.up) input.
+int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);
+// dw += sum_b,pos x (x) dy ; db += sum dy (db may be null). Accumulates (caller zeroes).
+int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, const ConvGeom& g,
+                         cudaStream_t st);
+
+// ---- elementwise / reductions (elementwise.cu) ----
+int ew_assemble_gen_input(const float* latent, const float* cond, int scen_per_cond, int b_off, float* x0,
+                          int B, int ncondflat, cudaStream_t st);
+int ew_pixelnorm(const float* x, float* y, long long rows, int C, int lrelu, cudaStream_t st);
+int ew_pixelnorm_lrelu_bwd(const float* x_pre, const float* dy, float* dx, long long rows, int C,
+                           cudaStream_t st);
+int ew_softmax_hours(const float* logits, float* out, long long B, int P, const float* cond,
+                     int scen_per_cond, int ncond, float scale, int out_mm, int* nonfinite,
+                     cudaStream_t st);
+int ew_softmax_hours_bwd(const float* y, const float* dy, float* dlogits, long long B, int P,
+                         cudaStream_t st);
+int ew_lrelu_bwd(const float* pre, const float* dy, float* dx, long long n, const float* mask,
+                 float mask_scale, cudaStream_t st);
+int ew_upsample_pool(const float* d_up, float* d_lo, int B, int T, int H, int W, int C, cudaStream_t st);
+int ew_critic_input(const float* sample, const float* cond, float* x, int B, int nd, int ncond,
+                    cudaStream_t st);
+int ew_fill_normal(float* dst, long long n, uint64_t seed, uint64_t offset, cudaStream_t st);
+int ew_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1,
+            float beta2, float eps, float grad_scale, cudaStream_t st);
+
+// ---- tensor-core generator (gen_tc.cu) ----
+struct TcLayerPlan;   // opaque, owned by the context

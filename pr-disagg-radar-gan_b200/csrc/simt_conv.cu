@@ -1,0 +1,252 @@
+// FP32 SIMT 3-D convolution primitives (forward, backward-data, backward-filter) over
+// channels-last tensors, as implicit GEMMs with 64x64x16 shared-memory tiles and 4x4
+// register micro-tiles.  These are the FP32-mode / training building blocks; the BF16/FP16
+// generator forward uses the tcgen05 kernels in gen_tc.cu instead.
+//
+// Semantics follow Keras Conv3D as used by the reference (cross-correlation, kernel layout
+// (kt,kh,kw,Cin,Cout), TF 'same'/'valid' padding expressed as pad-before + output size):
+// gan_train_cwgangp_pixelnorm.py:286-301 (critic, stride 2) and :331-345 (generator, stride 1
+// after UpSampling3D, which is fused into the gather here via ConvGeom::up).
+#include "rdg_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+struct PosDec { int b, t, h, w; };
+
+__device__ __forceinline__ PosDec decode_pos(long long m, int T, int H, int W) {
+    PosDec p;
+    p.w = (int)(m % W); m /= W;
+    p.h = (int)(m % H); m /= H;
+    p.t = (int)(m % T); p.b = (int)(m / T);
+    return p;
+}
+
+__device__ __forceinline__ void fma_tile(float (&acc)[4][4], const float (*As)[BM + 4], const float (*Bs)[BN + 4],
+                                         int ty, int tx) {
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+        float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+
+// MODE 0: forward.   M = output positions, N = Co, K = taps*Ci
+// MODE 1: bwd-data.  M = logical input positions, N = Ci, K = taps*Co
+template <int MODE>
+__global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ dst,
+                                                       ConvGeom g, int act, const float* __restrict__ mask,
+                                                       float mask_scale) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int upf = g.up ? 2 : 1;
+    const int LT = g.Ti * upf, LH = g.Hi * upf, LW = g.Wi * upf;   // logical input dims
+    const int MT = MODE == 0 ? g.To : LT, MH = MODE == 0 ? g.Ho : LH, MW = MODE == 0 ? g.Wo : LW;
+    const long long M = (long long)g.B * MT * MH * MW;
+    const int N = MODE == 0 ? g.Co : g.Ci;
+    const int KC = MODE == 0 ? g.Ci : g.Co;                        // reduction channels per tap
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    const int a_m = tid >> 2, a_k = (tid & 3) * 4;
+    const long long am = m0 + a_m;
+    const bool am_ok = am < M;
+    PosDec ap = decode_pos(am_ok ? am : 0, MT, MH, MW);
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int ntaps = g.KT * g.KH * g.KW;
+    for (int tap = 0; tap < ntaps; ++tap) {
+        const int kw_ = tap % g.KW, kh_ = (tap / g.KW) % g.KH, kt_ = tap / (g.KW * g.KH);
+        bool ok = am_ok;
+        long long base = 0;
+        if (MODE == 0) {
+            int lt = ap.t * g.stride + kt_ - g.pt, lh = ap.h * g.stride + kh_ - g.ph, lw = ap.w * g.stride + kw_ - g.pw;
+            ok = ok && lt >= 0 && lt < LT && lh >= 0 && lh < LH && lw >= 0 && lw < LW;
+            if (g.up) { lt >>= 1; lh >>= 1; lw >>= 1; }
+            base = ((((long long)ap.b * g.Ti + lt) * g.Hi + lh) * g.Wi + lw) * g.Ci;
+        } else {
+            int nt = ap.t + g.pt - kt_, nh = ap.h + g.ph - kh_, nw = ap.w + g.pw - kw_;
+            ok = ok && nt >= 0 && nh >= 0 && nw >= 0 && (nt % g.stride) == 0 && (nh % g.stride) == 0 &&
+                 (nw % g.stride) == 0;
+            nt /= g.stride; nh /= g.stride; nw /= g.stride;
+            ok = ok && nt < g.To && nh < g.Ho && nw < g.Wo;
+            base = ((((long long)ap.b * g.To + nt) * g.Ho + nh) * g.Wo + nw) * g.Co;
+        }
+        for (int c0 = 0; c0 < KC; c0 += BK) {
+            // A tile: 64 positions x 16 reduction channels
+            float av[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ok) {
+                const float* p = src + base + c0 + a_k;
+                if (c0 + a_k + 3 < KC && ((KC & 3) == 0)) {
+                    float4 v = *reinterpret_cast<const float4*>(p);
+                    av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (c0 + a_k + j < KC) av[j] = p[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[a_k + j][a_m] = av[j];
+            // B tile: 16 reduction channels x 64 outputs
+            if (MODE == 0) {
+                const int bk = tid >> 4, bn = (tid & 15) * 4;
+                const int ci = c0 + bk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int n = n0 + bn + j;
+                    Bs[bk][bn + j] = (ci < g.Ci && n < g.Co) ? w[((long long)tap * g.Ci + ci) * g.Co + n] : 0.f;
+                }
+            } else {
+                const int bk = tid & 15;
+                const int co = c0 + bk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int nn = (tid >> 4) + j * 16;
+                    int ci = n0 + nn;
+                    Bs[bk][nn] = (co < g.Co && ci < g.Ci) ? w[((long long)tap * g.Ci + ci) * g.Co + co] : 0.f;
+                }
+            }
+            __syncthreads();
+            fma_tile(acc, As, Bs, ty, tx);
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (MODE == 0) {
+                if (bias) v += bias[n];
+                if (act == ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
+                if (mask) v *= mask[m * N + n] * mask_scale;
+            }
+            dst[m * N + n] = v;
+        }
+    }
+}
+
+// dW[tap][ci][co] += sum_m x[gather(m,tap)][ci] * dy[m][co]; grid (ci tiles, co tiles, taps*ksplit)
+__global__ void __launch_bounds__(NT) conv_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             float* __restrict__ dw, ConvGeom g, int ksplit) {
+    __shared__ __align__(16) float As[BK][BM + 4];   // [pos][ci]
+    __shared__ __align__(16) float Bs[BK][BN + 4];   // [pos][co]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int upf = g.up ? 2 : 1;
+    const int LT = g.Ti * upf, LH = g.Hi * upf, LW = g.Wi * upf;
+    const long long M = (long long)g.B * g.To * g.Ho * g.Wo;
+    const int tap = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
+    const int kw_ = tap % g.KW, kh_ = (tap / g.KW) % g.KH, kt_ = tap / (g.KW * g.KH);
+    const int ci0 = blockIdx.x * BM, co0 = blockIdx.y * BN;
+    const long long per = ((M + ksplit - 1) / ksplit + BK - 1) / BK * BK;
+    const long long mbeg = ks * per, mend = mbeg + per < M ? mbeg + per : M;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int lp = tid >> 4;            // position within chunk (0..15)
+    const int lc = (tid & 15) * 4;      // channel quad
+    for (long long mc = mbeg; mc < mend; mc += BK) {
+        long long m = mc + lp;
+        bool okm = m < mend;
+        PosDec p = decode_pos(okm ? m : 0, g.To, g.Ho, g.Wo);
+        int lt = p.t * g.stride + kt_ - g.pt, lh = p.h * g.stride + kh_ - g.ph, lw = p.w * g.stride + kw_ - g.pw;
+        bool okx = okm && lt >= 0 && lt < LT && lh >= 0 && lh < LH && lw >= 0 && lw < LW;
+        if (g.up) { lt >>= 1; lh >>= 1; lw >>= 1; }
+        const float* xp = x + ((((long long)p.b * g.Ti + lt) * g.Hi + lh) * g.Wi + lw) * g.Ci;
+        const float* yp = dy + m * g.Co;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int ci = ci0 + lc + j, co = co0 + lc + j;
+            As[lp][lc + j] = (okx && ci < g.Ci) ? xp[ci] : 0.f;
+            Bs[lp][lc + j] = (okm && co < g.Co) ? yp[co] : 0.f;
+        }
+        __syncthreads();
+        fma_tile(acc, As, Bs, ty, tx);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int ci = ci0 + ty * 4 + i;
+        if (ci >= g.Ci) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = co0 + tx * 4 + j;
+            if (co >= g.Co) continue;
+            atomicAdd(&dw[((long long)tap * g.Ci + ci) * g.Co + co], acc[i][j]);
+        }
+    }
+}
+
+// db[c] += sum_m dy[m][c]
+__global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, long long M, int C,
+                              long long rows_per_block) {
+    long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (long long r = r0; r < r1; ++r) s += dy[r * C + c];
+        atomicAdd(&db[c], s);
+    }
+}
+
+}  // namespace
+
+int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int act,
+                  const float* mask, float mask_scale, cudaStream_t st) {
+    long long M = (long long)g.B * g.To * g.Ho * g.Wo;
+    if (M == 0) return 0;
+    dim3 grid(ceil_div(M, BM), ceil_div(g.Co, BN));
+    conv_gemm_kernel<0><<<grid, NT, 0, st>>>(x, w, bias, y, g, act, mask, mask_scale);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st) {
+    int upf = g.up ? 2 : 1;
+    long long M = (long long)g.B * g.Ti * upf * g.Hi * upf * g.Wi * upf;
+    if (M == 0) return 0;
+    dim3 grid(ceil_div(M, BM), ceil_div(g.Ci, BN));
+    conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, ACT_NONE, nullptr, 1.f);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, const ConvGeom& g,
+                         cudaStream_t st) {
+    long long M = (long long)g.B * g.To * g.Ho * g.Wo;
+    if (M == 0) return 0;
+    int ntaps = g.KT * g.KH * g.KW;
+    int tiles = ceil_div(g.Ci, BM) * ceil_div(g.Co, BN) * ntaps;
+    int ksplit = 1;
+    while (tiles * ksplit < 592 && (M / (ksplit * 2)) >= 256) ksplit *= 2;
+    dim3 grid(ceil_div(g.Ci, BM), ceil_div(g.Co, BN), ntaps * ksplit);
+    conv_bwd_filter_kernel<<<grid, NT, 0, st>>>(x, dy, dw, g, ksplit);
+    RDG_LAUNCH_CHECK();
+    if (db) {
+        long long rpb = 256;
+        colsum_kernel<<<ceil_div(M, rpb), 128, 0, st>>>(dy, db, M, g.Co, rpb);
+        RDG_LAUNCH_CHECK();
+    }
+    return 0;
+}
