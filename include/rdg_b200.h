@@ -117,6 +117,13 @@ int  rdg_pixelnorm(const float* x_dev, float* y_dev, long long rows, int C, int 
 /* softmax over the hour axis of logits [B,24,P] (gan_train...py:347) */
 int  rdg_softmax_hours(const float* logits_dev, float* out_dev, long long B, int P, void* stream);
 
+/* instrumentation: per-layer CUDA-event timing on the launching stream (layer ids: 0 input concat,
+ * 1 dense, 2 f32->16-bit, 3..5 upsampled convs, 6 output conv + softmax, 7 pixelnorm in FP32 mode)
+ * and a count of kernels launched by this context. */
+int  rdg_profile_enable(rdg_ctx* ctx, int on);
+int  rdg_profile_collect(rdg_ctx* ctx, double* ms_sum8, long long* launches8, long long* units8);
+long long rdg_launch_count(const rdg_ctx* ctx);
+
 /* one tensor-core generator layer (0..2) in isolation: UpSampling3D + Conv3D + PixelNorm + LeakyReLU
  * (gan_train_cwgangp_pixelnorm.py:330-343); x f32 [B,T,H,W,Cin] is rounded to the mode's 16-bit type,
  * y f32 [B,2T,2H,2W,Cout] is the widened 16-bit result. */

@@ -275,6 +275,48 @@ extern "C" int rdg_critic_get_weights(rdg_ctx* c, float* const* tensors, const s
     return download_params(c->c_params, c->c_off, c->c_size, tensors, sizes, n, "critic weights");
 }
 
+// ------------------------------------------------------------------ instrumentation
+namespace {
+struct ProfScope {
+    rdg_ctx* c; cudaStream_t st; rdg_ctx::ProfRec rec; bool on;
+    ProfScope(rdg_ctx* c_, cudaStream_t st_, int layer, int units, int nlaunch) : c(c_), st(st_), on(c_->prof_on) {
+        c->launches += nlaunch;
+        if (!on) return;
+        auto get = [&]() { cudaEvent_t e; if (c->prof_pool.empty()) cudaEventCreate(&e); else { e = c->prof_pool.back(); c->prof_pool.pop_back(); } return e; };
+        rec.a = get(); rec.b = get(); rec.layer = layer; rec.units = units;
+        cudaEventRecord(rec.a, st);
+    }
+    ~ProfScope() { if (on) { cudaEventRecord(rec.b, st); c->prof_recs.push_back(rec); } }
+};
+}  // namespace
+
+extern "C" int rdg_profile_enable(rdg_ctx* c, int on) {
+    if (!c) return RDG_E_BADARG;
+    c->prof_on = on != 0;
+    return 0;
+}
+extern "C" long long rdg_launch_count(const rdg_ctx* c) { return c ? c->launches : -1; }
+// Sums the CUDA-event durations recorded since the last collect, per layer id
+// (0 input concat, 1 dense, 2 f32->16bit, 3..5 upsampled convs, 6 output conv + softmax, 7 pixelnorm (fp32 mode)).
+extern "C" int rdg_profile_collect(rdg_ctx* c, double* ms_sum8, long long* launches8, long long* units8) {
+    if (!c) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < 8; ++i) { if (ms_sum8) ms_sum8[i] = 0; if (launches8) launches8[i] = 0; if (units8) units8[i] = 0; }
+    for (auto& r : c->prof_recs) {
+        RDG_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        RDG_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.layer >= 0 && r.layer < 8) {
+            if (ms_sum8) ms_sum8[r.layer] += ms;
+            if (launches8) launches8[r.layer] += 1;
+            if (units8) units8[r.layer] += r.units;
+        }
+        c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+    }
+    c->prof_recs.clear();
+    return 0;
+}
+
 // ------------------------------------------------------------------ generator forward
 // One chunk of n samples starting at global sample index b_off (for the cond lookup).
 static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond, int spc, int b_off, float* out, int n,
@@ -286,8 +328,10 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
     float* x0 = (float*)take((size_t)n * dg.Ci * 4);
     float* d0 = (float*)take((size_t)n * dg.Co * 4);
     int r;
-    if ((r = ew_assemble_gen_input(latent, cond, spc, b_off, x0, n, nd * nd * c->ncond, st))) return r;
-    if ((r = simt_conv_fwd(x0, c->g_params + c->g_off[0], c->g_params + c->g_off[1], d0, dg, ACT_LRELU, nullptr, 1.f, st))) return r;
+    { ProfScope ps(c, st, 0, n, 1);
+      if ((r = ew_assemble_gen_input(latent, cond, spc, b_off, x0, n, nd * nd * c->ncond, st))) return r; }
+    { ProfScope ps(c, st, 1, n, 1);
+      if ((r = simt_conv_fwd(x0, c->g_params + c->g_off[0], c->g_params + c->g_off[1], d0, dg, ACT_LRELU, nullptr, 1.f, st))) return r; }
     const float* w4 = c->g_params + c->g_off[8];
     const float* b4 = c->g_params + c->g_off[9];
     if (mode == RDG_MODE_FP32) {
@@ -295,24 +339,30 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
         for (int l = 0; l < 3; ++l) {
             ConvGeom g = rdg_gen_conv_geom(c, l, n);
             float* y = (float*)take((size_t)n * gen_act_elems(c, l + 1) * 4);
-            if ((r = simt_conv_fwd(cur, c->g_params + c->g_off[2 + 2 * l], c->g_params + c->g_off[3 + 2 * l], y, g, ACT_NONE, nullptr, 1.f, st))) return r;
-            if ((r = ew_pixelnorm(y, y, (long long)n * g.To * g.Ho * g.Wo, g.Co, 1, st))) return r;
+            { ProfScope ps(c, st, 3 + l, n, 1);
+              if ((r = simt_conv_fwd(cur, c->g_params + c->g_off[2 + 2 * l], c->g_params + c->g_off[3 + 2 * l], y, g, ACT_NONE, nullptr, 1.f, st))) return r; }
+            { ProfScope ps(c, st, 7, n, 1);
+              if ((r = ew_pixelnorm(y, y, (long long)n * g.To * g.Ho * g.Wo, g.Co, 1, st))) return r; }
             cur = y;
         }
+        ProfScope ps(c, st, 6, n, 1);
         return conv_out_softmax(RDG_HALF_F32, cur, w4, b4, out, cond, n, nd, spc, b_off, c->ncond, norm_scale,
                                 out_kind == RDG_OUT_MM, flag, st);
     }
     const int hk = mode == RDG_MODE_BF16 ? RDG_HALF_BF16 : RDG_HALF_FP16;
     void* h = take((size_t)n * gen_act_elems(c, 0) * 2);
-    if ((r = f32_to_half(hk, d0, h, (long long)n * dg.Co, st))) return r;
+    { ProfScope ps(c, st, 2, n, 1);
+      if ((r = f32_to_half(hk, d0, h, (long long)n * dg.Co, st))) return r; }
     static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
     for (int l = 0; l < 3; ++l) {
         const int f = 1 << l;
         void* y = take((size_t)n * gen_act_elems(c, l + 1) * 2);
-        if ((r = tc_upconv_pixelnorm(hk, h, c->g_wpack[hk == RDG_HALF_BF16 ? 0 : 1][l], c->g_params + c->g_off[3 + 2 * l], y, n,
-                                     3 * f, s * f, s * f, cin[l], cout[l], c->sm_count, st))) return r;
+        { ProfScope ps(c, st, 3 + l, n, 1);
+          if ((r = tc_upconv_pixelnorm(hk, h, c->g_wpack[hk == RDG_HALF_BF16 ? 0 : 1][l], c->g_params + c->g_off[3 + 2 * l], y, n,
+                                       3 * f, s * f, s * f, cin[l], cout[l], c->sm_count, st))) return r; }
         h = y;
     }
+    ProfScope ps(c, st, 6, n, 1);
     return conv_out_softmax(hk, h, w4, b4, out, cond, n, nd, spc, b_off, c->ncond, norm_scale, out_kind == RDG_OUT_MM, flag, st);
 }
 

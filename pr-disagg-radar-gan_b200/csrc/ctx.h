@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <vector>
 #include "rdg_common.cuh"
 
 struct rdg_ctx {
@@ -23,6 +24,12 @@ struct rdg_ctx {
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
     float* e2e_lat[2] = {}; float* e2e_out[2] = {}; float* e2e_cond = nullptr; size_t e2e_cond_cap = 0;
+    // instrumentation: kernel launch counter and optional per-layer CUDA-event timing
+    long long launches = 0;
+    bool prof_on = false;
+    struct ProfRec { cudaEvent_t a, b; int layer; int units; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 ConvGeom rdg_gen_conv_geom(const rdg_ctx* c, int layer, int B);
