@@ -158,20 +158,28 @@ template <int COUT, int NPH> struct TcCfg {
     static constexpr int kAStages = 4;
     static constexpr int kBStages = (200 * 1024 - kAStages * kATile) / kBTile > 12
                                         ? 12 : (200 * 1024 - kAStages * kATile) / kBTile;
-    static constexpr int kSmem = 1024 + kAStages * kATile + kBStages * kBTile + COUT * 4 + 512;
+    static constexpr int kSmem = 1024 + kAStages * kATile + kBStages * kBTile + (COUT == 64 ? kATile + 4096 : 0) + COUT * 4 + 512;
     static_assert(kAccCols * kAccStages <= 512, "TMEM overflow");
     static_assert(kBStages >= 2, "need at least 2 weight stages");
 };
 
-template <typename HT, int COUT, int NPH>
+// FUSE (Cout=64 layer only): the epilogue does not store the activations y; it writes them as a
+// 128B-swizzled A tile to shared memory and multiplies by the output conv's 27 tap vectors
+// (W4 as a [32 x 64] B tile) on the tensor core:  P[pos][tap] = sum_c y[pos][c] * w4[tap][c].
+// P (f32, 32 per position) goes to HBM instead of y; gather_softmax_kernel then forms
+// logit[q] = b + sum_tap P[q + offset(tap)][tap] and the softmax over the 24 hours.
+template <typename HT, int COUT, int NPH, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs args) {
     using Cfg = TcCfg<COUT, NPH>;
+    static_assert(!FUSE || COUT == 64, "fused output conv needs Cout == 64");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;
     uint8_t* b_buf = a_buf + Cfg::kAStages * kATile;
-    float* s_bias = reinterpret_cast<float*>(b_buf + Cfg::kBStages * Cfg::kBTile);
+    uint8_t* y_tile = b_buf + Cfg::kBStages * Cfg::kBTile;            // FUSE: [128 x 64] 16-bit, 16 KB
+    uint8_t* w4_tile = y_tile + (FUSE ? kATile : 0);                  // FUSE: [32 x 64] 16-bit, 4 KB
+    float* s_bias = reinterpret_cast<float*>(w4_tile + (FUSE ? 4096 : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + COUT);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + Cfg::kAStages;
@@ -179,14 +187,22 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
     uint64_t* b_empty = b_full + Cfg::kBStages;
     uint64_t* acc_full = b_empty + Cfg::kBStages;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* p_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = args.Cin / 64;
     const int n_hblk = args.H / args.Hb;
 
     for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = args.bias[i];
+    if (FUSE) {
+        const uint4* src = reinterpret_cast<const uint4*>(args.w4tile);
+        uint4* dst = reinterpret_cast<uint4*>(w4_tile);
+        for (int i = threadIdx.x; i < 4096 / 16; i += kThreads) dst[i] = src[i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (MMA)
+    }
     if (threadIdx.x == 0) {
+        mbar_init(p_full, 1);
         for (int i = 0; i < Cfg::kAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
@@ -288,7 +304,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         const int r = q * 32 + lane;            // accumulator row = position within the tile
         const int bl = r / (args.Hb * args.W), hl = (r / args.W) % args.Hb, w = r % args.W;
         HT* out = reinterpret_cast<HT*>(args.out);
-        uint32_t acc_it = 0;
+        uint32_t acc_it = 0, p_it = 0;
         for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
             const int hblk = tile % n_hblk, t = (tile / n_hblk) % args.T, bblk = tile / (n_hblk * args.T);
             const int b = bblk * args.Bt + bl, h = hblk * args.Hb + hl;
@@ -313,8 +329,8 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                         }
                     }
                     const float inv = 1.0f / sqrtf(ss * (1.0f / COUT) + 1.0e-8f);
-                    const size_t o_row = ((((size_t)b * (2 * args.T) + (2 * t + (p >> 2))) * (2 * args.H) +
-                                           (2 * h + ((p >> 1) & 1))) * (2 * args.W) + (2 * w + (p & 1))) * COUT;
+                    const size_t o_pos = (((size_t)b * (2 * args.T) + (2 * t + (p >> 2))) * (2 * args.H) +
+                                          (2 * h + ((p >> 1) & 1))) * (2 * args.W) + (2 * w + (p & 1));
 #pragma unroll 1
                     for (int c0 = 0; c0 < COUT; c0 += 32) {
                         uint32_t v[32];
@@ -328,11 +344,45 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                             x1 = x1 > 0.f ? x1 : 0.2f * x1;
                             pk[j] = HalfOps<HT>::pack(x0, x1);
                         }
-                        if (valid) {
-                            uint4* dst = reinterpret_cast<uint4*>(out + o_row + c0);
+                        if (FUSE) {
+                            // row r of the K-major SWIZZLE_128B tile: 16-byte chunk j lives at chunk (j ^ (r & 7))
+                            uint8_t* yrow = y_tile + r * 128;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(yrow + ((((c0 >> 3) + j) ^ (r & 7)) << 4)) =
+                                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        } else if (valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(out + o_pos * COUT + c0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                    }
+                    if (FUSE) {
+                        // all 128 rows of y written and all reads of this slot's accumulator done
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        tc_fence_before();
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (warp == 2 && lane == 0) {
+                            tc_fence_after();
+                            constexpr uint32_t idesc_p = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
+                                                         ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                            const uint64_t yd = make_sdesc(smem_u32(y_tile)), wd = make_sdesc(smem_u32(w4_tile));
+                            const uint32_t d_p = tmem_base + as * Cfg::kAccCols + s * COUT;   // reuse the consumed accumulator
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) tc_mma_f16(d_p, yd + 2 * k, wd + 2 * k, idesc_p, k > 0 ? 1u : 0u);
+                            tc_commit(p_full);
+                        }
+                        mbar_wait(p_full, p_it & 1);
+                        ++p_it;
+                        tc_fence_after();
+                        uint32_t pv[32];
+                        tc_ld32(taddr, pv);
+                        if (valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(args.p_out + o_pos * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                dst[j] = make_uint4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
                         }
                     }
                 }
@@ -480,6 +530,75 @@ conv_out_softmax_kernel(const TI* __restrict__ x, const float* __restrict__ w4, 
     if (bad && nonfinite) atomicOr(nonfinite, 1);
 }
 
+// logit[q] = b + sum_{27 taps} P[q + offset(tap)][tap]; softmax over the 24 hours; optional mm rescale.
+// One CTA = one sample x 256 pixels (HB rows x nd); one thread per pixel.  The P planes (hour by hour)
+// are staged in shared memory with a zero halo and a 33-word position stride (bank-conflict free);
+// input hour t feeds logits t+1, t, t-1 through taps kt = 0, 1, 2.
+__global__ void __launch_bounds__(256)
+gather_softmax_kernel(const float* __restrict__ P, const float* __restrict__ b4, float* __restrict__ out,
+                      const float* __restrict__ cond, int lognd, int HB, int spc, int b_off, int ncond, float scale,
+                      int out_mm, int* __restrict__ nonfinite) {
+    extern __shared__ __align__(16) float ps[];          // [(HB+2)][(nd+2)][33]
+    const int nd = 1 << lognd, W2 = nd + 2;
+    const int n_hblk = nd / HB;
+    const int b = blockIdx.x / n_hblk, h0 = (blockIdx.x % n_hblk) * HB;
+    const int tid = threadIdx.x;
+    const int ph = tid >> lognd, pw = tid & (nd - 1);
+    for (int i = tid; i < (HB + 2) * W2 * 33; i += 256) ps[i] = 0.f;
+    float acc[RDG_NHOURS + 2];
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS + 2; ++t) acc[t] = 0.f;
+    const float* pb = P + (size_t)b * RDG_NHOURS * nd * nd * 32;
+    const int f4_per_row = nd * 8;                       // float4 per h-row (nd positions x 32 floats)
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) {
+        __syncthreads();
+        for (int rr = 0; rr < HB + 2; ++rr) {
+            const int h = h0 + rr - 1;
+            if (h < 0 || h >= nd) continue;              // stays zero (zeroed once; never written)
+            const float4* srow = reinterpret_cast<const float4*>(pb + ((size_t)t * nd + h) * nd * 32);
+            float* drow = ps + ((size_t)rr * W2 + 1) * 33;
+            for (int i = tid; i < f4_per_row; i += 256) {
+                const float4 v = srow[i];
+                float* d = drow + (i >> 3) * 33 + (i & 7) * 4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+        __syncthreads();
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                // output pixel (ph,pw) with tap (kh,kw) reads input pixel (ph+kh-1, pw+kw-1); slab index has +1 halo
+                const float* q = ps + ((size_t)(ph + kh) * W2 + (pw + kw)) * 33;
+                s0 += q[(0 * 3 + kh) * 3 + kw];          // kt = 0: this plane is hour (t_out - 1) -> t_out = t + 1
+                s1 += q[(1 * 3 + kh) * 3 + kw];          // kt = 1: t_out = t
+                s2 += q[(2 * 3 + kh) * 3 + kw];          // kt = 2: t_out = t - 1
+            }
+        acc[t + 2] += s0; acc[t + 1] += s1; acc[t] += s2;   // acc index = t_out + 1
+    }
+    const int h = h0 + ph;
+    const float bias = b4[0];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) { acc[t + 1] += bias; mx = fmaxf(mx, acc[t + 1]); }
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) { acc[t + 1] = expf(acc[t + 1] - mx); s += acc[t + 1]; }
+    float mul = 1.f;
+    if (out_mm) mul = cond[(((size_t)((b_off + b) / spc) * nd + h) * nd + pw) * ncond] * scale;
+    bool bad = false;
+    float* ob = out + (size_t)b * RDG_NHOURS * nd * nd + (size_t)h * nd + pw;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) {
+        const float f = acc[t + 1] / s;
+        bad |= !isfinite(f);
+        ob[(size_t)t * nd * nd] = f * mul;
+    }
+    if (bad && nonfinite) atomicOr(nonfinite, 1);
+}
+
 template <typename HT>
 __global__ void f32_to_half_kernel(const float* __restrict__ src, HT* __restrict__ dst, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,9 +623,9 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <typename HT, int COUT, int NPH>
-int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, int B, int T, int H, int W, int Cin,
-                  int sm_count, cudaStream_t st) {
+template <typename HT, int COUT, int NPH, bool FUSE>
+int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
+                  int T, int H, int W, int Cin, int sm_count, cudaStream_t st) {
     using Cfg = TcCfg<COUT, NPH>;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { rdg_set_error("cuTensorMapEncodeTiled entry point not available"); return RDG_TC_E_DRIVER; }
@@ -518,7 +637,7 @@ int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, 
     else { a.Hb = H; a.Bt = 128 / rows_per_sample_plane; }
     if (a.Hb < 1 || H % a.Hb) { rdg_set_error("tc upconv: H not divisible by tile rows"); return RDG_TC_E_SHAPE; }
     a.n_tiles = ceil_div(B, a.Bt) * T * (H / a.Hb);
-    a.wpack = wpack; a.bias = bias; a.out = y;
+    a.wpack = wpack; a.bias = bias; a.out = y; a.w4tile = w4tile; a.p_out = p_out;
 
     CUtensorMap tmap;
     cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
@@ -532,7 +651,7 @@ int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, 
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return RDG_TC_E_DRIVER; }
 
-    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH>;
+    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH, FUSE>;
     static bool attr_set = false;
     if (!attr_set) {
         RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -545,11 +664,12 @@ int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, 
 }
 
 template <typename HT>
-int tc_upconv_dispatch(const void* x, const void* wpack, const float* bias, void* y, int B, int T, int H, int W,
-                       int Cin, int Cout, int sm_count, cudaStream_t st) {
-    if (Cout == 256) return launch_upconv<HT, 256, 1>(x, wpack, bias, y, B, T, H, W, Cin, sm_count, st);
-    if (Cout == 128) return launch_upconv<HT, 128, 2>(x, wpack, bias, y, B, T, H, W, Cin, sm_count, st);
-    if (Cout == 64) return launch_upconv<HT, 64, 4>(x, wpack, bias, y, B, T, H, W, Cin, sm_count, st);
+int tc_upconv_dispatch(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out,
+                       int B, int T, int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st) {
+    if (Cout == 256) return launch_upconv<HT, 256, 1, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 128) return launch_upconv<HT, 128, 2, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 64 && p_out) return launch_upconv<HT, 64, 4, true>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 64) return launch_upconv<HT, 64, 4, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
     rdg_set_error("tc upconv: unsupported Cout %d", Cout);
     return RDG_TC_E_SHAPE;
 }
@@ -579,12 +699,30 @@ int launch_conv_out(const void* x, const float* w4, const float* b4, float* out,
 
 }  // namespace
 
-int tc_upconv_pixelnorm(int half_kind, const void* x, const void* wpack, const float* bias, void* y, int B, int T,
-                        int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st) {
+int tc_upconv_pixelnorm(int half_kind, const void* x, const void* wpack, const float* bias, void* y, const void* w4tile,
+                        float* p_out, int B, int T, int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st) {
     if (B <= 0) return 0;
     if (half_kind == RDG_HALF_BF16)
-        return tc_upconv_dispatch<__nv_bfloat16>(x, wpack, bias, y, B, T, H, W, Cin, Cout, sm_count, st);
-    return tc_upconv_dispatch<__half>(x, wpack, bias, y, B, T, H, W, Cin, Cout, sm_count, st);
+        return tc_upconv_dispatch<__nv_bfloat16>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, Cout, sm_count, st);
+    return tc_upconv_dispatch<__half>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, Cout, sm_count, st);
+}
+
+int gather_softmax(const float* p, const float* b4, float* out, const float* cond, int B, int nd, int spc, int b_off,
+                   int ncond, float scale, int out_mm, int* nonfinite, cudaStream_t st) {
+    if (B <= 0) return 0;
+    int lognd = 0;
+    while ((1 << lognd) < nd) ++lognd;
+    if ((1 << lognd) != nd || nd > 256 || nd < 16) { rdg_set_error("gather_softmax: nd must be a power of two in [16,256]"); return RDG_TC_E_SHAPE; }
+    const int HB = 256 / nd;
+    const size_t smem = (size_t)(HB + 2) * (nd + 2) * 33 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDG_CUDA(cudaFuncSetAttribute(gather_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    gather_softmax_kernel<<<B * (nd / HB), 256, smem, st>>>(p, b4, out, cond, lognd, HB, spc, b_off, ncond, scale, out_mm, nonfinite);
+    RDG_LAUNCH_CHECK();
+    return 0;
 }
 
 int conv_out_softmax(int in_kind, const void* x, const float* w4, const float* b4, float* out, const float* cond,

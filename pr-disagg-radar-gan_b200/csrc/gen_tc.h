@@ -17,12 +17,18 @@ struct TcConvArgs {
     int n_tiles;
     const void* wpack;  // [8 phases][8 taps][Cin/64][Cout rows x 64 k] 16-bit, rows pre-swizzled (128B)
     const float* bias;
-    void* out;          // [B,2T,2H,2W,Cout] 16-bit
+    void* out;          // [B,2T,2H,2W,Cout] 16-bit (unused when the output conv is fused)
+    const void* w4tile; // fused output conv: [32 taps x 64 ch] 16-bit swizzled tile (taps >= 27 zero)
+    float* p_out;       // fused output conv: [B,2T,2H,2W,32] f32 per-tap partial products
 };
 
 // y[B,2T,2H,2W,Cout] = LeakyReLU(PixelNorm(conv3x3x3(upsample2(x[B,T,H,W,Cin])) + bias))
-int tc_upconv_pixelnorm(int half_kind, const void* x, const void* wpack, const float* bias, void* y, int B, int T,
-                        int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st);
+// If p_out != null (Cout == 64 only) the output Conv3D(64->1) tap products P are produced instead of y.
+int tc_upconv_pixelnorm(int half_kind, const void* x, const void* wpack, const float* bias, void* y, const void* w4tile,
+                        float* p_out, int B, int T, int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st);
+// out[B,24,nd,nd] = softmax_hours(b + sum_taps P[q+off(tap)][tap]) (* cond * scale), P [B,24,nd,nd,32] f32
+int gather_softmax(const float* p, const float* b4, float* out, const float* cond, int B, int nd, int spc, int b_off,
+                   int ncond, float scale, int out_mm, int* nonfinite, cudaStream_t st);
 // out[B,24,nd,nd] = softmax_hours(conv3x3x3(x[B,24,nd,nd,64]) + b) (* cond * scale)
 int conv_out_softmax(int in_kind, const void* x, const float* w4, const float* b4, float* out, const float* cond,
                      int B, int nd, int spc, int b_off, int ncond, float scale, int out_mm, int* nonfinite, cudaStream_t st);
