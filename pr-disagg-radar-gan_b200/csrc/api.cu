@@ -130,6 +130,7 @@ extern "C" int rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int 
     per16 += (size_t)(d.Ci + d.Co) * 4;
     per32 += (size_t)(d.Ci + d.Co) * 4;
     for (int l = 0; l < 4; ++l) { per16 += gen_act_elems(c, l) * 2; per32 += (l ? gen_act_elems(c, l) * 4 : 0); }
+    per16 += gen_act_elems(c, 3) / 64 * 32 * 4;   // f32 tap products P of the fused output conv
     c->per_sample16 = per16; c->per_sample32 = per32;
     c->ws_bytes = per16 * (size_t)max_chunk + 4096 * 8;
     RDG_CUDA(cudaMalloc(&c->ws, c->ws_bytes));
@@ -155,6 +156,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     cudaFree(c->g_grads); cudaFree(c->g_m); cudaFree(c->g_v);
     cudaFree(c->c_grads); cudaFree(c->c_m); cudaFree(c->c_v);
     for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) cudaFree(c->g_wpack[k][l]);
+    for (int k = 0; k < 2; ++k) cudaFree(c->g_w4pack[k]);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->e2e_lat[i]); cudaFree(c->e2e_out[i]);
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
@@ -232,6 +234,24 @@ int rdg_repack_generator(rdg_ctx* c, const float* const* host_tensors) {
         }
         RDG_CUDA(cudaMemcpy(c->g_wpack[0][l], pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
         RDG_CUDA(cudaMemcpy(c->g_wpack[1][l], ph.data(), ph.size() * 2, cudaMemcpyHostToDevice));
+    }
+    // output conv (3,3,3,64,1): row n = tap (27 used of 32), k = channel; same 128B swizzle as the other B tiles
+    {
+        const float* k4 = host_tensors[8];
+        std::vector<__nv_bfloat16> tb(32 * 64, __float2bfloat16_rn(0.f));
+        std::vector<__half> th(32 * 64, __float2half_rn(0.f));
+        for (int n = 0; n < 27; ++n)
+            for (int j = 0; j < 8; ++j)
+                for (int e = 0; e < 8; ++e) {
+                    const float v = k4[(size_t)n * 64 + j * 8 + e];
+                    const size_t d = (size_t)n * 64 + ((j ^ (n & 7)) * 8) + e;
+                    tb[d] = __float2bfloat16_rn(v);
+                    th[d] = __float2half_rn(v);
+                }
+        for (int k = 0; k < 2; ++k)
+            if (!c->g_w4pack[k]) RDG_CUDA(cudaMalloc(&c->g_w4pack[k], 32 * 64 * 2));
+        RDG_CUDA(cudaMemcpy(c->g_w4pack[0], tb.data(), 32 * 64 * 2, cudaMemcpyHostToDevice));
+        RDG_CUDA(cudaMemcpy(c->g_w4pack[1], th.data(), 32 * 64 * 2, cudaMemcpyHostToDevice));
     }
     return 0;
 }
@@ -354,16 +374,21 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
     { ProfScope ps(c, st, 2, n, 1);
       if ((r = f32_to_half(hk, d0, h, (long long)n * dg.Co, st))) return r; }
     static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
+    const int wk = hk == RDG_HALF_BF16 ? 0 : 1;
+    float* pbuf = nullptr;
     for (int l = 0; l < 3; ++l) {
         const int f = 1 << l;
-        void* y = take((size_t)n * gen_act_elems(c, l + 1) * 2);
+        void* y = nullptr;
+        if (l < 2) y = take((size_t)n * gen_act_elems(c, l + 1) * 2);
+        else pbuf = (float*)take((size_t)n * gen_act_elems(c, 3) / 64 * 32 * 4);
         { ProfScope ps(c, st, 3 + l, n, 1);
-          if ((r = tc_upconv_pixelnorm(hk, h, c->g_wpack[hk == RDG_HALF_BF16 ? 0 : 1][l], c->g_params + c->g_off[3 + 2 * l], y, n,
+          if ((r = tc_upconv_pixelnorm(hk, h, c->g_wpack[wk][l], c->g_params + c->g_off[3 + 2 * l], y,
+                                       l == 2 ? c->g_w4pack[wk] : nullptr, l == 2 ? pbuf : nullptr, n,
                                        3 * f, s * f, s * f, cin[l], cout[l], c->sm_count, st))) return r; }
         h = y;
     }
     ProfScope ps(c, st, 6, n, 1);
-    return conv_out_softmax(hk, h, w4, b4, out, cond, n, nd, spc, b_off, c->ncond, norm_scale, out_kind == RDG_OUT_MM, flag, st);
+    return gather_softmax(pbuf, b4, out, cond, n, nd, spc, b_off, c->ncond, norm_scale, out_kind == RDG_OUT_MM, flag, st);
 }
 
 static int chunk_for_mode(const rdg_ctx* c, int mode) {
@@ -495,8 +520,8 @@ extern "C" int rdg_tc_layer(rdg_ctx* c, int layer, int mode, const float* x_dev,
     uint8_t* yout = xin + (n_in * 2 + 255) / 256 * 256;
     int r;
     if ((r = f32_to_half(hk, x_dev, xin, (long long)n_in, st))) return r;
-    if ((r = tc_upconv_pixelnorm(hk, xin, c->g_wpack[hk == RDG_HALF_BF16 ? 0 : 1][layer], c->g_params + c->g_off[3 + 2 * layer], yout, B,
-                                 3 * f, s * f, s * f, cin[layer], cout[layer], c->sm_count, st))) return r;
+    if ((r = tc_upconv_pixelnorm(hk, xin, c->g_wpack[hk == RDG_HALF_BF16 ? 0 : 1][layer], c->g_params + c->g_off[3 + 2 * layer], yout,
+                                 nullptr, nullptr, B, 3 * f, s * f, s * f, cin[layer], cout[layer], c->sm_count, st))) return r;
     return half_to_f32(hk, yout, y_dev, (long long)n_out, st);
 }
 

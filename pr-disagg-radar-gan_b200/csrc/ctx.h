@@ -13,6 +13,7 @@ struct rdg_ctx {
     bool gen_ready = false, critic_ready = false, gen_packed_stale = false;
     // folded + swizzled 16-bit operand tiles of the three upsampled convs: [0]=bf16, [1]=fp16
     void* g_wpack[2][3] = {};
+    void* g_w4pack[2] = {};   // output conv as a [32 taps x 64 ch] swizzled 16-bit B tile
     // training state (allocated on first use)
     float* g_grads = nullptr; float* g_m = nullptr; float* g_v = nullptr;
     float* c_grads = nullptr; float* c_m = nullptr; float* c_v = nullptr;
