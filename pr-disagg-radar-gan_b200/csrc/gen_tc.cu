@@ -12,8 +12,8 @@
 // every phase that needs that offset.  The epilogue warps read the accumulators back with
 // tcgen05.ld, apply bias + PixelNorm + LeakyReLU in FP32 and store 16-bit channels-last output.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each).
+// Warp roles (224 threads): warp 0 = activation (A) TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warp 2 = weight (B) bulk-copy producer, warps 3..6 = epilogue (one TMEM lane quarter each).
 #include "rdg_common.cuh"
 #include "gen_tc.h"
 #include <cuda.h>
@@ -37,6 +37,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
+}
+// non-blocking probe; issued early so its latency overlaps other work, result consumed later
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -123,7 +134,7 @@ template <> struct HalfOps<__half> {
 // For pass `pass` (phases pass*NPH .. pass*NPH+NPH-1) walk the 27 low-res offsets; an offset
 // (dt,dh,dw) serves phase p=(pt,ph,pw) with tap a=(dt+1-pt, dh+1-ph, dw+1-pw) if all in {0,1}.
 template <int NPH, typename FA, typename FB>
-__device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk, FA&& on_a, FB&& on_b) {
+__device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk, int kc, FA&& on_a, FB&& on_b) {
     for (int o = 0; o < 27; ++o) {
         const int dt = o / 9 - 1, dh = (o / 3) % 3 - 1, dw = o % 3 - 1;
         if (t + dt < 0 || t + dt >= T) continue;   // whole tile in the zero padding
@@ -135,7 +146,7 @@ __device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk
             if ((unsigned)at < 2u && (unsigned)ah < 2u && (unsigned)aw < 2u) mask |= 1u << s;
         }
         if (!mask) continue;
-        for (int c = 0; c < nchunk; ++c) {
+        for (int c = 0; c < nchunk; c += kc) {       // kc consecutive 64-channel chunks per stage
             on_a(dt, dh, dw, c);
 #pragma unroll
             for (int s = 0; s < NPH; ++s) {
@@ -148,19 +159,25 @@ __device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk
     }
 }
 
-constexpr int kThreads = 192;
-constexpr int kATile = 128 * 128;   // 128 rows x 64 x 2 B
+constexpr int kThreads = 224;       // warp 0: A producer, 1: MMA issuer, 2: B producer, 3..6: epilogue
+constexpr int kATile = 128 * 128;   // 128 rows x 64 x 2 B (one 64-channel chunk)
 
-template <int COUT, int NPH> struct TcCfg {
-    static constexpr int kBTile = COUT * 128;
+// KC = 64-channel chunks per pipeline stage: a stage carries K = 64*KC, i.e. 4*KC MMAs per weight tile,
+// which amortises the mbarrier round trip of the single-thread producer / issuer loops.
+template <int COUT, int NPH, int KC> struct TcCfg {
+    static constexpr int kBTile = COUT * 128;            // one (phase, tap, chunk) weight tile
+    static constexpr int kAStage = KC * kATile;
+    static constexpr int kBStage = KC * kBTile;
     static constexpr int kAccCols = NPH * COUT;
     static constexpr int kAccStages = (kAccCols * 2 <= 512) ? 2 : 1;
-    static constexpr int kAStages = 4;
-    static constexpr int kBStages = (200 * 1024 - kAStages * kATile) / kBTile > 12
-                                        ? 12 : (200 * 1024 - kAStages * kATile) / kBTile;
-    static constexpr int kSmem = 1024 + kAStages * kATile + kBStages * kBTile + (COUT == 64 ? kATile + 4096 : 0) + COUT * 4 + 512;
+    static constexpr int kFuseBytes = COUT == 64 ? kATile + 4096 : 0;
+    static constexpr int kAStages = KC == 1 ? 4 : 3;
+    static constexpr int kBudget = 218 * 1024 - kFuseBytes - kAStages * kAStage;
+    static constexpr int kBStages = kBudget / kBStage > 8 ? 8 : kBudget / kBStage;
+    static constexpr int kSmem = 1024 + kAStages * kAStage + kBStages * kBStage + kFuseBytes + COUT * 4 + 512;
     static_assert(kAccCols * kAccStages <= 512, "TMEM overflow");
     static_assert(kBStages >= 2, "need at least 2 weight stages");
+    static_assert(kSmem <= 227 * 1024, "shared memory overflow");
 };
 
 // FUSE (Cout=64 layer only): the epilogue does not store the activations y; it writes them as a
@@ -168,16 +185,16 @@ template <int COUT, int NPH> struct TcCfg {
 // (W4 as a [32 x 64] B tile) on the tensor core:  P[pos][tap] = sum_c y[pos][c] * w4[tap][c].
 // P (f32, 32 per position) goes to HBM instead of y; gather_softmax_kernel then forms
 // logit[q] = b + sum_tap P[q + offset(tap)][tap] and the softmax over the 24 hours.
-template <typename HT, int COUT, int NPH, bool FUSE>
+template <typename HT, int COUT, int NPH, int KC, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs args) {
-    using Cfg = TcCfg<COUT, NPH>;
+    using Cfg = TcCfg<COUT, NPH, KC>;
     static_assert(!FUSE || COUT == 64, "fused output conv needs Cout == 64");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;
-    uint8_t* b_buf = a_buf + Cfg::kAStages * kATile;
-    uint8_t* y_tile = b_buf + Cfg::kBStages * Cfg::kBTile;            // FUSE: [128 x 64] 16-bit, 16 KB
+    uint8_t* b_buf = a_buf + Cfg::kAStages * Cfg::kAStage;
+    uint8_t* y_tile = b_buf + Cfg::kBStages * Cfg::kBStage;           // FUSE: [128 x 64] 16-bit, 16 KB
     uint8_t* w4_tile = y_tile + (FUSE ? kATile : 0);                  // FUSE: [32 x 64] 16-bit, 4 KB
     float* s_bias = reinterpret_cast<float*>(w4_tile + (FUSE ? 4096 : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + COUT);
@@ -220,30 +237,52 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= A producer (activation tiles, TMA 5-D box loads) =================
         if (lane == 0) {
-            uint32_t ai = 0, bi = 0;   // running slot counters
+            uint32_t ai = 0;
+            uint32_t free_next = mbar_test(&a_empty[0], 1);
             for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
                 const int hblk = tile % n_hblk, t = (tile / n_hblk) % args.T, bblk = tile / (n_hblk * args.T);
                 const int h0 = hblk * args.Hb, b0 = bblk * args.Bt;
                 for (int pass = 0; pass < 8 / NPH; ++pass) {
                     for_each_step<NPH>(
-                        pass, t, args.T, nchunk,
+                        pass, t, args.T, nchunk, KC,
                         [&](int dt, int dh, int dw, int c) {
                             const uint32_t s = ai % Cfg::kAStages, ph = (ai / Cfg::kAStages) & 1;
-                            mbar_wait(&a_empty[s], ph ^ 1);
-                            mbar_expect_tx(&a_full[s], kATile);
-                            tma_load_5d(a_buf + s * kATile, &tmap, &a_full[s], c * 64, dw, h0 + dh, t + dt, b0);
+                            if (!free_next) mbar_wait(&a_empty[s], ph ^ 1);
                             ++ai;
+                            const uint32_t s2 = ai % Cfg::kAStages, ph2 = (ai / Cfg::kAStages) & 1;
+                            free_next = mbar_test(&a_empty[s2], ph2 ^ 1);
+                            mbar_expect_tx(&a_full[s], Cfg::kAStage);
+#pragma unroll
+                            for (int k = 0; k < KC; ++k)
+                                tma_load_5d(a_buf + s * Cfg::kAStage + k * kATile, &tmap, &a_full[s], (c + k) * 64, dw,
+                                            h0 + dh, t + dt, b0);
                         },
+                        [&](int, int) {});
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================= B producer (pre-swizzled weight tiles, 1-D bulk copies) =================
+        if (lane == 0) {
+            uint32_t bi = 0;
+            uint32_t free_next = mbar_test(&b_empty[0], 1);
+            for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+                const int t = (tile / n_hblk) % args.T;
+                for (int pass = 0; pass < 8 / NPH; ++pass) {
+                    for_each_step<NPH>(
+                        pass, t, args.T, nchunk, KC, [&](int, int, int, int) {},
                         [&](int, int wtile) {
                             const uint32_t s = bi % Cfg::kBStages, ph = (bi / Cfg::kBStages) & 1;
-                            mbar_wait(&b_empty[s], ph ^ 1);
-                            mbar_expect_tx(&b_full[s], Cfg::kBTile);
-                            bulk_load_1d(b_buf + s * Cfg::kBTile,
-                                         reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile,
-                                         Cfg::kBTile, &b_full[s]);
+                            if (!free_next) mbar_wait(&b_empty[s], ph ^ 1);
                             ++bi;
+                            const uint32_t s2 = bi % Cfg::kBStages, ph2 = (bi / Cfg::kBStages) & 1;
+                            free_next = mbar_test(&b_empty[s2], ph2 ^ 1);
+                            mbar_expect_tx(&b_full[s], Cfg::kBStage);
+                            bulk_load_1d(b_buf + s * Cfg::kBStage,
+                                         reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile,
+                                         Cfg::kBStage, &b_full[s]);
                         });
                 }
             }
@@ -254,6 +293,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
             constexpr uint32_t idesc = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
                                        ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             uint32_t ai = 0, bi = 0, acc_it = 0;
+            uint32_t a_ready = 0, b_ready = 0;       // results of early probes of the next full barriers
             for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
                 const int t = (tile / n_hblk) % args.T;
                 for (int pass = 0; pass < 8 / NPH; ++pass, ++acc_it) {
@@ -266,32 +306,35 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                     bool have_a = false;
                     uint32_t prev_a_slot = 0;
                     for_each_step<NPH>(
-                        pass, t, args.T, nchunk,
+                        pass, t, args.T, nchunk, KC,
                         [&](int, int, int, int) {
-                            if (have_a) tc_commit(&a_empty[prev_a_slot]);   // all MMAs reading the previous A tile issued
+                            if (have_a) tc_commit(&a_empty[prev_a_slot]);   // all MMAs reading the previous A stage issued
                             const uint32_t s = ai % Cfg::kAStages, ph = (ai / Cfg::kAStages) & 1;
-                            mbar_wait(&a_full[s], ph);
+                            if (!a_ready) mbar_wait(&a_full[s], ph);
+                            ++ai;
+                            a_ready = mbar_test(&a_full[ai % Cfg::kAStages], (ai / Cfg::kAStages) & 1);
                             tc_fence_after();
-                            cur_a = smem_u32(a_buf + s * kATile);
+                            cur_a = smem_u32(a_buf + s * Cfg::kAStage);
                             prev_a_slot = s;
                             have_a = true;
-                            ++ai;
                         },
                         [&](int slot, int) {
                             const uint32_t s = bi % Cfg::kBStages, ph = (bi / Cfg::kBStages) & 1;
-                            mbar_wait(&b_full[s], ph);
+                            if (!b_ready) mbar_wait(&b_full[s], ph);
+                            ++bi;
+                            b_ready = mbar_test(&b_full[bi % Cfg::kBStages], (bi / Cfg::kBStages) & 1);
                             tc_fence_after();
-                            const uint32_t b_addr = smem_u32(b_buf + s * Cfg::kBTile);
-                            const uint64_t ad = make_sdesc(cur_a), bd = make_sdesc(b_addr);
+                            const uint32_t b_addr = smem_u32(b_buf + s * Cfg::kBStage);
+                            const uint32_t acc0 = (started >> slot) & 1u;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                // +32 B per K=16 step inside the 128 B swizzle atom (encoded >>4)
-                                tc_mma_f16(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc,
-                                           ((started >> slot) & 1u) | (k > 0 ? 1u : 0u));
+                            for (int c = 0; c < KC; ++c) {
+                                const uint64_t ad = make_sdesc(cur_a + c * kATile), bd = make_sdesc(b_addr + c * Cfg::kBTile);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)   // +32 B per K=16 step inside the 128 B swizzle atom (encoded >>4)
+                                    tc_mma_f16(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc, acc0 | ((c | k) ? 1u : 0u));
                             }
                             started |= 1u << slot;
                             tc_commit(&b_empty[s]);
-                            ++bi;
                         });
                     if (have_a) tc_commit(&a_empty[prev_a_slot]);
                     tc_commit(&acc_full[as]);
@@ -300,7 +343,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         }
     } else {
         // ================= epilogue =================
-        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int q = warp & 3;                 // TMEM lane quarter this warp may touch (warps 3..6 -> 3,0,1,2)
         const int r = q * 32 + lane;            // accumulator row = position within the tile
         const int bl = r / (args.Hb * args.W), hl = (r / args.W) % args.Hb, w = r % args.W;
         HT* out = reinterpret_cast<HT*>(args.out);
@@ -363,7 +406,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         tc_fence_before();
                         asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (warp == 2 && lane == 0) {
+                        if (warp == 3 && lane == 0) {
                             tc_fence_after();
                             constexpr uint32_t idesc_p = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
                                                          ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -623,13 +666,13 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <typename HT, int COUT, int NPH, bool FUSE>
+template <typename HT, int COUT, int NPH, int KC, bool FUSE>
 int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
                   int T, int H, int W, int Cin, int sm_count, cudaStream_t st) {
-    using Cfg = TcCfg<COUT, NPH>;
+    using Cfg = TcCfg<COUT, NPH, KC>;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { rdg_set_error("cuTensorMapEncodeTiled entry point not available"); return RDG_TC_E_DRIVER; }
-    if (Cin % 64 || W > 128 || (128 % W) != 0) { rdg_set_error("tc upconv: unsupported shape"); return RDG_TC_E_SHAPE; }
+    if (Cin % (64 * KC) || W > 128 || (128 % W) != 0) { rdg_set_error("tc upconv: unsupported shape"); return RDG_TC_E_SHAPE; }
     TcConvArgs a;
     a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin;
     int rows_per_sample_plane = H * W;
@@ -651,7 +694,7 @@ int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, 
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return RDG_TC_E_DRIVER; }
 
-    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH, FUSE>;
+    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH, KC, FUSE>;
     static bool attr_set = false;
     if (!attr_set) {
         RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -666,10 +709,10 @@ int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, 
 template <typename HT>
 int tc_upconv_dispatch(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out,
                        int B, int T, int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st) {
-    if (Cout == 256) return launch_upconv<HT, 256, 1, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
-    if (Cout == 128) return launch_upconv<HT, 128, 2, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
-    if (Cout == 64 && p_out) return launch_upconv<HT, 64, 4, true>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
-    if (Cout == 64) return launch_upconv<HT, 64, 4, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 256) return launch_upconv<HT, 256, 1, 1, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 128) return launch_upconv<HT, 128, 2, 2, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 64 && p_out) return launch_upconv<HT, 64, 4, 2, true>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    if (Cout == 64) return launch_upconv<HT, 64, 4, 2, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
     rdg_set_error("tc upconv: unsupported Cout %d", Cout);
     return RDG_TC_E_SHAPE;
 }
