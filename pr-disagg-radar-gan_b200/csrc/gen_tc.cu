@@ -38,6 +38,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+// one lane of the (converged) warp; keeps the surrounding control flow warp-uniform so that
+// descriptors / addresses stay in uniform registers
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}" : "+r"(pred));
+    return pred;
+}
 // non-blocking probe; issued early so its latency overlaps other work, result consumed later
 __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -238,7 +251,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
 
     if (warp == 0) {
         // ================= A producer (activation tiles, TMA 5-D box loads) =================
-        if (lane == 0) {
+        {
             uint32_t ai = 0;
             uint32_t free_next = mbar_test(&a_empty[0], 1);
             for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
@@ -253,11 +266,13 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                             ++ai;
                             const uint32_t s2 = ai % Cfg::kAStages, ph2 = (ai / Cfg::kAStages) & 1;
                             free_next = mbar_test(&a_empty[s2], ph2 ^ 1);
-                            mbar_expect_tx(&a_full[s], Cfg::kAStage);
+                            if (elect_one()) {
+                                mbar_expect_tx(&a_full[s], Cfg::kAStage);
 #pragma unroll
-                            for (int k = 0; k < KC; ++k)
-                                tma_load_5d(a_buf + s * Cfg::kAStage + k * kATile, &tmap, &a_full[s], (c + k) * 64, dw,
-                                            h0 + dh, t + dt, b0);
+                                for (int k = 0; k < KC; ++k)
+                                    tma_load_5d(a_buf + s * Cfg::kAStage + k * kATile, &tmap, &a_full[s], (c + k) * 64, dw,
+                                                h0 + dh, t + dt, b0);
+                            }
                         },
                         [&](int, int) {});
                 }
@@ -265,7 +280,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         }
     } else if (warp == 2) {
         // ================= B producer (pre-swizzled weight tiles, 1-D bulk copies) =================
-        if (lane == 0) {
+        {
             uint32_t bi = 0;
             uint32_t free_next = mbar_test(&b_empty[0], 1);
             for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
@@ -279,17 +294,19 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                             ++bi;
                             const uint32_t s2 = bi % Cfg::kBStages, ph2 = (bi / Cfg::kBStages) & 1;
                             free_next = mbar_test(&b_empty[s2], ph2 ^ 1);
-                            mbar_expect_tx(&b_full[s], Cfg::kBStage);
-                            bulk_load_1d(b_buf + s * Cfg::kBStage,
-                                         reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile,
-                                         Cfg::kBStage, &b_full[s]);
+                            if (elect_one()) {
+                                mbar_expect_tx(&b_full[s], Cfg::kBStage);
+                                bulk_load_1d(b_buf + s * Cfg::kBStage,
+                                             reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile,
+                                             Cfg::kBStage, &b_full[s]);
+                            }
                         });
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (whole warp walks the schedule; one elected lane issues) =================
+        {
             constexpr uint32_t idesc = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
                                        ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             uint32_t ai = 0, bi = 0, acc_it = 0;
@@ -308,7 +325,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                     for_each_step<NPH>(
                         pass, t, args.T, nchunk, KC,
                         [&](int, int, int, int) {
-                            if (have_a) tc_commit(&a_empty[prev_a_slot]);   // all MMAs reading the previous A stage issued
+                            if (have_a && elect_one()) tc_commit(&a_empty[prev_a_slot]);   // MMAs reading the previous A stage issued
                             const uint32_t s = ai % Cfg::kAStages, ph = (ai / Cfg::kAStages) & 1;
                             if (!a_ready) mbar_wait(&a_full[s], ph);
                             ++ai;
@@ -326,18 +343,23 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                             tc_fence_after();
                             const uint32_t b_addr = smem_u32(b_buf + s * Cfg::kBStage);
                             const uint32_t acc0 = (started >> slot) & 1u;
+                            if (elect_one()) {
 #pragma unroll
-                            for (int c = 0; c < KC; ++c) {
-                                const uint64_t ad = make_sdesc(cur_a + c * kATile), bd = make_sdesc(b_addr + c * Cfg::kBTile);
+                                for (int c = 0; c < KC; ++c) {
+                                    const uint64_t ad = make_sdesc(cur_a + c * kATile), bd = make_sdesc(b_addr + c * Cfg::kBTile);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)   // +32 B per K=16 step inside the 128 B swizzle atom (encoded >>4)
-                                    tc_mma_f16(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc, acc0 | ((c | k) ? 1u : 0u));
+                                    for (int k = 0; k < 4; ++k)   // +32 B per K=16 step inside the 128 B swizzle atom (encoded >>4)
+                                        tc_mma_f16(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc, acc0 | ((c | k) ? 1u : 0u));
+                                }
+                                tc_commit(&b_empty[s]);
                             }
                             started |= 1u << slot;
-                            tc_commit(&b_empty[s]);
                         });
-                    if (have_a) tc_commit(&a_empty[prev_a_slot]);
-                    tc_commit(&acc_full[as]);
+                    if (elect_one()) {
+                        if (have_a) tc_commit(&a_empty[prev_a_slot]);
+                        tc_commit(&acc_full[as]);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -406,7 +428,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         tc_fence_before();
                         asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (warp == 3 && lane == 0) {
+                        if (warp == 3 && elect_one()) {
                             tc_fence_after();
                             constexpr uint32_t idesc_p = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
                                                          ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
