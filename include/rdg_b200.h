@@ -117,6 +117,13 @@ int  rdg_pixelnorm(const float* x_dev, float* y_dev, long long rows, int C, int 
 /* softmax over the hour axis of logits [B,24,P] (gan_train...py:347) */
 int  rdg_softmax_hours(const float* logits_dev, float* out_dev, long long B, int P, void* stream);
 
+/* The FP32 SIMT Conv3D primitives behind the critic / training path (Keras Conv3D semantics,
+ * gan_train_cwgangp_pixelnorm.py:286-301, :331-345).  geom17 = {B, Ti,Hi,Wi,Ci, To,Ho,Wo,Co, KT,KH,KW, stride,
+ * pad_before_t,h,w, upsample_input}.  op 0: out = act(conv(a, w=b) + bias); op 1: out = d/d(input) given
+ * dy=a, w=b (w.r.t. the upsampled input if upsample_input); op 2: out += d/dw given x=a, dy=b, out2 += d/dbias. */
+int  rdg_conv3d(int op, const int* geom17, const float* a, const float* b, const float* bias, float* out,
+                float* out2, int act, void* stream);
+
 /* instrumentation: per-layer CUDA-event timing on the launching stream (layer ids: 0 input concat,
  * 1 dense, 2 f32->16-bit, 3..5 upsampled convs, 6 output conv + softmax, 7 pixelnorm in FP32 mode)
  * and a count of kernels launched by this context. */

@@ -182,37 +182,6 @@ extern "C" int rdg_ctx_info(const rdg_ctx* c, int* nd, int* ncond, int* max_chun
 extern "C" size_t rdg_ctx_workspace_bytes(const rdg_ctx* c) { return c ? c->ws_bytes : 0; }
 
 // ------------------------------------------------------------------ weight packing
-// Fold nearest-x2 upsample + 3^3 conv into 8 phases x 8 taps and lay each
-// (phase, tap, 64-channel chunk) out as a [Cout rows x 64 k] K-major tile whose 16-byte chunks are
-// XOR-swizzled by (row & 7): the exact shared-memory image tcgen05.mma reads with SWIZZLE_128B.
-template <typename HT, typename CVT>
-static void pack_folded(const float* k, int Cin, int Cout, std::vector<HT>& dst, CVT cvt) {
-    const int nchunk = Cin / 64;
-    dst.assign((size_t)64 * nchunk * Cout * 64, cvt(0.f));
-    std::vector<float> wf((size_t)Cin * Cout);
-    // per-axis tap sets: phase 0: tap0 <- {0}, tap1 <- {1,2}; phase 1: tap0 <- {0,1}, tap1 <- {2}
-    auto lo = [](int ph, int a) { return ph == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2); };
-    auto hi = [](int ph, int a) { return ph == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2); };
-    for (int p = 0; p < 8; ++p)
-        for (int a = 0; a < 8; ++a) {
-            const int pt = p >> 2, ph = (p >> 1) & 1, pw = p & 1, at = a >> 2, ah = (a >> 1) & 1, aw = a & 1;
-            std::fill(wf.begin(), wf.end(), 0.f);
-            for (int kt = lo(pt, at); kt <= hi(pt, at); ++kt)
-                for (int kh = lo(ph, ah); kh <= hi(ph, ah); ++kh)
-                    for (int kw = lo(pw, aw); kw <= hi(pw, aw); ++kw) {
-                        const float* src = k + (size_t)((kt * 3 + kh) * 3 + kw) * Cin * Cout;
-                        for (size_t i = 0; i < (size_t)Cin * Cout; ++i) wf[i] += src[i];
-                    }
-            for (int c = 0; c < nchunk; ++c) {
-                HT* tile = dst.data() + ((size_t)(p * 8 + a) * nchunk + c) * Cout * 64;
-                for (int n = 0; n < Cout; ++n)
-                    for (int j = 0; j < 8; ++j)
-                        for (int e = 0; e < 8; ++e)
-                            tile[(size_t)n * 64 + ((j ^ (n & 7)) * 8) + e] = cvt(wf[(size_t)(c * 64 + j * 8 + e) * Cout + n]);
-            }
-        }
-}
-
 static int upload_params(float* dev, const size_t* off, const size_t* size, const float* const* tensors,
                          const size_t* sizes, int n, const char* what) {
     if (n != 10) { rdg_set_error("%s: expected 10 tensors, got %d", what, n); return RDG_E_BADARG; }
@@ -222,37 +191,22 @@ static int upload_params(float* dev, const size_t* off, const size_t* size, cons
     return 0;
 }
 
-int rdg_repack_generator(rdg_ctx* c, const float* const* host_tensors) {
+// (Re)build the folded + swizzled 16-bit operand tiles from the f32 master weights, on the device.
+int rdg_repack_generator(rdg_ctx* c, cudaStream_t st) {
     static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
-    for (int l = 0; l < 3; ++l) {
-        std::vector<__nv_bfloat16> pb;
-        std::vector<__half> ph;
-        pack_folded<__nv_bfloat16>(host_tensors[2 + 2 * l], cin[l], cout[l], pb, [](float f) { return __float2bfloat16_rn(f); });
-        pack_folded<__half>(host_tensors[2 + 2 * l], cin[l], cout[l], ph, [](float f) { return __float2half_rn(f); });
-        for (int k = 0; k < 2; ++k) {
-            if (!c->g_wpack[k][l]) RDG_CUDA(cudaMalloc(&c->g_wpack[k][l], pb.size() * 2));
+    for (int k = 0; k < 2; ++k) {
+        const int hk = k == 0 ? RDG_HALF_BF16 : RDG_HALF_FP16;
+        for (int l = 0; l < 3; ++l) {
+            if (!c->g_wpack[k][l]) RDG_CUDA(cudaMalloc(&c->g_wpack[k][l], (size_t)64 * cin[l] * cout[l] * 2));
+            int r = pack_folded_weights(hk, c->g_params + c->g_off[2 + 2 * l], c->g_wpack[k][l], cin[l], cout[l], st);
+            if (r) return r;
         }
-        RDG_CUDA(cudaMemcpy(c->g_wpack[0][l], pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
-        RDG_CUDA(cudaMemcpy(c->g_wpack[1][l], ph.data(), ph.size() * 2, cudaMemcpyHostToDevice));
+        if (!c->g_w4pack[k]) RDG_CUDA(cudaMalloc(&c->g_w4pack[k], 32 * 64 * 2));
+        int r = pack_w4_tile(hk, c->g_params + c->g_off[8], c->g_w4pack[k], st);
+        if (r) return r;
     }
-    // output conv (3,3,3,64,1): row n = tap (27 used of 32), k = channel; same 128B swizzle as the other B tiles
-    {
-        const float* k4 = host_tensors[8];
-        std::vector<__nv_bfloat16> tb(32 * 64, __float2bfloat16_rn(0.f));
-        std::vector<__half> th(32 * 64, __float2half_rn(0.f));
-        for (int n = 0; n < 27; ++n)
-            for (int j = 0; j < 8; ++j)
-                for (int e = 0; e < 8; ++e) {
-                    const float v = k4[(size_t)n * 64 + j * 8 + e];
-                    const size_t d = (size_t)n * 64 + ((j ^ (n & 7)) * 8) + e;
-                    tb[d] = __float2bfloat16_rn(v);
-                    th[d] = __float2half_rn(v);
-                }
-        for (int k = 0; k < 2; ++k)
-            if (!c->g_w4pack[k]) RDG_CUDA(cudaMalloc(&c->g_w4pack[k], 32 * 64 * 2));
-        RDG_CUDA(cudaMemcpy(c->g_w4pack[0], tb.data(), 32 * 64 * 2, cudaMemcpyHostToDevice));
-        RDG_CUDA(cudaMemcpy(c->g_w4pack[1], th.data(), 32 * 64 * 2, cudaMemcpyHostToDevice));
-    }
+    c->launches += 8;
+    c->gen_packed_stale = false;
     return 0;
 }
 
@@ -261,8 +215,9 @@ extern "C" int rdg_generator_set_weights(rdg_ctx* c, const float* const* tensors
     RDG_CUDA(cudaSetDevice(c->device));
     int r = upload_params(c->g_params, c->g_off, c->g_size, tensors, sizes, n, "generator weights");
     if (r) return r;
-    r = rdg_repack_generator(c, tensors);
+    r = rdg_repack_generator(c, nullptr);
     if (r) return r;
+    RDG_CUDA(cudaDeviceSynchronize());
     c->gen_ready = true;
     return 0;
 }
@@ -403,6 +358,7 @@ extern "C" int rdg_generator_forward(rdg_ctx* c, const float* latent_dev, const 
     if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
     RDG_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->gen_packed_stale && mode != RDG_MODE_FP32) { int r = rdg_repack_generator(c, st); if (r) return r; }
     const int chunk = chunk_for_mode(c, mode);
     const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
     for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -420,6 +376,7 @@ extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const flo
     if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
     if (B == 0) return 0;
     RDG_CUDA(cudaSetDevice(c->device));
+    if (c->gen_packed_stale && mode != RDG_MODE_FP32) { int r = rdg_repack_generator(c, c->s_comp); if (r) return r; }
     const int chunk = chunk_for_mode(c, mode);
     const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
     const size_t ncf = (size_t)c->nd * c->nd * c->ncond;
@@ -504,6 +461,24 @@ extern "C" int rdg_critic_forward(rdg_ctx* c, const float* sample_dev, const flo
 }
 
 // ------------------------------------------------------------------ building blocks for tests
+static ConvGeom geom_from(const int* g) {
+    ConvGeom c{};
+    c.B = g[0]; c.Ti = g[1]; c.Hi = g[2]; c.Wi = g[3]; c.Ci = g[4]; c.To = g[5]; c.Ho = g[6]; c.Wo = g[7]; c.Co = g[8];
+    c.KT = g[9]; c.KH = g[10]; c.KW = g[11]; c.stride = g[12]; c.pt = g[13]; c.ph = g[14]; c.pw = g[15]; c.up = g[16];
+    return c;
+}
+// op 0: y = act(conv(x,w)+bias); op 1: dx = conv_bwd_data(dy=a, w); op 2: dw += bwd_filter(x=a, dy=b), db += colsum
+extern "C" int rdg_conv3d(int op, const int* geom17, const float* a, const float* b, const float* bias, float* out,
+                          float* out2, int act, void* stream) {
+    if (!geom17 || !a || !out) return RDG_E_BADARG;
+    ConvGeom g = geom_from(geom17);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (op == 0) return simt_conv_fwd(a, b, bias, out, g, act, nullptr, 1.f, st);
+    if (op == 1) return simt_conv_bwd_data(a, b, out, g, st);
+    if (op == 2) return simt_conv_bwd_filter(a, b, out, out2, g, st);
+    return RDG_E_BADARG;
+}
+
 // One tensor-core layer in isolation: x f32 [B,T,H,W,Cin] -> rounded to 16 bit -> layer -> y f32 [B,2T,2H,2W,Cout]
 extern "C" int rdg_tc_layer(rdg_ctx* c, int layer, int mode, const float* x_dev, float* y_dev, int B, void* stream) {
     if (!c || layer < 0 || layer > 2 || (mode != RDG_MODE_BF16 && mode != RDG_MODE_FP16)) return RDG_E_BADARG;

@@ -37,4 +37,4 @@ ConvGeom rdg_gen_conv_geom(const rdg_ctx* c, int layer, int B);
 ConvGeom rdg_gen_dense_geom(const rdg_ctx* c, int B);
 ConvGeom rdg_critic_conv_geom(const rdg_ctx* c, int layer, int B);
 ConvGeom rdg_critic_dense_geom(const rdg_ctx* c, int B);
-int rdg_repack_generator(rdg_ctx* c, const float* const* host_tensors);
+int rdg_repack_generator(rdg_ctx* c, cudaStream_t st);

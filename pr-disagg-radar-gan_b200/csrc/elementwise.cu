@@ -190,6 +190,68 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
 
+__global__ void interp_kernel(const float* __restrict__ xr, const float* __restrict__ xf, const float* __restrict__ alpha,
+                              float* __restrict__ xh, long long n, long long per) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = alpha[i / per];
+    xh[i] = a * xr[i] + (1.f - a) * xf[i];          // RandomWeightedAverage, gan_train_cwgangp_pixelnorm.py:221-224
+}
+__global__ void fill_kernel(float* __restrict__ d, long long n, float v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = v;
+}
+__device__ __forceinline__ float block_sum(float v) {
+    __shared__ float sh[32];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;   // valid in warp 0
+}
+__global__ void mean_scaled_kernel(const float* __restrict__ x, long long n, float scale, float* __restrict__ out) {
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[0] = scale * s / (float)n;
+}
+// one block per sample: || g0[b, :, channel 0] ||_2   (GradientPenalty, gan_train_cwgangp_pixelnorm.py:240-241)
+__global__ void gp_norm_kernel(const float* __restrict__ g0, int C, long long per, float* __restrict__ norm) {
+    const float* g = g0 + (long long)blockIdx.x * per * C;
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < per; i += blockDim.x) { float v = g[i * C]; s = fmaf(v, v, s); }
+    s = block_sum(s);
+    if (threadIdx.x == 0) norm[blockIdx.x] = sqrtf(s);      // no epsilon, like the reference
+}
+__global__ void gp_cotangent_kernel(const float* __restrict__ g0, const float* __restrict__ norm, float coef,
+                                    float* __restrict__ u0, int C, long long n, long long per) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % C);
+    const long long b = i / (per * C);
+    const float nb = norm[b];
+    u0[i] = c == 0 ? coef * (nb - 1.f) / nb * g0[i] : 0.f;
+}
+__global__ void gp_loss_kernel(const float* __restrict__ norm, int B, float* __restrict__ out) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) { float d = norm[i] - 1.f; s = fmaf(d, d, s); }
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[0] = s / (float)B;
+}
+__global__ void extract_channel0_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int C) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x[i * C];
+}
+__global__ void combine_losses_kernel(const float* lv, const float* lf, const float* lgp, float w, float* out4) {
+    out4[1] = lv[0]; out4[2] = lf[0]; out4[3] = lgp[0];
+    out4[0] = lv[0] + lf[0] + w * lgp[0];     // loss_weights [1, 1, 10], gan_train_cwgangp_pixelnorm.py:388-392
+}
+
 }  // namespace
 
 #define EW_GRID(n) ceil_div((n), 256), 256, 0, st
@@ -258,6 +320,54 @@ int ew_adam(float* p, const float* g, float* m, float* v, long long n, float lr_
             float eps, float grad_scale, cudaStream_t st) {
     if (!n) return 0;
     adam_kernel<<<EW_GRID(n)>>>(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int ew_interp(const float* xr, const float* xf, const float* alpha, float* xhat, int B, long long per, cudaStream_t st) {
+    long long n = (long long)B * per;
+    if (!n) return 0;
+    interp_kernel<<<EW_GRID(n)>>>(xr, xf, alpha, xhat, n, per);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_fill(float* dst, long long n, float v, cudaStream_t st) {
+    if (!n) return 0;
+    fill_kernel<<<EW_GRID(n)>>>(dst, n, v);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_mean_scaled(const float* x, long long n, float scale, float* out, cudaStream_t st) {
+    mean_scaled_kernel<<<1, 256, 0, st>>>(x, n, scale, out);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_gp_norm(const float* g0, int C, int B, long long per, float* norm, cudaStream_t st) {
+    if (!B) return 0;
+    gp_norm_kernel<<<B, 256, 0, st>>>(g0, C, per, norm);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_gp_cotangent(const float* g0, const float* norm, float coef, float* u0, int C, int B, long long per, cudaStream_t st) {
+    long long n = (long long)B * per * C;
+    if (!n) return 0;
+    gp_cotangent_kernel<<<EW_GRID(n)>>>(g0, norm, coef, u0, C, n, per);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_gp_loss(const float* norm, int B, float* out, cudaStream_t st) {
+    gp_loss_kernel<<<1, 256, 0, st>>>(norm, B, out);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_extract_channel0(const float* x, float* out, long long n, int C, cudaStream_t st) {
+    if (!n) return 0;
+    extract_channel0_kernel<<<EW_GRID(n)>>>(x, out, n, C);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_combine_losses(const float* lv, const float* lf, const float* lgp, float gp_weight, float* out4, cudaStream_t st) {
+    combine_losses_kernel<<<1, 1, 0, st>>>(lv, lf, lgp, gp_weight, out4);
     RDG_LAUNCH_CHECK();
     return 0;
 }

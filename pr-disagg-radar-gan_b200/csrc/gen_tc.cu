@@ -772,6 +772,62 @@ int tc_upconv_pixelnorm(int half_kind, const void* x, const void* wpack, const f
     return tc_upconv_dispatch<__half>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, Cout, sm_count, st);
 }
 
+// ------------------------------------------------------------------ weight packing (device side)
+namespace {
+// One thread per packed element.  Folds the nearest-x2 upsample into the 3^3 kernel:
+// per axis, phase 0: tap0 <- {k0}, tap1 <- {k1,k2}; phase 1: tap0 <- {k0,k1}, tap1 <- {k2}; sums in f32,
+// rounded once to 16 bit, stored as [phase][tap][chunk][Cout rows x 64 k] with the 16-byte chunks of
+// row n XOR-swizzled by (n & 7) -- the SWIZZLE_128B K-major image tcgen05.mma reads.
+template <typename HT>
+__global__ void pack_folded_kernel(const float* __restrict__ k, HT* __restrict__ dst, int Cin, int Cout) {
+    const long long total = (long long)64 * Cin * Cout;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int nchunk = Cin / 64;
+    const int within = (int)(idx % ((long long)Cout * 64));
+    long long tile = idx / ((long long)Cout * 64);
+    const int chunk = (int)(tile % nchunk); tile /= nchunk;
+    const int a = (int)(tile % 8), p = (int)(tile / 8);
+    const int n = within / 64, pos = within % 64;
+    const int j = (pos >> 3) ^ (n & 7), e = pos & 7;
+    const int ci = chunk * 64 + j * 8 + e;
+    const int pt = p >> 2, ph = (p >> 1) & 1, pw = p & 1, at = a >> 2, ah = (a >> 1) & 1, aw = a & 1;
+    auto lo = [](int phs, int tp) { return phs == 0 ? (tp == 0 ? 0 : 1) : (tp == 0 ? 0 : 2); };
+    auto hi = [](int phs, int tp) { return phs == 0 ? (tp == 0 ? 0 : 2) : (tp == 0 ? 1 : 2); };
+    float sum = 0.f;
+    for (int kt = lo(pt, at); kt <= hi(pt, at); ++kt)
+        for (int kh = lo(ph, ah); kh <= hi(ph, ah); ++kh)
+            for (int kw = lo(pw, aw); kw <= hi(pw, aw); ++kw)
+                sum += k[((long long)((kt * 3 + kh) * 3 + kw) * Cin + ci) * Cout + n];
+    dst[idx] = HalfOps<HT>::from_float(sum);
+}
+// output conv (3,3,3,64,1) as a [32 taps x 64 ch] swizzled B tile (taps 27..31 zero)
+template <typename HT>
+__global__ void pack_w4_kernel(const float* __restrict__ k4, HT* __restrict__ dst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 32 * 64) return;
+    const int n = idx / 64, pos = idx % 64;
+    const int j = (pos >> 3) ^ (n & 7), e = pos & 7;
+    dst[idx] = HalfOps<HT>::from_float(n < 27 ? k4[n * 64 + j * 8 + e] : 0.f);
+}
+}  // namespace
+
+int pack_folded_weights(int half_kind, const float* k, void* dst, int Cin, int Cout, cudaStream_t st) {
+    const long long total = (long long)64 * Cin * Cout;
+    if (half_kind == RDG_HALF_BF16)
+        pack_folded_kernel<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, st>>>(k, (__nv_bfloat16*)dst, Cin, Cout);
+    else
+        pack_folded_kernel<__half><<<ceil_div(total, 256), 256, 0, st>>>(k, (__half*)dst, Cin, Cout);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int pack_w4_tile(int half_kind, const float* k4, void* dst, cudaStream_t st) {
+    if (half_kind == RDG_HALF_BF16) pack_w4_kernel<__nv_bfloat16><<<8, 256, 0, st>>>(k4, (__nv_bfloat16*)dst);
+    else pack_w4_kernel<__half><<<8, 256, 0, st>>>(k4, (__half*)dst);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
 int gather_softmax(const float* p, const float* b4, float* out, const float* cond, int B, int nd, int spc, int b_off,
                    int ncond, float scale, int out_mm, int* nonfinite, cudaStream_t st) {
     if (B <= 0) return 0;

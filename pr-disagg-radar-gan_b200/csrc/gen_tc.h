@@ -34,3 +34,6 @@ int conv_out_softmax(int in_kind, const void* x, const float* w4, const float* b
                      int B, int nd, int spc, int b_off, int ncond, float scale, int out_mm, int* nonfinite, cudaStream_t st);
 int f32_to_half(int half_kind, const float* src, void* dst, long long n, cudaStream_t st);
 int half_to_f32(int half_kind, const void* src, float* dst, long long n, cudaStream_t st);
+// device-side packing of the master f32 weights into the tcgen05 operand images
+int pack_folded_weights(int half_kind, const float* k, void* dst, int Cin, int Cout, cudaStream_t st);
+int pack_w4_tile(int half_kind, const float* k4, void* dst, cudaStream_t st);

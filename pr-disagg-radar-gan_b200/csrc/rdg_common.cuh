@@ -49,7 +49,9 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // ---- SIMT FP32 primitives (simt_conv.cu) ----
 // y = act(conv(x, w) + bias) [* mask * mask_scale]; w is Keras (KT,KH,KW,Ci,Co) f32.
 int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g,
-                  int act, const float* mask, float mask_scale, cudaStream_t st);
+                  int act, const float* mask, float mask_scale, cudaStream_t st, float* pre = nullptr);
+// out[c] += sum_r x[r][c]
+int simt_colsum(const float* x, float* out, long long rows, int C, cudaStream_t st);
 // dx = conv_transpose(dy, w): gradient w.r.t. the (logical, i.e. upsampled if g.up) input.
 int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);
 // dw += sum_b,pos x (x) dy ; db += sum dy (db may be null). Accumulates (caller zeroes).
@@ -76,5 +78,12 @@ int ew_fill_normal(float* dst, long long n, uint64_t seed, uint64_t offset, cuda
 int ew_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1,
             float beta2, float eps, float grad_scale, cudaStream_t st);
 
-// ---- tensor-core generator (gen_tc.cu) ----
-struct TcLayerPlan;   // opaque, owned by the context
+// training-step helpers
+int ew_interp(const float* xr, const float* xf, const float* alpha, float* xhat, int B, long long per, cudaStream_t st);
+int ew_fill(float* dst, long long n, float v, cudaStream_t st);
+int ew_mean_scaled(const float* x, long long n, float scale, float* out, cudaStream_t st);   // out = scale * mean(x)
+int ew_gp_norm(const float* g0, int C, int B, long long per, float* norm, cudaStream_t st);   // ||g0[b,...,0]||_2
+int ew_gp_cotangent(const float* g0, const float* norm, float coef, float* u0, int C, int B, long long per, cudaStream_t st);
+int ew_gp_loss(const float* norm, int B, float* out, cudaStream_t st);                       // mean((norm-1)^2)
+int ew_extract_channel0(const float* x, float* out, long long n, int C, cudaStream_t st);
+int ew_combine_losses(const float* lv, const float* lf, const float* lgp, float gp_weight, float* out4, cudaStream_t st);

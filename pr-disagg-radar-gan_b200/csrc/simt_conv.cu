@@ -43,7 +43,7 @@ template <int MODE>
 __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ dst,
                                                        ConvGeom g, int act, const float* __restrict__ mask,
-                                                       float mask_scale) {
+                                                       float mask_scale, float* __restrict__ pre) {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
             float v = acc[i][j];
             if (MODE == 0) {
                 if (bias) v += bias[n];
+                if (pre) pre[m * N + n] = v;            // pre-activation, kept for the backward pass
                 if (act == ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
                 if (mask) v *= mask[m * N + n] * mask_scale;
             }
@@ -213,11 +214,11 @@ __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ 
 }  // namespace
 
 int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int act,
-                  const float* mask, float mask_scale, cudaStream_t st) {
+                  const float* mask, float mask_scale, cudaStream_t st, float* pre) {
     long long M = (long long)g.B * g.To * g.Ho * g.Wo;
     if (M == 0) return 0;
     dim3 grid(ceil_div(M, BM), ceil_div(g.Co, BN));
-    conv_gemm_kernel<0><<<grid, NT, 0, st>>>(x, w, bias, y, g, act, mask, mask_scale);
+    conv_gemm_kernel<0><<<grid, NT, 0, st>>>(x, w, bias, y, g, act, mask, mask_scale, pre);
     RDG_LAUNCH_CHECK();
     return 0;
 }
@@ -227,7 +228,7 @@ int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeo
     long long M = (long long)g.B * g.Ti * upf * g.Hi * upf * g.Wi * upf;
     if (M == 0) return 0;
     dim3 grid(ceil_div(M, BM), ceil_div(g.Ci, BN));
-    conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, ACT_NONE, nullptr, 1.f);
+    conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, ACT_NONE, nullptr, 1.f, nullptr);
     RDG_LAUNCH_CHECK();
     return 0;
 }
@@ -243,10 +244,14 @@ int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, 
     dim3 grid(ceil_div(g.Ci, BM), ceil_div(g.Co, BN), ntaps * ksplit);
     conv_bwd_filter_kernel<<<grid, NT, 0, st>>>(x, dy, dw, g, ksplit);
     RDG_LAUNCH_CHECK();
-    if (db) {
-        long long rpb = 256;
-        colsum_kernel<<<ceil_div(M, rpb), 128, 0, st>>>(dy, db, M, g.Co, rpb);
-        RDG_LAUNCH_CHECK();
-    }
+    if (db) return simt_colsum(dy, db, M, g.Co, st);
+    return 0;
+}
+
+int simt_colsum(const float* x, float* out, long long rows, int C, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    long long rpb = 256;
+    colsum_kernel<<<ceil_div(rows, rpb), 128, 0, st>>>(x, out, rows, C, rpb);
+    RDG_LAUNCH_CHECK();
     return 0;
 }

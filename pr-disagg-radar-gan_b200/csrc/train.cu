@@ -4,6 +4,7 @@
 #include "ctx.h"
 #include "../../include/rdg_b200.h"
 #include <cmath>
+#include <algorithm>
 
 static int ensure_train_state(rdg_ctx* c) {
     if (!c->g_grads) {
@@ -63,14 +64,262 @@ extern "C" int rdg_adam_reset(rdg_ctx* c, int which) {
     return 0;
 }
 
+// ------------------------------------------------------------------ workspace
+namespace {
+
+struct Bump {
+    uint8_t* p; uint8_t* end;
+    float* f(size_t n) {
+        uint8_t* r = p;
+        p += (n * 4 + 255) / 256 * 256;
+        return p <= end ? reinterpret_cast<float*>(r) : nullptr;
+    }
+};
+
+int ensure_train_ws(rdg_ctx* c, size_t bytes) {
+    if (c->train_ws_bytes >= bytes) return 0;
+    if (c->train_ws) { RDG_CUDA(cudaDeviceSynchronize()); RDG_CUDA(cudaFree(c->train_ws)); c->train_ws = nullptr; c->train_ws_bytes = 0; }
+    RDG_CUDA(cudaMalloc(&c->train_ws, bytes));
+    c->train_ws_bytes = bytes;
+    return 0;
+}
+
+size_t critic_act_elems(const rdg_ctx* c, int l) {   // l = 0: input (with cond channels), 1..4: conv outputs
+    if (l == 0) return (size_t)RDG_NHOURS * c->nd * c->nd * (1 + c->ncond);
+    ConvGeom g = rdg_critic_conv_geom(c, l - 1, 1);
+    return (size_t)g.To * g.Ho * g.Wo * g.Co;
+}
+
+// activations of one critic invocation kept for the backward passes
+struct CriticActs {
+    float* h[5];     // h[0] = input [B,24,nd,nd,1+ncond]; h[l] = dropout(lrelu(a[l]))
+    float* a[5];     // a[l] = conv_l(h[l-1]) + b_l (pre-activation), l = 1..4
+    float* score;    // [B]
+};
+
+#define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
+
+int critic_alloc(const rdg_ctx* c, Bump& ws, int B, CriticActs& A) {
+    for (int l = 0; l < 5; ++l) {
+        A.h[l] = ws.f((size_t)B * critic_act_elems(c, l));
+        A.a[l] = l ? ws.f((size_t)B * critic_act_elems(c, l)) : nullptr;
+        if (!A.h[l] || (l && !A.a[l])) return RDG_E_NOMEM;
+    }
+    A.score = ws.f(B);
+    return A.score ? 0 : RDG_E_NOMEM;
+}
+
+// critic([sample, cond]) keeping pre-activations (gan_train_cwgangp_pixelnorm.py:275-304)
+int critic_fwd_train(rdg_ctx* c, const float* sample, const float* cond, const float* const* masks, int B, CriticActs& A,
+                     cudaStream_t st) {
+    TRY(ew_critic_input(sample, cond, A.h[0], B, c->nd, c->ncond, st));
+    for (int l = 0; l < 4; ++l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l, B);
+        TRY(simt_conv_fwd(A.h[l], c->c_params + c->c_off[2 * l], c->c_params + c->c_off[2 * l + 1], A.h[l + 1], g, ACT_LRELU,
+                          masks ? masks[l] : nullptr, 1.f / 0.75f, st, A.a[l + 1]));
+    }
+    ConvGeom d = rdg_critic_dense_geom(c, B);
+    return simt_conv_fwd(A.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A.score, d, ACT_NONE, nullptr, 1.f, st);
+}
+
+// Backward of sum_b dscore[b] * D(x_b) through the critic.  Accumulates weight gradients into `grads`
+// (if non-null) and, if dx0 != null, returns the gradient w.r.t. the critic input h[0].
+// tmp0/tmp1: scratch, each >= B * max_l act elems.
+int critic_bwd(rdg_ctx* c, const CriticActs& A, const float* const* masks, const float* dscore, int B, float* grads,
+               float* dx0, float* tmp0, float* tmp1, cudaStream_t st) {
+    ConvGeom d = rdg_critic_dense_geom(c, B);
+    if (grads) TRY(simt_conv_bwd_filter(A.h[4], dscore, grads + c->c_off[8], grads + c->c_off[9], d, st));
+    float* dh = tmp0;   // gradient w.r.t. h[l]
+    float* da = tmp1;   // gradient w.r.t. a[l]
+    TRY(simt_conv_bwd_data(dscore, c->c_params + c->c_off[8], dh, d, st));
+    for (int l = 4; l >= 1; --l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
+        const long long n = (long long)B * critic_act_elems(c, l);
+        TRY(ew_lrelu_bwd(A.a[l], dh, da, n, masks ? masks[l - 1] : nullptr, 1.f / 0.75f, st));
+        if (grads) TRY(simt_conv_bwd_filter(A.h[l - 1], da, grads + c->c_off[2 * (l - 1)], grads + c->c_off[2 * (l - 1) + 1], g, st));
+        if (l > 1) TRY(simt_conv_bwd_data(da, c->c_params + c->c_off[2 * (l - 1)], dh, g, st));
+        else if (dx0) TRY(simt_conv_bwd_data(da, c->c_params + c->c_off[0], dx0, g, st));
+    }
+    return 0;
+}
+
+size_t gen_act(const rdg_ctx* c, int l) {   // 0 dense out, 1..3 conv outs (per sample elements)
+    const int s = c->nd / 8, f = 1 << l;
+    static const int ch[4] = {256, 256, 128, 64};
+    return (size_t)3 * f * s * f * s * f * ch[l];
+}
+
+struct GenActs {
+    float* x0;        // [B, 100 + nd*nd*ncond]
+    float* d0_pre;    // dense pre-activation
+    float* y[4];      // y[0] = lrelu(dense); y[l] = lrelu(pixelnorm(cpre[l]))
+    float* cpre[4];   // conv outputs + bias (pre-norm), l = 1..3
+    float* logits;    // [B,24,nd,nd]
+    float* img;       // [B,24,nd,nd] fractions
+};
+
+int gen_alloc(const rdg_ctx* c, Bump& ws, int B, GenActs& G) {
+    ConvGeom dg = rdg_gen_dense_geom(c, 1);
+    G.x0 = ws.f((size_t)B * dg.Ci);
+    G.d0_pre = ws.f((size_t)B * dg.Co);
+    bool ok = G.x0 && G.d0_pre;
+    for (int l = 0; l < 4; ++l) {
+        G.y[l] = ws.f((size_t)B * gen_act(c, l));
+        G.cpre[l] = l ? ws.f((size_t)B * gen_act(c, l)) : nullptr;
+        ok = ok && G.y[l] && (!l || G.cpre[l]);
+    }
+    const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
+    G.logits = ws.f((size_t)B * px);
+    G.img = ws.f((size_t)B * px);
+    return ok && G.logits && G.img ? 0 : RDG_E_NOMEM;
+}
+
+// FP32 generator forward keeping everything the backward needs (gan_train_cwgangp_pixelnorm.py:319-350)
+int gen_fwd_train(rdg_ctx* c, const float* latent, const float* cond, int B, GenActs& G, cudaStream_t st) {
+    ConvGeom dg = rdg_gen_dense_geom(c, B);
+    TRY(ew_assemble_gen_input(latent, cond, 1, 0, G.x0, B, c->nd * c->nd * c->ncond, st));
+    TRY(simt_conv_fwd(G.x0, c->g_params + c->g_off[0], c->g_params + c->g_off[1], G.y[0], dg, ACT_LRELU, nullptr, 1.f, st, G.d0_pre));
+    for (int l = 0; l < 3; ++l) {
+        ConvGeom g = rdg_gen_conv_geom(c, l, B);
+        TRY(simt_conv_fwd(G.y[l], c->g_params + c->g_off[2 + 2 * l], c->g_params + c->g_off[3 + 2 * l], G.cpre[l + 1], g, ACT_NONE, nullptr, 1.f, st));
+        TRY(ew_pixelnorm(G.cpre[l + 1], G.y[l + 1], (long long)B * g.To * g.Ho * g.Wo, g.Co, 1, st));
+    }
+    ConvGeom g4 = rdg_gen_conv_geom(c, 3, B);
+    TRY(simt_conv_fwd(G.y[3], c->g_params + c->g_off[8], c->g_params + c->g_off[9], G.logits, g4, ACT_NONE, nullptr, 1.f, st));
+    return ew_softmax_hours(G.logits, G.img, B, c->nd * c->nd, nullptr, 1, 1, 1.f, 0, nullptr, st);
+}
+
+}  // namespace
+
+// critic_model.train_on_batch evaluation without the optimizer update
+// (gan_train_cwgangp_pixelnorm.py:365-392, 472): losses4 = [total, l_valid, l_fake, l_gp]; gradients of
+// `total` w.r.t. the critic weights are left in the critic gradient buffer.
 extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const float* cond_dev, const float* latent_dev,
                                      const float* alpha_dev, const float* const* masks_fake, const float* const* masks_real,
                                      const float* const* masks_hat, int B, int gen_mode, float* losses4_dev, void* stream) {
-    rdg_set_error("rdg_critic_step_grads: not implemented yet");
-    return RDG_E_BADARG;
+    if (!c || B < 1 || !x_real_dev || !cond_dev || !latent_dev || !alpha_dev || !losses4_dev) { rdg_set_error("rdg_critic_step_grads: bad arguments"); return RDG_E_BADARG; }
+    if (!c->gen_ready || !c->critic_ready) { rdg_set_error("weights not set"); return RDG_E_NOWEIGHT; }
+    RDG_CUDA(cudaSetDevice(c->device));
+    TRY(ensure_train_state(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
+    size_t max_act = 0, sum_act = 0;
+    for (int l = 0; l < 5; ++l) { max_act = std::max(max_act, critic_act_elems(c, l)); sum_act += critic_act_elems(c, l); }
+    const size_t need = ((size_t)B * (3 * (2 * sum_act + 64) + 6 * max_act + 3 * px) + 4096) * 4 + 64 * 256;
+    TRY(ensure_train_ws(c, need));
+    Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
+    CriticActs Af, Ar, Ah;
+    TRY(critic_alloc(c, ws, B, Af)); TRY(critic_alloc(c, ws, B, Ar)); TRY(critic_alloc(c, ws, B, Ah));
+    float* fake_img = ws.f((size_t)B * px);
+    float* xhat = ws.f((size_t)B * px);
+    float* t0 = ws.f((size_t)B * max_act); float* t1 = ws.f((size_t)B * max_act);
+    float* gbuf = ws.f((size_t)B * max_act);   // first-order gradient g_l of D(xhat)
+    float* ubuf = ws.f((size_t)B * max_act);   // second-order cotangent u_l
+    float* vbuf = ws.f((size_t)B * max_act);
+    float* delta[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int l = 1; l <= 4; ++l) delta[l] = ws.f((size_t)B * critic_act_elems(c, l));
+    float* dscore = ws.f(B); float* norm = ws.f(B); float* lsc = ws.f(8);
+    if (!lsc || !delta[4]) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
+
+    // frozen generator forward (:370, generator.trainable = False :363)
+    TRY(rdg_generator_forward(c, latent_dev, cond_dev, 1, fake_img, B, gen_mode, RDG_OUT_FRACTION, 1.f, nullptr, stream));
+    RDG_CUDA(cudaMemsetAsync(c->c_grads, 0, c->c_total * 4, st));
+
+    // three critic invocations in graph order: fake (:372), real (:373), interpolated (:379)
+    TRY(critic_fwd_train(c, fake_img, cond_dev, masks_fake, B, Af, st));
+    TRY(critic_fwd_train(c, x_real_dev, cond_dev, masks_real, B, Ar, st));
+    TRY(ew_interp(x_real_dev, fake_img, alpha_dev, xhat, B, (long long)px, st));
+    TRY(critic_fwd_train(c, xhat, cond_dev, masks_hat, B, Ah, st));
+
+    // Wasserstein terms: l_valid = mean(-D(real)), l_fake = mean(+D(fake))  (:215-216, targets :452-454)
+    TRY(ew_mean_scaled(Ar.score, B, -1.f, lsc + 0, st));
+    TRY(ew_mean_scaled(Af.score, B, 1.f, lsc + 1, st));
+    TRY(ew_fill(dscore, B, -1.f / (float)B, st));
+    TRY(critic_bwd(c, Ar, masks_real, dscore, B, c->c_grads, nullptr, t0, t1, st));
+    TRY(ew_fill(dscore, B, 1.f / (float)B, st));
+    TRY(critic_bwd(c, Af, masks_fake, dscore, B, c->c_grads, nullptr, t0, t1, st));
+
+    // gradient penalty (:230-244): first-order backward of sum_b D(xhat_b) to xhat, keeping delta_l
+    {
+        ConvGeom d = rdg_critic_dense_geom(c, B);
+        TRY(ew_fill(dscore, B, 1.f, st));
+        TRY(simt_conv_bwd_data(dscore, c->c_params + c->c_off[8], gbuf, d, st));          // g_4 = W5 broadcast
+        for (int l = 4; l >= 1; --l) {
+            ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
+            TRY(ew_lrelu_bwd(Ah.a[l], gbuf, delta[l], (long long)B * critic_act_elems(c, l), masks_hat ? masks_hat[l - 1] : nullptr, 1.f / 0.75f, st));
+            TRY(simt_conv_bwd_data(delta[l], c->c_params + c->c_off[2 * (l - 1)], gbuf, g, st));   // g_{l-1}
+        }
+        const int C0 = 1 + c->ncond;
+        TRY(ew_gp_norm(gbuf, C0, B, (long long)px, norm, st));                            // ||grad_xhat D||_2 per sample
+        TRY(ew_gp_loss(norm, B, lsc + 2, st));                                           // 'mse' against zeros
+        // cotangent of 10 * mean((n-1)^2) w.r.t. g_0 (sample channel only)
+        TRY(ew_gp_cotangent(gbuf, norm, 10.f * 2.f / (float)B, ubuf, C0, B, (long long)px, st));
+        // second-order pass: g_{l-1} = convT_l(delta_l) is bilinear in (W_l, delta_l); LeakyReLU'' = 0
+        for (int l = 1; l <= 4; ++l) {
+            ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
+            TRY(simt_conv_bwd_filter(ubuf, delta[l], c->c_grads + c->c_off[2 * (l - 1)], nullptr, g, st));      // d/dW_l
+            TRY(simt_conv_fwd(ubuf, c->c_params + c->c_off[2 * (l - 1)], nullptr, vbuf, g, ACT_NONE, nullptr, 1.f, st));   // d/d delta_l
+            TRY(ew_lrelu_bwd(Ah.a[l], vbuf, ubuf, (long long)B * critic_act_elems(c, l), masks_hat ? masks_hat[l - 1] : nullptr, 1.f / 0.75f, st));
+        }
+        TRY(simt_colsum(ubuf, c->c_grads + c->c_off[8], B, (int)critic_act_elems(c, 4), st));                   // d/dW5
+    }
+    TRY(ew_combine_losses(lsc + 0, lsc + 1, lsc + 2, 10.f, losses4_dev, st));
+    return 0;
 }
+
+// generator_model.train_on_batch evaluation without the optimizer update (:395-408, :482):
+// loss = mean(-D(G(z, c), c)); gradients w.r.t. the generator weights are left in the generator gradient buffer.
 extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, const float* cond_dev, const float* const* masks,
                                         int B, float* loss_dev, void* stream) {
-    rdg_set_error("rdg_generator_step_grads: not implemented yet");
-    return RDG_E_BADARG;
+    if (!c || B < 1 || !latent_dev || !cond_dev || !loss_dev) { rdg_set_error("rdg_generator_step_grads: bad arguments"); return RDG_E_BADARG; }
+    if (!c->gen_ready || !c->critic_ready) { rdg_set_error("weights not set"); return RDG_E_NOWEIGHT; }
+    RDG_CUDA(cudaSetDevice(c->device));
+    TRY(ensure_train_state(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
+    size_t cmax = 0, csum = 0, gsum = 0, gmax = 0;
+    for (int l = 0; l < 5; ++l) { cmax = std::max(cmax, critic_act_elems(c, l)); csum += critic_act_elems(c, l); }
+    for (int l = 0; l < 4; ++l) { gsum += gen_act(c, l); gmax = std::max(gmax, gen_act(c, l)); }
+    ConvGeom dg1 = rdg_gen_dense_geom(c, 1);
+    const size_t up_max = gmax / 64 * 128 ;   // largest upsampled-input gradient: [24,nd,nd,128]
+    const size_t need = ((size_t)B * (2 * csum + 3 * cmax + 2 * gsum + dg1.Ci + dg1.Co + 4 * px + 2 * gmax + 2 * up_max + 64) + 4096) * 4 + 64 * 256;
+    TRY(ensure_train_ws(c, need));
+    Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
+    GenActs G; CriticActs A;
+    TRY(gen_alloc(c, ws, B, G)); TRY(critic_alloc(c, ws, B, A));
+    float* t0 = ws.f((size_t)B * cmax); float* t1 = ws.f((size_t)B * cmax);
+    float* dx0 = ws.f((size_t)B * cmax);
+    float* dimg = ws.f((size_t)B * px); float* dlog = ws.f((size_t)B * px);
+    float* dy = ws.f((size_t)B * gmax); float* dc = ws.f((size_t)B * gmax);
+    float* dup = ws.f((size_t)B * up_max);
+    float* dscore = ws.f(B);
+    if (!dscore || !dup) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
+
+    TRY(gen_fwd_train(c, latent_dev, cond_dev, B, G, st));
+    TRY(critic_fwd_train(c, G.img, cond_dev, masks, B, A, st));            // critic frozen (:395), dropout active
+    TRY(ew_mean_scaled(A.score, B, -1.f, loss_dev, st));                   // wasserstein_loss with target -1 (:408, :452)
+    TRY(ew_fill(dscore, B, -1.f / (float)B, st));
+    TRY(critic_bwd(c, A, masks, dscore, B, nullptr, dx0, t0, t1, st));
+    TRY(ew_extract_channel0(dx0, dimg, (long long)B * px, 1 + c->ncond, st));
+    RDG_CUDA(cudaMemsetAsync(c->g_grads, 0, c->g_total * 4, st));
+    TRY(ew_softmax_hours_bwd(G.img, dimg, dlog, B, c->nd * c->nd, st));
+    {   // output conv
+        ConvGeom g4 = rdg_gen_conv_geom(c, 3, B);
+        TRY(simt_conv_bwd_filter(G.y[3], dlog, c->g_grads + c->g_off[8], c->g_grads + c->g_off[9], g4, st));
+        TRY(simt_conv_bwd_data(dlog, c->g_params + c->g_off[8], dy, g4, st));
+    }
+    for (int l = 2; l >= 0; --l) {   // upsample + conv + pixelnorm + lrelu blocks
+        ConvGeom g = rdg_gen_conv_geom(c, l, B);
+        const long long rows = (long long)B * g.To * g.Ho * g.Wo;
+        TRY(ew_pixelnorm_lrelu_bwd(G.cpre[l + 1], dy, dc, rows, g.Co, st));
+        TRY(simt_conv_bwd_filter(G.y[l], dc, c->g_grads + c->g_off[2 + 2 * l], c->g_grads + c->g_off[3 + 2 * l], g, st));
+        TRY(simt_conv_bwd_data(dc, c->g_params + c->g_off[2 + 2 * l], dup, g, st));        // w.r.t. the upsampled input
+        TRY(ew_upsample_pool(dup, dy, B, g.Ti, g.Hi, g.Wi, g.Ci, st));                     // UpSampling3D backward
+    }
+    {   // dense + lrelu
+        ConvGeom dg = rdg_gen_dense_geom(c, B);
+        TRY(ew_lrelu_bwd(G.d0_pre, dy, dc, (long long)B * dg.Co, nullptr, 1.f, st));
+        TRY(simt_conv_bwd_filter(G.x0, dc, c->g_grads + c->g_off[0], c->g_grads + c->g_off[1], dg, st));
+    }
+    return 0;
 }

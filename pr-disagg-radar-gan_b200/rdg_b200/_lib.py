@@ -53,6 +53,8 @@ SIGNATURES = {
     "rdg_adam_reset": (C.c_int, [C.c_void_p, C.c_int]),
     "rdg_pixelnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "rdg_softmax_hours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "rdg_conv3d": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_int, C.c_void_p]),
     "rdg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "rdg_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong),
                                       C.POINTER(C.c_longlong)]),

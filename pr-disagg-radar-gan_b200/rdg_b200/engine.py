@@ -189,3 +189,154 @@ class Critic:
         out = self.forward_device(s, c, m)
         torch.cuda.synchronize(self.ctx.device)
         return out.cpu().numpy().reshape(-1, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# training (gan_train_cwgangp_pixelnorm.py:360-408, 431-491)
+# --------------------------------------------------------------------------------------------
+class _DevBuf:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class Adam:
+    """tf.optimizers.Adam(lr, beta_1, beta_2) in its Keras OptimizerV2 form.  ONE object is
+    shared by the critic and the generator models (gan_train_cwgangp_pixelnorm.py:385, 391, 408), so
+    the step counter `iterations` is shared as well."""
+
+    def __init__(self, lr=0.0001, beta_1=0.0, beta_2=0.9, epsilon=1e-7):
+        self.lr, self.beta_1, self.beta_2, self.epsilon = lr, beta_1, beta_2, epsilon
+        self.iterations = 0
+
+
+class GanTrainer:
+    """The two compiled Keras models of the reference (`critic_model`, `generator_model`) as one object.
+
+    Data-parallel: if torch.distributed is initialised, gradients are summed over ranks with one NCCL
+    all-reduce of the flat FP32 gradient buffer per optimizer step and scaled by 1/world (the losses are
+    batch means, :215-216), so N ranks with batch B each reproduce one rank with batch N*B.
+    """
+
+    WHICH_GEN, WHICH_CRITIC = 0, 1
+
+    def __init__(self, generator, critic, optimizer=None, gen_mode="fp32", seed=0, process_group=None):
+        assert generator.ctx is critic.ctx, "generator and critic must share one Context"
+        self.ctx, self.generator, self.critic = generator.ctx, generator, critic
+        self.optimizer = optimizer or Adam()
+        self.gen_mode = gen_mode
+        self.pg = process_group
+        self._gen = torch.Generator(device=f"cuda:{self.ctx.device}")
+        self._gen.manual_seed(seed)
+        self.last_comm_ms = 0.0
+        self._bufs = {}
+
+    # -- helpers
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.pg) if dist.is_available() and dist.is_initialized() else 1
+
+    def grad_tensor(self, which):
+        """Flat FP32 gradient buffer of the generator (0) / critic (1) as a torch view."""
+        if ("g", which) not in self._bufs:
+            p, n = C.c_void_p(), C.c_size_t()
+            _lib.check(self.ctx.lib.rdg_grad_buffer(self.ctx.handle, which, C.byref(p), C.byref(n)))
+            self._bufs[("g", which)] = torch.as_tensor(_DevBuf(p.value, n.value), device=f"cuda:{self.ctx.device}")
+        return self._bufs[("g", which)]
+
+    def param_tensor(self, which):
+        if ("p", which) not in self._bufs:
+            p, n = C.c_void_p(), C.c_size_t()
+            _lib.check(self.ctx.lib.rdg_param_buffer(self.ctx.handle, which, C.byref(p), C.byref(n)))
+            self._bufs[("p", which)] = torch.as_tensor(_DevBuf(p.value, n.value), device=f"cuda:{self.ctx.device}")
+        return self._bufs[("p", which)]
+
+    def critic_mask_shapes(self, B):
+        shapes, chans = [], (64, 128, 256, 256)
+        for (_, out, _), ch in zip(W.critic_geometry(self.ctx.nd), chans):
+            shapes.append((B,) + tuple(out) + (ch,))
+        return shapes
+
+    def draw_masks(self, B):
+        """Bernoulli(keep=0.75) dropout masks for one critic invocation (Dropout(0.25), :289-301)."""
+        dev = f"cuda:{self.ctx.device}"
+        return [(torch.rand(s, device=dev, generator=self._gen) < 0.75).float() for s in self.critic_mask_shapes(B)]
+
+    @staticmethod
+    def _maskptrs(masks):
+        if masks is None:
+            return None
+        return (C.c_void_p * 4)(*[C.c_void_p(m.data_ptr()) for m in masks])
+
+    def _apply(self, which):
+        import torch.distributed as dist
+        world = self._world()
+        if world > 1:
+            g = self.grad_tensor(which)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            e1.record()
+            self._comm_events = getattr(self, "_comm_events", []) + [(e0, e1)]
+        opt = self.optimizer
+        opt.iterations += 1
+        _lib.check(self.ctx.lib.rdg_adam_apply(self.ctx.handle, which, opt.lr, opt.beta_1, opt.beta_2, opt.epsilon,
+                                               opt.iterations, 1.0 / world, self.ctx._stream()))
+
+    # -- the two train_on_batch calls
+    def critic_grads(self, x_real, cond, latent, alpha=None, masks3="draw"):
+        """Losses + gradients of one critic step, no update.  masks3: "draw" | None | (mf, mr, mh)."""
+        ctx = self.ctx
+        xr, c, z = ctx.dev(x_real), ctx.dev(cond), ctx.dev(latent)
+        B = int(xr.shape[0])
+        if alpha is None:
+            alpha = torch.rand(B, device=xr.device, generator=self._gen)      # tf.random.uniform((batch_size,1,1,1,1)) :223
+        al = ctx.dev(alpha).reshape(-1)
+        if isinstance(masks3, str):
+            masks3 = (self.draw_masks(B), self.draw_masks(B), self.draw_masks(B))
+        mf, mr, mh = (None, None, None) if masks3 is None else [[ctx.dev(m) for m in ms] for ms in masks3]
+        losses = torch.empty(4, device=xr.device, dtype=torch.float32)
+        self._keep = (xr, c, z, al, mf, mr, mh)
+        _lib.check(ctx.lib.rdg_critic_step_grads(
+            ctx.handle, C.c_void_p(xr.data_ptr()), C.c_void_p(c.data_ptr()), C.c_void_p(z.data_ptr()),
+            C.c_void_p(al.data_ptr()), self._maskptrs(mf), self._maskptrs(mr), self._maskptrs(mh), B,
+            _lib.MODES[self.gen_mode], C.c_void_p(losses.data_ptr()), ctx._stream()))
+        return losses
+
+    def critic_train_on_batch(self, inputs, targets=None, alpha=None, masks3="draw"):
+        """critic_model.train_on_batch([X_real, cond_real, latent], [valid, fake, dummy]) ->
+        [total, l_valid, l_fake, l_gp]  (gan_train_cwgangp_pixelnorm.py:472).  The targets are the
+        reference's constants (-1, +1, 0; :452-454) and are accepted only for signature parity."""
+        x_real, cond, latent = inputs
+        losses = self.critic_grads(x_real, cond, latent, alpha, masks3)
+        self._apply(self.WHICH_CRITIC)
+        return [float(v) for v in losses.cpu().numpy()]
+
+    def generator_grads(self, latent, cond, masks="draw"):
+        ctx = self.ctx
+        z, c = ctx.dev(latent), ctx.dev(cond)
+        B = int(z.shape[0])
+        if isinstance(masks, str):
+            masks = self.draw_masks(B)
+        m = None if masks is None else [ctx.dev(x) for x in masks]
+        loss = torch.empty(1, device=z.device, dtype=torch.float32)
+        self._keep = (z, c, m)
+        _lib.check(ctx.lib.rdg_generator_step_grads(ctx.handle, C.c_void_p(z.data_ptr()), C.c_void_p(c.data_ptr()),
+                                                    self._maskptrs(m), B, C.c_void_p(loss.data_ptr()), ctx._stream()))
+        return loss
+
+    def generator_train_on_batch(self, inputs, target=None, masks="draw"):
+        """generator_model.train_on_batch([latent, cond], valid) -> g_loss (:482)."""
+        latent, cond = inputs
+        loss = self.generator_grads(latent, cond, masks)
+        self._apply(self.WHICH_GEN)
+        return float(loss.item())
+
+    def comm_ms(self):
+        """Sum of the all-reduce durations recorded so far (device time), then reset."""
+        ev = getattr(self, "_comm_events", [])
+        torch.cuda.synchronize(self.ctx.device)
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        self._comm_events = []
+        return ms

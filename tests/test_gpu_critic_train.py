@@ -1,0 +1,194 @@
+"""GPU parity of the critic forward, the WGAN-GP critic step, the generator step and Adam
+ against the CPU oracle (torch autograd with create_graph=True)."""
+import numpy as np
+import pytest
+import torch
+
+import rdg_oracle as O
+from rdg_b200 import weights as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def nets(ctx16):
+    from rdg_b200.engine import Critic, Generator
+    gw = W.randomize_biases(W.init_generator_weights(0))
+    cw = W.randomize_biases(W.init_critic_weights(1), seed=9)
+    return Generator(gw, ctx=ctx16), Critic(cw, ctx=ctx16), gw, cw
+
+
+def _batch(B, seed=3, nd=16):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, 24, nd, nd, 1)) * 2
+    x = np.exp(x - x.max(axis=1, keepdims=True)); x = (x / x.sum(axis=1, keepdims=True)).astype(np.float32)
+    cond = (np.clip(rng.gamma(0.8, 12.0, size=(B, nd, nd, 1)), 0, 200) / 127.4).astype(np.float32)
+    z = rng.standard_normal((B, 100)).astype(np.float32)
+    alpha = rng.random((B, 1, 1, 1, 1)).astype(np.float32)
+    return x, cond, z, alpha, rng
+
+
+def _masks(rng, B):
+    return [(rng.random(s) < 0.75).astype(np.float32) for s in O.critic_mask_shapes(16, B)]
+
+
+@pytest.mark.parametrize("B,use_masks", [(1, False), (5, False), (32, True)])
+def test_critic_forward(nets, B, use_masks):
+    gen, crit, gw, cw = nets
+    x, cond, _, _, rng = _batch(B)
+    masks = _masks(rng, B) if use_masks else None
+    ref = O.critic_forward(cw, x, cond, masks, torch.float64)
+    out = crit.predict([x, cond], masks)
+    assert out.shape == (B, 1)
+    assert np.max(np.abs(out - ref)) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("use_masks", [False, True])
+def test_critic_step_losses_and_grads(nets, use_masks):
+    """Config #3: B=32 critic scoring + WGAN-GP step; 4 losses and all 10 weight gradients vs autograd."""
+    from rdg_b200.engine import GanTrainer
+    gen, crit, gw, cw = nets
+    B = 32
+    x, cond, z, alpha, rng = _batch(B, seed=11)
+    masks3 = [_masks(rng, B) for _ in range(3)] if use_masks else None
+    ref_losses, ref_grads, extras = O.critic_step(gw, cw, x, cond, z, alpha, masks3, torch.float64)
+    tr = GanTrainer(gen, crit, gen_mode="fp32")
+    losses = tr.critic_grads(x, cond, z, alpha.reshape(-1), masks3).cpu().numpy()
+    np.testing.assert_allclose(losses, ref_losses, rtol=2e-5, atol=1e-6)
+    g = tr.grad_tensor(1).cpu().numpy()
+    off = 0
+    for i, (rg, shp) in enumerate(zip(ref_grads, W.critic_shapes(16, 1))):
+        n = int(np.prod(shp))
+        mine = g[off:off + n].reshape(shp)
+        off += (n + 3) // 4 * 4
+        assert _rel_l2(mine, rg) <= 2e-5, f"critic grad tensor {i} {shp}: rel l2 {_rel_l2(mine, rg):.3e}"
+
+
+def _gen_grads(tr, z, cond, masks):
+    loss = float(tr.generator_grads(z, cond, masks).item())
+    torch.cuda.synchronize()
+    g = tr.grad_tensor(0).cpu().numpy().copy()
+    out, off = [], 0
+    for shp in W.generator_shapes(16, 1):
+        n = int(np.prod(shp))
+        out.append(g[off:off + n].reshape(shp))
+        off += (n + 3) // 4 * 4
+    return loss, out
+
+
+def _one_sample(seed):
+    rng = np.random.default_rng(seed)
+    cond = (np.clip(rng.gamma(0.8, 12.0, size=(1, 16, 16, 1)), 0, 200) / 127.4).astype(np.float32)
+    z = rng.standard_normal((1, 100)).astype(np.float32)
+    m = [(rng.random(s) < 0.75).astype(np.float32) for s in O.critic_mask_shapes(16, 1)]
+    return z, cond, m
+
+
+# LeakyReLU has a kinked derivative: a pre-activation within FP32 rounding of zero takes slope 1 in one
+# precision and 0.2 in the other, and that ONE element moves every upstream gradient by ~1/sqrt(#elements)
+# (~1e-3 with the 393 216-element last hidden layer).  About a third of random samples contain such an
+# element, so FP32-vs-FP64 gradient parity is asserted strictly on samples without one (found by scanning
+# seeds, tools/debug_genstep4.py), and batches are pinned through exact linearity in the batch instead.
+FLIP_FREE_SEEDS = [1001, 1003, 1004, 1005]
+
+
+@pytest.mark.parametrize("seed", FLIP_FREE_SEEDS)
+def test_generator_step_loss_and_grads(nets, seed):
+    from rdg_b200.engine import GanTrainer
+    gen, crit, gw, cw = nets
+    z, cond, masks = _one_sample(seed)
+    ref_loss, ref_grads = O.generator_step(gw, cw, z, cond, masks, torch.float64)
+    loss, grads = _gen_grads(GanTrainer(gen, crit), z, cond, masks)
+    assert abs(loss - ref_loss) <= 2e-5 * max(1.0, abs(ref_loss))
+    for i, (mine, rg) in enumerate(zip(grads[:9], ref_grads[:9])):
+        assert _rel_l2(mine, rg) <= 2e-5, f"generator grad tensor {i}: rel l2 {_rel_l2(mine, rg):.3e}"
+    # d loss / d (output-conv bias) is exactly 0 (softmax over hours is shift invariant)
+    assert abs(float(grads[9][0])) <= 1e-9 and abs(float(ref_grads[9][0])) <= 1e-12
+
+
+def test_generator_step_batch(nets):
+    """B=8 mixed batch: exact linearity in the batch (mean of the per-sample gradients) and a loose
+    bound against the FP64 oracle (see the LeakyReLU note above)."""
+    from rdg_b200.engine import GanTrainer
+    gen, crit, gw, cw = nets
+    tr = GanTrainer(gen, crit)
+    samples = [_one_sample(2000 + i) for i in range(8)]
+    z = np.concatenate([s[0] for s in samples]); cond = np.concatenate([s[1] for s in samples])
+    masks = [np.concatenate([s[2][l] for s in samples]) for l in range(4)]
+    loss, grads = _gen_grads(tr, z, cond, masks)
+    each = [_gen_grads(tr, *s) for s in samples]
+    assert abs(loss - np.mean([e[0] for e in each])) <= 1e-6
+    for i in range(9):
+        avg = sum(e[1][i] for e in each) / 8
+        assert _rel_l2(grads[i], avg) <= 1e-5, f"tensor {i} not linear in the batch"
+    ref_loss, ref_grads = O.generator_step(gw, cw, z, cond, masks, torch.float64)
+    assert abs(loss - ref_loss) <= 2e-5 * max(1.0, abs(ref_loss))
+    for i in range(9):
+        assert _rel_l2(grads[i], ref_grads[i]) <= 1e-2
+
+
+def test_adam_kernel_exact(ctx16):
+    """Keras OptimizerV2 Adam given explicit gradients, three steps, incl. zero / tiny gradients."""
+    from rdg_b200.engine import Adam, Critic, GanTrainer, Generator
+    cw = W.randomize_biases(W.init_critic_weights(4))
+    gen, crit = Generator(W.init_generator_weights(3), ctx=ctx16), Critic(cw, ctx=ctx16)
+    tr = GanTrainer(gen, crit, Adam(1e-4, 0.0, 0.9))
+    ctx16.lib.rdg_adam_reset(ctx16.handle, 1)
+    rng = np.random.default_rng(0)
+    shapes = W.critic_shapes(16, 1)
+    ref, v = [w.copy() for w in cw], [np.zeros_like(w) for w in cw]
+    gt = tr.grad_tensor(1)
+    for t in (1, 2, 3):
+        grads = [(rng.standard_normal(s) * 10.0 ** rng.integers(-9, 0)).astype(np.float32) for s in shapes]
+        grads[1][:8] = 0.0
+        flat = np.zeros(gt.numel(), np.float32); off = 0
+        for g in grads:
+            flat[off:off + g.size] = g.ravel(); off += (g.size + 3) // 4 * 4
+        gt.copy_(torch.as_tensor(flat))
+        ref, v, _ = O.adam_update(ref, grads, v, t)
+        tr._apply(1)
+    assert tr.optimizer.iterations == 3
+    for mine, r in zip(crit.get_weights(), ref):
+        np.testing.assert_allclose(mine, r, rtol=2e-6, atol=2e-9)
+
+
+def test_adam_trajectory_shared_counter(ctx16):
+    """Three real updates (critic, generator, critic) with ONE shared step counter (:385, 391, 408).
+    With beta_1 = 0 the first Adam steps are sign-SGD (|step| ~ lr for every element), so elements whose
+    FP32 gradient is within rounding of zero may move the other way than in FP64: the trajectory is
+    compared as a distribution (>= 97 % of each tensor within 2e-6, none further than a few steps)."""
+    from rdg_b200.engine import Adam, Critic, GanTrainer, Generator
+    gw = W.randomize_biases(W.init_generator_weights(3))
+    cw = W.randomize_biases(W.init_critic_weights(4))
+    gen, crit = Generator(gw, ctx=ctx16), Critic(cw, ctx=ctx16)
+    tr = GanTrainer(gen, crit, Adam(1e-4, 0.0, 0.9))
+    ctx16.lib.rdg_adam_reset(ctx16.handle, 0); ctx16.lib.rdg_adam_reset(ctx16.handle, 1)
+    B = 4
+    x, cond, z, alpha, rng = _batch(B, seed=5)
+    ref_c, ref_g = [w.copy() for w in cw], [w.copy() for w in gw]
+    vc, vg = [np.zeros_like(w) for w in cw], [np.zeros_like(w) for w in gw]
+    t = 0
+    for step in range(3):
+        t += 1
+        if step != 1:
+            _, grads, _ = O.critic_step(ref_g, ref_c, x, cond, z, alpha, None, torch.float64)
+            ref_c, vc, _ = O.adam_update(ref_c, grads, vc, t)
+            tr.critic_train_on_batch([x, cond, z], alpha=alpha.reshape(-1), masks3=None)
+        else:
+            _, grads = O.generator_step(ref_g, ref_c, z, cond, None, torch.float64)
+            ref_g, vg, _ = O.adam_update(ref_g, grads, vg, t)
+            tr.generator_train_on_batch([z, cond], masks=None)
+    assert tr.optimizer.iterations == 3
+    for mine_all, ref_all in ((crit.get_weights(), ref_c), (gen.get_weights(), ref_g)):
+        for mine, ref in zip(mine_all[:9], ref_all[:9]):
+            d = np.abs(mine - ref)
+            assert np.mean(d <= 2e-6) >= 0.97 and d.max() <= 1e-3
+    # the tensor-core operand tiles follow the updated master weights (device-side repack)
+    out16 = gen.predict([z, cond], mode="fp16")
+    ref = O.generator_forward(gen.get_weights(), z, cond, torch.float64)
+    assert np.max(np.abs(out16 - ref) / np.abs(ref)) <= 1e-2
