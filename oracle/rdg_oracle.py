@@ -252,7 +252,7 @@ def critic_step(gen_w, crit_w, x_real, cond, latent, alpha, masks3, dtype=torch.
     l_gp = torch.mean((gp - 0.0) ** 2)                         # 'mse' vs dummy zeros
     total = l_valid + l_fake + GP_WEIGHT * l_gp                # loss_weights [1,1,10] :392
     grads = torch.autograd.grad(total, cw)
-    losses = [float(total), float(l_valid), float(l_fake), float(l_gp)]
+    losses = [float(total.detach()), float(l_valid.detach()), float(l_fake.detach()), float(l_gp.detach())]
     extras = dict(fake_img=fake_img.numpy(), fake=fake.detach().numpy(), valid=valid.detach().numpy(),
                   gp=gp.detach().numpy(), xhat_grad=g.detach().numpy())
     return losses, [gr.numpy() for gr in grads], extras
@@ -270,7 +270,7 @@ def generator_step(gen_w, crit_w, latent, cond, masks=None, dtype=torch.float32)
     valid = _critic_graph(cw, img, c, mk)
     loss = torch.mean(-1.0 * valid)
     grads = torch.autograd.grad(loss, gw)
-    return float(loss), [g.numpy() for g in grads]
+    return float(loss.detach()), [g.numpy() for g in grads]
 
 
 def adam_update(params, grads, v_state, t, lr=1e-4, beta1=0.0, beta2=0.9, eps=1e-7, m_state=None):

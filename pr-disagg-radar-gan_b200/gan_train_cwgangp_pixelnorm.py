@@ -1,0 +1,252 @@
+"""Drop-in for the model / training-step surface of the reference's `gan_train_cwgangp_pixelnorm.py`.
+
+The reference is a flat script that loads cluster data at import time and trains immediately
+(:81-140, :524-529).  This module keeps its names, constants, signatures and step semantics but
+builds nothing at import: call `setup(...)` (optionally with your own `(days,24,ny,nx)` array and
+`valid_indices`; otherwise synthetic radar-shaped data, BASELINE config #4) and then `train(...)`,
+or drive `critic_model.train_on_batch` / `generator_model.train_on_batch` yourself.
+
+Reference symbol                                   -> here
+  create_generator() / create_discriminator() :272-357 -> same names, return rdg_b200 Generator / Critic
+  PixelNormalization / RandomWeightedAverage / GradientPenalty / wasserstein_loss :215-270
+                                                    -> thin classes/functions (the fused CUDA steps implement them)
+  critic_model.train_on_batch([X_real, cond_real, latent],[valid,fake,dummy]) :472
+  generator_model.train_on_batch([latent, cond], valid) :482
+  generate_real_samples / generate_latent_points / generate_fake_samples / generate :143-211
+  train(n_epochs, _batch_size, start_epoch=0) :431-521 (plots omitted; hist.csv + .h5 checkpoints kept)
+"""
+import os
+
+import numpy as np
+
+from rdg_b200 import hdf5 as _hdf5
+from rdg_b200 import weights as _W
+
+# ---- constants, reference :48-78
+startdate, enddate = '20090101', '20161231'
+ndomain = 16
+stride = 16
+tres = 1
+nhours = 24 // tres
+tp_thresh_daily = 5
+n_thresh = 20
+norm_scale = 127.4
+n_disc = 5
+GRADIENT_PENALTY_WEIGHT = 10
+latent_dim = 100
+batch_size = 32
+n_epoch_and_batch_size_list = ((50, 32),)
+n_channel = 1
+name = 'wgancp_pixelnorm'
+params = f'{startdate}-{enddate}-tp_thresh_daily{tp_thresh_daily}_n_thresh{n_thresh}_ndomain{ndomain}_stride{stride}'
+outdir = os.environ.get('RDG_OUTDIR', 'trained_models')
+
+data = None          # (days, 24, ny, nx) float32 mm/h, reference :120-138
+indices_all = None   # (n,3) int (tidx, yidx, xidx), reference :117-119
+n_samples = 0
+generator = critic = critic_model = generator_model = optimizer = None
+hist = {'d_loss': [], 'g_loss': []}
+
+
+def wasserstein_loss(y_true, y_pred):
+    """reference :215-216"""
+    return np.mean(np.asarray(y_true) * np.asarray(y_pred))
+
+
+class RandomWeightedAverage:
+    """alpha*real + (1-alpha)*fake with alpha~U[0,1) per sample (reference :219-227); the CUDA critic
+    step fuses this, the class is kept for API parity / host-side use."""
+
+    def call(self, inputs, alpha=None, **kwargs):
+        real, fake = np.asarray(inputs[0]), np.asarray(inputs[1])
+        if alpha is None:
+            alpha = np.random.uniform(size=(batch_size, 1, 1, 1, 1))
+        return alpha * real + (1 - alpha) * fake
+
+    __call__ = call
+
+
+class GradientPenalty:
+    """sqrt(sum(grad^2)) - 1 per sample (reference :230-244).  K.gradients has no host equivalent: the
+    gradient w.r.t. the interpolated sample is produced inside rdg_critic_step_grads."""
+
+    def call(self, grad):
+        g = np.asarray(grad)
+        return np.sqrt(np.sum(g.reshape(g.shape[0], -1) ** 2, axis=1, keepdims=True)) - 1
+
+    __call__ = call
+
+
+def _PixelNormalization():
+    from raindisagg_gan_pretrained import PixelNormalization as P   # same class, reference :249-270
+    return P
+
+
+def _ctx():
+    global _CTX
+    try:
+        return _CTX
+    except NameError:
+        from rdg_b200.engine import Context
+        _CTX = Context(ndomain, n_channel)
+        return _CTX
+
+
+def create_discriminator():
+    """reference :272-309 (glorot_uniform kernels, zero biases)"""
+    from rdg_b200.engine import Critic
+    return Critic(_W.init_critic_weights(int(np.random.randint(2 ** 31)), ndomain, n_channel), ctx=_ctx())
+
+
+def create_generator():
+    """reference :312-357 (RandomNormal(0.02) kernels, zero biases)"""
+    from rdg_b200.engine import Generator
+    return Generator(_W.init_generator_weights(int(np.random.randint(2 ** 31)), ndomain, n_channel), ctx=_ctx(),
+                     mode=os.environ.get('RDG_MODE', 'fp16'))
+
+
+class _CriticModel:
+    """critic_model (reference :387-392): outputs [valid, fake, disc_gp], losses [wasserstein, wasserstein, mse],
+    loss_weights [1, 1, 10], Adam shared with generator_model."""
+
+    def __init__(self, trainer):
+        self._t = trainer
+
+    def train_on_batch(self, inputs, targets=None, alpha=None, masks3="draw"):
+        return self._t.critic_train_on_batch(inputs, targets, alpha, masks3)
+
+    def predict(self, inputs):
+        """[valid, fake, gp] without updating (reference :461 uses it to build the graph)."""
+        x_real, cond, latent = inputs
+        fake_img = generator.predict([latent, cond])
+        return [critic.predict([x_real, cond]), critic.predict([fake_img, cond]), None]
+
+
+class _GeneratorModel:
+    """generator_model (reference :395-408)."""
+
+    def __init__(self, trainer):
+        self._t = trainer
+
+    def train_on_batch(self, inputs, target=None, masks="draw"):
+        return self._t.generator_train_on_batch(inputs, target, masks)
+
+
+def synthetic_radar(days=64, ny=64, nx=64, seed=0):
+    """Radar-shaped stand-in for the SMHI data (reference :120-138): (days,24,ny,nx) float32 mm/h with a
+    skewed intensity distribution and smooth hourly structure; every day is wet enough to pass the
+    reference's validity filter (compute_valid_indices.py:46-48)."""
+    rng = np.random.default_rng(seed)
+    base = rng.gamma(0.8, 12.0, size=(days, 1, ny, nx)).astype(np.float32)
+    prof = rng.standard_normal((days, 24, ny, nx)).astype(np.float32) * 2
+    prof = np.exp(prof - prof.max(axis=1, keepdims=True))
+    prof /= prof.sum(axis=1, keepdims=True)
+    return (base * prof).astype(np.float32)
+
+
+def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None):
+    """Build what the reference builds at import (:117-140, :360-408)."""
+    global data, indices_all, n_samples, generator, critic, critic_model, generator_model, optimizer, trainer
+    from rdg_b200.engine import Adam, GanTrainer
+    np.random.seed(seed)
+    data = synthetic_radar(seed=seed) if data_array is None else np.asarray(data_array, np.float32)
+    assert data.ndim == 4 and data.shape[1] == nhours
+    if valid_indices is None:
+        ny, nx = data.shape[2:]
+        valid_indices = [(t, y, x) for t in range(data.shape[0]) for y in range(0, ny - ndomain + 1, stride)
+                         for x in range(0, nx - ndomain + 1, stride)]
+    indices_all = np.array(valid_indices)
+    n_samples = len(indices_all)
+    generator = create_generator()        # generator first, like the reference (:361-362)
+    critic = create_discriminator()
+    optimizer = Adam(lr=0.0001, beta_1=0, beta_2=0.9)     # reference :385
+    trainer = GanTrainer(generator, critic, optimizer, gen_mode=gen_mode or os.environ.get('RDG_TRAIN_GEN_MODE', 'fp32'),
+                         seed=seed)
+    critic_model = _CriticModel(trainer)
+    generator_model = _GeneratorModel(trainer)
+    return trainer
+
+
+def _windows(ixs):
+    idcs = indices_all[ixs]
+    batch = np.stack([data[t, :, y:y + ndomain, x:x + ndomain] for t, y, x in idcs])   # view_as_windows, :151-152
+    return np.expand_dims(batch, -1)
+
+
+def generate_real_samples(n_batch):
+    """reference :143-174"""
+    while True:
+        ixs = np.random.randint(n_samples, size=n_batch)
+        batch = _windows(ixs)
+        batch_cond = np.sum(batch, axis=1)
+        for i in range(n_batch):
+            batch[i] = batch[i] / batch_cond[i]
+        batch_cond = batch_cond / norm_scale
+        assert batch.shape == (n_batch, nhours, ndomain, ndomain, 1)
+        assert batch_cond.shape == (n_batch, ndomain, ndomain, 1)
+        assert ~np.any(np.isnan(batch)) and ~np.any(np.isnan(batch_cond))
+        assert np.max(batch) <= 1 and np.min(batch) >= 0
+        yield [batch, batch_cond]
+
+
+def generate_latent_points(n_batch):
+    """reference :177-193"""
+    latent = np.random.normal(size=(n_batch, latent_dim))
+    ixs = np.random.randint(0, n_samples, size=n_batch)
+    batch_cond = np.sum(_windows(ixs), axis=1) / norm_scale
+    assert batch_cond.shape == (n_batch, ndomain, ndomain, 1)
+    assert ~np.any(np.isnan(batch_cond))
+    return [latent, batch_cond]
+
+
+def generate_latent_points_as_generator(n_batch):
+    while True:
+        yield generate_latent_points(n_batch)
+
+
+def generate_fake_samples(n_batch):
+    """reference :201-206"""
+    latent, cond = generate_latent_points(n_batch)
+    return [generator.predict([latent, cond]), cond]
+
+
+def generate(cond):
+    """reference :209-212"""
+    latent = np.random.normal(size=(1, latent_dim))
+    return generator.predict([latent, np.expand_dims(cond, 0)])
+
+
+def train(n_epochs, _batch_size, start_epoch=0, bat_per_epo=None, save=True):
+    """reference :431-521.  Same schedule (n_disc critic steps, then one generator step), same NaN guard
+    (:487-488), same per-epoch checkpoints (:520-521) written as Keras-layout HDF5; the matplotlib sample /
+    loss figures (:494-518) are outside the accelerated path and omitted, hist.csv is kept."""
+    global batch_size
+    batch_size = _batch_size
+    sample_gen = generate_real_samples(batch_size)                 # GeneratorEnqueuer worker processes in the reference
+    gan_sample_gen = generate_latent_points_as_generator(batch_size)
+    valid = -np.ones((batch_size, 1)); fake = np.ones((batch_size, 1)); dummy = np.zeros((batch_size, 1))
+    if bat_per_epo is None:
+        bat_per_epo = int(n_samples / batch_size)
+    for i in range(n_epochs):
+        epoch = 1 + i + start_epoch
+        for j in range(bat_per_epo):
+            for _ in range(n_disc):
+                X_real, cond_real = next(sample_gen)
+                latent = np.random.normal(size=(batch_size, latent_dim))
+                d_loss = critic_model.train_on_batch([X_real, cond_real, latent], [valid, fake, dummy])
+                d_loss = np.mean([d_loss[1], d_loss[2]])
+            latent, cond = next(gan_sample_gen)
+            g_loss = generator_model.train_on_batch([latent, cond], valid)
+            print(f'{epoch}, {j + 1}/{bat_per_epo}, d_loss {d_loss} g:{g_loss} ')
+            if np.isnan(g_loss) or np.isnan(d_loss):
+                raise ValueError('encountered nan in g_loss and/or d_loss')
+            hist['d_loss'].append(d_loss)
+            hist['g_loss'].append(g_loss)
+        with open('hist.csv', 'w') as f:
+            f.write(',d_loss,g_loss\n')
+            for k, (d, g) in enumerate(zip(hist['d_loss'], hist['g_loss'])):
+                f.write(f'{k},{d},{g}\n')
+        if save:
+            os.makedirs(outdir, exist_ok=True)
+            _hdf5.save_keras_weights(f'{outdir}/gen_{params}_{epoch:04d}.h5', generator.get_weights(), 'generator')
+            _hdf5.save_keras_weights(f'{outdir}/disc_{params}_{epoch:04d}.h5', critic.get_weights(), 'critic')

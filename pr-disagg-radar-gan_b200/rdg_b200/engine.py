@@ -75,7 +75,7 @@ class Generator:
         self.ctx = ctx or Context(nd, ncond)
         self.nd, self.ncond = self.ctx.nd, self.ctx.ncond
         self.latent_dim = W.LATENT_DIM
-        self.mode = mode or _DEFAULT_MODE
+        self.mode = mode or os.environ.get("RDG_MODE", _DEFAULT_MODE)
         # Keras-like metadata used by the reference: gen.inputs[0].shape[1] (raindisagg_gan_pretrained.py:47)
         self.input_shapes = [(None, self.latent_dim), (None, self.nd, self.nd, self.ncond)]
         self.output_shape = (None, W.NHOURS, self.nd, self.nd, 1)
@@ -270,13 +270,13 @@ class GanTrainer:
         return (C.c_void_p * 4)(*[C.c_void_p(m.data_ptr()) for m in masks])
 
     def _apply(self, which):
-        import torch.distributed as dist
+        from .dist import allreduce_sum_
         world = self._world()
         if world > 1:
             g = self.grad_tensor(which)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            allreduce_sum_(g, self.pg)           # 1/world is folded into the fused Adam kernel (grad_scale)
             e1.record()
             self._comm_events = getattr(self, "_comm_events", []) + [(e0, e1)]
         opt = self.optimizer

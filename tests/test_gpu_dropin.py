@@ -1,0 +1,103 @@
+"""The reference's Python surface, driven the way example.py / the training script drive it."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import rdg_oracle as O
+from rdg_b200 import hdf5, weights as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pretrained(tmp_path_factory):
+    d = tmp_path_factory.mktemp("trained_models")
+    gw = W.randomize_biases(W.init_generator_weights(42))
+    path = str(d / "gen_fixture.h5")
+    hdf5.save_keras_weights(path, gw, "generator")
+    os.environ["RDG_GENERATOR_FILE"] = path
+    os.environ["RDG_MODE"] = "fp32"
+    sys.modules.pop("raindisagg_gan_pretrained", None)
+    mod = importlib.import_module("raindisagg_gan_pretrained")
+    yield mod, gw
+    os.environ.pop("RDG_GENERATOR_FILE", None); os.environ.pop("RDG_MODE", None)
+
+
+def test_example_py(pretrained):
+    """example.py: cond = 10 mm/day everywhere, n_scenarios = 10 (BASELINE config #1)."""
+    mod, gw = pretrained
+    assert mod.norm_scale == 127.4 and mod.latent_dim == 100
+    cond1 = 10 * np.ones((16, 16, 1))
+    np.random.seed(354)
+    out = mod.generate_scenarios(cond1, 10)
+    assert out.shape == (10, 24, 16, 16) and out.dtype == np.float64
+    np.random.seed(354)
+    ref = O.generate_scenarios(gw, cond1, 10, torch.float64)
+    assert np.max(np.abs(out - ref) / np.abs(ref)) <= 1e-5
+    assert np.max(np.abs(out.sum(axis=1) - 10.0)) / 10.0 <= 1e-5          # daily-sum conservation
+
+
+def test_single_scenario_squeeze_quirk_and_dry_pixels(pretrained):
+    mod, gw = pretrained
+    cond = np.random.default_rng(0).gamma(0.8, 12.0, size=(16, 16, 1))
+    cond[:2, :2] = 0.0
+    np.random.seed(1)
+    out = mod.generate_scenarios(cond, 1)
+    assert out.shape == (24, 16, 16)                                      # squeeze() drops the batch axis when n == 1
+    assert np.all(out[:, :2, :2] == 0.0)
+    nz = cond[..., 0] > 0
+    assert np.max(np.abs(out.sum(axis=0)[nz] - cond[..., 0][nz]) / cond[..., 0][nz]) <= 1e-5
+
+
+def test_predict_shape_errors(pretrained):
+    mod, _ = pretrained
+    with pytest.raises(ValueError):
+        mod.gen.predict([np.zeros((2, 100)), np.zeros((3, 16, 16, 1))])
+    assert mod.gen.predict([np.zeros((0, 100)), np.zeros((0, 16, 16, 1))]).shape == (0, 24, 16, 16, 1)
+
+
+def test_nonfinite_output_raises(pretrained):
+    """tf.debugging.check_numerics on the generator output (gan_train_cwgangp_pixelnorm.py:349-350)."""
+    mod, gw = pretrained
+    from rdg_b200 import NonFiniteError
+    z = np.zeros((2, 100), np.float32); z[0, 0] = np.nan
+    with pytest.raises(NonFiniteError):
+        mod.gen.predict([z, np.ones((2, 16, 16, 1), np.float32)])
+
+
+def test_pixelnorm_layer(pretrained):
+    mod, _ = pretrained
+    x = np.random.default_rng(3).standard_normal((5, 7, 64)).astype(np.float32)
+    y = mod.PixelNormalization()(x)
+    ref = x / np.sqrt(np.mean(x.astype(np.float64) ** 2, axis=-1, keepdims=True) + 1e-8)
+    np.testing.assert_allclose(y, ref, rtol=2e-6, atol=1e-7)
+    assert np.allclose(mod.PixelNormalization()(np.zeros((3, 8), np.float32)), 0.0)   # epsilon keeps 0/0 finite
+
+
+def test_training_script_surface(tmp_path, monkeypatch):
+    """A few iterations of train() on synthetic radar-shaped data: schedule, loss bookkeeping, checkpoints."""
+    monkeypatch.chdir(tmp_path)
+    sys.modules.pop("gan_train_cwgangp_pixelnorm", None)
+    m = importlib.import_module("gan_train_cwgangp_pixelnorm")
+    m.outdir = str(tmp_path / "ckpt")
+    m.hist = {'d_loss': [], 'g_loss': []}
+    tr = m.setup(seed=3)
+    X, c = next(m.generate_real_samples(4))
+    assert X.shape == (4, 24, 16, 16, 1) and np.allclose(X.sum(axis=1), 1.0, atol=1e-5)
+    w0 = [w.copy() for w in m.critic.get_weights()]
+    m.train(1, 8, bat_per_epo=2)
+    assert len(m.hist['d_loss']) == 2 and len(m.hist['g_loss']) == 2 and np.isfinite(m.hist['g_loss']).all()
+    assert tr.optimizer.iterations == 2 * (m.n_disc + 1)                  # one shared Adam step counter
+    assert any(np.any(a != b) for a, b in zip(w0, m.critic.get_weights()))
+    gen_ckpt = [f for f in os.listdir(m.outdir) if f.startswith("gen_")]
+    assert len(gen_ckpt) == 1
+    back = hdf5.load_keras_weights(os.path.join(m.outdir, gen_ckpt[0]))
+    for a, b in zip(back, m.generator.get_weights()):
+        assert np.array_equal(a, b)
+    assert os.path.exists("hist.csv")
+    out = m.generate(np.full((16, 16, 1), 0.1, np.float32))
+    assert out.shape == (1, 24, 16, 16, 1) and abs(out.sum() - 256.0) < 1e-2
