@@ -1,0 +1,64 @@
+"""Large-domain variant (alternative_domains/gan_train_cwgangp_pixelnorm_largedomain.py: ndomain=64,
+Dense 4196->49152, Reshape (3,8,8,256), critic Flatten 8192) -- SURVEY 8a row a18 / BASELINE config #5."""
+import numpy as np
+import pytest
+import torch
+
+import rdg_oracle as O
+from rdg_b200 import weights as W
+
+pytestmark = pytest.mark.gpu
+ND = 64
+
+
+@pytest.fixture(scope="module")
+def big():
+    from rdg_b200.engine import Context, Critic, Generator
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ctx = Context(ND, 1, max_chunk=8)
+    gw = W.randomize_biases(W.init_generator_weights(0, ND))
+    cw = W.randomize_biases(W.init_critic_weights(1, ND), seed=9)
+    yield Generator(gw, ctx=ctx), Critic(cw, ctx=ctx), gw, cw
+    ctx.close()
+
+
+def _inputs(B, seed=64):
+    rng = np.random.default_rng(seed)
+    cond = (np.clip(rng.gamma(0.8, 12.0, size=(B, ND, ND, 1)), 0, 200) / 127.4).astype(np.float32)
+    z = rng.standard_normal((B, 100)).astype(np.float32)
+    return z, cond, rng
+
+
+def test_generator_forward_all_modes(big):
+    gen, _, gw, _ = big
+    z, cond, _ = _inputs(3)
+    ref = O.generator_forward(gw, z, cond, torch.float64)
+    assert ref.shape == (3, 24, ND, ND, 1)
+    for mode, tol in (("fp32", 1e-5), ("fp16", 1e-2), ("bf16", 4e-2)):
+        out = gen.predict([z, cond], mode=mode)
+        assert out.shape == ref.shape
+        assert float(np.max(np.abs(out - ref) / np.abs(ref))) <= tol, mode
+        assert float(np.max(np.abs(out.sum(axis=1) - 1.0))) <= 1e-5
+
+
+def test_critic_forward_and_step(big):
+    from rdg_b200.engine import GanTrainer
+    gen, crit, gw, cw = big
+    B = 2
+    z, cond, rng = _inputs(B, seed=5)
+    x = rng.standard_normal((B, 24, ND, ND, 1)) * 2
+    x = np.exp(x - x.max(axis=1, keepdims=True)); x = (x / x.sum(axis=1, keepdims=True)).astype(np.float32)
+    ref = O.critic_forward(cw, x, cond, None, torch.float64)
+    out = crit.predict([x, cond])
+    assert np.max(np.abs(out - ref)) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    alpha = rng.random((B, 1, 1, 1, 1)).astype(np.float32)
+    ref_losses, ref_grads, _ = O.critic_step(gw, cw, x, cond, z, alpha, None, torch.float64)
+    tr = GanTrainer(gen, crit, gen_mode="fp32")
+    losses = tr.critic_grads(x, cond, z, alpha.reshape(-1), None).cpu().numpy()
+    np.testing.assert_allclose(losses, ref_losses, rtol=5e-5, atol=1e-6)
+    g = tr.grad_tensor(1).cpu().numpy()
+    off = 0
+    for i, (rg, shp) in enumerate(zip(ref_grads, W.critic_shapes(ND, 1))):
+        n = int(np.prod(shp)); mine = g[off:off + n].reshape(shp); off += (n + 3) // 4 * 4
+        rel = np.linalg.norm(mine - rg) / (np.linalg.norm(rg) + 1e-30)
+        assert rel <= 1e-3, f"critic grad {i}: {rel:.2e}"      # loose: LeakyReLU sign flips, see test_gpu_critic_train.py
