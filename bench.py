@@ -145,8 +145,9 @@ def main():
     ap.add_argument("--conditions", type=int, default=N_COND)
     ap.add_argument("--scen-per-cond", type=int, default=SCEN_PER_COND)
     ap.add_argument("--chunk", type=int, default=0, help="samples per internal pass (0 = library default)")
-    ap.add_argument("--ref-conditions", type=int, default=2, help="conditions per step of the CPU reference arm")
-    ap.add_argument("--cpu-conditions", type=int, default=5, help="conditions of the cpu_baseline sample")
+    ap.add_argument("--ref-conditions", type=int, default=10, help="conditions per step of the CPU reference arm")
+    ap.add_argument("--cpu-conditions", type=int, default=40, help="conditions of the cpu_baseline sample")
+    ap.add_argument("--e2e-group", type=int, default=1000, help="conditions per host-API call in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -233,14 +234,22 @@ def main():
     # ---- end-to-end through the host-buffer C-ABI call
     e2e = None
     if not args.no_e2e:
+        # pinned host latent for the whole step; results stream through a reusable pinned buffer in groups of
+        # conditions (the reference's loop also consumes each condition's ensemble before the next,
+        # generate_and_evaluate_crps.py:177-195) so host memory stays bounded at any rank count
+        grp_cond = min(n_cond, args.e2e_group)
+        grp = grp_cond * spc
         lat_h = torch.empty((B, 100), dtype=torch.float32, pin_memory=True)
         lat_h.copy_(latent)
-        out_h = torch.empty((B, 24, 16, 16), dtype=torch.float32, pin_memory=True)
+        out_h = torch.empty((grp, 24, 16, 16), dtype=torch.float32, pin_memory=True)
         cond_p = torch.as_tensor(cond_h).pin_memory()
         torch.cuda.synchronize()
 
         def e2e_step():
-            gen.generate_ensemble_host(lat_h, cond_p, spc, out=out_h, mode=args.mode, out_mm=True)
+            for c0 in range(0, n_cond, grp_cond):
+                c1 = min(n_cond, c0 + grp_cond)
+                gen.generate_ensemble_host(lat_h[c0 * spc:c1 * spc], cond_p[c0:c1], spc, out=out_h[:(c1 - c0) * spc],
+                                           mode=args.mode, out_mm=True)
 
         e2e_step()
         barrier()
@@ -255,10 +264,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B / float(t.item()), "unit": "scenarios/s",
                "h2d_bytes_per_step": int(lat_h.numel() * 4 + cond_p.numel() * 4),
-               "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": n_e2e,
-               "api": "rdg_generate_host (pinned host buffers, 3-stream chunk pipeline)"}
-        # e2e result equals the device-resident result
-        assert torch.equal(out_h[:1000], out[:1000].cpu()), "e2e output differs from device-resident output"
+               "d2h_bytes_per_step": int(B * 24 * 16 * 16 * 4), "steps": n_e2e,
+               "api": f"rdg_generate_host (pinned host buffers, 3-stream chunk pipeline), {grp_cond} conditions per call"}
+        # the last group's e2e result equals the device-resident result
+        last0 = ((n_cond - 1) // grp_cond) * grp_cond * spc
+        assert torch.equal(out_h[:1000], out[last0:last0 + 1000].cpu()), "e2e output differs from device-resident output"
         del out_h, lat_h
 
     if rank != 0:

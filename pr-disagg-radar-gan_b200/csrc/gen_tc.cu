@@ -617,16 +617,28 @@ gather_softmax_kernel(const float* __restrict__ P, const float* __restrict__ b4,
     const int f4_per_row = nd * 8;                       // float4 per h-row (nd positions x 32 floats)
 #pragma unroll
     for (int t = 0; t < RDG_NHOURS; ++t) {
+        // the HB+2 rows of this hour are one contiguous run of (HB+2)*nd*8 float4 (minus rows outside the
+        // domain, which stay zero: zeroed once, never written).  All loads of a thread are issued before its
+        // first shared-memory store so their latencies overlap.
+        const int r_lo = h0 - 1 < 0 ? 1 : 0, r_hi = h0 + HB + 1 > nd ? HB + 1 : HB + 2;      // valid slab rows [r_lo, r_hi)
+        const int n_f4 = (r_hi - r_lo) * f4_per_row;
+        const float4* src = reinterpret_cast<const float4*>(pb + ((size_t)t * nd + (h0 - 1 + r_lo)) * nd * 32);
         __syncthreads();
-        for (int rr = 0; rr < HB + 2; ++rr) {
-            const int h = h0 + rr - 1;
-            if (h < 0 || h >= nd) continue;              // stays zero (zeroed once; never written)
-            const float4* srow = reinterpret_cast<const float4*>(pb + ((size_t)t * nd + h) * nd * 32);
-            float* drow = ps + ((size_t)rr * W2 + 1) * 33;
-            for (int i = tid; i < f4_per_row; i += 256) {
-                const float4 v = srow[i];
-                float* d = drow + (i >> 3) * 33 + (i & 7) * 4;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        for (int base = 0; base < n_f4; base += 256 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = base + k * 256 + tid;
+                if (i < n_f4) v[k] = src[i];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = base + k * 256 + tid;
+                if (i < n_f4) {
+                    const int rr = r_lo + (i >> (lognd + 3)), j = i & (f4_per_row - 1);
+                    float* d = ps + ((size_t)rr * W2 + 1 + (j >> 3)) * 33 + (j & 7) * 4;
+                    d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
+                }
             }
         }
         __syncthreads();
