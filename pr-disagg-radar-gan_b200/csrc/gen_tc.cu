@@ -17,6 +17,7 @@
 #include "rdg_common.cuh"
 #include "gen_tc.h"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace {
 
@@ -81,10 +82,33 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// weight tile to the same shared-memory offset of every CTA in ctaMask; each destination CTA's barrier at the
+// same offset receives the complete_tx
+__device__ __forceinline__ void bulk_load_1d_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// arrive on the barrier at this offset in every CTA of ctaMask once all prior MMAs of this thread completed
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -146,11 +170,15 @@ template <> struct HalfOps<__half> {
 // One source of truth for the K-loop order, shared by the producer and the MMA issuer.
 // For pass `pass` (phases pass*NPH .. pass*NPH+NPH-1) walk the 27 low-res offsets; an offset
 // (dt,dh,dw) serves phase p=(pt,ph,pw) with tap a=(dt+1-pt, dh+1-ph, dw+1-pw) if all in {0,1}.
-template <int NPH, typename FA, typename FB>
+// SKIP_OOB: offsets whose whole activation tile lies in the zero padding (t+dt outside the grid) are dropped.
+// With weight multicast (cluster > 1) every CTA of the cluster must walk the SAME weight sequence, so the step
+// is kept (oob = true): no activation load, no MMA, but the weight stage is still consumed.
+template <int NPH, bool SKIP_OOB, typename FA, typename FB>
 __device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk, int kc, FA&& on_a, FB&& on_b) {
     for (int o = 0; o < 27; ++o) {
         const int dt = o / 9 - 1, dh = (o / 3) % 3 - 1, dw = o % 3 - 1;
-        if (t + dt < 0 || t + dt >= T) continue;   // whole tile in the zero padding
+        const bool oob = t + dt < 0 || t + dt >= T;   // whole tile in the zero padding
+        if (SKIP_OOB && oob) continue;
         uint32_t mask = 0;
 #pragma unroll
         for (int s = 0; s < NPH; ++s) {
@@ -160,13 +188,13 @@ __device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk
         }
         if (!mask) continue;
         for (int c = 0; c < nchunk; c += kc) {       // kc consecutive 64-channel chunks per stage
-            on_a(dt, dh, dw, c);
+            on_a(dt, dh, dw, c, oob);
 #pragma unroll
             for (int s = 0; s < NPH; ++s) {
                 if (!(mask & (1u << s))) continue;
                 const int p = pass * NPH + s;
                 const int a = ((dt + 1 - (p >> 2)) << 2) | ((dh + 1 - ((p >> 1) & 1)) << 1) | (dw + 1 - (p & 1));
-                on_b(s, (p * 8 + a) * nchunk + c);
+                on_b(s, (p * 8 + a) * nchunk + c, oob);
             }
         }
     }
@@ -198,10 +226,17 @@ template <int COUT, int NPH, int KC> struct TcCfg {
 // (W4 as a [32 x 64] B tile) on the tensor core:  P[pos][tap] = sum_c y[pos][c] * w4[tap][c].
 // P (f32, 32 per position) goes to HBM instead of y; gather_softmax_kernel then forms
 // logit[q] = b + sum_tap P[q + offset(tap)][tap] and the softmax over the 24 hours.
-template <typename HT, int COUT, int NPH, int KC, bool FUSE>
+// CL = CTAs per cluster.  CL > 1: the CTAs of a cluster work on different position tiles but walk the same
+// weight sequence; rank 0 fetches every weight stage once and TMA-multicasts it into all CL shared memories,
+// and a stage is refilled only after the MMA issuers of ALL CL CTAs released it (multicast tcgen05.commit).
+template <typename HT, int COUT, int NPH, int KC, bool FUSE, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs args) {
     using Cfg = TcCfg<COUT, NPH, KC>;
+    constexpr bool kSkip = CL == 1;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+    const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;   // a unit = CL consecutive tiles
     static_assert(!FUSE || COUT == 64, "fused output conv needs Cout == 64");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -234,7 +269,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
     if (threadIdx.x == 0) {
         mbar_init(p_full, 1);
         for (int i = 0; i < Cfg::kAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -246,6 +281,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // peers' barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -254,13 +290,15 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         {
             uint32_t ai = 0;
             uint32_t free_next = mbar_test(&a_empty[0], 1);
-            for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+            for (int unit = unit0; unit * CL < args.n_tiles; unit += unit_stride) {
+                const int tile = unit * CL + (int)cta_rank;     // may be >= n_tiles: then b0 >= B, TMA zero-fills, epilogue masks
                 const int hblk = tile % n_hblk, t = (tile / n_hblk) % args.T, bblk = tile / (n_hblk * args.T);
                 const int h0 = hblk * args.Hb, b0 = bblk * args.Bt;
                 for (int pass = 0; pass < 8 / NPH; ++pass) {
-                    for_each_step<NPH>(
+                    for_each_step<NPH, kSkip>(
                         pass, t, args.T, nchunk, KC,
-                        [&](int dt, int dh, int dw, int c) {
+                        [&](int dt, int dh, int dw, int c, bool oob) {
+                            if (oob) return;                  // tile entirely in the zero padding: nothing to load
                             const uint32_t s = ai % Cfg::kAStages, ph = (ai / Cfg::kAStages) & 1;
                             if (!free_next) mbar_wait(&a_empty[s], ph ^ 1);
                             ++ai;
@@ -274,7 +312,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                                                 h0 + dh, t + dt, b0);
                             }
                         },
-                        [&](int, int) {});
+                        [&](int, int, bool) {});
                 }
             }
         }
@@ -283,22 +321,24 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         {
             uint32_t bi = 0;
             uint32_t free_next = mbar_test(&b_empty[0], 1);
-            for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+            for (int unit = unit0; unit * CL < args.n_tiles; unit += unit_stride) {
+                const int tile = unit * CL + (int)cta_rank;     // may be >= n_tiles: then b0 >= B, TMA zero-fills, epilogue masks
                 const int t = (tile / n_hblk) % args.T;
                 for (int pass = 0; pass < 8 / NPH; ++pass) {
-                    for_each_step<NPH>(
-                        pass, t, args.T, nchunk, KC, [&](int, int, int, int) {},
-                        [&](int, int wtile) {
+                    for_each_step<NPH, kSkip>(
+                        pass, t, args.T, nchunk, KC, [&](int, int, int, int, bool) {},
+                        [&](int, int wtile, bool) {
+                            // b_empty[s] completes once the MMA issuers of all CL CTAs released the stage
                             const uint32_t s = bi % Cfg::kBStages, ph = (bi / Cfg::kBStages) & 1;
                             if (!free_next) mbar_wait(&b_empty[s], ph ^ 1);
                             ++bi;
                             const uint32_t s2 = bi % Cfg::kBStages, ph2 = (bi / Cfg::kBStages) & 1;
                             free_next = mbar_test(&b_empty[s2], ph2 ^ 1);
                             if (elect_one()) {
-                                mbar_expect_tx(&b_full[s], Cfg::kBStage);
-                                bulk_load_1d(b_buf + s * Cfg::kBStage,
-                                             reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile,
-                                             Cfg::kBStage, &b_full[s]);
+                                mbar_expect_tx(&b_full[s], Cfg::kBStage);          // every CTA arms its own barrier
+                                const uint8_t* src = reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile;
+                                if (CL == 1) bulk_load_1d(b_buf + s * Cfg::kBStage, src, Cfg::kBStage, &b_full[s]);
+                                else if (cta_rank == 0) bulk_load_1d_mc(b_buf + s * Cfg::kBStage, src, Cfg::kBStage, &b_full[s], kMask);
                             }
                         });
                 }
@@ -311,7 +351,8 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                                        ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             uint32_t ai = 0, bi = 0, acc_it = 0;
             uint32_t a_ready = 0, b_ready = 0;       // results of early probes of the next full barriers
-            for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+            for (int unit = unit0; unit * CL < args.n_tiles; unit += unit_stride) {
+                const int tile = unit * CL + (int)cta_rank;     // may be >= n_tiles: then b0 >= B, TMA zero-fills, epilogue masks
                 const int t = (tile / n_hblk) % args.T;
                 for (int pass = 0; pass < 8 / NPH; ++pass, ++acc_it) {
                     const uint32_t as = acc_it % Cfg::kAccStages, aph = (acc_it / Cfg::kAccStages) & 1;
@@ -322,9 +363,10 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                     uint32_t cur_a = 0;
                     bool have_a = false;
                     uint32_t prev_a_slot = 0;
-                    for_each_step<NPH>(
+                    for_each_step<NPH, kSkip>(
                         pass, t, args.T, nchunk, KC,
-                        [&](int, int, int, int) {
+                        [&](int, int, int, int, bool oob) {
+                            if (oob) return;
                             if (have_a && elect_one()) tc_commit(&a_empty[prev_a_slot]);   // MMAs reading the previous A stage issued
                             const uint32_t s = ai % Cfg::kAStages, ph = (ai / Cfg::kAStages) & 1;
                             if (!a_ready) mbar_wait(&a_full[s], ph);
@@ -335,7 +377,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                             prev_a_slot = s;
                             have_a = true;
                         },
-                        [&](int slot, int) {
+                        [&](int slot, int, bool oob) {
                             const uint32_t s = bi % Cfg::kBStages, ph = (bi / Cfg::kBStages) & 1;
                             if (!b_ready) mbar_wait(&b_full[s], ph);
                             ++bi;
@@ -344,16 +386,19 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                             const uint32_t b_addr = smem_u32(b_buf + s * Cfg::kBStage);
                             const uint32_t acc0 = (started >> slot) & 1u;
                             if (elect_one()) {
+                                if (!oob) {
 #pragma unroll
-                                for (int c = 0; c < KC; ++c) {
-                                    const uint64_t ad = make_sdesc(cur_a + c * kATile), bd = make_sdesc(b_addr + c * Cfg::kBTile);
+                                    for (int c = 0; c < KC; ++c) {
+                                        const uint64_t ad = make_sdesc(cur_a + c * kATile), bd = make_sdesc(b_addr + c * Cfg::kBTile);
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k)   // +32 B per K=16 step inside the 128 B swizzle atom (encoded >>4)
-                                        tc_mma_f16(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc, acc0 | ((c | k) ? 1u : 0u));
+                                        for (int k = 0; k < 4; ++k)   // +32 B per K=16 step inside the 128 B swizzle atom (encoded >>4)
+                                            tc_mma_f16(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc, acc0 | ((c | k) ? 1u : 0u));
+                                    }
                                 }
-                                tc_commit(&b_empty[s]);
+                                if (CL == 1) tc_commit(&b_empty[s]);
+                                else tc_commit_mc(&b_empty[s], kMask);      // release the stage in every CTA of the cluster
                             }
-                            started |= 1u << slot;
+                            if (!oob) started |= 1u << slot;
                         });
                     if (elect_one()) {
                         if (have_a) tc_commit(&a_empty[prev_a_slot]);
@@ -370,7 +415,8 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         const int bl = r / (args.Hb * args.W), hl = (r / args.W) % args.Hb, w = r % args.W;
         HT* out = reinterpret_cast<HT*>(args.out);
         uint32_t acc_it = 0, p_it = 0;
-        for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+        for (int unit = unit0; unit * CL < args.n_tiles; unit += unit_stride) {
+                const int tile = unit * CL + (int)cta_rank;     // may be >= n_tiles: then b0 >= B, TMA zero-fills, epilogue masks
             const int hblk = tile % n_hblk, t = (tile / n_hblk) % args.T, bblk = tile / (n_hblk * args.T);
             const int b = bblk * args.Bt + bl, h = hblk * args.Hb + hl;
             const bool valid = b < args.B;
@@ -459,6 +505,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / signal its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -700,8 +747,8 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <typename HT, int COUT, int NPH, int KC, bool FUSE>
-int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
+template <typename HT, int COUT, int NPH, int KC, bool FUSE, int CL>
+int launch_upconv_cl(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
                   int T, int H, int W, int Cin, int sm_count, cudaStream_t st) {
     using Cfg = TcCfg<COUT, NPH, KC>;
     EncodeTiledFn enc = get_encode_fn();
@@ -728,24 +775,56 @@ int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, 
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return RDG_TC_E_DRIVER; }
 
-    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH, KC, FUSE>;
+    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH, KC, FUSE, CL>;
     static bool attr_set = false;
     if (!attr_set) {
         RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
         attr_set = true;
     }
-    int grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
-    kern<<<grid, kThreads, Cfg::kSmem, st>>>(tmap, a);
-    RDG_LAUNCH_CHECK();
+    const int units = ceil_div(a.n_tiles, CL);
+    const int max_clusters = sm_count / CL;
+    const int grid = (units < max_clusters ? units : max_clusters) * CL;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    RDG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, a));
     return 0;
+}
+
+template <typename HT, int COUT, int NPH, int KC, bool FUSE>
+int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
+                  int T, int H, int W, int Cin, int sm_count, cudaStream_t st) {
+    // CTAs per cluster sharing each weight stage through TMA multicast (1 = no cluster)
+    static const int cl = getenv("RDG_CLUSTER") ? atoi(getenv("RDG_CLUSTER")) : 1;   // measured: 453k / 440k / 247k scenarios/s at 1 / 2 / 4
+    if (cl == 4) return launch_upconv_cl<HT, COUT, NPH, KC, FUSE, 4>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    if (cl == 2) return launch_upconv_cl<HT, COUT, NPH, KC, FUSE, 2>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    return launch_upconv_cl<HT, COUT, NPH, KC, FUSE, 1>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
 }
 
 template <typename HT>
 int tc_upconv_dispatch(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out,
                        int B, int T, int H, int W, int Cin, int Cout, int sm_count, cudaStream_t st) {
-    if (Cout == 256) return launch_upconv<HT, 256, 1, 1, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
-    if (Cout == 128) return launch_upconv<HT, 128, 2, 2, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
-    if (Cout == 64 && p_out) return launch_upconv<HT, 64, 4, 2, true>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    // phases per pass (NPH): more phases share each activation stage (fewer L2 re-reads) but NPH*Cout > 256
+    // TMEM columns forfeits the double-buffered accumulator (no MMA/epilogue overlap).  Tunable for experiments.
+    static const int nph64 = getenv("RDG_NPH64") ? atoi(getenv("RDG_NPH64")) : 4;
+    static const int nph128 = getenv("RDG_NPH128") ? atoi(getenv("RDG_NPH128")) : 2;
+    static const int nph256 = getenv("RDG_NPH256") ? atoi(getenv("RDG_NPH256")) : 1;
+    if (Cout == 256) {
+        if (nph256 == 2) return launch_upconv<HT, 256, 2, 1, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+        return launch_upconv<HT, 256, 1, 1, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+    }
+    if (Cout == 128) {
+        if (nph128 == 4) return launch_upconv<HT, 128, 4, 2, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+        return launch_upconv<HT, 128, 2, 2, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
+    }
+    if (Cout == 64 && p_out) {
+        if (nph64 == 8) return launch_upconv<HT, 64, 8, 2, true>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+        if (nph64 == 2) return launch_upconv<HT, 64, 2, 2, true>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+        return launch_upconv<HT, 64, 4, 2, true>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    }
     if (Cout == 64) return launch_upconv<HT, 64, 4, 2, false>(x, wpack, bias, y, nullptr, nullptr, B, T, H, W, Cin, sm_count, st);
     rdg_set_error("tc upconv: unsupported Cout %d", Cout);
     return RDG_TC_E_SHAPE;
