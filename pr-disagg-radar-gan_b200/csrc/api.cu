@@ -10,6 +10,7 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <cstdlib>
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -115,6 +116,10 @@ extern "C" int rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int 
     if (prop.major != 10) { rdg_set_error("device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); delete c; return RDG_E_NODEVICE; }
     if (max_chunk <= 0) max_chunk = nd == 16 ? 32 * c->sm_count : std::max(32, 2 * c->sm_count);
     c->max_chunk = max_chunk;
+    {
+        const char* e = getenv("RDG_CONV3");
+        c->conv3_planes = nd == 16 && !(e && strcmp(e, "tiles") == 0);
+    }
     gen_shapes(c, c->g_size);
     critic_shapes(c, c->c_size);
     c->g_total = c->c_total = 0;
@@ -156,7 +161,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     cudaFree(c->g_grads); cudaFree(c->g_m); cudaFree(c->g_v);
     cudaFree(c->c_grads); cudaFree(c->c_m); cudaFree(c->c_v);
     for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) cudaFree(c->g_wpack[k][l]);
-    for (int k = 0; k < 2; ++k) cudaFree(c->g_w4pack[k]);
+    for (int k = 0; k < 2; ++k) { cudaFree(c->g_w4pack[k]); cudaFree(c->g_wpack_planes[k]); }
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->e2e_lat[i]); cudaFree(c->e2e_out[i]);
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
@@ -200,6 +205,12 @@ int rdg_repack_generator(rdg_ctx* c, cudaStream_t st) {
             if (!c->g_wpack[k][l]) RDG_CUDA(cudaMalloc(&c->g_wpack[k][l], (size_t)64 * cin[l] * cout[l] * 2));
             int r = pack_folded_weights(hk, c->g_params + c->g_off[2 + 2 * l], c->g_wpack[k][l], cin[l], cout[l], st);
             if (r) return r;
+        }
+        if (c->conv3_planes) {
+            if (!c->g_wpack_planes[k]) RDG_CUDA(cudaMalloc(&c->g_wpack_planes[k], (size_t)64 * 128 * 64 * 2));
+            int r2 = pack_folded_weights_planes(hk, c->g_params + c->g_off[6], c->g_wpack_planes[k], st);
+            if (r2) return r2;
+            c->launches += 1;
         }
         if (!c->g_w4pack[k]) RDG_CUDA(cudaMalloc(&c->g_w4pack[k], 32 * 64 * 2));
         int r = pack_w4_tile(hk, c->g_params + c->g_off[8], c->g_w4pack[k], st);
@@ -337,9 +348,14 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
         if (l < 2) y = take((size_t)n * gen_act_elems(c, l + 1) * 2);
         else pbuf = (float*)take((size_t)n * gen_act_elems(c, 3) / 64 * 32 * 4);
         { ProfScope ps(c, st, 3 + l, n, 1);
-          if ((r = tc_upconv_pixelnorm(hk, h, c->g_wpack[wk][l], c->g_params + c->g_off[3 + 2 * l], y,
-                                       l == 2 ? c->g_w4pack[wk] : nullptr, l == 2 ? pbuf : nullptr, n,
-                                       3 * f, s * f, s * f, cin[l], cout[l], c->sm_count, st))) return r; }
+          if (l == 2 && c->conv3_planes)
+              r = tc_upconv64_planes(hk, h, c->g_wpack_planes[wk], c->g_params + c->g_off[7], nullptr, c->g_w4pack[wk], pbuf, n,
+                                     3 * f, c->sm_count, st);
+          else
+              r = tc_upconv_pixelnorm(hk, h, c->g_wpack[wk][l], c->g_params + c->g_off[3 + 2 * l], y,
+                                      l == 2 ? c->g_w4pack[wk] : nullptr, l == 2 ? pbuf : nullptr, n,
+                                      3 * f, s * f, s * f, cin[l], cout[l], c->sm_count, st);
+          if (r) return r; }
         h = y;
     }
     ProfScope ps(c, st, 6, n, 1);
@@ -495,8 +511,13 @@ extern "C" int rdg_tc_layer(rdg_ctx* c, int layer, int mode, const float* x_dev,
     uint8_t* yout = xin + (n_in * 2 + 255) / 256 * 256;
     int r;
     if ((r = f32_to_half(hk, x_dev, xin, (long long)n_in, st))) return r;
-    if ((r = tc_upconv_pixelnorm(hk, xin, c->g_wpack[hk == RDG_HALF_BF16 ? 0 : 1][layer], c->g_params + c->g_off[3 + 2 * layer], yout,
-                                 nullptr, nullptr, B, 3 * f, s * f, s * f, cin[layer], cout[layer], c->sm_count, st))) return r;
+    const int wk = hk == RDG_HALF_BF16 ? 0 : 1;
+    if (layer == 2 && c->conv3_planes)
+        r = tc_upconv64_planes(hk, xin, c->g_wpack_planes[wk], c->g_params + c->g_off[7], yout, nullptr, nullptr, B, 3 * f, c->sm_count, st);
+    else
+        r = tc_upconv_pixelnorm(hk, xin, c->g_wpack[wk][layer], c->g_params + c->g_off[3 + 2 * layer], yout,
+                                nullptr, nullptr, B, 3 * f, s * f, s * f, cin[layer], cout[layer], c->sm_count, st);
+    if (r) return r;
     return half_to_f32(hk, yout, y_dev, (long long)n_out, st);
 }
 

@@ -37,3 +37,9 @@ int half_to_f32(int half_kind, const void* src, float* dst, long long n, cudaStr
 // device-side packing of the master f32 weights into the tcgen05 operand images
 int pack_folded_weights(int half_kind, const float* k, void* dst, int Cin, int Cout, cudaStream_t st);
 int pack_w4_tile(int half_kind, const float* k4, void* dst, cudaStream_t st);
+
+// Resident-plane kernel for the 128 -> 64 layer on an 8x8 low-res grid (ndomain 16), gen_tc_planes.cu.
+// y (16-bit, [B,2T,16,16,64]) or, if p_out != null, the fused output-conv tap products P.
+int tc_upconv64_planes(int half_kind, const void* x, const void* wpack_planes, const float* bias, void* y, const void* w4tile,
+                       float* p_out, int B, int T, int sm_count, cudaStream_t st);
+int pack_folded_weights_planes(int half_kind, const float* k, void* dst, cudaStream_t st);

@@ -1,0 +1,450 @@
+// Resident-plane tensor-core kernel for the dominant generator layer at ndomain = 16:
+// UpSampling3D(2) + Conv3D(128 -> 64, 3^3, 'same') + bias + PixelNormalization + LeakyReLU(0.2)
+// (gan_train_cwgangp_pixelnorm.py:340-343) with the output Conv3D(64 -> 1) (:345) fused as tap products.
+//
+// Why a second kernel: the tile-per-offset kernel in gen_tc.cu re-fetches every shifted activation tile
+// and every weight tile from L2 (2.2 MB per 128-position tile) and is bound by the L2 -> SM stream
+// (profiles/r1c_ncu_conv3_summary.md).  Here
+//   * a CTA owns a PAIR of samples and sweeps their 12 low-res hour planes; three planes stay resident in
+//     shared memory as zero-haloed images written by ONE TMA box load each ([h' 10][sample 2][w' 9] rows of
+//     64 channels, SWIZZLE_128B).  All 27 (dt,dh,dw) operand views of a plane are plain descriptor offsets
+//     (start row (1+dh)*18 + (1+dw), 8-row group stride 9 rows): tcgen05 and TMA both swizzle on absolute
+//     shared-memory address bits, so views need not be 1024-byte aligned (tools/umma_shift_probe.cu).
+//     The zero halos are shared between neighbouring lines / buffers, so a plane costs 40.5 KB, not 64 KB.
+//   * two M tiles (hour planes t0, t0+1 of the pair) share every weight stage, and the two w-phases that
+//     need the same view (dw = 0) are one N = 128 MMA; the operand stream per 128 positions drops from
+//     2.2 MB to 0.55 MB and shared-memory operand reads per MMA from 6 KB/32 clk to <= 4 KB + 2 KB*N/64.
+//
+// Pass structure: super-tile = (pair, t0 even); pass = (pt, ph) with accumulators [M tile m][pw][64] = 256
+// TMEM columns, double buffered; per pass 16 weight stages of 16 KB: for (at, ah, chunk): stage X = the two
+// dw = 0 tiles (pw0,aw1 | pw1,aw0) -> one N=128 MMA per k16 and M tile; stage Y = (pw0,aw0) for dw = -1 and
+// (pw1,aw1) for dw = +1 -> two N=64 MMAs.
+//
+// Warp roles (224 threads): 0 = plane producer (TMA), 1 = TMEM alloc + MMA issuer, 2 = weight producer,
+// 3..6 = epilogue (bias + PixelNorm + LeakyReLU, fused output-conv tap products, stores).
+#include "rdg_common.cuh"
+#include "gen_tc.h"
+#include "tc_ptx.cuh"
+#include <cuda.h>
+
+using namespace rdg_tc;
+
+namespace {
+
+constexpr int kThreads = 224;
+constexpr int kRow = 128;                       // bytes per row: 64 channels x 2 B
+constexpr int kWp = 9;                          // rows per (h', sample) line: w' = 0..8 <-> w = -1..7; w = 8 is the next line's w' = 0
+constexpr int kLine = 2 * kWp;                  // rows per h' line (the two samples interleaved)
+constexpr int kHp = 9;                          // h' lines per buffer; line 9 (h = 8) is the next buffer's line 0
+constexpr int kBufBytes = kHp * kLine * kRow;   // 20736: one plane, one 64-channel chunk
+constexpr int kBoxBytes = 10 * kLine * kRow;    // 23040: what one TMA box writes (10 lines)
+constexpr int kSlots = 3;                       // resident planes
+constexpr int kChunks = 2;                      // Cin = 128
+constexpr int kARegion = ((kSlots * kChunks * kBufBytes + (kLine + 1) * kRow) + 1023) / 1024 * 1024;
+constexpr int kBStage = 16384;                  // two [64 x 64] weight tiles
+constexpr int kBStages = 5;
+constexpr int kStagesPerPass = 16;
+constexpr int kYTile = 16384, kW4Tile = 4096;
+constexpr int kSmem = 1024 + kBStages * kBStage + kYTile + kW4Tile + kARegion + 64 * 4 + 256;
+static_assert(kSmem <= 227 * 1024, "shared memory overflow");
+constexpr int kAccCols = 256;
+constexpr uint32_t kSboA = kWp * kRow;          // 8-row group stride of an activation view
+
+__device__ __forceinline__ uint64_t make_sdesc_sbo(uint32_t saddr, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <typename HT>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* b_buf = smem;
+    uint8_t* y_tile = b_buf + kBStages * kBStage;
+    uint8_t* w4_tile = y_tile + kYTile;
+    uint8_t* a_reg = w4_tile + kW4Tile;
+    float* s_bias = reinterpret_cast<float*>(a_reg + kARegion);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + kSlots;
+    uint64_t* b_full = a_empty + kSlots;
+    uint64_t* b_empty = b_full + kBStages;
+    uint64_t* acc_full = b_empty + kBStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* p_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = args.T, n_super = T / 2;
+    const int n_units = (args.B + 1) / 2;
+    const bool fuse = args.p_out != nullptr;
+
+    for (int i = threadIdx.x; i < 64; i += kThreads) s_bias[i] = args.bias[i];
+    {
+        // halo rows shared between buffers (and the row past the last line) must read as zero from the start
+        uint4* z = reinterpret_cast<uint4*>(a_reg);
+        for (int i = threadIdx.x; i < kARegion / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        if (fuse) {
+            const uint4* src = reinterpret_cast<const uint4*>(args.w4tile);
+            uint4* dst = reinterpret_cast<uint4*>(w4_tile);
+            for (int i = threadIdx.x; i < kW4Tile / 16; i += kThreads) dst[i] = src[i];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (TMA, MMA)
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(p_full, 1);
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= plane producer: one haloed box per plane and 64-channel chunk =================
+        uint32_t li = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int b0 = unit * 2;
+            for (int p = 0; p < T; ++p, ++li) {
+                const uint32_t s = li % kSlots, ph = (li / kSlots) & 1;
+                mbar_wait(&a_empty[s], ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&a_full[s], kChunks * kBoxBytes);
+#pragma unroll
+                    for (int c = 0; c < kChunks; ++c)   // tensor dims (C, W, B, H, T): w and h start at -1 (zero halo)
+                        tma_load_5d(a_reg + (s * kChunks + c) * kBufBytes, &tmap, &a_full[s], c * 64, -1, b0, -1, p);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ================= weight producer: the 1 MB stage sequence of a super-tile, streamed in order =================
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(args.wpack);
+        uint32_t bi = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x)
+            for (int sup = 0; sup < n_super; ++sup)
+                for (int st = 0; st < 4 * kStagesPerPass; ++st, ++bi) {
+                    const uint32_t s = bi % kBStages, ph = (bi / kBStages) & 1;
+                    mbar_wait(&b_empty[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&b_full[s], kBStage);
+                        bulk_load_1d(b_buf + s * kBStage, wsrc + (size_t)st * kBStage, kBStage, &b_full[s]);
+                    }
+                    __syncwarp();
+                }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp walks the schedule; one elected lane issues) =================
+        constexpr uint32_t kF = HalfOps<HT>::kFmt;
+        constexpr uint32_t idesc128 = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc64 = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_base = smem_u32(a_reg), b_base = smem_u32(b_buf);
+        uint32_t bi = 0, acc_it = 0, li0 = 0;        // li0 = plane-load index of plane 0 of the current unit
+        uint32_t b_ready = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, li0 += T) {
+            int ready = -1;                          // highest plane of this unit known to have landed
+            for (int sup = 0; sup < n_super; ++sup)
+                for (int pass = 0; pass < 4; ++pass, ++acc_it) {
+                    const int pt = pass >> 1, ph = pass & 1;
+                    const int w = 2 * sup + pt;      // window: planes w-1, w, w+1
+                    const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                    mbar_wait(&acc_empty[as], aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_base = tmem_base + as * kAccCols;
+                    uint32_t started = 0;
+#pragma unroll 1
+                    for (int g = 0; g < 8; ++g) {    // g = (at, ah, chunk)
+                        const int at = g >> 2, ah = (g >> 1) & 1, c = g & 1;
+                        const int dh = ph - 1 + ah;
+                        // activation views of the two M tiles for this (dt, dh, chunk); plane index may be outside [0,T)
+                        uint32_t a_view[2];
+                        bool a_ok[2];
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            const int plane = 2 * sup + m + pt - 1 + at;
+                            a_ok[m] = plane >= 0 && plane < T;
+                            const uint32_t l = li0 + (uint32_t)(a_ok[m] ? plane : 0);
+                            if (a_ok[m]) {
+                                while (ready < plane) {
+                                    ++ready;
+                                    const uint32_t lr = li0 + (uint32_t)ready;
+                                    mbar_wait(&a_full[lr % kSlots], (lr / kSlots) & 1);
+                                }
+                            }
+                            a_view[m] = a_base + ((l % kSlots) * kChunks + c) * kBufBytes + ((1 + dh) * kLine + 1) * kRow;
+                        }
+                        tc_fence_after();
+                        // ---- stage X: dw = 0, both w-phases in one N = 128 MMA
+                        {
+                            const uint32_t s = bi % kBStages, bph = (bi / kBStages) & 1;
+                            if (!b_ready) mbar_wait(&b_full[s], bph);
+                            ++bi;
+                            b_ready = mbar_test(&b_full[bi % kBStages], (bi / kBStages) & 1);
+                            tc_fence_after();
+                            const uint32_t b_addr = b_base + s * kBStage;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int m = 0; m < 2; ++m) {
+                                    if (!a_ok[m]) continue;
+                                    const uint64_t ad = make_sdesc_sbo(a_view[m], kSboA), bd = make_sdesc(b_addr);
+                                    const uint32_t acc0 = (started >> m) & 1u;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        tc_mma_f16(d_base + m * 128, ad + 2 * k, bd + 2 * k, idesc128, acc0 | (k ? 1u : 0u));
+                                }
+                                tc_commit(&b_empty[s]);
+                            }
+                            if (a_ok[0]) started |= 1u;
+                            if (a_ok[1]) started |= 2u;
+                            __syncwarp();
+                        }
+                        // ---- stage Y: dw = -1 feeds pw = 0 (tile 0), dw = +1 feeds pw = 1 (tile 1)
+                        {
+                            const uint32_t s = bi % kBStages, bph = (bi / kBStages) & 1;
+                            if (!b_ready) mbar_wait(&b_full[s], bph);
+                            ++bi;
+                            b_ready = mbar_test(&b_full[bi % kBStages], (bi / kBStages) & 1);
+                            tc_fence_after();
+                            const uint32_t b_addr = b_base + s * kBStage;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int m = 0; m < 2; ++m) {
+                                    if (!a_ok[m]) continue;
+                                    const uint64_t al = make_sdesc_sbo(a_view[m] - kRow, kSboA), ar = make_sdesc_sbo(a_view[m] + kRow, kSboA);
+                                    const uint64_t b0d = make_sdesc(b_addr), b1d = make_sdesc(b_addr + 8192);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        tc_mma_f16(d_base + m * 128, al + 2 * k, b0d + 2 * k, idesc64, 1u);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        tc_mma_f16(d_base + m * 128 + 64, ar + 2 * k, b1d + 2 * k, idesc64, 1u);
+                                }
+                                tc_commit(&b_empty[s]);
+                            }
+                            __syncwarp();
+                        }
+                        // plane w-1 is read for the last time by the at = 0 half of the ph = 1 pass of window w
+                        if (g == 3 && ph == 1 && w >= 1) {
+                            const uint32_t l = li0 + (uint32_t)(w - 1);
+                            if (elect_one()) tc_commit(&a_empty[l % kSlots]);
+                            __syncwarp();
+                        }
+                    }
+                    if (elect_one()) {
+                        if (sup == n_super - 1 && pass == 3) {            // last pass of the unit: plane T-1 is done too
+                            const uint32_t l = li0 + (uint32_t)(T - 1);
+                            tc_commit(&a_empty[l % kSlots]);
+                        }
+                        tc_commit(&acc_full[as]);
+                    }
+                    __syncwarp();
+                }
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may touch (warps 3..6 -> 3,0,1,2)
+        const int r = q * 32 + lane;            // accumulator row: r = (h*2 + sample)*8 + w
+        const int h = r >> 4, bl = (r >> 3) & 1, wq = r & 7;
+        HT* out = reinterpret_cast<HT*>(args.out);
+        const int H2 = 16, W2 = 16, T2 = 2 * T;
+        uint32_t acc_it = 0, p_it = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int b = unit * 2 + bl;
+            const bool valid = b < args.B;
+            for (int sup = 0; sup < n_super; ++sup)
+                for (int pass = 0; pass < 4; ++pass, ++acc_it) {
+                    const int pt = pass >> 1, ph = pass & 1;
+                    const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                    mbar_wait(&acc_full[as], aph);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int a = 0; a < 4; ++a) {
+                        const int m = a >> 1, pw = a & 1;
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccCols + a * 64;
+                        float ss = 0.f;
+#pragma unroll 1
+                        for (int c0 = 0; c0 < 64; c0 += 32) {
+                            uint32_t v[32];
+                            tc_ld32(taddr + c0, v);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = __uint_as_float(v[j]) + s_bias[c0 + j];
+                                ss = fmaf(x, x, ss);
+                            }
+                        }
+                        const float inv = 1.0f / sqrtf(ss * (1.0f / 64) + 1.0e-8f);
+                        const size_t o_pos = (((size_t)b * T2 + (2 * (2 * sup + m) + pt)) * H2 + (2 * h + ph)) * W2 + (2 * wq + pw);
+#pragma unroll 1
+                        for (int c0 = 0; c0 < 64; c0 += 32) {
+                            uint32_t v[32];
+                            tc_ld32(taddr + c0, v);
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float x0 = (__uint_as_float(v[2 * j]) + s_bias[c0 + 2 * j]) * inv;
+                                float x1 = (__uint_as_float(v[2 * j + 1]) + s_bias[c0 + 2 * j + 1]) * inv;
+                                x0 = x0 > 0.f ? x0 : 0.2f * x0;
+                                x1 = x1 > 0.f ? x1 : 0.2f * x1;
+                                pk[j] = HalfOps<HT>::pack(x0, x1);
+                            }
+                            if (fuse) {
+                                // row r of the K-major SWIZZLE_128B tile: 16-byte chunk j lives at chunk (j ^ (r & 7))
+                                uint8_t* yrow = y_tile + r * 128;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    *reinterpret_cast<uint4*>(yrow + ((((c0 >> 3) + j) ^ (r & 7)) << 4)) =
+                                        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                            } else if (valid) {
+                                uint4* dst = reinterpret_cast<uint4*>(out + o_pos * 64 + c0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                            }
+                        }
+                        if (fuse) {
+                            // all 128 rows of y written and all reads of this accumulator done
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            tc_fence_before();
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            if (warp == 3 && elect_one()) {
+                                tc_fence_after();
+                                constexpr uint32_t kF = HalfOps<HT>::kFmt;
+                                constexpr uint32_t idesc_p = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(32 >> 3) << 17) |
+                                                             ((uint32_t)(128 >> 4) << 24);
+                                const uint64_t yd = make_sdesc(smem_u32(y_tile)), wd = make_sdesc(smem_u32(w4_tile));
+                                const uint32_t d_p = tmem_base + as * kAccCols + a * 64;   // reuse the consumed accumulator
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) tc_mma_f16(d_p, yd + 2 * k, wd + 2 * k, idesc_p, k > 0 ? 1u : 0u);
+                                tc_commit(p_full);
+                            }
+                            mbar_wait(p_full, p_it & 1);
+                            ++p_it;
+                            tc_fence_after();
+                            uint32_t pv[32];
+                            tc_ld32(taddr, pv);
+                            if (valid) {
+                                uint4* dst = reinterpret_cast<uint4*>(args.p_out + o_pos * 32);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    dst[j] = make_uint4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[as]);
+                }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <typename HT>
+int launch_planes(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
+                  int T, int sm_count, cudaStream_t st) {
+    constexpr int H = 8, W = 8, Cin = 128;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { rdg_set_error("cuTensorMapEncodeTiled entry point not available"); return RDG_TC_E_DRIVER; }
+    if (T < 2 || (T & 1)) { rdg_set_error("tc planes: T must be even"); return RDG_TC_E_SHAPE; }
+    TcConvArgs a{};
+    a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin;
+    a.wpack = wpack; a.bias = bias; a.out = y; a.w4tile = w4tile; a.p_out = p_out;
+
+    // tensor dims ordered (C, W, B, H, T) so that the box lands as [h'][sample][w'][64 ch] rows
+    CUtensorMap tmap;
+    cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)B, (cuuint64_t)H, (cuuint64_t)T};
+    cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)T * H * W * Cin * 2, (cuuint64_t)W * Cin * 2,
+                          (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)kWp, 2, 10, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMapDataType dt = HalfOps<HT>::kFmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = enc(&tmap, dt, 5, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled (planes) failed: %d", (int)r); return RDG_TC_E_DRIVER; }
+
+    auto kern = tc_upconv64_planes_kernel<HT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr_set = true;
+    }
+    const int n_units = (B + 1) / 2;
+    const int grid = n_units < sm_count ? n_units : sm_count;
+    kern<<<grid, kThreads, kSmem, st>>>(tmap, a);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+// Folded weights of the 128 -> 64 layer in the stage order of tc_upconv64_planes_kernel:
+// [pt][ph][at][ah][chunk][X|Y][tile 2][64 cout rows x 64 k], rows 128B-swizzled.  X tiles: (pw0,aw1), (pw1,aw0);
+// Y tiles: (pw0,aw0), (pw1,aw1).  Fold rule as in pack_folded_kernel: sums in f32, rounded once.
+template <typename HT>
+__global__ void pack_folded_planes_kernel(const float* __restrict__ k, HT* __restrict__ dst) {
+    constexpr int Cin = 128, Cout = 64;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 64 * 8192) return;
+    const int sidx = idx >> 13, el = idx & 8191;
+    const int j = el >> 12, n = (el >> 6) & 63, pos = el & 63;
+    const int xy = sidx & 1, c = (sidx >> 1) & 1, ah = (sidx >> 2) & 1, at = (sidx >> 3) & 1, ph = (sidx >> 4) & 1, pt = (sidx >> 5) & 1;
+    const int pw = j, aw = xy == 0 ? 1 - j : j;
+    const int ci = c * 64 + (((pos >> 3) ^ (n & 7)) << 3) + (pos & 7);
+    auto lo = [](int phs, int tp) { return phs == 0 ? (tp == 0 ? 0 : 1) : (tp == 0 ? 0 : 2); };
+    auto hi = [](int phs, int tp) { return phs == 0 ? (tp == 0 ? 0 : 2) : (tp == 0 ? 1 : 2); };
+    float sum = 0.f;
+    for (int kt = lo(pt, at); kt <= hi(pt, at); ++kt)
+        for (int kh = lo(ph, ah); kh <= hi(ph, ah); ++kh)
+            for (int kw = lo(pw, aw); kw <= hi(pw, aw); ++kw)
+                sum += k[((size_t)((kt * 3 + kh) * 3 + kw) * Cin + ci) * Cout + n];
+    dst[idx] = HalfOps<HT>::from_float(sum);
+}
+
+}  // namespace
+
+int tc_upconv64_planes(int half_kind, const void* x, const void* wpack, const float* bias, void* y, const void* w4tile,
+                       float* p_out, int B, int T, int sm_count, cudaStream_t st) {
+    if (B <= 0) return 0;
+    if (half_kind == RDG_HALF_BF16) return launch_planes<__nv_bfloat16>(x, wpack, bias, y, w4tile, p_out, B, T, sm_count, st);
+    return launch_planes<__half>(x, wpack, bias, y, w4tile, p_out, B, T, sm_count, st);
+}
+
+int pack_folded_weights_planes(int half_kind, const float* k, void* dst, cudaStream_t st) {
+    if (half_kind == RDG_HALF_BF16) pack_folded_planes_kernel<__nv_bfloat16><<<64 * 8192 / 256, 256, 0, st>>>(k, (__nv_bfloat16*)dst);
+    else pack_folded_planes_kernel<__half><<<64 * 8192 / 256, 256, 0, st>>>(k, (__half*)dst);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}

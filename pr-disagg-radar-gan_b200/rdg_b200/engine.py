@@ -112,6 +112,16 @@ class Generator:
             raise _lib.NonFiniteError("found nan in output of per_gridpoint_softmax")
         return out
 
+    def tc_layer_device(self, layer, x, mode="fp16"):
+        """One tensor-core layer alone (tests): x [B,T,H,W,Cin] cuda f32 (rounded to 16 bit inside) ->
+        LeakyReLU(PixelNorm(conv3(upsample2(x)) + b)) [B,2T,2H,2W,Cout] cuda f32 (gan_train...py:330-343)."""
+        cout = (256, 128, 64)[layer]
+        B, T, H, Wd, _ = x.shape
+        y = torch.empty((B, 2 * T, 2 * H, 2 * Wd, cout), device=x.device, dtype=torch.float32)
+        _lib.check(self.ctx.lib.rdg_tc_layer(self.ctx.handle, int(layer), _lib.MODES[mode], C.c_void_p(x.data_ptr()),
+                                             C.c_void_p(y.data_ptr()), int(B), self.ctx._stream()))
+        return y
+
     # ---- Keras surface
     def predict(self, inputs, batch_size=None, mode=None):
         """gen.predict([latent, cond_batch]) -> (B,24,nd,nd,1) float32 fractions
