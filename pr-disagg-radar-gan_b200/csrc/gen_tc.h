@@ -20,6 +20,7 @@ struct TcConvArgs {
     void* out;          // [B,2T,2H,2W,Cout] 16-bit (unused when the output conv is fused)
     const void* w4tile; // fused output conv: [32 taps x 64 ch] 16-bit swizzled tile (taps >= 27 zero)
     float* p_out;       // fused output conv: [B,2T,2H,2W,32] f32 per-tap partial products
+    int dbg;            // experiments only (RDG_DBG): 1 = epilogue does not touch TMEM, 2 = no output-conv MMA, 4 = skip N=64 MMAs
 };
 
 // y[B,2T,2H,2W,Cout] = LeakyReLU(PixelNorm(conv3x3x3(upsample2(x[B,T,H,W,Cin])) + bias))

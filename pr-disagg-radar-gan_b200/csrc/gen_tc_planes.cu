@@ -20,18 +20,22 @@
 // dw = 0 tiles (pw0,aw1 | pw1,aw0) -> one N=128 MMA per k16 and M tile; stage Y = (pw0,aw0) for dw = -1 and
 // (pw1,aw1) for dw = +1 -> two N=64 MMAs.
 //
-// Warp roles (224 threads): 0 = plane producer (TMA), 1 = TMEM alloc + MMA issuer, 2 = weight producer,
-// 3..6 = epilogue (bias + PixelNorm + LeakyReLU, fused output-conv tap products, stores).
+// Warp roles (384 threads): 0 = plane producer (TMA), 1 = TMEM alloc + MMA issuer of M tile 0, 2 = weight producer,
+// 3 = MMA issuer of M tile 1, 4..7 / 8..11 = epilogue warpgroup of M tile 0 / 1 (bias + PixelNorm + LeakyReLU, fused
+// output-conv tap products, stores); each M tile has its own accumulator full/empty barriers, y tile and P barrier.
+// Two issuers because ONE thread sustains at most one tcgen05.mma per ~77 clk (tools/umma_rate_probe.cu): a single
+// issuer caps N=64 / N=128 MMAs at 42 % / 84 % of the pipe, two reach the SM limits (48 clk smem-bound / 64 clk).
 #include "rdg_common.cuh"
 #include "gen_tc.h"
 #include "tc_ptx.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 using namespace rdg_tc;
 
 namespace {
 
-constexpr int kThreads = 224;
+constexpr int kThreads = 384;
 constexpr int kRow = 128;                       // bytes per row: 64 channels x 2 B
 constexpr int kWp = 9;                          // rows per (h', sample) line: w' = 0..8 <-> w = -1..7; w = 8 is the next line's w' = 0
 constexpr int kLine = 2 * kWp;                  // rows per h' line (the two samples interleaved)
@@ -42,10 +46,10 @@ constexpr int kSlots = 3;                       // resident planes
 constexpr int kChunks = 2;                      // Cin = 128
 constexpr int kARegion = ((kSlots * kChunks * kBufBytes + (kLine + 1) * kRow) + 1023) / 1024 * 1024;
 constexpr int kBStage = 16384;                  // two [64 x 64] weight tiles
-constexpr int kBStages = 5;
+constexpr int kBStages = 6;
 constexpr int kStagesPerPass = 16;
-constexpr int kYTile = 16384, kW4Tile = 4096;
-constexpr int kSmem = 1024 + kBStages * kBStage + kYTile + kW4Tile + kARegion + 64 * 4 + 256;
+constexpr int kW4Tile = 4096;
+constexpr int kSmem = 1024 + kBStages * kBStage + kW4Tile + kARegion + 64 * 4 + 256;
 static_assert(kSmem <= 227 * 1024, "shared memory overflow");
 constexpr int kAccCols = 256;
 constexpr uint32_t kSboA = kWp * kRow;          // 8-row group stride of an activation view
@@ -65,8 +69,7 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* b_buf = smem;
-    uint8_t* y_tile = b_buf + kBStages * kBStage;
-    uint8_t* w4_tile = y_tile + kYTile;
+    uint8_t* w4_tile = b_buf + kBStages * kBStage;
     uint8_t* a_reg = w4_tile + kW4Tile;
     float* s_bias = reinterpret_cast<float*>(a_reg + kARegion);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
@@ -74,10 +77,10 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
     uint64_t* a_empty = a_full + kSlots;
     uint64_t* b_full = a_empty + kSlots;
     uint64_t* b_empty = b_full + kBStages;
-    uint64_t* acc_full = b_empty + kBStages;
-    uint64_t* acc_empty = acc_full + 2;
-    uint64_t* p_full = acc_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
+    uint64_t* acc_full = b_empty + kBStages;     // [stage 2][M tile 2]
+    uint64_t* acc_empty = acc_full + 4;          // [stage 2][M tile 2]
+    uint64_t* p_full = acc_empty + 4;            // [M tile 2][w-phase 2]: one commit and one wait per pass each
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = args.T, n_super = T / 2;
@@ -97,10 +100,10 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (TMA, MMA)
     }
     if (threadIdx.x == 0) {
-        mbar_init(p_full, 1);
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 1);
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }     // both issuers release
+        for (int i = 0; i < kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -146,8 +149,10 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                     }
                     __syncwarp();
                 }
-    } else if (warp == 1) {
-        // ================= MMA issuer (whole warp walks the schedule; one elected lane issues) =================
+    } else if (warp == 1 || warp == 3) {
+        // ================= MMA issuers: warp 1 owns M tile 0 (hour plane t0), warp 3 owns M tile 1 (t0 + 1) =================
+        // The whole warp walks the schedule; one elected lane issues.  Both issuers consume every weight stage.
+        const int m = warp == 3 ? 1 : 0;
         constexpr uint32_t kF = HalfOps<HT>::kFmt;
         constexpr uint32_t idesc128 = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         constexpr uint32_t idesc64 = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -161,32 +166,26 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                     const int pt = pass >> 1, ph = pass & 1;
                     const int w = 2 * sup + pt;      // window: planes w-1, w, w+1
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                    mbar_wait(&acc_empty[as], aph ^ 1);
+                    mbar_wait(&acc_empty[as * 2 + m], aph ^ 1);
                     tc_fence_after();
-                    const uint32_t d_base = tmem_base + as * kAccCols;
+                    const uint32_t d_acc = tmem_base + as * kAccCols + m * 128;
                     uint32_t started = 0;
 #pragma unroll 1
                     for (int g = 0; g < 8; ++g) {    // g = (at, ah, chunk)
                         const int at = g >> 2, ah = (g >> 1) & 1, c = g & 1;
                         const int dh = ph - 1 + ah;
-                        // activation views of the two M tiles for this (dt, dh, chunk); plane index may be outside [0,T)
-                        uint32_t a_view[2];
-                        bool a_ok[2];
-#pragma unroll
-                        for (int m = 0; m < 2; ++m) {
-                            const int plane = 2 * sup + m + pt - 1 + at;
-                            a_ok[m] = plane >= 0 && plane < T;
-                            const uint32_t l = li0 + (uint32_t)(a_ok[m] ? plane : 0);
-                            if (a_ok[m]) {
-                                while (ready < plane) {
-                                    ++ready;
-                                    const uint32_t lr = li0 + (uint32_t)ready;
-                                    mbar_wait(&a_full[lr % kSlots], (lr / kSlots) & 1);
-                                }
+                        // activation view of this M tile for (dt, dh, chunk); the plane may lie outside [0,T) (zero padding in t)
+                        const int plane = 2 * sup + m + pt - 1 + at;
+                        const bool a_ok = plane >= 0 && plane < T;
+                        const uint32_t l = li0 + (uint32_t)(a_ok ? plane : 0);
+                        if (a_ok) {
+                            while (ready < plane) {
+                                ++ready;
+                                const uint32_t lr = li0 + (uint32_t)ready;
+                                mbar_wait(&a_full[lr % kSlots], (lr / kSlots) & 1);
                             }
-                            a_view[m] = a_base + ((l % kSlots) * kChunks + c) * kBufBytes + ((1 + dh) * kLine + 1) * kRow;
                         }
-                        tc_fence_after();
+                        const uint32_t a_view = a_base + ((l % kSlots) * kChunks + c) * kBufBytes + ((1 + dh) * kLine + 1) * kRow;
                         // ---- stage X: dw = 0, both w-phases in one N = 128 MMA
                         {
                             const uint32_t s = bi % kBStages, bph = (bi / kBStages) & 1;
@@ -196,19 +195,15 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                             tc_fence_after();
                             const uint32_t b_addr = b_base + s * kBStage;
                             if (elect_one()) {
-#pragma unroll
-                                for (int m = 0; m < 2; ++m) {
-                                    if (!a_ok[m]) continue;
-                                    const uint64_t ad = make_sdesc_sbo(a_view[m], kSboA), bd = make_sdesc(b_addr);
-                                    const uint32_t acc0 = (started >> m) & 1u;
+                                if (a_ok) {
+                                    const uint64_t ad = make_sdesc_sbo(a_view, kSboA), bd = make_sdesc(b_addr);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        tc_mma_f16(d_base + m * 128, ad + 2 * k, bd + 2 * k, idesc128, acc0 | (k ? 1u : 0u));
+                                        tc_mma_f16(d_acc, ad + 2 * k, bd + 2 * k, idesc128, started | (k ? 1u : 0u));
                                 }
                                 tc_commit(&b_empty[s]);
                             }
-                            if (a_ok[0]) started |= 1u;
-                            if (a_ok[1]) started |= 2u;
+                            if (a_ok) started = 1u;
                             __syncwarp();
                         }
                         // ---- stage Y: dw = -1 feeds pw = 0 (tile 0), dw = +1 feeds pw = 1 (tile 1)
@@ -220,17 +215,15 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                             tc_fence_after();
                             const uint32_t b_addr = b_base + s * kBStage;
                             if (elect_one()) {
-#pragma unroll
-                                for (int m = 0; m < 2; ++m) {
-                                    if (!a_ok[m]) continue;
-                                    const uint64_t al = make_sdesc_sbo(a_view[m] - kRow, kSboA), ar = make_sdesc_sbo(a_view[m] + kRow, kSboA);
+                                if (a_ok && !(args.dbg & 4)) {
+                                    const uint64_t al = make_sdesc_sbo(a_view - kRow, kSboA), ar = make_sdesc_sbo(a_view + kRow, kSboA);
                                     const uint64_t b0d = make_sdesc(b_addr), b1d = make_sdesc(b_addr + 8192);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        tc_mma_f16(d_base + m * 128, al + 2 * k, b0d + 2 * k, idesc64, 1u);
+                                        tc_mma_f16(d_acc, al + 2 * k, b0d + 2 * k, idesc64, 1u);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        tc_mma_f16(d_base + m * 128 + 64, ar + 2 * k, b1d + 2 * k, idesc64, 1u);
+                                        tc_mma_f16(d_acc + 64, ar + 2 * k, b1d + 2 * k, idesc64, 1u);
                                 }
                                 tc_commit(&b_empty[s]);
                             }
@@ -238,28 +231,37 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                         }
                         // plane w-1 is read for the last time by the at = 0 half of the ph = 1 pass of window w
                         if (g == 3 && ph == 1 && w >= 1) {
-                            const uint32_t l = li0 + (uint32_t)(w - 1);
-                            if (elect_one()) tc_commit(&a_empty[l % kSlots]);
+                            const uint32_t lw = li0 + (uint32_t)(w - 1);
+                            if (elect_one()) tc_commit(&a_empty[lw % kSlots]);
                             __syncwarp();
                         }
                     }
                     if (elect_one()) {
                         if (sup == n_super - 1 && pass == 3) {            // last pass of the unit: plane T-1 is done too
-                            const uint32_t l = li0 + (uint32_t)(T - 1);
-                            tc_commit(&a_empty[l % kSlots]);
+                            const uint32_t lw = li0 + (uint32_t)(T - 1);
+                            tc_commit(&a_empty[lw % kSlots]);
                         }
-                        tc_commit(&acc_full[as]);
+                        tc_commit(&acc_full[as * 2 + m]);
                     }
                     __syncwarp();
                 }
         }
     } else {
         // ================= epilogue =================
-        const int q = warp & 3;                 // TMEM lane quarter this warp may touch (warps 3..6 -> 3,0,1,2)
+        // Per accumulator (M tile m, w-phase pw; thread = position = TMEM lane): read the 64 channels once, bias +
+        // PixelNorm + LeakyReLU in f32, round to 16 bit.  Fused mode: the 16-bit activations go back into the drained
+        // accumulator's own columns 0..31 (two per column) and the output conv is one more tensor-core product with A
+        // from TMEM:  P[pos][tap] = sum_c y[pos][c] * w4[tap][c]  -> columns 32..63; while it completes the group
+        // already works on its second accumulator (software pipelined), then stores P (f32, 32 per position).
+        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int m = warp >= 8 ? 1 : 0;        // epilogue warpgroup = M tile
         const int r = q * 32 + lane;            // accumulator row: r = (h*2 + sample)*8 + w
         const int h = r >> 4, bl = (r >> 3) & 1, wq = r & 7;
         HT* out = reinterpret_cast<HT*>(args.out);
         const int H2 = 16, W2 = 16, T2 = 2 * T;
+        constexpr uint32_t kF = HalfOps<HT>::kFmt;
+        constexpr uint32_t idesc_p = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t wd = make_sdesc(smem_u32(w4_tile));
         uint32_t acc_it = 0, p_it = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int b = unit * 2 + bl;
@@ -268,83 +270,76 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                 for (int pass = 0; pass < 4; ++pass, ++acc_it) {
                     const int pt = pass >> 1, ph = pass & 1;
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                    mbar_wait(&acc_full[as], aph);
+                    mbar_wait(&acc_full[as * 2 + m], aph);
                     tc_fence_after();
+                    const size_t o_row = (((size_t)b * T2 + (2 * (2 * sup + m) + pt)) * H2 + (2 * h + ph)) * W2 + 2 * wq;
+                    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccCols + m * 128;
+                    if (!(args.dbg & 1)) {
 #pragma unroll 1
-                    for (int a = 0; a < 4; ++a) {
-                        const int m = a >> 1, pw = a & 1;
-                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccCols + a * 64;
-                        float ss = 0.f;
-#pragma unroll 1
-                        for (int c0 = 0; c0 < 64; c0 += 32) {
-                            uint32_t v[32];
-                            tc_ld32(taddr + c0, v);
+                        for (int pw = 0; pw < 2; ++pw) {
+                            const uint32_t taddr = lane_base + pw * 64;
+                            uint32_t v0[32], v1[32];
+                            tc_ld32_nowait(taddr, v0);
+                            tc_ld32_nowait(taddr + 32, v1);
+                            tc_ld_wait();
+                            float ss = 0.f;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                float x = __uint_as_float(v[j]) + s_bias[c0 + j];
-                                ss = fmaf(x, x, ss);
+                                const float x0 = __uint_as_float(v0[j]) + s_bias[j], x1 = __uint_as_float(v1[j]) + s_bias[32 + j];
+                                v0[j] = __float_as_uint(x0); v1[j] = __float_as_uint(x1);
+                                ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
                             }
-                        }
-                        const float inv = 1.0f / sqrtf(ss * (1.0f / 64) + 1.0e-8f);
-                        const size_t o_pos = (((size_t)b * T2 + (2 * (2 * sup + m) + pt)) * H2 + (2 * h + ph)) * W2 + (2 * wq + pw);
-#pragma unroll 1
-                        for (int c0 = 0; c0 < 64; c0 += 32) {
-                            uint32_t v[32];
-                            tc_ld32(taddr + c0, v);
-                            uint32_t pk[16];
+                            const float inv = 1.0f / sqrtf(ss * (1.0f / 64) + 1.0e-8f);
+                            uint32_t pk[32];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                float x0 = (__uint_as_float(v[2 * j]) + s_bias[c0 + 2 * j]) * inv;
-                                float x1 = (__uint_as_float(v[2 * j + 1]) + s_bias[c0 + 2 * j + 1]) * inv;
-                                x0 = x0 > 0.f ? x0 : 0.2f * x0;
-                                x1 = x1 > 0.f ? x1 : 0.2f * x1;
-                                pk[j] = HalfOps<HT>::pack(x0, x1);
+                                float a0 = __uint_as_float(v0[2 * j]) * inv, a1 = __uint_as_float(v0[2 * j + 1]) * inv;
+                                float c0 = __uint_as_float(v1[2 * j]) * inv, c1 = __uint_as_float(v1[2 * j + 1]) * inv;
+                                a0 = a0 > 0.f ? a0 : 0.2f * a0; a1 = a1 > 0.f ? a1 : 0.2f * a1;
+                                c0 = c0 > 0.f ? c0 : 0.2f * c0; c1 = c1 > 0.f ? c1 : 0.2f * c1;
+                                pk[j] = HalfOps<HT>::pack(a0, a1);
+                                pk[16 + j] = HalfOps<HT>::pack(c0, c1);
                             }
                             if (fuse) {
-                                // row r of the K-major SWIZZLE_128B tile: 16-byte chunk j lives at chunk (j ^ (r & 7))
-                                uint8_t* yrow = y_tile + r * 128;
+                                tc_st32(taddr, pk);                        // y as the A operand of the tap product
+                                tc_fence_before();
+                                asm volatile("bar.sync %0, 128;" ::"r"(1 + m) : "memory");
+                                if (q == 0 && !(args.dbg & 2)) {
+                                    tc_fence_after();
+                                    if (elect_one()) {
+                                        const uint32_t a_t = tmem_base + as * kAccCols + m * 128 + pw * 64;   // lane 0
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    *reinterpret_cast<uint4*>(yrow + ((((c0 >> 3) + j) ^ (r & 7)) << 4)) =
-                                        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                                        for (int k = 0; k < 4; ++k) tc_mma_f16_ts(a_t + 32, a_t + 8 * k, wd + 2 * k, idesc_p, k > 0 ? 1u : 0u);
+                                        tc_commit(&p_full[m * 2 + pw]);
+                                    }
+                                    __syncwarp();
+                                }
                             } else if (valid) {
-                                uint4* dst = reinterpret_cast<uint4*>(out + o_pos * 64 + c0);
+                                uint4* dst = reinterpret_cast<uint4*>(out + (o_row + pw) * 64);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
+                                for (int j = 0; j < 8; ++j)
                                     dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                             }
                         }
-                        if (fuse) {
-                            // all 128 rows of y written and all reads of this accumulator done
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            tc_fence_before();
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
-                            if (warp == 3 && elect_one()) {
+                        if (fuse && !(args.dbg & 2)) {
+#pragma unroll 1
+                            for (int pw = 0; pw < 2; ++pw) {
+                                mbar_wait(&p_full[m * 2 + pw], p_it & 1);
                                 tc_fence_after();
-                                constexpr uint32_t kF = HalfOps<HT>::kFmt;
-                                constexpr uint32_t idesc_p = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(32 >> 3) << 17) |
-                                                             ((uint32_t)(128 >> 4) << 24);
-                                const uint64_t yd = make_sdesc(smem_u32(y_tile)), wd = make_sdesc(smem_u32(w4_tile));
-                                const uint32_t d_p = tmem_base + as * kAccCols + a * 64;   // reuse the consumed accumulator
+                                uint32_t pv[32];
+                                tc_ld32(lane_base + pw * 64 + 32, pv);
+                                if (valid) {
+                                    uint4* dst = reinterpret_cast<uint4*>(args.p_out + (o_row + pw) * 32);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) tc_mma_f16(d_p, yd + 2 * k, wd + 2 * k, idesc_p, k > 0 ? 1u : 0u);
-                                tc_commit(p_full);
-                            }
-                            mbar_wait(p_full, p_it & 1);
-                            ++p_it;
-                            tc_fence_after();
-                            uint32_t pv[32];
-                            tc_ld32(taddr, pv);
-                            if (valid) {
-                                uint4* dst = reinterpret_cast<uint4*>(args.p_out + o_pos * 32);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    dst[j] = make_uint4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+                                    for (int j = 0; j < 8; ++j)
+                                        dst[j] = make_uint4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+                                }
                             }
                         }
                     }
+                    ++p_it;
                     tc_fence_before();
-                    mbar_arrive(&acc_empty[as]);
+                    mbar_arrive(&acc_empty[as * 2 + m]);
                 }
         }
     }
@@ -384,6 +379,8 @@ int launch_planes(const void* x, const void* wpack, const float* bias, void* y, 
     TcConvArgs a{};
     a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin;
     a.wpack = wpack; a.bias = bias; a.out = y; a.w4tile = w4tile; a.p_out = p_out;
+    static const int dbg = getenv("RDG_DBG") ? atoi(getenv("RDG_DBG")) : 0;
+    a.dbg = dbg;
 
     // tensor dims ordered (C, W, B, H, T) so that the box lands as [h'][sample][w'][64 ch] rows
     CUtensorMap tmap;
