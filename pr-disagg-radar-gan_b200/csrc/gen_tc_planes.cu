@@ -49,7 +49,7 @@ constexpr int kBStage = 16384;                  // two [64 x 64] weight tiles
 constexpr int kBStages = 6;
 constexpr int kStagesPerPass = 16;
 constexpr int kW4Tile = 4096;
-constexpr int kSmem = 1024 + kBStages * kBStage + kW4Tile + kARegion + 64 * 4 + 256;
+constexpr int kSmem = 1024 + kBStages * kBStage + kW4Tile + kARegion + 256;
 static_assert(kSmem <= 227 * 1024, "shared memory overflow");
 constexpr int kAccCols = 256;
 constexpr uint32_t kSboA = kWp * kRow;          // 8-row group stride of an activation view
@@ -71,8 +71,8 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
     uint8_t* b_buf = smem;
     uint8_t* w4_tile = b_buf + kBStages * kBStage;
     uint8_t* a_reg = w4_tile + kW4Tile;
-    float* s_bias = reinterpret_cast<float*>(a_reg + kARegion);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+    __shared__ float s_bias[64];                 // static: read with LDS, not generic loads
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_reg + kARegion);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + kSlots;
     uint64_t* b_full = a_empty + kSlots;
