@@ -146,9 +146,10 @@ def _bf16(x):
 def generator_forward_folded(weights, latent, cond, dtype=torch.float32, emulate_bf16=False,
                              return_logits=False):
     """Same function computed with the upsample fold; optional emulation of the BF16
-    tensor-core mode's rounding points (dense fp32 -> bf16 activations; folded weights
-    rounded once to bf16; fp32 accumulate, PixelNorm/LeakyReLU in fp32, activations
-    stored bf16; last conv + softmax in fp32 on the bf16 activations).
+    tensor-core mode's rounding points (dense inputs and kernel rounded to bf16, fp32
+    accumulate, bf16 activations; folded weights rounded once to bf16; fp32 accumulate,
+    PixelNorm/LeakyReLU in fp32, activations stored bf16; last conv with bf16 weights on the
+    bf16 activations, fp32 accumulate; softmax in fp32).
     """
     w = [_t(a, dtype) for a in weights]
     z = _t(latent, dtype)
@@ -157,11 +158,11 @@ def generator_forward_folded(weights, latent, cond, dtype=torch.float32, emulate
     s = nd // 8
     q = _bf16 if emulate_bf16 else (lambda t: t)
     x = torch.cat([z, c.reshape(B, -1)], dim=1)
-    x = q(lrelu(x @ w[0] + w[1])).reshape(B, 3, s, s, 256)
+    x = q(lrelu(q(x) @ q(w[0]) + w[1])).reshape(B, 3, s, s, 256)
     for i in (2, 4, 6):
         kf = q(fold_upsample_conv(w[i]))
         x = q(lrelu(pixel_norm(_folded_layer(x, kf, w[i + 1]))))
-    logits = _conv3d_keras(x, w[8], w[9], 1, "same")
+    logits = _conv3d_keras(x, q(w[8]), w[9], 1, "same")
     out = torch.softmax(logits, dim=1)
     if return_logits:
         return out.numpy(), logits.numpy()

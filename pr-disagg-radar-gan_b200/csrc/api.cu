@@ -119,6 +119,8 @@ extern "C" int rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int 
     {
         const char* e = getenv("RDG_CONV3");
         c->conv3_planes = nd == 16 && !(e && strcmp(e, "tiles") == 0);
+        const char* e2 = getenv("RDG_DENSE");
+        c->dense_tc = nd == 16 && ncond == 1 && !(e2 && strcmp(e2, "simt") == 0);
     }
     gen_shapes(c, c->g_size);
     critic_shapes(c, c->c_size);
@@ -161,7 +163,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     cudaFree(c->g_grads); cudaFree(c->g_m); cudaFree(c->g_v);
     cudaFree(c->c_grads); cudaFree(c->c_m); cudaFree(c->c_v);
     for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) cudaFree(c->g_wpack[k][l]);
-    for (int k = 0; k < 2; ++k) { cudaFree(c->g_w4pack[k]); cudaFree(c->g_wpack_planes[k]); }
+    for (int k = 0; k < 2; ++k) { cudaFree(c->g_w4pack[k]); cudaFree(c->g_wpack_planes[k]); cudaFree(c->g_wpack_dense[k]); }
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->e2e_lat[i]); cudaFree(c->e2e_out[i]);
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
@@ -209,6 +211,12 @@ int rdg_repack_generator(rdg_ctx* c, cudaStream_t st) {
         if (c->conv3_planes) {
             if (!c->g_wpack_planes[k]) RDG_CUDA(cudaMalloc(&c->g_wpack_planes[k], (size_t)64 * 128 * 64 * 2));
             int r2 = pack_folded_weights_planes(hk, c->g_params + c->g_off[6], c->g_wpack_planes[k], st);
+            if (r2) return r2;
+            c->launches += 1;
+        }
+        if (c->dense_tc) {
+            if (!c->g_wpack_dense[k]) RDG_CUDA(cudaMalloc(&c->g_wpack_dense[k], tc_dense_pack_bytes()));
+            int r2 = pack_dense_weights(hk, c->g_params + c->g_off[0], c->g_wpack_dense[k], st);
             if (r2) return r2;
             c->launches += 1;
         }
@@ -311,13 +319,18 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
     const ConvGeom dg = rdg_gen_dense_geom(c, n);
     uint8_t* p = reinterpret_cast<uint8_t*>(c->ws);
     auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) / 256 * 256; return r; };
-    float* x0 = (float*)take((size_t)n * dg.Ci * 4);
-    float* d0 = (float*)take((size_t)n * dg.Co * 4);
     int r;
-    { ProfScope ps(c, st, 0, n, 1);
-      if ((r = ew_assemble_gen_input(latent, cond, spc, b_off, x0, n, nd * nd * c->ncond, st))) return r; }
-    { ProfScope ps(c, st, 1, n, 1);
-      if ((r = simt_conv_fwd(x0, c->g_params + c->g_off[0], c->g_params + c->g_off[1], d0, dg, ACT_LRELU, nullptr, 1.f, st))) return r; }
+    float* x0 = nullptr;
+    float* d0 = nullptr;
+    const bool front_tc = mode != RDG_MODE_FP32 && c->dense_tc;
+    if (!front_tc) {
+        x0 = (float*)take((size_t)n * dg.Ci * 4);
+        d0 = (float*)take((size_t)n * dg.Co * 4);
+        { ProfScope ps(c, st, 0, n, 1);
+          if ((r = ew_assemble_gen_input(latent, cond, spc, b_off, x0, n, nd * nd * c->ncond, st))) return r; }
+        { ProfScope ps(c, st, 1, n, 1);
+          if ((r = simt_conv_fwd(x0, c->g_params + c->g_off[0], c->g_params + c->g_off[1], d0, dg, ACT_LRELU, nullptr, 1.f, st))) return r; }
+    }
     const float* w4 = c->g_params + c->g_off[8];
     const float* b4 = c->g_params + c->g_off[9];
     if (mode == RDG_MODE_FP32) {
@@ -337,8 +350,13 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
     }
     const int hk = mode == RDG_MODE_BF16 ? RDG_HALF_BF16 : RDG_HALF_FP16;
     void* h = take((size_t)n * gen_act_elems(c, 0) * 2);
-    { ProfScope ps(c, st, 2, n, 1);
-      if ((r = f32_to_half(hk, d0, h, (long long)n * dg.Co, st))) return r; }
+    if (front_tc) {
+        ProfScope ps(c, st, 1, n, 1);
+        if ((r = tc_dense_lrelu(hk, latent, cond, spc, b_off, c->g_wpack_dense[hk == RDG_HALF_BF16 ? 0 : 1], c->g_params + c->g_off[1], h, n, st))) return r;
+    } else {
+        ProfScope ps(c, st, 2, n, 1);
+        if ((r = f32_to_half(hk, d0, h, (long long)n * dg.Co, st))) return r;
+    }
     static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
     const int wk = hk == RDG_HALF_BF16 ? 0 : 1;
     float* pbuf = nullptr;

@@ -44,3 +44,10 @@ int pack_w4_tile(int half_kind, const float* k4, void* dst, cudaStream_t st);
 int tc_upconv64_planes(int half_kind, const void* x, const void* wpack_planes, const float* bias, void* y, const void* w4tile,
                        float* p_out, int B, int T, int sm_count, cudaStream_t st);
 int pack_folded_weights_planes(int half_kind, const float* k, void* dst, cudaStream_t st);
+
+// Fused Concatenate + Dense(3072) + LeakyReLU on tcgen05 (nd == 16, ncond == 1 only), gen_dense_tc.cu:
+// out[B,3072] 16-bit = lrelu([latent | cond[(b_off+b)/spc]] @ W + bias); wpack from pack_dense_weights.
+int tc_dense_lrelu(int half_kind, const float* latent, const float* cond, int spc, int b_off, const void* wpack,
+                   const float* bias, void* out, int B, cudaStream_t st);
+size_t tc_dense_pack_bytes();
+int pack_dense_weights(int half_kind, const float* w, void* dst, cudaStream_t st);
