@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int a_off, int sbo,
         long long t0 = clock64();
         for (int r = 0; r < reps; ++r) {
             const uint32_t d = tmem_base + (uint32_t)((r % ndst) * dst_stride) + (uint32_t)(iw * 256);
-            const uint64_t ad = make_sdesc(smem_u32(a_buf) + a_off + ((a_alt && (r & 1)) ? 23040 : 0), sbo);
+            const uint64_t ad = make_sdesc(smem_u32(a_buf) + a_off + ((a_alt && (r & 1)) ? 23040 : 0) + ((a_alt & 2) ? iw * 23040 : 0), sbo);
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc_mma_f16(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
         }
@@ -89,6 +89,9 @@ int main() {
         {64, sh, 1152, 2, 64, 0, "N=64  shifted 2 issuer warps", 2},
         {128, sh, 1152, 2, 128, 0, "N=128 shifted 2 issuer warps", 2},
         {256, sh, 1152, 1, 0, 0, "N=256 shifted 2 issuer warps", 2},
+        {64, sh, 1152, 2, 64, 2, "N=64  2 issuers, different A", 2},
+        {128, sh, 1152, 2, 128, 2, "N=128 2 issuers, different A", 2},
+        {64, 0, 1024, 2, 64, 2, "N=64  2 issuers, diff A, aligned", 2},
         {64, sh, 1152, 2, 64, 0, "N=64  M=64 shifted", 1, 64},
         {128, sh, 1152, 2, 128, 0, "N=128 M=64 shifted", 1, 64},
         {256, sh, 1152, 1, 0, 0, "N=256 M=64 shifted", 1, 64},
