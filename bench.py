@@ -115,6 +115,13 @@ def cpu_reference_rate(n_cond, spc, threads, reps=1):
     return n_cond * spc / best, best
 
 
+def workload_config(n_cond, spc):
+    """config block shared by both arms: the reference arm times a bounded sample of the SAME workload."""
+    return {"workload": f"ensemble generation: {n_cond} synthetic gamma(0.8,12) daily-sum 16x16 conditions x "
+                        f"{spc} scenarios per GPU, seeded random-init generator (pretrained .h5 not shipped)",
+            "scenarios_per_step_per_gpu": n_cond * spc}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -132,8 +139,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "scenarios/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ensemble generation: 10k synthetic daily-sum 16x16 conditions x 100 scenarios, "
-                                   "seeded random-init generator", "sample": sample},
+            "config": dict(workload_config(args.conditions, args.scen_per_cond), sample=sample,
+                           note="each step is a bounded sample of the workload; rate = sample scenarios / sample time"),
             "cpu_baseline": {"value": value, "unit": "scenarios/s", "cores": threads, "kind": "port", "sample": sample,
                              "note": "torch-CPU FP32 restatement of the Keras generator; TensorFlow is not installed"},
             "e2e": {"value": value, "unit": "scenarios/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -318,11 +325,9 @@ def main():
                                            "bf16": "bf16 operands, f32 accumulate (tcgen05 kind::f16)",
                                            "fp32": "f32"}[args.mode],
             "data": "synthetic",
-            "config": {"workload": f"ensemble generation: {n_cond} synthetic gamma(0.8,12) daily-sum 16x16 conditions x "
-                                   f"{spc} scenarios per GPU, seeded random-init generator (pretrained .h5 not shipped)",
-                       "scenarios_per_step_per_gpu": B, "chunk": ctx.max_chunk, "mode": args.mode,
+            "config": dict(workload_config(n_cond, spc), **{"chunk": ctx.max_chunk, "mode": args.mode,
                        "l2": "inputs (410 MB latent+cond) and outputs (24.6 GB) per step exceed the 126 MB L2",
-                       "parallelism": f"shard{world}-independent"},
+                       "parallelism": f"shard{world}-independent"}),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "conservation_rel_err": cons}
     print(json.dumps(line), flush=True)
