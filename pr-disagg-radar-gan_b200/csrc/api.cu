@@ -119,6 +119,7 @@ extern "C" int rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int 
     {
         const char* e = getenv("RDG_CONV3");
         c->conv3_planes = nd == 16 && !(e && strcmp(e, "tiles") == 0);
+        c->conv3_logits = !(e && strcmp(e, "planes_p") == 0);   // planes_p: tap products through HBM + gather kernel
         const char* e2 = getenv("RDG_DENSE");
         c->dense_tc = nd == 16 && ncond == 1 && !(e2 && strcmp(e2, "simt") == 0);
     }
@@ -220,11 +221,11 @@ int rdg_repack_generator(rdg_ctx* c, cudaStream_t st) {
             if (r2) return r2;
             c->launches += 1;
         }
-        if (!c->g_w4pack[k]) RDG_CUDA(cudaMalloc(&c->g_w4pack[k], 32 * 64 * 2));
+        if (!c->g_w4pack[k]) RDG_CUDA(cudaMalloc(&c->g_w4pack[k], RDG_W4PACK_BYTES));
         int r = pack_w4_tile(hk, c->g_params + c->g_off[8], c->g_w4pack[k], st);
         if (r) return r;
     }
-    c->launches += 8;
+    c->launches += 10;
     c->gen_packed_stale = false;
     return 0;
 }
@@ -360,15 +361,17 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
     static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
     const int wk = hk == RDG_HALF_BF16 ? 0 : 1;
     float* pbuf = nullptr;
+    // resident-plane kernel: the output conv is summed on chip, `out` carries the fixed-point logits to the softmax
+    const bool logits_on_chip = c->conv3_planes && c->conv3_logits;
     for (int l = 0; l < 3; ++l) {
         const int f = 1 << l;
         void* y = nullptr;
         if (l < 2) y = take((size_t)n * gen_act_elems(c, l + 1) * 2);
-        else pbuf = (float*)take((size_t)n * gen_act_elems(c, 3) / 64 * 32 * 4);
+        else if (!logits_on_chip) pbuf = (float*)take((size_t)n * gen_act_elems(c, 3) / 64 * 32 * 4);
         { ProfScope ps(c, st, 3 + l, n, 1);
           if (l == 2 && c->conv3_planes)
-              r = tc_upconv64_planes(hk, h, c->g_wpack_planes[wk], c->g_params + c->g_off[7], nullptr, c->g_w4pack[wk], pbuf, n,
-                                     3 * f, c->sm_count, st);
+              r = tc_upconv64_planes(hk, h, c->g_wpack_planes[wk], c->g_params + c->g_off[7], nullptr, c->g_w4pack[wk], pbuf,
+                                     logits_on_chip ? reinterpret_cast<int*>(out) : nullptr, flag, n, 3 * f, c->sm_count, st);
           else
               r = tc_upconv_pixelnorm(hk, h, c->g_wpack[wk][l], c->g_params + c->g_off[3 + 2 * l], y,
                                       l == 2 ? c->g_w4pack[wk] : nullptr, l == 2 ? pbuf : nullptr, n,
@@ -377,6 +380,8 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
         h = y;
     }
     ProfScope ps(c, st, 6, n, 1);
+    if (logits_on_chip)
+        return softmax_fixed_inplace(out, c->g_w4pack[wk], b4, cond, n, spc, b_off, c->ncond, norm_scale, out_kind == RDG_OUT_MM, flag, st);
     return gather_softmax(pbuf, b4, out, cond, n, nd, spc, b_off, c->ncond, norm_scale, out_kind == RDG_OUT_MM, flag, st);
 }
 
@@ -531,7 +536,7 @@ extern "C" int rdg_tc_layer(rdg_ctx* c, int layer, int mode, const float* x_dev,
     if ((r = f32_to_half(hk, x_dev, xin, (long long)n_in, st))) return r;
     const int wk = hk == RDG_HALF_BF16 ? 0 : 1;
     if (layer == 2 && c->conv3_planes)
-        r = tc_upconv64_planes(hk, xin, c->g_wpack_planes[wk], c->g_params + c->g_off[7], yout, nullptr, nullptr, B, 3 * f, c->sm_count, st);
+        r = tc_upconv64_planes(hk, xin, c->g_wpack_planes[wk], c->g_params + c->g_off[7], yout, nullptr, nullptr, nullptr, nullptr, B, 3 * f, c->sm_count, st);
     else
         r = tc_upconv_pixelnorm(hk, xin, c->g_wpack[wk][layer], c->g_params + c->g_off[3 + 2 * layer], yout,
                                 nullptr, nullptr, B, 3 * f, s * f, s * f, cin[layer], cout[layer], c->sm_count, st);

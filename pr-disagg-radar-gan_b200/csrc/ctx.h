@@ -15,6 +15,7 @@ struct rdg_ctx {
     void* g_wpack[2][3] = {};
     void* g_wpack_planes[2] = {};   // 128 -> 64 layer in the stage order of the resident-plane kernel (nd == 16 only)
     bool conv3_planes = false;      // nd == 16 and not disabled by RDG_CONV3=tiles
+    bool conv3_logits = true;       // planes kernel sums the output conv on chip (RDG_CONV3=planes_p: P through HBM)
     void* g_wpack_dense[2] = {};    // Dense kernel as tcgen05 B tiles (nd == 16, ncond == 1 only)
     bool dense_tc = false;
     void* g_w4pack[2] = {};   // output conv as a [32 taps x 64 ch] swizzled 16-bit B tile

@@ -759,7 +759,68 @@ __global__ void pack_w4_kernel(const float* __restrict__ k4, HT* __restrict__ ds
     const int j = (pos >> 3) ^ (n & 7), e = pos & 7;
     dst[idx] = HalfOps<HT>::from_float(n < 27 ? k4[n * 64 + j * 8 + e] : 0.f);
 }
+// Fixed-point scale of the on-chip output-conv sum (gen_tc_planes.cu): |sum_k P_k| <= sum_k |y|_2 |w_k|_2 and
+// PixelNorm bounds |y|_2 <= sqrt(64) = 8, so 2 * 8 * sum_k |w_k|_2 (2x margin for the 16-bit roundings) bounds every
+// partial sum; scale = largest power of two keeping that below 2^31.
+__global__ void w4_scale_kernel(const float* __restrict__ k4, float* __restrict__ dst) {
+    float s = 0.f;
+    for (int tap = 0; tap < 27; ++tap) {
+        float q = 0.f;
+        for (int c = threadIdx.x; c < 64; c += 32) q += k4[tap * 64 + c] * k4[tap * 64 + c];
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        s += sqrtf(q);
+    }
+    if (threadIdx.x == 0) {
+        const float bound = 16.f * s;
+        int e = 20;
+        if (bound > 0.f && bound < INFINITY) {
+            e = 30 - (int)ceilf(log2f(bound));
+            e = e > 30 ? 30 : (e < -60 ? -60 : e);
+        }
+        dst[0] = exp2f((float)e);
+        dst[1] = exp2f((float)-e);
+    }
+}
+
+// One thread per (sample, pixel): the 24 fixed-point logits of the pixel -> softmax over the hours, in place.
+__global__ void __launch_bounds__(256)
+softmax_fixed_kernel(float* __restrict__ out, const float* __restrict__ scales, const float* __restrict__ b4,
+                     const float* __restrict__ cond, int spc, int b_off, int ncond, float norm_scale, int out_mm,
+                     int* __restrict__ nonfinite) {
+    const int b = blockIdx.x, px = threadIdx.x;
+    const float inv = scales[1], bias = b4[0];
+    float* ob = out + (size_t)b * RDG_NHOURS * 256 + px;
+    float v[RDG_NHOURS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) {
+        v[t] = (float)__float_as_int(ob[t * 256]) * inv + bias;
+        mx = fmaxf(mx, v[t]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) { v[t] = expf(v[t] - mx); s += v[t]; }
+    float mul = 1.f;
+    if (out_mm) mul = cond[((size_t)((b_off + b) / spc) * 256 + px) * ncond] * norm_scale;
+    bool bad = false;
+#pragma unroll
+    for (int t = 0; t < RDG_NHOURS; ++t) {
+        const float f = v[t] / s;
+        bad |= !isfinite(f);
+        ob[t * 256] = f * mul;
+    }
+    if (bad && nonfinite) atomicOr(nonfinite, 1);
+}
 }  // namespace
+
+int softmax_fixed_inplace(float* out, const void* w4tile, const float* b4, const float* cond, int B, int spc, int b_off,
+                          int ncond, float norm_scale, int out_mm, int* nonfinite, cudaStream_t st) {
+    if (B <= 0) return 0;
+    const float* scales = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(w4tile) + 32 * 64 * 2);
+    softmax_fixed_kernel<<<B, 256, 0, st>>>(out, scales, b4, cond, spc, b_off, ncond, norm_scale, out_mm, nonfinite);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
 
 int pack_folded_weights(int half_kind, const float* k, void* dst, int Cin, int Cout, cudaStream_t st) {
     const long long total = (long long)64 * Cin * Cout;
@@ -773,6 +834,8 @@ int pack_folded_weights(int half_kind, const float* k, void* dst, int Cin, int C
 int pack_w4_tile(int half_kind, const float* k4, void* dst, cudaStream_t st) {
     if (half_kind == RDG_HALF_BF16) pack_w4_kernel<__nv_bfloat16><<<8, 256, 0, st>>>(k4, (__nv_bfloat16*)dst);
     else pack_w4_kernel<__half><<<8, 256, 0, st>>>(k4, (__half*)dst);
+    RDG_LAUNCH_CHECK();
+    w4_scale_kernel<<<1, 32, 0, st>>>(k4, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dst) + 32 * 64 * 2));
     RDG_LAUNCH_CHECK();
     return 0;
 }

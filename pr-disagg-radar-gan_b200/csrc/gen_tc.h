@@ -20,6 +20,8 @@ struct TcConvArgs {
     void* out;          // [B,2T,2H,2W,Cout] 16-bit (unused when the output conv is fused)
     const void* w4tile; // fused output conv: [32 taps x 64 ch] 16-bit swizzled tile (taps >= 27 zero)
     float* p_out;       // fused output conv: [B,2T,2H,2W,32] f32 per-tap partial products
+    int* logit_out;     // planes kernel only: fused output conv summed on chip -> [B,2T,16,16] fixed-point logits (no bias)
+    int* nonfinite;     // planes kernel, logit mode: set to 1 if any activation is Inf / NaN
     int dbg;            // experiments only (RDG_DBG): 1 = epilogue does not touch TMEM, 2 = no output-conv MMA, 4 = skip N=64 MMAs
 };
 
@@ -40,9 +42,14 @@ int pack_folded_weights(int half_kind, const float* k, void* dst, int Cin, int C
 int pack_w4_tile(int half_kind, const float* k4, void* dst, cudaStream_t st);
 
 // Resident-plane kernel for the 128 -> 64 layer on an 8x8 low-res grid (ndomain 16), gen_tc_planes.cu.
-// y (16-bit, [B,2T,16,16,64]) or, if p_out != null, the fused output-conv tap products P.
+// y (16-bit, [B,2T,16,16,64]) or, if p_out != null, the fused output-conv tap products P, or, if logit_out != null,
+// the output-conv logits (without bias) as int32 fixed point with the scale pack_w4_tile stored behind the w4 tile.
 int tc_upconv64_planes(int half_kind, const void* x, const void* wpack_planes, const float* bias, void* y, const void* w4tile,
-                       float* p_out, int B, int T, int sm_count, cudaStream_t st);
+                       float* p_out, int* logit_out, int* nonfinite, int B, int T, int sm_count, cudaStream_t st);
+// in place: out[B,24,256] int32 fixed-point logits -> softmax over the hours of (v / scale + b) (* cond * norm_scale)
+int softmax_fixed_inplace(float* out, const void* w4tile, const float* b4, const float* cond, int B, int spc, int b_off,
+                          int ncond, float norm_scale, int out_mm, int* nonfinite, cudaStream_t st);
+#define RDG_W4PACK_BYTES (32 * 64 * 2 + 16)   // swizzled tile + {fixed-point scale, 1/scale} (f32)
 int pack_folded_weights_planes(int half_kind, const float* k, void* dst, cudaStream_t st);
 
 // Fused Concatenate + Dense(3072) + LeakyReLU on tcgen05 (nd == 16, ncond == 1 only), gen_dense_tc.cu:

@@ -46,10 +46,17 @@ constexpr int kSlots = 3;                       // resident planes
 constexpr int kChunks = 2;                      // Cin = 128
 constexpr int kARegion = ((kSlots * kChunks * kBufBytes + (kLine + 1) * kRow) + 1023) / 1024 * 1024;
 constexpr int kBStage = 16384;                  // two [64 x 64] weight tiles
-constexpr int kBStages = 6;
+constexpr int kBStages = 5;
 constexpr int kStagesPerPass = 16;
 constexpr int kW4Tile = 4096;
-constexpr int kSmem = 1024 + kBStages * kBStage + kW4Tile + kARegion + 256;
+// Fused-logit mode: rolling ring of 8 output hours, fixed-point int32 logits of the sample pair.
+// word = slot * kRingPlane + h * kRingPitch + w * 2 + sample; pitch 33 makes the scatter of a warp
+// (lanes = 8 w x 2 samples x 2 h) hit 32 distinct banks.
+constexpr int kRingPitch = 33;
+constexpr int kRingPlane = 16 * kRingPitch;
+constexpr int kRingSlots = 8;
+constexpr int kRingBytes = kRingSlots * kRingPlane * 4;
+constexpr int kSmem = 1024 + kBStages * kBStage + kW4Tile + kARegion + 256 + kRingBytes;
 static_assert(kSmem <= 227 * 1024, "shared memory overflow");
 constexpr int kAccCols = 256;
 constexpr uint32_t kSboA = kWp * kRow;          // 8-row group stride of an activation view
@@ -81,17 +88,20 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
     uint64_t* acc_empty = acc_full + 4;          // [stage 2][M tile 2]
     uint64_t* p_full = acc_empty + 4;            // [M tile 2][w-phase 2]: one commit and one wait per pass each
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 4);
+    int* ring = reinterpret_cast<int*>(a_reg + kARegion + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = args.T, n_super = T / 2;
     const int n_units = (args.B + 1) / 2;
-    const bool fuse = args.p_out != nullptr;
+    const bool logit_mode = args.logit_out != nullptr;          // output conv accumulated on chip (fixed point)
+    const bool fuse = args.p_out != nullptr || logit_mode;
 
     for (int i = threadIdx.x; i < 64; i += kThreads) s_bias[i] = args.bias[i];
     {
         // halo rows shared between buffers (and the row past the last line) must read as zero from the start
         uint4* z = reinterpret_cast<uint4*>(a_reg);
         for (int i = threadIdx.x; i < kARegion / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < kRingSlots * kRingPlane; i += kThreads) ring[i] = 0;
         if (fuse) {
             const uint4* src = reinterpret_cast<const uint4*>(args.w4tile);
             uint4* dst = reinterpret_cast<uint4*>(w4_tile);
@@ -263,6 +273,9 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
         constexpr uint32_t idesc_p = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t wd = make_sdesc(smem_u32(w4_tile));
         uint32_t acc_it = 0, p_it = 0;
+        const int et = threadIdx.x - 128;       // 0..255 over both epilogue groups
+        const float fx_scale = logit_mode ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(args.w4tile) + kW4Tile)[0] : 0.f;
+        bool bad = false;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int b = unit * 2 + bl;
             const bool valid = b < args.B;
@@ -290,6 +303,7 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                                 ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
                             }
                             const float inv = 1.0f / sqrtf(ss * (1.0f / 64) + 1.0e-8f);
+                            bad |= !(ss < INFINITY);                       // Inf / NaN anywhere upstream ends up in ss
                             uint32_t pk[32];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
@@ -328,7 +342,29 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                                 tc_fence_after();
                                 uint32_t pv[32];
                                 tc_ld32(lane_base + pw * 64 + 32, pv);
-                                if (valid) {
+                                if (logit_mode) {
+                                    // out[q] = sum_k P[q + (k - 1)][k]: this position feeds the 27 logits q = pos + 1 - k.
+                                    // Fixed-point integer adds: order independent, so results are bit-reproducible.
+                                    const int tq = 2 * (2 * sup + m) + pt, hq = 2 * h + ph, wq2 = 2 * wq + pw;
+                                    const uint32_t base = smem_u32(ring) + (uint32_t)(hq * kRingPitch + wq2 * 2 + bl) * 4u;
+#pragma unroll
+                                    for (int kt = 0; kt < 3; ++kt) {
+                                        const int to = tq + 1 - kt;
+                                        if (to < 0 || to >= T2) continue;            // warp-uniform
+                                        const uint32_t bt = base + (uint32_t)((to & (kRingSlots - 1)) * kRingPlane) * 4u;
+#pragma unroll
+                                        for (int kh = 0; kh < 3; ++kh) {
+                                            const bool ok_h = (unsigned)(hq + 1 - kh) < 16u;
+#pragma unroll
+                                            for (int kw = 0; kw < 3; ++kw) {
+                                                const bool ok_w = (unsigned)(wq2 + 1 - kw) < 16u;
+                                                const int v = __float2int_rn(__uint_as_float(pv[(kt * 3 + kh) * 3 + kw]) * fx_scale);
+                                                if (ok_h && ok_w)
+                                                    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(bt + (uint32_t)(((1 - kh) * kRingPitch + (1 - kw) * 2) * 4)), "r"(v) : "memory");
+                                            }
+                                        }
+                                    }
+                                } else if (valid) {
                                     uint4* dst = reinterpret_cast<uint4*>(args.p_out + (o_row + pw) * 32);
 #pragma unroll
                                     for (int j = 0; j < 8; ++j)
@@ -340,8 +376,27 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                     ++p_it;
                     tc_fence_before();
                     mbar_arrive(&acc_empty[as * 2 + m]);
+                    if (logit_mode && pass == 3) {
+                        // End of a super-tile (low-res planes 2sup, 2sup+1 = hours 4sup..4sup+3): hours up to 4sup+2 have
+                        // all their contributions.  Both epilogue groups flush them (raw fixed point; the softmax kernel
+                        // finishes in place) and clear the ring slots for reuse.
+                        asm volatile("bar.sync 3, 256;" ::: "memory");
+                        const int h_lo = sup == 0 ? 0 : 4 * sup - 1;
+                        const int h_hi = sup == n_super - 1 ? T2 - 1 : 4 * sup + 2;
+                        const int n = (h_hi - h_lo + 1) * 512;
+                        for (int i = et; i < n; i += 256) {
+                            const int hour = h_lo + (i >> 9), s2 = (i >> 8) & 1, pix = i & 255;
+                            int* rp = ring + (hour & (kRingSlots - 1)) * kRingPlane + (pix >> 4) * kRingPitch + (pix & 15) * 2 + s2;
+                            const int v = *rp;
+                            *rp = 0;
+                            const int bb = unit * 2 + s2;
+                            if (bb < args.B) args.logit_out[((size_t)bb * T2 + hour) * 256 + pix] = v;
+                        }
+                        asm volatile("bar.sync 3, 256;" ::: "memory");
+                    }
                 }
         }
+        if (bad && args.nonfinite) atomicOr(args.nonfinite, 1);
     }
 
     tc_fence_before();
@@ -370,15 +425,15 @@ EncodeTiledFn get_encode_fn() {
 }
 
 template <typename HT>
-int launch_planes(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
-                  int T, int sm_count, cudaStream_t st) {
+int launch_planes(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out,
+                  int* logit_out, int* nonfinite, int B, int T, int sm_count, cudaStream_t st) {
     constexpr int H = 8, W = 8, Cin = 128;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { rdg_set_error("cuTensorMapEncodeTiled entry point not available"); return RDG_TC_E_DRIVER; }
     if (T < 2 || (T & 1)) { rdg_set_error("tc planes: T must be even"); return RDG_TC_E_SHAPE; }
     TcConvArgs a{};
     a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin;
-    a.wpack = wpack; a.bias = bias; a.out = y; a.w4tile = w4tile; a.p_out = p_out;
+    a.wpack = wpack; a.bias = bias; a.out = y; a.w4tile = w4tile; a.p_out = p_out; a.logit_out = logit_out; a.nonfinite = nonfinite;
     static const int dbg = getenv("RDG_DBG") ? atoi(getenv("RDG_DBG")) : 0;
     a.dbg = dbg;
 
@@ -433,10 +488,11 @@ __global__ void pack_folded_planes_kernel(const float* __restrict__ k, HT* __res
 }  // namespace
 
 int tc_upconv64_planes(int half_kind, const void* x, const void* wpack, const float* bias, void* y, const void* w4tile,
-                       float* p_out, int B, int T, int sm_count, cudaStream_t st) {
+                       float* p_out, int* logit_out, int* nonfinite, int B, int T, int sm_count, cudaStream_t st) {
     if (B <= 0) return 0;
-    if (half_kind == RDG_HALF_BF16) return launch_planes<__nv_bfloat16>(x, wpack, bias, y, w4tile, p_out, B, T, sm_count, st);
-    return launch_planes<__half>(x, wpack, bias, y, w4tile, p_out, B, T, sm_count, st);
+    if (half_kind == RDG_HALF_BF16)
+        return launch_planes<__nv_bfloat16>(x, wpack, bias, y, w4tile, p_out, logit_out, nonfinite, B, T, sm_count, st);
+    return launch_planes<__half>(x, wpack, bias, y, w4tile, p_out, logit_out, nonfinite, B, T, sm_count, st);
 }
 
 int pack_folded_weights_planes(int half_kind, const float* k, void* dst, cudaStream_t st) {

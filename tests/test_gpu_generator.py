@@ -77,3 +77,36 @@ def test_device_forward_mm_scaling_and_conservation(gen):
         nz = want > 0
         assert np.max(np.abs(daily[nz] - want[nz]) / want[nz]) <= 1e-5
         assert np.all(out[:spc, :, :3, :3] == 0.0)
+
+
+def test_on_chip_output_conv_matches_tap_product_path(gen):
+    """The resident-plane kernel sums the fused Conv3D(64->1) on chip as int32 fixed point (order independent);
+    RDG_CONV3=planes_p keeps the earlier route (f32 tap products through HBM + gather kernel).  Same MMAs, so
+    the two differ only by the fixed-point quantum and f32 summation order; the on-chip path is bit-reproducible."""
+    import os
+    from rdg_b200.engine import Context, Generator
+    g, gw = gen
+    z, cond = _inputs(37, seed=23)
+    a1 = g.predict([z, cond], mode="fp16")
+    a2 = g.predict([z, cond], mode="fp16")
+    assert np.array_equal(a1, a2)
+    os.environ["RDG_CONV3"] = "planes_p"
+    try:
+        ctx = Context(16, 1, max_chunk=64)
+    finally:
+        os.environ.pop("RDG_CONV3", None)
+    try:
+        b = Generator(gw, ctx=ctx).predict([z, cond], mode="fp16")
+    finally:
+        ctx.close()
+    assert _rel(a1.astype(np.float64), b.astype(np.float64)) <= 5e-6
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_nonfinite_latent_is_flagged_in_tensor_core_modes(gen, mode):
+    from rdg_b200 import NonFiniteError
+    g, _ = gen
+    z, cond = _inputs(5, seed=3)
+    z[3, 7] = np.inf
+    with pytest.raises(NonFiniteError):
+        g.predict([z, cond], mode=mode)
