@@ -45,8 +45,8 @@ constexpr int kBoxBytes = 10 * kLine * kRow;    // 23040: what one TMA box write
 constexpr int kSlots = 3;                       // resident planes
 constexpr int kChunks = 2;                      // Cin = 128
 constexpr int kARegion = ((kSlots * kChunks * kBufBytes + (kLine + 1) * kRow) + 1023) / 1024 * 1024;
-constexpr int kBStage = 16384;                  // two [64 x 64] weight tiles
-constexpr int kBStages = 5;
+constexpr int kBStageFull = 16384;              // two [64 x 64] weight tiles (a CTA of a pair holds half of each)
+constexpr int kBBytes = 5 * kBStageFull;        // weight ring: 5 stages (CG = 1) / 10 stages (CG = 2)
 constexpr int kStagesPerPass = 16;
 constexpr int kW4Tile = 4096;
 // Fused-logit mode: rolling ring of 8 output hours, fixed-point int32 logits of the sample pair.
@@ -56,7 +56,7 @@ constexpr int kRingPitch = 33;
 constexpr int kRingPlane = 16 * kRingPitch;
 constexpr int kRingSlots = 8;
 constexpr int kRingBytes = kRingSlots * kRingPlane * 4;
-constexpr int kSmem = 1024 + kBStages * kBStage + kW4Tile + kARegion + 256 + kRingBytes;
+constexpr int kSmem = 1024 + kBBytes + kW4Tile + kARegion + 512 + kRingBytes;
 static_assert(kSmem <= 227 * 1024, "shared memory overflow");
 constexpr int kAccCols = 256;
 constexpr uint32_t kSboA = kWp * kRow;          // 8-row group stride of an activation view
@@ -70,13 +70,83 @@ __device__ __forceinline__ uint64_t make_sdesc_sbo(uint32_t saddr, uint32_t sbo)
     return d;
 }
 
-template <typename HT>
+// 2-CTA helpers (CG == 2): the CTA pair of a cluster shares every MMA (M = 256: 128 rows per CTA, each CTA's shared
+// memory holds its own activation planes and HALF of the rows of every weight tile), issued by the leader (rank 0).
+// Data barriers live in the leader: both CTAs' TMA loads complete on them (.cta_group::2 + mapa address); stage /
+// accumulator releases are multicast commits to both CTAs; the peer's epilogue signals the leader by remote arrives.
+// Primitives verified on values by tools/umma_2cta_probe.cu.
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+template <int CG> __device__ __forceinline__ void tc_commit_g(uint64_t* bar) {
+    if (CG == 1) tc_commit(bar);
+    else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                      ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int CG> __device__ __forceinline__ void tc_mma_g(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                           uint32_t accumulate) {
+    if (CG == 1) tc_mma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int CG> __device__ __forceinline__ void tc_mma_ts_g(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                              uint32_t accumulate) {
+    if (CG == 1) tc_mma_f16_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+    else asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_cg2(void* dst, const CUtensorMap* tmap, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* tmap, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+template <typename HT, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs args) {
+tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w, TcConvArgs args) {
+    constexpr int kBStage = kBStageFull / CG;       // bytes of a weight stage in THIS CTA's shared memory
+    constexpr int kBStages = kBBytes / kBStage;
+    const uint32_t rank = CG > 1 ? cluster_ctarank() : 0;
+    const bool leader = rank == 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* b_buf = smem;
-    uint8_t* w4_tile = b_buf + kBStages * kBStage;
+    uint8_t* w4_tile = b_buf + kBBytes;
     uint8_t* a_reg = w4_tile + kW4Tile;
     __shared__ float s_bias[64];                 // static: read with LDS, not generic loads
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_reg + kARegion);
@@ -87,8 +157,9 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
     uint64_t* acc_full = b_empty + kBStages;     // [stage 2][M tile 2]
     uint64_t* acc_empty = acc_full + 4;          // [stage 2][M tile 2]
     uint64_t* p_full = acc_empty + 4;            // [M tile 2][w-phase 2]: one commit and one wait per pass each
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 4);
-    int* ring = reinterpret_cast<int*>(a_reg + kARegion + 256);
+    uint64_t* y_ready = p_full + 4;              // CG == 2, leader: [M tile 2][w-phase 2], one arrive per CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_ready + 4);
+    int* ring = reinterpret_cast<int*>(a_reg + kARegion + 512);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = args.T, n_super = T / 2;
@@ -103,9 +174,10 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
         for (int i = threadIdx.x; i < kARegion / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < kRingSlots * kRingPlane; i += kThreads) ring[i] = 0;
         if (fuse) {
-            const uint4* src = reinterpret_cast<const uint4*>(args.w4tile);
+            // CG == 2: this CTA holds tap rows rank*16 .. rank*16+15 of the [32 x 64] tile (N = 32 split over the pair)
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(args.w4tile) + rank * (kW4Tile / CG));
             uint4* dst = reinterpret_cast<uint4*>(w4_tile);
-            for (int i = threadIdx.x; i < kW4Tile / 16; i += kThreads) dst[i] = src[i];
+            for (int i = threadIdx.x; i < kW4Tile / CG / 16; i += kThreads) dst[i] = src[i];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (TMA, MMA)
     }
@@ -113,33 +185,42 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
         for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 1);
         for (int i = 0; i < kSlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }     // both issuers release
         for (int i = 0; i < kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        // accumulator release: one arrive per CTA (elected thread after the epilogue group's named barrier)
+        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CG); mbar_init(&y_ready[i], CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG > 1) cluster_sync_all();              // the peer's barriers are initialised before any remote arrive / multicast
     tc_fence_after();
+    const int grp0 = blockIdx.x / CG, grp_stride = gridDim.x / CG;   // a group = CG consecutive units, one per CTA of the pair
+    const int n_groups = (n_units + CG - 1) / CG;
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ================= plane producer: one haloed box per plane and 64-channel chunk =================
         uint32_t li = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const int b0 = unit * 2;
+        for (int grp = grp0; grp < n_groups; grp += grp_stride) {
+            const int b0 = (grp * CG + (int)rank) * 2;            // may be >= B (odd tail): TMA zero-fills, epilogue masks
             for (int p = 0; p < T; ++p, ++li) {
                 const uint32_t s = li % kSlots, ph = (li / kSlots) & 1;
                 mbar_wait(&a_empty[s], ph ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&a_full[s], kChunks * kBoxBytes);
+                    if (leader) mbar_expect_tx(&a_full[s], CG * kChunks * kBoxBytes);      // bytes of both CTAs' planes
 #pragma unroll
-                    for (int c = 0; c < kChunks; ++c)   // tensor dims (C, W, B, H, T): w and h start at -1 (zero halo)
-                        tma_load_5d(a_reg + (s * kChunks + c) * kBufBytes, &tmap, &a_full[s], c * 64, -1, b0, -1, p);
+                    for (int c = 0; c < kChunks; ++c) {  // tensor dims (C, W, B, H, T): w and h start at -1 (zero halo)
+                        if (CG == 1) tma_load_5d(a_reg + (s * kChunks + c) * kBufBytes, &tmap, &a_full[s], c * 64, -1, b0, -1, p);
+                        else tma_load_5d_cg2(a_reg + (s * kChunks + c) * kBufBytes, &tmap, mapa_rank(smem_u32(&a_full[s]), 0), c * 64, -1, b0, -1, p);
+                    }
                 }
                 __syncwarp();
             }
@@ -148,35 +229,48 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
         // ================= weight producer: the 1 MB stage sequence of a super-tile, streamed in order =================
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(args.wpack);
         uint32_t bi = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x)
+        for (int grp = grp0; grp < n_groups; grp += grp_stride)
             for (int sup = 0; sup < n_super; ++sup)
                 for (int st = 0; st < 4 * kStagesPerPass; ++st, ++bi) {
                     const uint32_t s = bi % kBStages, ph = (bi / kBStages) & 1;
                     mbar_wait(&b_empty[s], ph ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(&b_full[s], kBStage);
-                        bulk_load_1d(b_buf + s * kBStage, wsrc + (size_t)st * kBStage, kBStage, &b_full[s]);
+                        if (leader) mbar_expect_tx(&b_full[s], kBStageFull);
+                        if (CG == 1) {
+                            bulk_load_1d(b_buf + s * kBStage, wsrc + (size_t)st * kBStageFull, kBStageFull, &b_full[s]);
+                        } else {
+                            // weight image as rows of 128 B, 128 rows per stage.  X stage (one N = 128 operand): this CTA's 64
+                            // rows are contiguous; Y stage (two N = 64 operands): 32 rows of each tile.
+                            const uint32_t bar = mapa_rank(smem_u32(&b_full[s]), 0);
+                            const int row0 = st * 128, xy = st & 1;
+                            const int ra = row0 + (xy ? (int)rank * 32 : (int)rank * 64), rb = xy ? row0 + 64 + (int)rank * 32 : ra + 32;
+                            tma_load_2d_cg2(b_buf + s * kBStage, &tmap_w, bar, 0, ra);
+                            tma_load_2d_cg2(b_buf + s * kBStage + kBStage / 2, &tmap_w, bar, 0, rb);
+                        }
                     }
                     __syncwarp();
                 }
     } else if (warp == 1 || warp == 3) {
+      if (leader) {
         // ================= MMA issuers: warp 1 owns M tile 0 (hour plane t0), warp 3 owns M tile 1 (t0 + 1) =================
         // The whole warp walks the schedule; one elected lane issues.  Both issuers consume every weight stage.
         const int m = warp == 3 ? 1 : 0;
         constexpr uint32_t kF = HalfOps<HT>::kFmt;
-        constexpr uint32_t idesc128 = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t idesc64 = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t kM = 128 * CG;
+        constexpr uint32_t idesc128 = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+        constexpr uint32_t idesc64 = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
         const uint32_t a_base = smem_u32(a_reg), b_base = smem_u32(b_buf);
         uint32_t bi = 0, acc_it = 0, li0 = 0;        // li0 = plane-load index of plane 0 of the current unit
         uint32_t b_ready = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, li0 += T) {
+        for (int grp = grp0; grp < n_groups; grp += grp_stride, li0 += T) {
             int ready = -1;                          // highest plane of this unit known to have landed
             for (int sup = 0; sup < n_super; ++sup)
                 for (int pass = 0; pass < 4; ++pass, ++acc_it) {
                     const int pt = pass >> 1, ph = pass & 1;
                     const int w = 2 * sup + pt;      // window: planes w-1, w, w+1
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                    mbar_wait(&acc_empty[as * 2 + m], aph ^ 1);
+                    if (CG == 1) mbar_wait(&acc_empty[as * 2 + m], aph ^ 1);
+                    else mbar_wait_cluster(&acc_empty[as * 2 + m], aph ^ 1);
                     tc_fence_after();
                     const uint32_t d_acc = tmem_base + as * kAccCols + m * 128;
                     uint32_t started = 0;
@@ -209,9 +303,9 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                                     const uint64_t ad = make_sdesc_sbo(a_view, kSboA), bd = make_sdesc(b_addr);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        tc_mma_f16(d_acc, ad + 2 * k, bd + 2 * k, idesc128, started | (k ? 1u : 0u));
+                                        tc_mma_g<CG>(d_acc, ad + 2 * k, bd + 2 * k, idesc128, started | (k ? 1u : 0u));
                                 }
-                                tc_commit(&b_empty[s]);
+                                tc_commit_g<CG>(&b_empty[s]);
                             }
                             if (a_ok) started = 1u;
                             __syncwarp();
@@ -227,35 +321,36 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                             if (elect_one()) {
                                 if (a_ok && !(args.dbg & 4)) {
                                     const uint64_t al = make_sdesc_sbo(a_view - kRow, kSboA), ar = make_sdesc_sbo(a_view + kRow, kSboA);
-                                    const uint64_t b0d = make_sdesc(b_addr), b1d = make_sdesc(b_addr + 8192);
+                                    const uint64_t b0d = make_sdesc(b_addr), b1d = make_sdesc(b_addr + kBStage / 2);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        tc_mma_f16(d_acc, al + 2 * k, b0d + 2 * k, idesc64, 1u);
+                                        tc_mma_g<CG>(d_acc, al + 2 * k, b0d + 2 * k, idesc64, 1u);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        tc_mma_f16(d_acc + 64, ar + 2 * k, b1d + 2 * k, idesc64, 1u);
+                                        tc_mma_g<CG>(d_acc + 64, ar + 2 * k, b1d + 2 * k, idesc64, 1u);
                                 }
-                                tc_commit(&b_empty[s]);
+                                tc_commit_g<CG>(&b_empty[s]);
                             }
                             __syncwarp();
                         }
                         // plane w-1 is read for the last time by the at = 0 half of the ph = 1 pass of window w
                         if (g == 3 && ph == 1 && w >= 1) {
                             const uint32_t lw = li0 + (uint32_t)(w - 1);
-                            if (elect_one()) tc_commit(&a_empty[lw % kSlots]);
+                            if (elect_one()) tc_commit_g<CG>(&a_empty[lw % kSlots]);
                             __syncwarp();
                         }
                     }
                     if (elect_one()) {
                         if (sup == n_super - 1 && pass == 3) {            // last pass of the unit: plane T-1 is done too
                             const uint32_t lw = li0 + (uint32_t)(T - 1);
-                            tc_commit(&a_empty[lw % kSlots]);
+                            tc_commit_g<CG>(&a_empty[lw % kSlots]);
                         }
-                        tc_commit(&acc_full[as * 2 + m]);
+                        tc_commit_g<CG>(&acc_full[as * 2 + m]);
                     }
                     __syncwarp();
                 }
         }
+      }
     } else {
         // ================= epilogue =================
         // Per accumulator (M tile m, w-phase pw; thread = position = TMEM lane): read the 64 channels once, bias +
@@ -270,13 +365,14 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
         HT* out = reinterpret_cast<HT*>(args.out);
         const int H2 = 16, W2 = 16, T2 = 2 * T;
         constexpr uint32_t kF = HalfOps<HT>::kFmt;
-        constexpr uint32_t idesc_p = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc_p = (1u << 4) | (kF << 7) | (kF << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
         const uint64_t wd = make_sdesc(smem_u32(w4_tile));
         uint32_t acc_it = 0, p_it = 0;
         const int et = threadIdx.x - 128;       // 0..255 over both epilogue groups
         const float fx_scale = logit_mode ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(args.w4tile) + kW4Tile)[0] : 0.f;
         bool bad = false;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        for (int grp = grp0; grp < n_groups; grp += grp_stride) {
+            const int unit = grp * CG + (int)rank;
             const int b = unit * 2 + bl;
             const bool valid = b < args.B;
             for (int sup = 0; sup < n_super; ++sup)
@@ -319,12 +415,18 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                                 tc_fence_before();
                                 asm volatile("bar.sync %0, 128;" ::"r"(1 + m) : "memory");
                                 if (q == 0 && !(args.dbg & 2)) {
+                                    if (CG > 1) {
+                                        // both CTAs' y tiles must be in TMEM before the leader issues the pair's product
+                                        if (elect_one()) mbar_arrive_cluster(mapa_rank(smem_u32(&y_ready[m * 2 + pw]), 0));
+                                        __syncwarp();
+                                        if (leader) mbar_wait_cluster(&y_ready[m * 2 + pw], p_it & 1);
+                                    }
                                     tc_fence_after();
-                                    if (elect_one()) {
+                                    if (leader && elect_one()) {
                                         const uint32_t a_t = tmem_base + as * kAccCols + m * 128 + pw * 64;   // lane 0
 #pragma unroll
-                                        for (int k = 0; k < 4; ++k) tc_mma_f16_ts(a_t + 32, a_t + 8 * k, wd + 2 * k, idesc_p, k > 0 ? 1u : 0u);
-                                        tc_commit(&p_full[m * 2 + pw]);
+                                        for (int k = 0; k < 4; ++k) tc_mma_ts_g<CG>(a_t + 32, a_t + 8 * k, wd + 2 * k, idesc_p, k > 0 ? 1u : 0u);
+                                        tc_commit_g<CG>(&p_full[m * 2 + pw]);
                                     }
                                     __syncwarp();
                                 }
@@ -375,7 +477,11 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
                     }
                     ++p_it;
                     tc_fence_before();
-                    mbar_arrive(&acc_empty[as * 2 + m]);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + m) : "memory");       // the whole group has drained the accumulator
+                    if ((threadIdx.x & 127) == 0) {
+                        if (CG == 1) mbar_arrive(&acc_empty[as * 2 + m]);
+                        else mbar_arrive_cluster(mapa_rank(smem_u32(&acc_empty[as * 2 + m]), 0));
+                    }
                     if (logit_mode && pass == 3) {
                         // End of a super-tile (low-res planes 2sup, 2sup+1 = hours 4sup..4sup+3): hours up to 4sup+2 have
                         // all their contributions.  Both epilogue groups flush them (raw fixed point; the softmax kernel
@@ -401,9 +507,11 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a
 
     tc_fence_before();
     __syncthreads();
+    if (CG > 1) cluster_sync_all();              // no CTA leaves while the pair's MMAs / multicasts may still touch it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -449,15 +557,46 @@ int launch_planes(const void* x, const void* wpack, const float* bias, void* y, 
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled (planes) failed: %d", (int)r); return RDG_TC_E_DRIVER; }
 
-    auto kern = tc_upconv64_planes_kernel<HT>;
+    // folded weight image as rows of 128 B (64 stages x 128 rows), boxes of 32 rows: the 2-CTA kernel's weight loads
+    CUtensorMap tmap_w;
+    {
+        cuuint64_t wdim[2] = {64, 64 * 128};
+        cuuint64_t wstr[1] = {128};
+        cuuint32_t wbox[2] = {64, 32};
+        cuuint32_t wes[2] = {1, 1};
+        r = enc(&tmap_w, dt, 2, const_cast<void*>(wpack), wdim, wstr, wbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled (planes weights) failed: %d", (int)r); return RDG_TC_E_DRIVER; }
+    }
+    const int n_units = (B + 1) / 2;
+    // CTA pairs (cta_group::2) halve the weight-operand reads and weight writes per SM; RDG_PLANES_CG=1: one CTA per unit
+    static const int cg = getenv("RDG_PLANES_CG") ? atoi(getenv("RDG_PLANES_CG")) : 2;
+    if (cg == 2 && n_units >= 2) {
+        auto kern = tc_upconv64_planes_kernel<HT, 2>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+            attr_set = true;
+        }
+        const int n_groups = (n_units + 1) / 2, max_clusters = sm_count / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * (n_groups < max_clusters ? n_groups : max_clusters));
+        cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        RDG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, tmap_w, a));
+        return 0;
+    }
+    auto kern = tc_upconv64_planes_kernel<HT, 1>;
     static bool attr_set = false;
     if (!attr_set) {
         RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set = true;
     }
-    const int n_units = (B + 1) / 2;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    kern<<<grid, kThreads, kSmem, st>>>(tmap, a);
+    kern<<<grid, kThreads, kSmem, st>>>(tmap, tmap_w, a);
     RDG_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,272 @@
+// Probe (test infrastructure): the cta_group::2 primitives the 2-CTA generator kernels rely on, checked on values.
+//   1. tcgen05.alloc/dealloc.cta_group::2 from one warp of each CTA of a (2,1,1) cluster
+//   2. tcgen05.mma.cta_group::2.kind::f16, M = 256 (128 rows per CTA), N = 128: each CTA's shared memory holds its own
+//      128 A rows and HALF of the B rows (CTA r: N rows r*64 .. r*64+63) at the same offsets; issued by the leader only
+//   3. multicast tcgen05.commit -> a barrier at the same offset in both CTAs
+//   4. cp.async.bulk.tensor.2d.cta_group::2 from BOTH CTAs completing on the LEADER's mbarrier (mapa address)
+//   5. remote mbarrier.arrive (peer -> leader) through a mapa address
+//   6. tcgen05.mma with A from TMEM (.ts form), cta_group::2, N = 32 (16 B rows per CTA)
+//   7. issue rate of N = 64 / 128 / 256 M = 256 MMAs (clock64 on the leader)
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_2cta_probe umma_2cta_probe.cu -lcuda
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(2); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred P1;\n\tWL:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra WD;\n\tbra WL;\n\tWD:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void commit_mc2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mma2_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma2_f16_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tma2d_cg2(void* dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF); d |= (uint64_t)(sbo >> 4) << 32; d |= (uint64_t)1 << 46; d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+          "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+          "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// A (global): [256][64] half, plain row-major.  B (global, via TMA): [128][64] half, rows PRE-SWIZZLED (chunk j of row n at
+// j ^ (n & 7)), so a linear copy is an MMA-ready tile.  W4 (global): [32][64] half pre-swizzled.
+// D out: [256][128] f32;  P out: [256][32] f32 = A(as y in TMEM) x W4^T.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict__ A, const __half* __restrict__ W4,
+             float* __restrict__ D, float* __restrict__ P, long long* __restrict__ cycles, int reps) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_tile = smem;                  // 16 KB: own 128 rows x 64 k
+    uint8_t* b_tile = smem + 16384;          // 8 KB: own 64 of the 128 N rows
+    uint8_t* w4_tile = smem + 16384 + 8192;  // 2 KB: own 16 of the 32 tap rows
+    uint8_t* zeros = smem + 32768;           // 64 KB of zeros for the rate test
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768 + 65536);
+    uint64_t* b_full = bars;       // leader: 1 arrival (expect_tx) + tx bytes of BOTH CTAs
+    uint64_t* mma_done = bars + 1; // both CTAs (multicast commit)
+    uint64_t* y_ready = bars + 2;  // leader: 2 arrivals (one per CTA)
+    uint64_t* p_done = bars + 3;   // both CTAs
+    uint64_t* rate_done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // A tile: own rows, swizzled by hand (generic proxy), zero region
+    for (int i = tid; i < 128 * 8; i += 128) {
+        const int r = i >> 3, j = i & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(A + ((size_t)(rank * 128 + r) * 64 + j * 8));
+        *reinterpret_cast<uint4*>(a_tile + r * 128 + ((j ^ (r & 7)) << 4)) = v;
+    }
+    for (int i = tid; i < 16 * 8; i += 128) {   // own 16 rows of W4: rows rank*16 ..; pre-swizzled with the GLOBAL row index
+        const int r = i >> 3, j = i & 7;
+        // local row r sits at local row position r; swizzle phase must follow the LOCAL row (address bits)
+        const int gr = rank * 16 + r;
+        const uint4 v = *reinterpret_cast<const uint4*>(W4 + ((size_t)gr * 64 + ((j ^ (gr & 7)) << 3)));   // undo global pre-swizzle
+        *reinterpret_cast<uint4*>(w4_tile + r * 128 + ((j ^ (r & 7)) << 4)) = v;
+    }
+    for (int i = tid; i < 65536 / 16; i += 128) reinterpret_cast<uint4*>(zeros)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (tid == 0) {
+        mbar_init(b_full, 1); mbar_init(mma_done, 1); mbar_init(y_ready, 2); mbar_init(p_done, 1); mbar_init(rate_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- B halves by TMA from both CTAs, completing on the leader's barrier
+    if (tid == 0) {
+        if (rank == 0) mbar_expect_tx(b_full, 2 * 8192);
+        tma2d_cg2(b_tile, &tmapB, mapa(smem_u32(b_full), 0), 0, (int)rank * 64);
+    }
+    // ---- leader: MMA M=256, N=128, K=64
+    if (rank == 0 && tid == 0) {
+        mbar_wait(b_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        const uint64_t ad = make_sdesc(smem_u32(a_tile), 1024), bd = make_sdesc(smem_u32(b_tile), 1024);
+        for (int k = 0; k < 4; ++k) mma2_f16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, k ? 1u : 0u);
+        commit_mc2(mma_done);
+    }
+    mbar_wait(mma_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(lane_base + c0, v);
+            for (int j = 0; j < 32; ++j) D[(size_t)(rank * 128 + tid) * 128 + c0 + j] = __uint_as_float(v[j]);
+        }
+    }
+    // ---- y (= own A row as 16-bit pairs) into TMEM columns 256..287, then P = y x W4^T with A from TMEM
+    {
+        uint32_t pk[32];
+        const uint32_t* arow = reinterpret_cast<const uint32_t*>(A + (size_t)(rank * 128 + tid) * 64);
+        for (int j = 0; j < 32; ++j) pk[j] = arow[j];
+        tc_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + 256, pk);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) mbar_arrive_remote(mapa(smem_u32(y_ready), 0));
+    }
+    if (rank == 0 && tid == 0) {
+        mbar_wait(y_ready, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        const uint64_t wd = make_sdesc(smem_u32(w4_tile), 1024);
+        for (int k = 0; k < 4; ++k) mma2_f16_ts(tmem_base + 320, tmem_base + 256 + 8 * k, wd + 2 * k, idesc, k ? 1u : 0u);
+        commit_mc2(p_done);
+    }
+    mbar_wait(p_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 320, v);
+        for (int j = 0; j < 32; ++j) P[(size_t)(rank * 128 + tid) * 32 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- rate: back-to-back M=256 MMAs on zero operands (row-shifted view with a 9-row group stride, like the planes kernel)
+    if (rank == 0 && tid == 0) {
+        int idx = 0;
+        for (int N = 64; N <= 256; N *= 2) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint64_t ad = make_sdesc(smem_u32(zeros) + 20 * 128, 1152), bd = make_sdesc(smem_u32(zeros) + 40960, 1024);
+            long long t0 = clock64();
+            for (int r = 0; r < reps; ++r) {
+                const uint32_t d = tmem_base + (uint32_t)((r & 1) * 256);
+                for (int k = 0; k < 4; ++k) mma2_f16(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
+            }
+            commit_mc2(rate_done);
+            mbar_wait(rate_done, idx & 1);
+            cycles[idx++] = clock64() - t0;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main() {
+    std::vector<__half> hA(256 * 64), hB(128 * 64), hBs(128 * 64), hW(32 * 64), hWs(32 * 64);
+    uint32_t s = 12345;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)((int)((s >> 16) % 17) - 8) / 8.0f; };
+    for (auto& v : hA) v = __float2half(rnd());
+    for (auto& v : hB) v = __float2half(rnd());
+    for (auto& v : hW) v = __float2half(rnd());
+    for (int n = 0; n < 128; ++n) for (int k = 0; k < 64; ++k) hBs[n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = hB[n * 64 + k];
+    for (int n = 0; n < 32; ++n) for (int k = 0; k < 64; ++k) hWs[n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = hW[n * 64 + k];
+    __half *dA, *dB, *dW; float *dD, *dP; long long* dc;
+    CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hBs.size() * 2)); CK(cudaMalloc(&dW, hWs.size() * 2));
+    CK(cudaMalloc(&dD, 256 * 128 * 4)); CK(cudaMalloc(&dP, 256 * 32 * 4)); CK(cudaMalloc(&dc, 64));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hBs.data(), hBs.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dW, hWs.data(), hWs.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, 256 * 128 * 4)); CK(cudaMemset(dP, 0xff, 256 * 32 * 4));
+
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    EncodeTiledFn enc = (EncodeTiledFn)p;
+    CUtensorMap tmap;
+    cuuint64_t gdim[2] = {64, 128}; cuuint64_t gstr[1] = {128}; cuuint32_t box[2] = {64, 64}; cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dB, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 2; }
+    const int smem = 1024 + 32768 + 65536 + 256;
+    CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int reps = 2000;
+    probe_kernel<<<2, 128, smem>>>(tmap, dA, dW, dD, dP, dc, reps);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<float> hD(256 * 128), hP(256 * 32);
+    long long hc[8];
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hP.data(), dP, hP.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hc, dc, 64, cudaMemcpyDeviceToHost));
+    double eD = 0, eP = 0;
+    for (int m = 0; m < 256; ++m)
+        for (int n = 0; n < 128; ++n) {
+            double ref = 0;
+            for (int k = 0; k < 64; ++k) ref += (double)__half2float(hA[m * 64 + k]) * __half2float(hB[n * 64 + k]);
+            double e = fabs(ref - hD[m * 128 + n]); if (e > eD) eD = e;
+        }
+    for (int m = 0; m < 256; ++m)
+        for (int n = 0; n < 32; ++n) {
+            double ref = 0;
+            for (int k = 0; k < 64; ++k) ref += (double)__half2float(hA[m * 64 + k]) * __half2float(hW[n * 64 + k]);
+            double e = fabs(ref - hP[m * 32 + n]); if (e > eP) eP = e;
+        }
+    printf("D = A x B^T   (M=256 2-CTA, N=128, B halves by TMA.cta_group::2): max abs err %.3g  %s\n", eD, eD < 1e-3 ? "PASS" : "FAIL");
+    printf("P = y x W4^T  (A from TMEM, N=32, remote y_ready arrive):         max abs err %.3g  %s\n", eP, eP < 1e-3 ? "PASS" : "FAIL");
+    const int Ns[3] = {64, 128, 256};
+    for (int i = 0; i < 3; ++i)
+        printf("rate M=256 N=%3d shifted view: %.1f clk per MMA (K=16), %lld clk total\n", Ns[i], (double)hc[i] / (reps * 4), hc[i]);
+    return (eD < 1e-3 && eP < 1e-3) ? 0 : 1;
+}
