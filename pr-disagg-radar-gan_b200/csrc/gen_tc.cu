@@ -63,8 +63,9 @@ constexpr int kATile = 128 * 128;   // 128 rows x 64 x 2 B (one 64-channel chunk
 
 // KC = 64-channel chunks per pipeline stage: a stage carries K = 64*KC, i.e. 4*KC MMAs per weight tile,
 // which amortises the mbarrier round trip of the single-thread producer / issuer loops.
-template <int COUT, int NPH, int KC> struct TcCfg {
-    static constexpr int kBTile = COUT * 128;            // one (phase, tap, chunk) weight tile
+// CG = CTAs sharing every MMA (tcgen05 cta_group): with CG = 2 a CTA's shared memory holds HALF the rows of each weight tile.
+template <int COUT, int NPH, int KC, int CG = 1> struct TcCfg {
+    static constexpr int kBTile = COUT * 128 / CG;       // this CTA's part of one (phase, tap, chunk) weight tile
     static constexpr int kAStage = KC * kATile;
     static constexpr int kBStage = KC * kBTile;
     static constexpr int kAccCols = NPH * COUT;
@@ -72,7 +73,7 @@ template <int COUT, int NPH, int KC> struct TcCfg {
     static constexpr int kFuseBytes = COUT == 64 ? kATile + 4096 : 0;
     static constexpr int kAStages = KC == 1 ? 4 : 3;
     static constexpr int kBudget = 218 * 1024 - kFuseBytes - kAStages * kAStage;
-    static constexpr int kBStages = kBudget / kBStage > 8 ? 8 : kBudget / kBStage;
+    static constexpr int kBStages = kBudget / kBStage > 8 * CG ? 8 * CG : kBudget / kBStage;
     static constexpr int kSmem = 1024 + kAStages * kAStage + kBStages * kBStage + kFuseBytes + COUT * 4 + 512;
     static_assert(kAccCols * kAccStages <= 512, "TMEM overflow");
     static_assert(kBStages >= 2, "need at least 2 weight stages");
@@ -84,18 +85,22 @@ template <int COUT, int NPH, int KC> struct TcCfg {
 // (W4 as a [32 x 64] B tile) on the tensor core:  P[pos][tap] = sum_c y[pos][c] * w4[tap][c].
 // P (f32, 32 per position) goes to HBM instead of y; gather_softmax_kernel then forms
 // logit[q] = b + sum_tap P[q + offset(tap)][tap] and the softmax over the 24 hours.
-// CL = CTAs per cluster.  CL > 1: the CTAs of a cluster work on different position tiles but walk the same
-// weight sequence; rank 0 fetches every weight stage once and TMA-multicasts it into all CL shared memories,
-// and a stage is refilled only after the MMA issuers of ALL CL CTAs released it (multicast tcgen05.commit).
-template <typename HT, int COUT, int NPH, int KC, bool FUSE, int CL>
+// CG = 2: CTA pairs (tcgen05 cta_group::2).  The two CTAs of a cluster work on two position tiles that differ only in
+// the sample block (same t and h block, so both walk the same step sequence); every MMA is M = 256 (128 rows per CTA),
+// issued by the leader (rank 0); each CTA's shared memory holds its own activation tiles and HALF of the rows of every
+// weight tile, so the weight-operand reads and weight writes per SM halve.  Full barriers live in the leader (both
+// CTAs' TMA loads complete on them: .cta_group::2 + mapa address), releases are multicast commits, the peer's epilogue
+// releases accumulators by a remote arrive.  Primitives verified by tools/umma_2cta_probe.cu.
+template <typename HT, int COUT, int NPH, int KC, bool FUSE, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs args) {
-    using Cfg = TcCfg<COUT, NPH, KC>;
-    constexpr bool kSkip = CL == 1;
-    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
-    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
-    const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;   // a unit = CL consecutive tiles
+tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w, TcConvArgs args) {
+    using Cfg = TcCfg<COUT, NPH, KC, CG>;
+    constexpr bool kSkip = true;
+    const uint32_t cta_rank = CG > 1 ? cluster_ctarank() : 0;
+    const bool leader = cta_rank == 0;
+    const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;   // a unit = CG tiles (one per CTA of the pair)
     static_assert(!FUSE || COUT == 64, "fused output conv needs Cout == 64");
+    static_assert(!FUSE || CG == 1, "the fused output conv is single-CTA only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;
@@ -116,6 +121,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = args.Cin / 64;
     const int n_hblk = args.H / args.Hb;
+    const int n_units = args.n_tiles / CG;           // host pads the sample-block count to a multiple of CG
 
     for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = args.bias[i];
     if (FUSE) {
@@ -127,19 +133,23 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
     if (threadIdx.x == 0) {
         mbar_init(p_full, 1);
         for (int i = 0; i < Cfg::kAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        // CG == 2: one arrive per CTA (elected epilogue thread after the group's named barrier)
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CG == 1 ? 128 : CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();          // peers' barriers are initialised before any remote arrive / multicast
+    if (CG > 1) cluster_sync_all();          // peers' barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -148,9 +158,9 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         {
             uint32_t ai = 0;
             uint32_t free_next = mbar_test(&a_empty[0], 1);
-            for (int unit = unit0; unit * CL < args.n_tiles; unit += unit_stride) {
-                const int tile = unit * CL + (int)cta_rank;     // may be >= n_tiles: then b0 >= B, TMA zero-fills, epilogue masks
-                const int hblk = tile % n_hblk, t = (tile / n_hblk) % args.T, bblk = tile / (n_hblk * args.T);
+            for (int unit = unit0; unit < n_units; unit += unit_stride) {
+                // the CTAs of a pair share (t, h block) and take sample blocks CG*k + rank (may be past B: TMA zero-fills, epilogue masks)
+                const int hblk = unit % n_hblk, t = (unit / n_hblk) % args.T, bblk = unit / (n_hblk * args.T) * CG + (int)cta_rank;
                 const int h0 = hblk * args.Hb, b0 = bblk * args.Bt;
                 for (int pass = 0; pass < 8 / NPH; ++pass) {
                     for_each_step<NPH, kSkip>(
@@ -163,11 +173,14 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                             const uint32_t s2 = ai % Cfg::kAStages, ph2 = (ai / Cfg::kAStages) & 1;
                             free_next = mbar_test(&a_empty[s2], ph2 ^ 1);
                             if (elect_one()) {
-                                mbar_expect_tx(&a_full[s], Cfg::kAStage);
+                                if (leader) mbar_expect_tx(&a_full[s], CG * Cfg::kAStage);      // both CTAs' tiles
 #pragma unroll
-                                for (int k = 0; k < KC; ++k)
-                                    tma_load_5d(a_buf + s * Cfg::kAStage + k * kATile, &tmap, &a_full[s], (c + k) * 64, dw,
-                                                h0 + dh, t + dt, b0);
+                                for (int k = 0; k < KC; ++k) {
+                                    if (CG == 1) tma_load_5d(a_buf + s * Cfg::kAStage + k * kATile, &tmap, &a_full[s], (c + k) * 64, dw,
+                                                             h0 + dh, t + dt, b0);
+                                    else tma_load_5d_cg2(a_buf + s * Cfg::kAStage + k * kATile, &tmap, mapa_rank(smem_u32(&a_full[s]), 0),
+                                                         (c + k) * 64, dw, h0 + dh, t + dt, b0);
+                                }
                             }
                         },
                         [&](int, int, bool) {});
@@ -179,9 +192,8 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         {
             uint32_t bi = 0;
             uint32_t free_next = mbar_test(&b_empty[0], 1);
-            for (int unit = unit0; unit * CL < args.n_tiles; unit += unit_stride) {
-                const int tile = unit * CL + (int)cta_rank;     // may be >= n_tiles: then b0 >= B, TMA zero-fills, epilogue masks
-                const int t = (tile / n_hblk) % args.T;
+            for (int unit = unit0; unit < n_units; unit += unit_stride) {
+                const int t = (unit / n_hblk) % args.T;
                 for (int pass = 0; pass < 8 / NPH; ++pass) {
                     for_each_step<NPH, kSkip>(
                         pass, t, args.T, nchunk, KC, [&](int, int, int, int, bool) {},
@@ -193,28 +205,36 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                             const uint32_t s2 = bi % Cfg::kBStages, ph2 = (bi / Cfg::kBStages) & 1;
                             free_next = mbar_test(&b_empty[s2], ph2 ^ 1);
                             if (elect_one()) {
-                                mbar_expect_tx(&b_full[s], Cfg::kBStage);          // every CTA arms its own barrier
-                                const uint8_t* src = reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile;
-                                if (CL == 1) bulk_load_1d(b_buf + s * Cfg::kBStage, src, Cfg::kBStage, &b_full[s]);
-                                else if (cta_rank == 0) bulk_load_1d_mc(b_buf + s * Cfg::kBStage, src, Cfg::kBStage, &b_full[s], kMask);
+                                if (leader) mbar_expect_tx(&b_full[s], CG * Cfg::kBStage);
+                                if (CG == 1) {
+                                    const uint8_t* src = reinterpret_cast<const uint8_t*>(args.wpack) + (size_t)wtile * Cfg::kBTile;
+                                    bulk_load_1d(b_buf + s * Cfg::kBStage, src, Cfg::kBStage, &b_full[s]);
+                                } else {
+                                    // weight image as rows of 128 B, COUT rows per tile: this CTA takes rows rank*COUT/2 .. of each tile
+                                    const uint32_t bar = mapa_rank(smem_u32(&b_full[s]), 0);
+#pragma unroll
+                                    for (int k = 0; k < KC; ++k)
+                                        tma_load_2d_cg2(b_buf + s * Cfg::kBStage + k * Cfg::kBTile, &tmap_w, bar, 0,
+                                                        (wtile + k) * COUT + (int)cta_rank * (COUT / 2));
+                                }
                             }
                         });
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (whole warp walks the schedule; one elected lane issues) =================
-        {
+        // ================= MMA issuer (whole warp walks the schedule; one elected lane issues; leader CTA only) =================
+        if (leader) {
             constexpr uint32_t idesc = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
-                                       ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                                       ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
             uint32_t ai = 0, bi = 0, acc_it = 0;
             uint32_t a_ready = 0, b_ready = 0;       // results of early probes of the next full barriers
-            for (int unit = unit0; unit * CL < args.n_tiles; unit += unit_stride) {
-                const int tile = unit * CL + (int)cta_rank;     // may be >= n_tiles: then b0 >= B, TMA zero-fills, epilogue masks
-                const int t = (tile / n_hblk) % args.T;
+            for (int unit = unit0; unit < n_units; unit += unit_stride) {
+                const int t = (unit / n_hblk) % args.T;
                 for (int pass = 0; pass < 8 / NPH; ++pass, ++acc_it) {
                     const uint32_t as = acc_it % Cfg::kAccStages, aph = (acc_it / Cfg::kAccStages) & 1;
-                    mbar_wait(&acc_empty[as], aph ^ 1);
+                    if (CG == 1) mbar_wait(&acc_empty[as], aph ^ 1);
+                    else mbar_wait_cluster(&acc_empty[as], aph ^ 1);
                     tc_fence_after();
                     const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
                     uint32_t started = 0;
@@ -225,7 +245,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                         pass, t, args.T, nchunk, KC,
                         [&](int, int, int, int, bool oob) {
                             if (oob) return;
-                            if (have_a && elect_one()) tc_commit(&a_empty[prev_a_slot]);   // MMAs reading the previous A stage issued
+                            if (have_a && elect_one()) tc_commit_g<CG>(&a_empty[prev_a_slot]);   // MMAs reading the previous A stage issued
                             const uint32_t s = ai % Cfg::kAStages, ph = (ai / Cfg::kAStages) & 1;
                             if (!a_ready) mbar_wait(&a_full[s], ph);
                             ++ai;
@@ -250,17 +270,16 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                                         const uint64_t ad = make_sdesc(cur_a + c * kATile), bd = make_sdesc(b_addr + c * Cfg::kBTile);
 #pragma unroll
                                         for (int k = 0; k < 4; ++k)   // +32 B per K=16 step inside the 128 B swizzle atom (encoded >>4)
-                                            tc_mma_f16(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc, acc0 | ((c | k) ? 1u : 0u));
+                                            tc_mma_g<CG>(d_base + slot * COUT, ad + 2 * k, bd + 2 * k, idesc, acc0 | ((c | k) ? 1u : 0u));
                                     }
                                 }
-                                if (CL == 1) tc_commit(&b_empty[s]);
-                                else tc_commit_mc(&b_empty[s], kMask);      // release the stage in every CTA of the cluster
+                                tc_commit_g<CG>(&b_empty[s]);       // CG == 2: releases the stage in both CTAs
                             }
                             if (!oob) started |= 1u << slot;
                         });
                     if (elect_one()) {
-                        if (have_a) tc_commit(&a_empty[prev_a_slot]);
-                        tc_commit(&acc_full[as]);
+                        if (have_a) tc_commit_g<CG>(&a_empty[prev_a_slot]);
+                        tc_commit_g<CG>(&acc_full[as]);
                     }
                     __syncwarp();
                 }
@@ -273,9 +292,8 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
         const int bl = r / (args.Hb * args.W), hl = (r / args.W) % args.Hb, w = r % args.W;
         HT* out = reinterpret_cast<HT*>(args.out);
         uint32_t acc_it = 0, p_it = 0;
-        for (int unit = unit0; unit * CL < args.n_tiles; unit += unit_stride) {
-                const int tile = unit * CL + (int)cta_rank;     // may be >= n_tiles: then b0 >= B, TMA zero-fills, epilogue masks
-            const int hblk = tile % n_hblk, t = (tile / n_hblk) % args.T, bblk = tile / (n_hblk * args.T);
+        for (int unit = unit0; unit < n_units; unit += unit_stride) {
+            const int hblk = unit % n_hblk, t = (unit / n_hblk) % args.T, bblk = unit / (n_hblk * args.T) * CG + (int)cta_rank;
             const int b = bblk * args.Bt + bl, h = hblk * args.Hb + hl;
             const bool valid = b < args.B;
             for (int pass = 0; pass < 8 / NPH; ++pass, ++acc_it) {
@@ -356,17 +374,23 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs 
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[as]);
+                if (CG == 1) {
+                    mbar_arrive(&acc_empty[as]);
+                } else {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps have drained the accumulator
+                    if (warp == 3 && lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&acc_empty[as]), 0));
+                }
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / signal its barriers
+    if (CG > 1) cluster_sync_all();          // no CTA leaves while the pair's MMAs / multicasts may still touch it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -605,10 +629,10 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <typename HT, int COUT, int NPH, int KC, bool FUSE, int CL>
-int launch_upconv_cl(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
+template <typename HT, int COUT, int NPH, int KC, bool FUSE, int CG>
+int launch_upconv_cg(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
                   int T, int H, int W, int Cin, int sm_count, cudaStream_t st) {
-    using Cfg = TcCfg<COUT, NPH, KC>;
+    using Cfg = TcCfg<COUT, NPH, KC, CG>;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { rdg_set_error("cuTensorMapEncodeTiled entry point not available"); return RDG_TC_E_DRIVER; }
     if (Cin % (64 * KC) || W > 128 || (128 % W) != 0) { rdg_set_error("tc upconv: unsupported shape"); return RDG_TC_E_SHAPE; }
@@ -618,7 +642,7 @@ int launch_upconv_cl(const void* x, const void* wpack, const float* bias, void* 
     if (rows_per_sample_plane >= 128) { a.Hb = 128 / W; a.Bt = 1; }
     else { a.Hb = H; a.Bt = 128 / rows_per_sample_plane; }
     if (a.Hb < 1 || H % a.Hb) { rdg_set_error("tc upconv: H not divisible by tile rows"); return RDG_TC_E_SHAPE; }
-    a.n_tiles = ceil_div(B, a.Bt) * T * (H / a.Hb);
+    a.n_tiles = ceil_div(ceil_div(B, a.Bt), CG) * CG * T * (H / a.Hb);    // sample blocks padded to a multiple of CG
     a.wpack = wpack; a.bias = bias; a.out = y; a.w4tile = w4tile; a.p_out = p_out;
 
     CUtensorMap tmap;
@@ -633,33 +657,45 @@ int launch_upconv_cl(const void* x, const void* wpack, const float* bias, void* 
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return RDG_TC_E_DRIVER; }
 
-    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH, KC, FUSE, CL>;
+    // folded weight image as rows of 128 B (COUT rows per (phase, tap, chunk) tile); box = one CTA's half tile (CG == 2)
+    CUtensorMap tmap_w;
+    {
+        cuuint64_t wdim[2] = {64, (cuuint64_t)64 * (Cin / 64) * COUT};
+        cuuint64_t wstr[1] = {128};
+        cuuint32_t wbox[2] = {64, (cuuint32_t)(COUT / 2)};
+        cuuint32_t wes[2] = {1, 1};
+        r = enc(&tmap_w, dt, 2, const_cast<void*>(wpack), wdim, wstr, wbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled (weights) failed: %d", (int)r); return RDG_TC_E_DRIVER; }
+    }
+    auto kern = tc_upconv_pixelnorm_kernel<HT, COUT, NPH, KC, FUSE, CG>;
     static bool attr_set = false;
     if (!attr_set) {
         RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
         attr_set = true;
     }
-    const int units = ceil_div(a.n_tiles, CL);
-    const int max_clusters = sm_count / CL;
-    const int grid = (units < max_clusters ? units : max_clusters) * CL;
+    const int units = a.n_tiles / CG;
+    const int max_clusters = sm_count / CG;
+    const int grid = (units < max_clusters ? units : max_clusters) * CG;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    RDG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, a));
+    RDG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, tmap_w, a));
     return 0;
 }
 
 template <typename HT, int COUT, int NPH, int KC, bool FUSE>
 int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
                   int T, int H, int W, int Cin, int sm_count, cudaStream_t st) {
-    // CTAs per cluster sharing each weight stage through TMA multicast (1 = no cluster)
-    static const int cl = getenv("RDG_CLUSTER") ? atoi(getenv("RDG_CLUSTER")) : 1;   // measured: 453k / 440k / 247k scenarios/s at 1 / 2 / 4
-    if (cl == 4) return launch_upconv_cl<HT, COUT, NPH, KC, FUSE, 4>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
-    if (cl == 2) return launch_upconv_cl<HT, COUT, NPH, KC, FUSE, 2>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
-    return launch_upconv_cl<HT, COUT, NPH, KC, FUSE, 1>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    // CTA pairs (cta_group::2) for the layers without the fused output conv; RDG_CG=1 forces single-CTA MMAs.
+    // (An earlier weight-multicast cluster variant of the single-CTA kernel measured no gain and was removed.)
+    static const int cg = getenv("RDG_CG") ? atoi(getenv("RDG_CG")) : 2;
+    if (!FUSE && cg == 2)
+        return launch_upconv_cg<HT, COUT, NPH, KC, FUSE, FUSE ? 1 : 2>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    return launch_upconv_cg<HT, COUT, NPH, KC, FUSE, 1>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
 }
 
 template <typename HT>

@@ -165,6 +165,72 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return d;
 }
 
+// 2-CTA helpers (CG == 2): the CTA pair of a cluster shares every MMA (M = 256: 128 rows per CTA, each CTA's shared
+// memory holds its own activation planes and HALF of the rows of every weight tile), issued by the leader (rank 0).
+// Data barriers live in the leader: both CTAs' TMA loads complete on them (.cta_group::2 + mapa address); stage /
+// accumulator releases are multicast commits to both CTAs; the peer's epilogue signals the leader by remote arrives.
+// Primitives verified on values by tools/umma_2cta_probe.cu.
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+template <int CG> __device__ __forceinline__ void tc_commit_g(uint64_t* bar) {
+    if (CG == 1) tc_commit(bar);
+    else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                      ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int CG> __device__ __forceinline__ void tc_mma_g(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                           uint32_t accumulate) {
+    if (CG == 1) tc_mma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int CG> __device__ __forceinline__ void tc_mma_ts_g(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                              uint32_t accumulate) {
+    if (CG == 1) tc_mma_f16_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+    else asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_cg2(void* dst, const CUtensorMap* tmap, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* tmap, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+
 template <typename HT> struct HalfOps;
 template <> struct HalfOps<__nv_bfloat16> {
     static constexpr uint32_t kFmt = 1;

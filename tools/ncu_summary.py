@@ -20,7 +20,12 @@ for i, h in enumerate(hdr):
         print(f"{h} [{units[i]}] = {vals[i]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]
+data = []
+for r in rows[2:]:
+    if len(r) != len(hdr): continue
+    if r == hdr: break          # next captured launch: keep the first table only
+    data.append(r)
 iS = hdr.index('# Samples'); iSrc = hdr.index('Source')
 stall = [i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
 tot = sum(int(r[iS]) for r in data)

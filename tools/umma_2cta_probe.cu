@@ -119,7 +119,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict
     for (int i = tid; i < 65536 / 16; i += 128) reinterpret_cast<uint4*>(zeros)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (tid == 0) {
-        mbar_init(b_full, 1); mbar_init(mma_done, 1); mbar_init(y_ready, 2); mbar_init(p_done, 1); mbar_init(rate_done, 1);
+        mbar_init(b_full, 1); mbar_init(mma_done, 1); mbar_init(y_ready, 2); mbar_init(p_done, 1); mbar_init(rate_done, 1); mbar_init(rate_done + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -185,21 +185,31 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict
     __syncthreads();
     cluster_sync();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- rate: back-to-back M=256 MMAs on zero operands (row-shifted view with a 9-row group stride, like the planes kernel)
-    if (rank == 0 && tid == 0) {
-        int idx = 0;
-        for (int N = 64; N <= 256; N *= 2) {
+    // ---- rate: back-to-back M=256 MMAs on zero operands.  cfg: N, A view (0 = 1024-aligned, 1 = row-shifted view with a
+    // 9-row group stride like the planes kernel), issuers (1 or 2 threads, second = warp 1 lane 0 on its own accumulators)
+    for (int cfg = 0; cfg < 24; ++cfg) {
+        const int N = 32 * (1 + (cfg % 8)), shifted = (cfg / 8) & 1, two = cfg / 16;
+        if (cfg >= 16 && N > 128) continue;
+        if (rank == 0 && (tid == 0 || (two && tid == 32))) {
+            const int iw = tid >> 5;
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-            const uint64_t ad = make_sdesc(smem_u32(zeros) + 20 * 128, 1152), bd = make_sdesc(smem_u32(zeros) + 40960, 1024);
+            const uint64_t ad = make_sdesc(smem_u32(zeros) + (shifted ? 20 * 128 : 0) + iw * 1024, shifted ? 1152 : 1024);
+            const uint64_t bd = make_sdesc(smem_u32(zeros) + 40960, 1024);
             long long t0 = clock64();
             for (int r = 0; r < reps; ++r) {
-                const uint32_t d = tmem_base + (uint32_t)((r & 1) * 256);
+                const uint32_t d = tmem_base + (uint32_t)(iw * 256 + (N <= 128 ? (r & 1) * 128 : 0));
                 for (int k = 0; k < 4; ++k) mma2_f16(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
             }
-            commit_mc2(rate_done);
-            mbar_wait(rate_done, idx & 1);
-            cycles[idx++] = clock64() - t0;
+            commit_mc2(&rate_done[iw]);
+            mbar_wait(&rate_done[iw], cfg & 1);
+            cycles[cfg * 2 + iw] = clock64() - t0;
         }
+        // every config completes a phase of both barriers in both CTAs, keeping the parities in step
+        if (rank == 0 && tid == 32 && !two) { commit_mc2(&rate_done[1]); }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        cluster_sync();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -225,7 +235,7 @@ int main() {
     for (int n = 0; n < 32; ++n) for (int k = 0; k < 64; ++k) hWs[n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = hW[n * 64 + k];
     __half *dA, *dB, *dW; float *dD, *dP; long long* dc;
     CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hBs.size() * 2)); CK(cudaMalloc(&dW, hWs.size() * 2));
-    CK(cudaMalloc(&dD, 256 * 128 * 4)); CK(cudaMalloc(&dP, 256 * 32 * 4)); CK(cudaMalloc(&dc, 64));
+    CK(cudaMalloc(&dD, 256 * 128 * 4)); CK(cudaMalloc(&dP, 256 * 32 * 4)); CK(cudaMalloc(&dc, 512)); CK(cudaMemset(dc, 0, 512));
     CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dB, hBs.data(), hBs.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dW, hWs.data(), hWs.size() * 2, cudaMemcpyHostToDevice));
@@ -241,15 +251,15 @@ int main() {
     if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 2; }
     const int smem = 1024 + 32768 + 65536 + 256;
     CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int reps = 2000;
+    const int reps = 1000;
     probe_kernel<<<2, 128, smem>>>(tmap, dA, dW, dD, dP, dc, reps);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     std::vector<float> hD(256 * 128), hP(256 * 32);
-    long long hc[8];
+    long long hc[64];
     CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hP.data(), dP, hP.size() * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(hc, dc, 64, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hc, dc, 512, cudaMemcpyDeviceToHost));
     double eD = 0, eP = 0;
     for (int m = 0; m < 256; ++m)
         for (int n = 0; n < 128; ++n) {
@@ -265,8 +275,12 @@ int main() {
         }
     printf("D = A x B^T   (M=256 2-CTA, N=128, B halves by TMA.cta_group::2): max abs err %.3g  %s\n", eD, eD < 1e-3 ? "PASS" : "FAIL");
     printf("P = y x W4^T  (A from TMEM, N=32, remote y_ready arrive):         max abs err %.3g  %s\n", eP, eP < 1e-3 ? "PASS" : "FAIL");
-    const int Ns[3] = {64, 128, 256};
-    for (int i = 0; i < 3; ++i)
-        printf("rate M=256 N=%3d shifted view: %.1f clk per MMA (K=16), %lld clk total\n", Ns[i], (double)hc[i] / (reps * 4), hc[i]);
+    for (int cfg = 0; cfg < 24; ++cfg) {
+        const int N = 32 * (1 + (cfg % 8)), shifted = (cfg / 8) & 1, two = cfg / 16;
+        if (cfg >= 16 && N > 128) continue;
+        printf("rate M=256 N=%3d %s view, %d issuer(s): %.1f", N, shifted ? "shifted" : "aligned", two + 1, (double)hc[cfg * 2] / (reps * 4));
+        if (two) printf(" / %.1f", (double)hc[cfg * 2 + 1] / (reps * 4));
+        printf(" clk per MMA (K=16) per issuer\n");
+    }
     return (eD < 1e-3 && eP < 1e-3) ? 0 : 1;
 }
