@@ -113,6 +113,13 @@ extern "C" int rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int 
     cudaDeviceProp prop;
     RDG_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    {   // the split-K partial buffers come from the stream-ordered pool: keep freed blocks cached instead of returning them
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (prop.major != 10) { rdg_set_error("device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); delete c; return RDG_E_NODEVICE; }
     if (max_chunk <= 0) max_chunk = nd == 16 ? 32 * c->sm_count : std::max(32, 2 * c->sm_count);
     c->max_chunk = max_chunk;

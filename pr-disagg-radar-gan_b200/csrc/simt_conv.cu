@@ -39,11 +39,15 @@ __device__ __forceinline__ void fma_tile(float (&acc)[4][4], const float (*As)[B
 
 // MODE 0: forward.   M = output positions, N = Co, K = taps*Ci
 // MODE 1: bwd-data.  M = logical input positions, N = Ci, K = taps*Co
+// Split-K (gridDim.z > 1): slice z reduces a contiguous range of the (tap, channel-chunk) steps and writes its raw
+// partial tile to part[z][M][N]; splitk_epilogue_kernel then sums the slices in fixed order (deterministic) and applies
+// the epilogue.  Used when the M x N tile grid alone cannot fill the GPU (the critic's deep layers: M = 64 .. 3072 rows
+// at batch 32 with K up to 6912), where a few CTAs walking hundreds of dependent load->sync->FMA steps are latency-bound.
 template <int MODE>
 __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ dst,
                                                        ConvGeom g, int act, const float* __restrict__ mask,
-                                                       float mask_scale, float* __restrict__ pre) {
+                                                       float mask_scale, float* __restrict__ pre, float* __restrict__ part) {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -68,7 +72,12 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
     const int ntaps = g.KT * g.KH * g.KW;
-    for (int tap = 0; tap < ntaps; ++tap) {
+    const int nck = (KC + BK - 1) / BK;                            // channel chunks per tap
+    const int total_steps = ntaps * nck;
+    const int per_slice = (total_steps + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int step_beg = (int)blockIdx.z * per_slice;
+    const int step_end = step_beg + per_slice < total_steps ? step_beg + per_slice : total_steps;
+    for (int tap = step_beg / nck; tap * nck < step_end; ++tap) {
         const int kw_ = tap % g.KW, kh_ = (tap / g.KW) % g.KH, kt_ = tap / (g.KW * g.KH);
         bool ok = am_ok;
         long long base = 0;
@@ -85,7 +94,9 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
             ok = ok && nt < g.To && nh < g.Ho && nw < g.Wo;
             base = ((((long long)ap.b * g.To + nt) * g.Ho + nh) * g.Wo + nw) * g.Co;
         }
-        for (int c0 = 0; c0 < KC; c0 += BK) {
+        const int ck_beg = tap * nck < step_beg ? step_beg - tap * nck : 0;
+        const int ck_end = (tap + 1) * nck > step_end ? step_end - tap * nck : nck;
+        for (int c0 = ck_beg * BK; c0 < ck_end * BK; c0 += BK) {
             // A tile: 64 positions x 16 reduction channels
             float av[4] = {0.f, 0.f, 0.f, 0.f};
             if (ok) {
@@ -133,6 +144,7 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
             int n = n0 + tx * 4 + j;
             if (n >= N) continue;
             float v = acc[i][j];
+            if (part) { part[((long long)blockIdx.z * M + m) * N + n] = v; continue; }
             if (MODE == 0) {
                 if (bias) v += bias[n];
                 if (pre) pre[m * N + n] = v;            // pre-activation, kept for the backward pass
@@ -142,6 +154,21 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
             dst[m * N + n] = v;
         }
     }
+}
+
+// dst = epilogue(sum_z part[z]); same epilogue as conv_gemm_kernel (bias, pre-activation copy, LeakyReLU, dropout mask)
+__global__ void splitk_epilogue_kernel(const float* __restrict__ part, int nslice, long long MN, int N,
+                                       const float* __restrict__ bias, float* __restrict__ dst, int act,
+                                       const float* __restrict__ mask, float mask_scale, float* __restrict__ pre) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MN) return;
+    float v = 0.f;
+    for (int z = 0; z < nslice; ++z) v += part[(long long)z * MN + i];
+    if (bias) v += bias[i % N];
+    if (pre) pre[i] = v;
+    if (act == ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
+    if (mask) v *= mask[i] * mask_scale;
+    dst[i] = v;
 }
 
 // dW[tap][ci][co] += sum_m x[gather(m,tap)][ci] * dy[m][co]; grid (ci tiles, co tiles, taps*ksplit)
@@ -213,12 +240,34 @@ __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ 
 
 }  // namespace
 
+// Reduction slices for a tile grid of `ctas` CTAs over `steps` K steps: aim at ~2 CTAs per SM, at least 4 steps per slice.
+static int splitk_slices(int ctas, int steps) {
+    if (ctas >= 148 || steps < 8) return 1;
+    int n = (296 + ctas - 1) / ctas;
+    if (n > steps / 4) n = steps / 4;
+    return n < 1 ? 1 : n;
+}
+
 int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int act,
                   const float* mask, float mask_scale, cudaStream_t st, float* pre) {
     long long M = (long long)g.B * g.To * g.Ho * g.Wo;
     if (M == 0) return 0;
     dim3 grid(ceil_div(M, BM), ceil_div(g.Co, BN));
-    conv_gemm_kernel<0><<<grid, NT, 0, st>>>(x, w, bias, y, g, act, mask, mask_scale, pre);
+    // slices chosen for a nominal batch of >= 32 so that a sample's summation order (hence its bits) is the same whether it
+    // is computed alone or inside a small batch (tests pin batches through exact linearity in the batch)
+    const int nslice = splitk_slices(ceil_div(M / g.B * (g.B < 32 ? 32 : g.B), BM) * grid.y, g.KT * g.KH * g.KW * ceil_div(g.Ci, BK));
+    if (nslice > 1) {
+        float* part = nullptr;
+        RDG_CUDA(cudaMallocAsync(&part, (size_t)nslice * M * g.Co * sizeof(float), st));
+        grid.z = nslice;
+        conv_gemm_kernel<0><<<grid, NT, 0, st>>>(x, w, nullptr, y, g, ACT_NONE, nullptr, 1.f, nullptr, part);
+        RDG_LAUNCH_CHECK();
+        splitk_epilogue_kernel<<<ceil_div(M * g.Co, 256), 256, 0, st>>>(part, nslice, M * g.Co, g.Co, bias, y, act, mask, mask_scale, pre);
+        RDG_LAUNCH_CHECK();
+        RDG_CUDA(cudaFreeAsync(part, st));
+        return 0;
+    }
+    conv_gemm_kernel<0><<<grid, NT, 0, st>>>(x, w, bias, y, g, act, mask, mask_scale, pre, nullptr);
     RDG_LAUNCH_CHECK();
     return 0;
 }
@@ -228,7 +277,19 @@ int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeo
     long long M = (long long)g.B * g.Ti * upf * g.Hi * upf * g.Wi * upf;
     if (M == 0) return 0;
     dim3 grid(ceil_div(M, BM), ceil_div(g.Ci, BN));
-    conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, ACT_NONE, nullptr, 1.f, nullptr);
+    const int nslice = splitk_slices(ceil_div(M / g.B * (g.B < 32 ? 32 : g.B), BM) * grid.y, g.KT * g.KH * g.KW * ceil_div(g.Co, BK));
+    if (nslice > 1) {
+        float* part = nullptr;
+        RDG_CUDA(cudaMallocAsync(&part, (size_t)nslice * M * g.Ci * sizeof(float), st));
+        grid.z = nslice;
+        conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, ACT_NONE, nullptr, 1.f, nullptr, part);
+        RDG_LAUNCH_CHECK();
+        splitk_epilogue_kernel<<<ceil_div(M * g.Ci, 256), 256, 0, st>>>(part, nslice, M * g.Ci, g.Ci, nullptr, dx, ACT_NONE, nullptr, 1.f, nullptr);
+        RDG_LAUNCH_CHECK();
+        RDG_CUDA(cudaFreeAsync(part, st));
+        return 0;
+    }
+    conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, ACT_NONE, nullptr, 1.f, nullptr, nullptr);
     RDG_LAUNCH_CHECK();
     return 0;
 }
