@@ -11,7 +11,7 @@ full ensemble, no data-path collective), seeded random-init generator of the ref
   roofline: dominant kernel (tc_upconv64_planes_kernel: tcgen05 upsample-folded conv 128->64 + PixelNorm +
            LeakyReLU + fused output-conv tap products), CUDA-event duration on the launch stream inside the
            timed steps, algorithmic FLOPs; `traffic` = DRAM bytes of one launch from the committed
-           ncu --set full capture (profiles/r1e_ncu_planes_summary.md), scaled to the units of a launch
+           ncu --set full capture (profiles/r1h_ncu_planes_cg2_summary.md), scaled to the units of a launch
   cpu_baseline / --impl reference: the oracle (torch-CPU restatement of the Keras graph; TensorFlow
            is not installed in this image) on a bounded sample of the same workload.
 """
@@ -35,8 +35,8 @@ MAC_TOTAL = 2_220_011_520
 MAC_CONV3 = 1_358_954_496          # Conv3D(128->64) on the 24x16x16 grid, direct form
 MAC_CONV3_FOLDED = 402_653_184     # what the folded kernel executes
 MAC_TOTAL_FOLDED = 666_021_888     # whole generator with the three upsample folds
-# dram__bytes_read.sum + dram__bytes_write.sum of one 4736-unit launch of the dominant kernel (profiles/r1e_ncu_planes_summary.md)
-CONV3_DRAM_BYTES_PER_UNIT = (940.64e6 + 3674.53e6) / 4736
+# dram__bytes_read.sum + dram__bytes_write.sum of one 4736-unit launch of the dominant kernel (profiles/r1h_ncu_planes_cg2_summary.md)
+CONV3_DRAM_BYTES_PER_UNIT = (932.31e6 + 111.21e6) / 4736
 
 
 def load_peaks():
@@ -292,10 +292,10 @@ def main():
     conv3_ms = ms_sum[5] / max(1, n_l[5])
     units_per_launch = n_u[5] / max(1, n_l[5])
     ach = units_per_launch * 2 * MAC_CONV3 / (conv3_ms * 1e-3) / 1e12 if conv3_ms > 0 else 0.0
-    layer_names = ["concat", "dense_front", "cvt16", "upconv256", "upconv128", "upconv64_planes", "gather_softmax", "pixelnorm"]
+    layer_names = ["concat", "dense_front", "cvt16", "upconv256", "upconv128", "upconv64_planes", "softmax_hours", "pixelnorm"]
     shares = {layer_names[i]: round(ms_sum[i] / args.steps, 3) for i in range(8) if n_l[i]}
     roofline = {"bound": "tensor", "kernel": "tc_upconv64_planes_kernel (UpSampling3D + Conv3D 128->64 + PixelNorm + LeakyReLU "
-                                              "+ fused Conv3D 64->1 tap products; resident-plane tcgen05 kernel)",
+                                              "+ fused Conv3D 64->1 summed on chip; resident-plane tcgen05 cta_group::2 kernel)",
                 "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
                 "peak_kind": f"{src} sustained bf16 cuBLAS (burst {burst})", "frac_of_burst": ach / burst,
                 "executed_tflops": ach * MAC_CONV3_FOLDED / MAC_CONV3,
@@ -305,8 +305,8 @@ def main():
                         "the MACs actually issued to the tensor pipe",
                 "ms_per_launch": conv3_ms, "units_per_launch": units_per_launch,
                 "flop_per_unit": 2 * MAC_CONV3, "traffic": CONV3_DRAM_BYTES_PER_UNIT * units_per_launch,
-                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1e_ncu_planes_summary.md)",
-                "algorithmic_bytes_per_launch": units_per_launch * (12 * 64 * 128 * 2 + 24 * 256 * 32 * 4),
+                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1h_ncu_planes_cg2_summary.md)",
+                "algorithmic_bytes_per_launch": units_per_launch * (12 * 64 * 128 * 2 + 24 * 256 * 4),
                 "layer_ms_per_step": shares,
                 "whole_path_frac": value / world * 2 * MAC_TOTAL / 1e12 / sustained,
                 "whole_path_executed_frac": value / world * 2 * MAC_TOTAL_FOLDED / 1e12 / sustained}
