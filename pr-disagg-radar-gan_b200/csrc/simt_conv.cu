@@ -226,6 +226,122 @@ __global__ void __launch_bounds__(NT) conv_bwd_filter_kernel(const float* __rest
     }
 }
 
+// ---- few-input-channel layers (the critic's first conv: Ci = 1 + ncond, gan_train_cwgangp_pixelnorm.py:286-287) ----
+// The 64x64-tile kernels waste 62/64 of a tile on them.  dx[m][ci] = sum_{valid taps} sum_co dy[n(m,tap)][co] * w[tap][ci][co]:
+// one thread per (input position, ci), weights in shared memory, dy rows read as float4.
+__global__ void __launch_bounds__(256) conv_bwd_data_smallci_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                    float* __restrict__ dx, ConvGeom g) {
+    extern __shared__ __align__(16) float ws[];              // [tap][ci][co]
+    const int ntaps = g.KT * g.KH * g.KW;
+    for (int i = threadIdx.x; i < ntaps * g.Ci * g.Co; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const long long M = (long long)g.B * g.Ti * g.Hi * g.Wi;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * g.Ci) return;
+    const int ci = (int)(idx % g.Ci);
+    const PosDec p = decode_pos(idx / g.Ci, g.Ti, g.Hi, g.Wi);
+    float acc = 0.f;
+    for (int kt = 0; kt < g.KT; ++kt) {
+        int nt = p.t + g.pt - kt;
+        if (nt < 0 || nt % g.stride) continue;
+        nt /= g.stride;
+        if (nt >= g.To) continue;
+        for (int kh = 0; kh < g.KH; ++kh) {
+            int nh = p.h + g.ph - kh;
+            if (nh < 0 || nh % g.stride) continue;
+            nh /= g.stride;
+            if (nh >= g.Ho) continue;
+            for (int kw = 0; kw < g.KW; ++kw) {
+                int nw = p.w + g.pw - kw;
+                if (nw < 0 || nw % g.stride) continue;
+                nw /= g.stride;
+                if (nw >= g.Wo) continue;
+                const float4* yp = reinterpret_cast<const float4*>(dy + ((((long long)p.b * g.To + nt) * g.Ho + nh) * g.Wo + nw) * g.Co);
+                const float4* wp = reinterpret_cast<const float4*>(ws + ((size_t)((kt * g.KH + kh) * g.KW + kw) * g.Ci + ci) * g.Co);
+                for (int c = 0; c < g.Co / 4; ++c) {
+                    const float4 a = yp[c], b = wp[c];
+                    acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+                }
+            }
+        }
+    }
+    dx[idx] = acc;
+}
+
+// dW[tap][ci][co] += sum_m x[gather(m,tap)][ci] * dy[m][co] when Ci * Co <= 256 (few input OR few output channels: the
+// critic's first conv, the generator's output conv): block = (tap, m-slice), thread = (ci, co); four positions per
+// iteration so that their loads are in flight together (the loop is otherwise one dependent global load per step).
+__global__ void __launch_bounds__(256) conv_bwd_filter_small_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                    float* __restrict__ dw, ConvGeom g, int nslice) {
+    const int tap = blockIdx.x, slice = blockIdx.y;
+    const int kw_ = tap % g.KW, kh_ = (tap / g.KW) % g.KH, kt_ = tap / (g.KW * g.KH);
+    const int co = threadIdx.x % g.Co, ci = threadIdx.x / g.Co;
+    const long long M = (long long)g.B * g.To * g.Ho * g.Wo;
+    const long long per = (M + nslice - 1) / nslice;
+    const long long mbeg = slice * per, mend = mbeg + per < M ? mbeg + per : M;
+    if (ci >= g.Ci || mbeg >= mend) return;
+    PosDec p = decode_pos(mbeg, g.To, g.Ho, g.Wo);
+    float acc = 0.f;
+    for (long long m = mbeg; m < mend; m += 4) {
+        float xv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int lt = p.t * g.stride + kt_ - g.pt, lh = p.h * g.stride + kh_ - g.ph, lw = p.w * g.stride + kw_ - g.pw;
+            const bool ok = m + u < mend && lt >= 0 && lt < g.Ti && lh >= 0 && lh < g.Hi && lw >= 0 && lw < g.Wi;
+            xv[u] = ok ? x[((((long long)p.b * g.Ti + lt) * g.Hi + lh) * g.Wi + lw) * g.Ci + ci] : 0.f;
+            yv[u] = ok ? dy[(m + u) * g.Co + co] : 0.f;
+            if (++p.w == g.Wo) { p.w = 0; if (++p.h == g.Ho) { p.h = 0; if (++p.t == g.To) { p.t = 0; ++p.b; } } }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc = fmaf(xv[u], yv[u], acc);
+    }
+    atomicAdd(&dw[((long long)tap * g.Ci + ci) * g.Co + co], acc);
+}
+
+// y[m][co] = act(sum_{tap,ci} x[gather(m,tap)][ci] * w[tap][ci][co] + bias) for Co <= 4 (the generator's output conv in the
+// training path): one thread per (position, co), weights transposed into shared memory as [tap][co][ci].
+__global__ void __launch_bounds__(256) conv_fwd_smallco_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ y,
+                                                               ConvGeom g, int act, float* __restrict__ pre) {
+    extern __shared__ __align__(16) float ws[];              // [tap][co][ci]
+    const int ntaps = g.KT * g.KH * g.KW;
+    for (int i = threadIdx.x; i < ntaps * g.Ci * g.Co; i += blockDim.x) {
+        const int co = i % g.Co, ci = (i / g.Co) % g.Ci, tap = i / (g.Co * g.Ci);
+        ws[((size_t)tap * g.Co + co) * g.Ci + ci] = w[i];
+    }
+    __syncthreads();
+    const long long M = (long long)g.B * g.To * g.Ho * g.Wo;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * g.Co) return;
+    const int co = (int)(idx % g.Co);
+    const PosDec p = decode_pos(idx / g.Co, g.To, g.Ho, g.Wo);
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int kt = 0; kt < g.KT; ++kt) {
+        const int lt = p.t * g.stride + kt - g.pt;
+        if (lt < 0 || lt >= g.Ti) continue;
+        for (int kh = 0; kh < g.KH; ++kh) {
+            const int lh = p.h * g.stride + kh - g.ph;
+            if (lh < 0 || lh >= g.Hi) continue;
+            for (int kw = 0; kw < g.KW; ++kw) {
+                const int lw = p.w * g.stride + kw - g.pw;
+                if (lw < 0 || lw >= g.Wi) continue;
+                const float4* xp = reinterpret_cast<const float4*>(x + ((((long long)p.b * g.Ti + lt) * g.Hi + lh) * g.Wi + lw) * g.Ci);
+                const float4* wp = reinterpret_cast<const float4*>(ws + ((size_t)((kt * g.KH + kh) * g.KW + kw) * g.Co + co) * g.Ci);
+                for (int c = 0; c < g.Ci / 4; c += 2) {
+                    const float4 a = xp[c], b = wp[c], a2 = xp[c + 1], b2 = wp[c + 1];
+                    acc0 = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc0))));
+                    acc1 = fmaf(a2.x, b2.x, fmaf(a2.y, b2.y, fmaf(a2.z, b2.z, fmaf(a2.w, b2.w, acc1))));
+                }
+            }
+        }
+    }
+    float v = acc0 + acc1;
+    if (bias) v += bias[co];
+    if (pre) pre[idx] = v;
+    if (act == ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
+    y[idx] = v;
+}
+
 // db[c] += sum_m dy[m][c]
 __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, long long M, int C,
                               long long rows_per_block) {
@@ -240,6 +356,94 @@ __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ 
 
 }  // namespace
 
+// ---- backward-data of a stride-2 convolution by parity classes ----
+// dx[p] only receives taps with k = (p + pad) mod 2 on every axis, so a generic tap loop spends 7/8 of its steps on
+// zeros.  Rows are enumerated class-major (class q = parity of p + pad per axis, 8 classes); a 64-row tile is
+// class-homogeneous and walks only its class's taps (k = q, q + 2, ...): 27 taps -> 8/4/4/2/4/2/2/1.
+struct ClsInfo { int tile_begin[9]; };
+
+__global__ void __launch_bounds__(NT) conv_bwd_data_s2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                              float* __restrict__ dx, ConvGeom g, ClsInfo ci_, float* __restrict__ part) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    int cls = 0;
+    while (cls < 7 && (int)blockIdx.x >= ci_.tile_begin[cls + 1]) ++cls;
+    const int qt = cls >> 2, qh = (cls >> 1) & 1, qw = cls & 1;
+    const int ot = (qt - g.pt) & 1, oh = (qh - g.ph) & 1, ow = (qw - g.pw) & 1;       // first position of the class per axis
+    const int ct = (g.Ti - ot + 1) / 2, ch = (g.Hi - oh + 1) / 2, cw = (g.Wi - ow + 1) / 2;   // positions of the class per axis
+    const long long rows = (long long)g.B * ct * ch * cw;
+    const long long r0 = (long long)((int)blockIdx.x - ci_.tile_begin[cls]) * BM;
+    const int n0 = blockIdx.y * BN;
+    const int nkt = (g.KT - qt + 1) / 2, nkh = (g.KH - qh + 1) / 2, nkw = (g.KW - qw + 1) / 2;
+    const int ntaps = nkt * nkh * nkw;
+
+    const int a_m = tid >> 2, a_k = (tid & 3) * 4;
+    const bool am_ok = r0 + a_m < rows;
+    const PosDec ap = decode_pos(am_ok ? r0 + a_m : 0, ct, ch, cw);
+    const int pt_ = ot + 2 * ap.t, ph_ = oh + 2 * ap.h, pw_ = ow + 2 * ap.w;          // actual input position
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int nck = (g.Co + BK - 1) / BK;
+    const int total_steps = ntaps * nck;
+    const int per_slice = (total_steps + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int step_beg = (int)blockIdx.z * per_slice;
+    const int step_end = step_beg + per_slice < total_steps ? step_beg + per_slice : total_steps;
+    for (int ti = step_beg / nck; ti * nck < step_end; ++ti) {
+        const int kt_ = qt + 2 * (ti / (nkh * nkw)), kh_ = qh + 2 * ((ti / nkw) % nkh), kw_ = qw + 2 * (ti % nkw);
+        const int tap = (kt_ * g.KH + kh_) * g.KW + kw_;
+        const int nt = (pt_ + g.pt - kt_) / 2, nh = (ph_ + g.ph - kh_) / 2, nw = (pw_ + g.pw - kw_) / 2;
+        const bool ok = am_ok && pt_ + g.pt >= kt_ && ph_ + g.ph >= kh_ && pw_ + g.pw >= kw_ && nt < g.To && nh < g.Ho && nw < g.Wo;
+        const long long base = ((((long long)ap.b * g.To + nt) * g.Ho + nh) * g.Wo + nw) * g.Co;
+        const int ck_beg = ti * nck < step_beg ? step_beg - ti * nck : 0;
+        const int ck_end = (ti + 1) * nck > step_end ? step_end - ti * nck : nck;
+        for (int c0 = ck_beg * BK; c0 < ck_end * BK; c0 += BK) {
+            float av[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ok) {
+                const float* p = dy + base + c0 + a_k;
+                if (c0 + a_k + 3 < g.Co && ((g.Co & 3) == 0)) {
+                    float4 v = *reinterpret_cast<const float4*>(p);
+                    av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (c0 + a_k + j < g.Co) av[j] = p[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[a_k + j][a_m] = av[j];
+            const int bk = tid & 15, co = c0 + bk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int nn = (tid >> 4) + j * 16, ci = n0 + nn;
+                Bs[bk][nn] = (co < g.Co && ci < g.Ci) ? w[((long long)tap * g.Ci + ci) * g.Co + co] : 0.f;
+            }
+            __syncthreads();
+            fma_tile(acc, As, Bs, ty, tx);
+            __syncthreads();
+        }
+    }
+    const long long Mtot = (long long)g.B * g.Ti * g.Hi * g.Wi;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + ty * 4 + i;
+        if (r >= rows) continue;
+        const PosDec q = decode_pos(r, ct, ch, cw);
+        const long long m = (((long long)q.b * g.Ti + (ot + 2 * q.t)) * g.Hi + (oh + 2 * q.h)) * g.Wi + (ow + 2 * q.w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.Ci) continue;
+            if (part) part[((long long)blockIdx.z * Mtot + m) * g.Ci + n] = acc[i][j];
+            else dx[m * g.Ci + n] = acc[i][j];
+        }
+    }
+}
+
 // Reduction slices for a tile grid of `ctas` CTAs over `steps` K steps: aim at ~2 CTAs per SM, at least 4 steps per slice.
 static int splitk_slices(int ctas, int steps) {
     if (ctas >= 148 || steps < 8) return 1;
@@ -252,6 +456,12 @@ int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, c
                   const float* mask, float mask_scale, cudaStream_t st, float* pre) {
     long long M = (long long)g.B * g.To * g.Ho * g.Wo;
     if (M == 0) return 0;
+    const int ntaps_ = g.KT * g.KH * g.KW;
+    if (!g.up && !mask && g.Co <= 4 && (g.Ci & 7) == 0 && (size_t)ntaps_ * g.Ci * g.Co * 4 <= 48 * 1024) {
+        conv_fwd_smallco_kernel<<<ceil_div(M * g.Co, 256), 256, (size_t)ntaps_ * g.Ci * g.Co * 4, st>>>(x, w, bias, y, g, act, pre);
+        RDG_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid(ceil_div(M, BM), ceil_div(g.Co, BN));
     // slices chosen for a nominal batch of >= 32 so that a sample's summation order (hence its bits) is the same whether it
     // is computed alone or inside a small batch (tests pin batches through exact linearity in the batch)
@@ -276,6 +486,44 @@ int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeo
     int upf = g.up ? 2 : 1;
     long long M = (long long)g.B * g.Ti * upf * g.Hi * upf * g.Wi * upf;
     if (M == 0) return 0;
+    const int ntaps_ = g.KT * g.KH * g.KW;
+    if (!g.up && g.Ci <= 4 && (g.Co & 3) == 0 && (size_t)ntaps_ * g.Ci * g.Co * 4 <= 48 * 1024) {
+        conv_bwd_data_smallci_kernel<<<ceil_div(M * g.Ci, 256), 256, (size_t)ntaps_ * g.Ci * g.Co * 4, st>>>(dy, w, dx, g);
+        RDG_LAUNCH_CHECK();
+        return 0;
+    }
+    if (!g.up && g.stride == 2) {
+        // parity classes; the slice count follows the largest class (8 of 27 taps) at the nominal batch, see simt_conv_fwd
+        ClsInfo ci{};
+        const int Bn = g.B < 32 ? 32 : g.B;
+        int tiles = 0, tiles_nom = 0;
+        for (int cls = 0; cls < 8; ++cls) {
+            const int qt = cls >> 2, qh = (cls >> 1) & 1, qw = cls & 1;
+            const int ot = (qt - g.pt) & 1, oh = (qh - g.ph) & 1, ow = (qw - g.pw) & 1;
+            const long long per = (long long)((g.Ti - ot + 1) / 2) * ((g.Hi - oh + 1) / 2) * ((g.Wi - ow + 1) / 2);
+            ci.tile_begin[cls] = tiles;
+            tiles += ceil_div(per * g.B, BM);
+            tiles_nom += ceil_div(per * Bn, BM);
+        }
+        ci.tile_begin[8] = tiles;
+        dim3 grid(tiles, ceil_div(g.Ci, BN));
+        const int steps_max = ((g.KT + 1) / 2) * ((g.KH + 1) / 2) * ((g.KW + 1) / 2) * ceil_div(g.Co, BK);
+        const int nslice = splitk_slices(tiles_nom * grid.y, steps_max);
+        if (nslice > 1) {
+            float* part = nullptr;
+            RDG_CUDA(cudaMallocAsync(&part, (size_t)nslice * M * g.Ci * sizeof(float), st));
+            grid.z = nslice;
+            conv_bwd_data_s2_kernel<<<grid, NT, 0, st>>>(dy, w, dx, g, ci, part);
+            RDG_LAUNCH_CHECK();
+            splitk_epilogue_kernel<<<ceil_div(M * g.Ci, 256), 256, 0, st>>>(part, nslice, M * g.Ci, g.Ci, nullptr, dx, ACT_NONE, nullptr, 1.f, nullptr);
+            RDG_LAUNCH_CHECK();
+            RDG_CUDA(cudaFreeAsync(part, st));
+            return 0;
+        }
+        conv_bwd_data_s2_kernel<<<grid, NT, 0, st>>>(dy, w, dx, g, ci, nullptr);
+        RDG_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid(ceil_div(M, BM), ceil_div(g.Ci, BN));
     const int nslice = splitk_slices(ceil_div(M / g.B * (g.B < 32 ? 32 : g.B), BM) * grid.y, g.KT * g.KH * g.KW * ceil_div(g.Co, BK));
     if (nslice > 1) {
@@ -299,6 +547,14 @@ int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, 
     long long M = (long long)g.B * g.To * g.Ho * g.Wo;
     if (M == 0) return 0;
     int ntaps = g.KT * g.KH * g.KW;
+    if (!g.up && (g.Ci <= 4 || g.Co <= 4) && g.Ci * g.Co <= 256) {
+        int nslice = 1;
+        while (ntaps * nslice * g.Ci * g.Co < 148 * 2048 * 2 && M / (nslice * 2) >= 32) nslice *= 2;
+        conv_bwd_filter_small_kernel<<<dim3(ntaps, nslice), g.Ci * g.Co, 0, st>>>(x, dy, dw, g, nslice);
+        RDG_LAUNCH_CHECK();
+        if (db) return simt_colsum(dy, db, M, g.Co, st);
+        return 0;
+    }
     int tiles = ceil_div(g.Ci, BM) * ceil_div(g.Co, BN) * ntaps;
     int ksplit = 1;
     while (tiles * ksplit < 592 && (M / (ksplit * 2)) >= 256) ksplit *= 2;
