@@ -271,31 +271,40 @@ __global__ void __launch_bounds__(256) conv_bwd_data_smallci_kernel(const float*
 // dW[tap][ci][co] += sum_m x[gather(m,tap)][ci] * dy[m][co] when Ci * Co <= 256 (few input OR few output channels: the
 // critic's first conv, the generator's output conv): block = (tap, m-slice), thread = (ci, co); four positions per
 // iteration so that their loads are in flight together (the loop is otherwise one dependent global load per step).
-__global__ void __launch_bounds__(256) conv_bwd_filter_small_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(512) conv_bwd_filter_small_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                     float* __restrict__ dw, ConvGeom g, int nslice) {
+    __shared__ float red[512];
     const int tap = blockIdx.x, slice = blockIdx.y;
     const int kw_ = tap % g.KW, kh_ = (tap / g.KW) % g.KH, kt_ = tap / (g.KW * g.KH);
-    const int co = threadIdx.x % g.Co, ci = threadIdx.x / g.Co;
+    const int npair = g.Ci * g.Co, nsub = blockDim.x / npair;      // row subgroups per block, reduced in shared memory
+    const int pair = threadIdx.x % npair, sub = threadIdx.x / npair;
+    const int co = pair % g.Co, ci = pair / g.Co;
     const long long M = (long long)g.B * g.To * g.Ho * g.Wo;
-    const long long per = (M + nslice - 1) / nslice;
-    const long long mbeg = slice * per, mend = mbeg + per < M ? mbeg + per : M;
-    if (ci >= g.Ci || mbeg >= mend) return;
-    PosDec p = decode_pos(mbeg, g.To, g.Ho, g.Wo);
+    const long long per = (M + (long long)nslice * nsub - 1) / ((long long)nslice * nsub);
+    const long long mbeg = ((long long)slice * nsub + sub) * per, mend = mbeg + per < M ? mbeg + per : M;
     float acc = 0.f;
-    for (long long m = mbeg; m < mend; m += 4) {
-        float xv[4], yv[4];
+    if (sub < nsub && mbeg < mend) {
+        PosDec p = decode_pos(mbeg, g.To, g.Ho, g.Wo);
+        for (long long m = mbeg; m < mend; m += 4) {
+            float xv[4], yv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int lt = p.t * g.stride + kt_ - g.pt, lh = p.h * g.stride + kh_ - g.ph, lw = p.w * g.stride + kw_ - g.pw;
-            const bool ok = m + u < mend && lt >= 0 && lt < g.Ti && lh >= 0 && lh < g.Hi && lw >= 0 && lw < g.Wi;
-            xv[u] = ok ? x[((((long long)p.b * g.Ti + lt) * g.Hi + lh) * g.Wi + lw) * g.Ci + ci] : 0.f;
-            yv[u] = ok ? dy[(m + u) * g.Co + co] : 0.f;
-            if (++p.w == g.Wo) { p.w = 0; if (++p.h == g.Ho) { p.h = 0; if (++p.t == g.To) { p.t = 0; ++p.b; } } }
+            for (int u = 0; u < 4; ++u) {
+                const int lt = p.t * g.stride + kt_ - g.pt, lh = p.h * g.stride + kh_ - g.ph, lw = p.w * g.stride + kw_ - g.pw;
+                const bool ok = m + u < mend && lt >= 0 && lt < g.Ti && lh >= 0 && lh < g.Hi && lw >= 0 && lw < g.Wi;
+                xv[u] = ok ? x[((((long long)p.b * g.Ti + lt) * g.Hi + lh) * g.Wi + lw) * g.Ci + ci] : 0.f;
+                yv[u] = ok ? dy[(m + u) * g.Co + co] : 0.f;
+                if (++p.w == g.Wo) { p.w = 0; if (++p.h == g.Ho) { p.h = 0; if (++p.t == g.To) { p.t = 0; ++p.b; } } }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc = fmaf(xv[u], yv[u], acc);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc = fmaf(xv[u], yv[u], acc);
     }
-    atomicAdd(&dw[((long long)tap * g.Ci + ci) * g.Co + co], acc);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (sub == 0) {
+        for (int k = 1; k < nsub; ++k) acc += red[k * npair + pair];
+        atomicAdd(&dw[((long long)tap * g.Ci + ci) * g.Co + co], acc);
+    }
 }
 
 // y[m][co] = act(sum_{tap,ci} x[gather(m,tap)][ci] * w[tap][ci][co] + bias) for Co <= 4 (the generator's output conv in the
@@ -548,9 +557,10 @@ int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, 
     if (M == 0) return 0;
     int ntaps = g.KT * g.KH * g.KW;
     if (!g.up && (g.Ci <= 4 || g.Co <= 4) && g.Ci * g.Co <= 256) {
-        int nslice = 1;
-        while (ntaps * nslice * g.Ci * g.Co < 148 * 2048 * 2 && M / (nslice * 2) >= 32) nslice *= 2;
-        conv_bwd_filter_small_kernel<<<dim3(ntaps, nslice), g.Ci * g.Co, 0, st>>>(x, dy, dw, g, nslice);
+        const int nsub = 512 / (g.Ci * g.Co);
+        int nslice = ceil_div(M, (long long)64 * nsub);             // ~64 rows per thread
+        if (nslice > 128) nslice = 128;
+        conv_bwd_filter_small_kernel<<<dim3(ntaps, nslice), 512, 0, st>>>(x, dy, dw, g, nslice);
         RDG_LAUNCH_CHECK();
         if (db) return simt_colsum(dy, db, M, g.Co, st);
         return 0;
