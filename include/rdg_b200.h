@@ -78,6 +78,22 @@ int  rdg_generate_host(rdg_ctx* ctx, const float* latent_host, const float* cond
                        int scen_per_cond, float* out_host, long long B, int mode, int out_kind,
                        float norm_scale);
 
+/* Ensemble statistics on the device -- the host reductions that follow gen.predict in the
+ * reference: area means np.mean(generated * cond * norm_scale, (2, 3)) (generate_and_evaluate.py:412-415, 533-535)
+ * and properscoring.crps_ensemble(real_precip, generated, axis=0) with its area mean
+ * (generate_and_evaluate_crps.py:189-191).  fields_dev [n_cond*scen_per_cond,24,nd,nd] (members of a condition
+ * contiguous), obs_dev [n_cond,24,nd,nd] or NULL.  Outputs (each optional): area_mean_dev [n_cond*scen_per_cond,24],
+ * crps_dev [n_cond,24,nd,nd], crps_area_mean_dev [n_cond,24]. */
+int  rdg_ensemble_stats(rdg_ctx* ctx, const float* fields_dev, int n_cond, int scen_per_cond,
+                        const float* obs_dev, float* area_mean_dev, float* crps_dev,
+                        float* crps_area_mean_dev, void* stream);
+/* rdg_generate_host + rdg_ensemble_stats fused per chunk: the fields never leave the GPU, only the statistics are
+ * copied back (the whole CRPS loop of generate_and_evaluate_crps.py:177-191 in one call).  obs_host [n_cond,24,nd,nd]
+ * mm/h or NULL; area_mean_host [B,24] or NULL; crps_area_mean_host [n_cond,24] or NULL.  B = n_cond * scen_per_cond. */
+int  rdg_generate_stats_host(rdg_ctx* ctx, const float* latent_host, const float* cond_host, int scen_per_cond,
+                             const float* obs_host, long long B, int mode, int out_kind, float norm_scale,
+                             float* area_mean_host, float* crps_area_mean_host);
+
 /* Device-side N(0,1) latent (counter-based Philox4x32-10 + Box-Muller), for throughput runs
  * where the reference would call np.random.normal (raindisagg_gan_pretrained.py:56). */
 int  rdg_fill_normal(float* dst_dev, long long n, uint64_t seed, uint64_t offset, void* stream);

@@ -288,3 +288,50 @@ def adam_update(params, grads, v_state, t, lr=1e-4, beta1=0.0, beta2=0.9, eps=1e
         p = p - np.float32(lr_t) * m / (np.sqrt(v) + np.float32(eps))
         new_p.append(p.astype(np.float32)); new_v.append(v.astype(np.float32)); new_m.append(m)
     return new_p, new_v, new_m
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ensemble statistics: host reductions that follow gen.predict in the reference
+# ---------------------------------------------------------------------------------------------------------
+def area_mean(fields):
+    """np.mean(generated * cond * norm_scale, (2, 3)) (generate_and_evaluate.py:533-535): fields [B,24,ny,nx] -> [B,24]."""
+    return np.asarray(fields, np.float64).mean(axis=(2, 3))
+
+
+def crps_ensemble(obs, forecasts):
+    """properscoring.crps_ensemble(obs, forecasts, axis=0) with equal weights, restated from its published algorithm
+    (properscoring 0.1, `_crps_ensemble_gufunc`: third-party dependency of generate_and_evaluate_crps.py:189, not in
+    /root/reference and not installed here): sort the members, integrate (F_ens(x) - 1{x >= obs})^2 dx piecewise.
+    obs [...], forecasts [n, ...] -> [...] (float64)."""
+    obs = np.asarray(obs, np.float64)
+    f = np.sort(np.asarray(forecasts, np.float64), axis=0)
+    n = f.shape[0]
+    flat_o, flat_f = obs.reshape(-1), f.reshape(n, -1)
+    res = np.empty_like(flat_o)
+    for p in range(flat_o.size):
+        o, integral, obs_cdf, fc_cdf, prev = flat_o[p], 0.0, 0.0, 0.0, 0.0
+        for k in range(n):
+            x = flat_f[k, p]
+            if obs_cdf == 0 and o < x:
+                integral += (o - prev) * fc_cdf ** 2
+                integral += (x - o) * (fc_cdf - 1) ** 2
+                obs_cdf = 1.0
+            else:
+                integral += (x - prev) * (fc_cdf - obs_cdf) ** 2
+            fc_cdf += 1.0 / n
+            prev = x
+        if obs_cdf == 0:
+            integral += o - prev
+        res[p] = integral
+    return res.reshape(obs.shape)
+
+
+def crps_ensemble_energy(obs, forecasts):
+    """Same score in the energy form mean|x - y| - 0.5 mean|x - x'| (vectorised; what the CUDA kernel evaluates)."""
+    f = np.asarray(forecasts, np.float64)
+    o = np.asarray(obs, np.float64)
+    a = np.abs(f - o[None]).mean(axis=0)
+    fs = np.sort(f, axis=0)
+    n = f.shape[0]
+    k = (2 * np.arange(1, n + 1) - n - 1).reshape((n,) + (1,) * (f.ndim - 1))
+    return a - (k * fs).sum(axis=0) / (n * n)

@@ -467,6 +467,71 @@ extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const flo
     return 0;
 }
 
+int rdg_stats_chunk(rdg_ctx* c, const float* fields, int n_cond, int spc, const float* obs, float* area_mean, float* crps_amean,
+                    cudaStream_t st);
+
+// Generation + ensemble statistics, chunked by whole conditions; only the statistics are copied back.
+extern "C" int rdg_generate_stats_host(rdg_ctx* c, const float* latent_host, const float* cond_host, int spc, const float* obs_host,
+                                       long long B, int mode, int out_kind, float norm_scale, float* area_mean_host,
+                                       float* crps_amean_host) {
+    if (!c || B < 0 || spc < 1 || mode < 0 || mode > 2 || B % spc) { rdg_set_error("rdg_generate_stats_host: bad arguments (B must be n_cond * scen_per_cond)"); return RDG_E_BADARG; }
+    if (crps_amean_host && !obs_host) { rdg_set_error("rdg_generate_stats_host: CRPS needs observations"); return RDG_E_BADARG; }
+    if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
+    if (B == 0) return 0;
+    RDG_CUDA(cudaSetDevice(c->device));
+    if (c->gen_packed_stale && mode != RDG_MODE_FP32) { int r = rdg_repack_generator(c, c->s_comp); if (r) return r; }
+    const int chunk_max = chunk_for_mode(c, mode);
+    if (spc > chunk_max) { rdg_set_error("rdg_generate_stats_host: %d members per condition exceed the chunk of %d samples", spc, chunk_max); return RDG_E_BADARG; }
+    const int cond_per_chunk = chunk_max / spc, chunk = cond_per_chunk * spc;
+    const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
+    const size_t ncf = (size_t)c->nd * c->nd * c->ncond;
+    const long long n_cond = B / spc;
+    for (int i = 0; i < 2; ++i) {
+        if (!c->e2e_lat[i]) RDG_CUDA(cudaMalloc(&c->e2e_lat[i], (size_t)c->max_chunk * RDG_LATENT * 4));
+        if (!c->e2e_out[i]) RDG_CUDA(cudaMalloc(&c->e2e_out[i], (size_t)c->max_chunk * plane * 4));
+    }
+    if (c->e2e_cond_cap < (size_t)n_cond * ncf) {
+        cudaFree(c->e2e_cond);
+        c->e2e_cond = nullptr;
+        RDG_CUDA(cudaMalloc(&c->e2e_cond, (size_t)n_cond * ncf * 4));
+        c->e2e_cond_cap = (size_t)n_cond * ncf;
+    }
+    float* obs_dev = nullptr; float* am_dev = nullptr; float* cr_dev = nullptr;
+    if (obs_host) RDG_CUDA(cudaMalloc(&obs_dev, (size_t)n_cond * plane * 4));
+    if (area_mean_host) RDG_CUDA(cudaMalloc(&am_dev, (size_t)B * RDG_NHOURS * 4));
+    if (crps_amean_host) RDG_CUDA(cudaMalloc(&cr_dev, (size_t)n_cond * RDG_NHOURS * 4));
+    auto cleanup = [&]() { cudaFree(obs_dev); cudaFree(am_dev); cudaFree(cr_dev); };
+#define RDG_CUDA_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rdg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return (int)e_; } } while (0)
+    RDG_CUDA_C(cudaMemsetAsync(c->flag_dev, 0, sizeof(int), c->s_comp));
+    RDG_CUDA_C(cudaMemcpyAsync(c->e2e_cond, cond_host, (size_t)n_cond * ncf * 4, cudaMemcpyHostToDevice, c->s_comp));
+    if (obs_host) RDG_CUDA_C(cudaMemcpyAsync(obs_dev, obs_host, (size_t)n_cond * plane * 4, cudaMemcpyHostToDevice, c->s_comp));
+    long long it = 0;
+    for (long long b0 = 0; b0 < B; b0 += chunk, ++it) {
+        const int n = (int)std::min<long long>(chunk, B - b0);
+        const int k = (int)(it & 1);
+        if (it >= 2) RDG_CUDA_C(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[k], 0));     // latent buffer k free after compute of chunk it-2
+        RDG_CUDA_C(cudaMemcpyAsync(c->e2e_lat[k], latent_host + b0 * RDG_LATENT, (size_t)n * RDG_LATENT * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        RDG_CUDA_C(cudaEventRecord(c->ev_in[k], c->s_h2d));
+        RDG_CUDA_C(cudaStreamWaitEvent(c->s_comp, c->ev_in[k], 0));
+        int r = gen_forward_chunk(c, c->e2e_lat[k], c->e2e_cond, spc, (int)b0, c->e2e_out[k], n, mode, out_kind, norm_scale,
+                                  c->flag_dev, c->s_comp);
+        if (!r) r = rdg_stats_chunk(c, c->e2e_out[k], n / spc, spc, obs_dev ? obs_dev + (b0 / spc) * plane : nullptr,
+                                    am_dev ? am_dev + b0 * RDG_NHOURS : nullptr, cr_dev ? cr_dev + (b0 / spc) * RDG_NHOURS : nullptr, c->s_comp);
+        if (r) { cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_h2d); cleanup(); return r; }
+        RDG_CUDA_C(cudaEventRecord(c->ev_comp[k], c->s_comp));
+    }
+    int flag = 0;
+    if (area_mean_host) RDG_CUDA_C(cudaMemcpyAsync(area_mean_host, am_dev, (size_t)B * RDG_NHOURS * 4, cudaMemcpyDeviceToHost, c->s_comp));
+    if (crps_amean_host) RDG_CUDA_C(cudaMemcpyAsync(crps_amean_host, cr_dev, (size_t)n_cond * RDG_NHOURS * 4, cudaMemcpyDeviceToHost, c->s_comp));
+    RDG_CUDA_C(cudaMemcpyAsync(&flag, c->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, c->s_comp));
+    RDG_CUDA_C(cudaStreamSynchronize(c->s_comp));
+    RDG_CUDA_C(cudaStreamSynchronize(c->s_h2d));
+#undef RDG_CUDA_C
+    cleanup();
+    if (flag) { rdg_set_error("found nan in output of per_gridpoint_softmax"); return RDG_E_NONFINITE; }
+    return 0;
+}
+
 extern "C" int rdg_fill_normal(float* dst_dev, long long n, uint64_t seed, uint64_t offset, void* stream) {
     if (!dst_dev || n < 0 || (offset & 3)) { rdg_set_error("rdg_fill_normal: bad arguments (offset must be a multiple of 4)"); return RDG_E_BADARG; }
     return ew_fill_normal(dst_dev, n, seed, offset, (cudaStream_t)stream);

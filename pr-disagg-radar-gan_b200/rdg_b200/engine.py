@@ -158,6 +158,50 @@ class Generator:
         return out
 
 
+    # ---- ensemble statistics on the device
+    def ensemble_stats_device(self, fields, scen_per_cond, obs=None, want_crps_field=False):
+        """fields [n_cond*spc,24,nd,nd] cuda f32 (members of a condition contiguous), obs [n_cond,24,nd,nd] cuda f32 or None
+        -> dict(area_mean [n_cond*spc,24], crps_area_mean [n_cond,24], crps [n_cond,24,nd,nd]) as cuda tensors:
+        np.mean(generated, (2,3)) (generate_and_evaluate.py:533-535) and properscoring.crps_ensemble(obs, generated, axis=0)
+        with its area mean (generate_and_evaluate_crps.py:189-191)."""
+        B = int(fields.shape[0])
+        spc = int(scen_per_cond)
+        if B % spc:
+            raise ValueError("ensemble_stats: the batch must hold whole ensembles")
+        n_cond = B // spc
+        dev = fields.device
+        out = {"area_mean": torch.empty((B, W.NHOURS), device=dev, dtype=torch.float32)}
+        crps = cam = None
+        if obs is not None:
+            cam = out["crps_area_mean"] = torch.empty((n_cond, W.NHOURS), device=dev, dtype=torch.float32)
+            if want_crps_field:
+                crps = out["crps"] = torch.empty((n_cond, W.NHOURS, self.nd, self.nd), device=dev, dtype=torch.float32)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(self.ctx.lib.rdg_ensemble_stats(self.ctx.handle, p(fields), n_cond, spc, p(obs), p(out["area_mean"]),
+                                                   p(crps), p(cam), self.ctx._stream()))
+        return out
+
+    def generate_ensemble_stats_host(self, latent, cond_norm, scen_per_cond, obs_mm=None, mode=None, out_mm=True,
+                                     norm_scale=W.NORM_SCALE):
+        """The CRPS loop of generate_and_evaluate_crps.py:177-191 in one call: generate scen_per_cond scenarios for every
+        condition and reduce them on the GPU; only the statistics come back.  latent [n_cond*spc,100], cond_norm
+        [n_cond,nd,nd,ncond], obs_mm [n_cond,24,nd,nd] (real_precip) or None -> (area_mean [n_cond*spc,24],
+        crps_area_mean [n_cond,24] or None).  numpy arrays or pinned CPU torch tensors."""
+        def ptr(a):
+            if a is None:
+                return None
+            return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else a.ctypes.data_as(C.c_void_p)
+        B = int(latent.shape[0])
+        n_cond = B // int(scen_per_cond)
+        am = np.empty((B, W.NHOURS), np.float32)
+        cr = np.empty((n_cond, W.NHOURS), np.float32) if obs_mm is not None else None
+        m = _lib.MODES[mode or self.mode]
+        _lib.check(self.ctx.lib.rdg_generate_stats_host(
+            self.ctx.handle, ptr(latent), ptr(cond_norm), int(scen_per_cond), ptr(obs_mm), B, m,
+            _lib.OUT_MM if out_mm else _lib.OUT_FRACTION, float(norm_scale), ptr(am), ptr(cr)))
+        return am, cr
+
+
 class Critic:
     """Stand-in for the Keras critic model (create_discriminator, gan_train...py:272-309)."""
 
