@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--e2e-group", type=int, default=1000, help="conditions per host-API call in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-iteration timing")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup
@@ -283,6 +284,81 @@ def main():
         assert torch.equal(out_h[:1000], out[last0:last0 + 1000].cpu()), "e2e output differs from device-resident output"
         del out_h, lat_h
 
+    # ---- the same ensemble workload through the statistics API: fields stay on the GPU, only the
+    # area means [B,24] and the area-mean CRPS [n_cond,24] come back (generate_and_evaluate_crps.py:177-191 per condition)
+    e2e_stats = None
+    if not args.no_e2e:
+        grp_cond = min(n_cond, args.e2e_group)
+        lat_h = torch.empty((B, 100), dtype=torch.float32, pin_memory=True)
+        lat_h.copy_(latent)
+        cond_p = torch.as_tensor(cond_h).pin_memory()
+        rng = np.random.default_rng(99 + rank)
+        obs_frac = rng.random((grp_cond, 24, 16, 16), dtype=np.float32)
+        obs_frac /= obs_frac.sum(axis=1, keepdims=True)
+        obs_p = torch.as_tensor(obs_frac).pin_memory()      # synthetic observations, one block reused by every group
+        torch.cuda.synchronize()
+
+        def stats_step():
+            last = None
+            for c0 in range(0, n_cond, grp_cond):
+                c1 = min(n_cond, c0 + grp_cond)
+                last = gen.generate_ensemble_stats_host(lat_h[c0 * spc:c1 * spc], cond_p[c0:c1], spc, obs_p[:c1 - c0],
+                                                        mode=args.mode, out_mm=True)
+            return last
+
+        stats_step()
+        barrier()
+        t0 = time.perf_counter()
+        am, cr = stats_step()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert np.isfinite(am).all() and np.isfinite(cr).all()
+        e2e_stats = {"value": world * B / float(t.item()), "unit": "scenarios/s",
+                     "h2d_bytes_per_step": int(lat_h.numel() * 4 + cond_p.numel() * 4 + n_cond * 24 * 256 * 4),
+                     "d2h_bytes_per_step": int(B * 24 * 4 + n_cond * 24 * 4),
+                     "api": f"rdg_generate_stats_host: generation + on-device area means and ensemble CRPS, {grp_cond} conditions per call"}
+        del lat_h
+
+    # ---- training iteration (configs #3/#4): 5 critic steps + 1 generator step, batch 32 per GPU, data-parallel over the ranks
+    train = None
+    if not args.no_train:
+        from rdg_b200.engine import Critic, GanTrainer
+        tctx = Context(16, 1, device=local, max_chunk=1024)
+        tgen = Generator(W.init_generator_weights(0), ctx=tctx)
+        tcrit = Critic(W.init_critic_weights(1), ctx=tctx)
+        tr = GanTrainer(tgen, tcrit, gen_mode="fp16", seed=100 + rank)
+        TB = 32
+        rng = np.random.default_rng(7 + rank)
+        lg = rng.standard_normal((TB, 24, 16, 16, 1)).astype(np.float32) * 2
+        ex = np.exp(lg - lg.max(axis=1, keepdims=True))
+        x_real = tctx.dev((ex / ex.sum(axis=1, keepdims=True)).astype(np.float32))
+        tcond = tctx.dev(synth_conditions(TB, 16, 1000 + rank))
+        tg = torch.Generator(device=dev); tg.manual_seed(5 + rank)
+
+        def iteration():
+            for _ in range(5):
+                losses = tr.critic_train_on_batch([x_real, tcond, torch.randn((TB, 100), device=dev, generator=tg)])
+            return losses, tr.generator_train_on_batch([torch.randn((TB, 100), device=dev, generator=tg), tcond])
+
+        for _ in range(3):
+            iteration()
+        barrier()
+        n_it = 5
+        t0 = time.perf_counter()
+        for _ in range(n_it):
+            losses, gl = iteration()
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / n_it], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        train = {"ms_per_iteration": 1e3 * float(t.item()), "samples_per_s": world * TB / float(t.item()),
+                 "config": "cWGAN-GP, 5 critic steps (3 critic passes + gradient penalty, frozen generator forward on tensor cores) "
+                           "+ 1 generator step, batch 32 per GPU, FP32 SIMT gradients, one flat-gradient all-reduce per optimizer step",
+                 "finite": bool(np.isfinite(losses).all() and np.isfinite(gl))}
+        tctx.close()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -328,7 +404,7 @@ def main():
             "config": dict(workload_config(n_cond, spc), **{"chunk": ctx.max_chunk, "mode": args.mode,
                        "l2": "inputs (410 MB latent+cond) and outputs (24.6 GB) per step exceed the 126 MB L2",
                        "parallelism": f"shard{world}-independent"}),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "e2e": e2e, "e2e_stats": e2e_stats, "train": train, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "conservation_rel_err": cons}
     print(json.dumps(line), flush=True)
     if dist is not None:

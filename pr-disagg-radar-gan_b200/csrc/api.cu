@@ -171,6 +171,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     cudaFree(c->g_grads); cudaFree(c->g_m); cudaFree(c->g_v);
     cudaFree(c->c_grads); cudaFree(c->c_m); cudaFree(c->c_v);
     for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) cudaFree(c->g_wpack[k][l]);
+    for (int i = 0; i < 4; ++i) cudaFree(c->st_buf[i]);
     for (int k = 0; k < 2; ++k) { cudaFree(c->g_w4pack[k]); cudaFree(c->g_wpack_planes[k]); cudaFree(c->g_wpack_dense[k]); }
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->e2e_lat[i]); cudaFree(c->e2e_out[i]);
@@ -467,8 +468,8 @@ extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const flo
     return 0;
 }
 
-int rdg_stats_chunk(rdg_ctx* c, const float* fields, int n_cond, int spc, const float* obs, float* area_mean, float* crps_amean,
-                    cudaStream_t st);
+int rdg_stats_chunk(rdg_ctx* c, const float* fields, int n_cond, int spc, const float* obs, float* area_mean, float* crps_scratch,
+                    float* crps_amean, cudaStream_t st);
 
 // Generation + ensemble statistics, chunked by whole conditions; only the statistics are copied back.
 extern "C" int rdg_generate_stats_host(rdg_ctx* c, const float* latent_host, const float* cond_host, int spc, const float* obs_host,
@@ -496,11 +497,21 @@ extern "C" int rdg_generate_stats_host(rdg_ctx* c, const float* latent_host, con
         RDG_CUDA(cudaMalloc(&c->e2e_cond, (size_t)n_cond * ncf * 4));
         c->e2e_cond_cap = (size_t)n_cond * ncf;
     }
-    float* obs_dev = nullptr; float* am_dev = nullptr; float* cr_dev = nullptr;
-    if (obs_host) RDG_CUDA(cudaMalloc(&obs_dev, (size_t)n_cond * plane * 4));
-    if (area_mean_host) RDG_CUDA(cudaMalloc(&am_dev, (size_t)B * RDG_NHOURS * 4));
-    if (crps_amean_host) RDG_CUDA(cudaMalloc(&cr_dev, (size_t)n_cond * RDG_NHOURS * 4));
-    auto cleanup = [&]() { cudaFree(obs_dev); cudaFree(am_dev); cudaFree(cr_dev); };
+    float* obs_dev = nullptr; float* am_dev = nullptr; float* cr_dev = nullptr; float* crps_tmp = nullptr;
+    {
+        const size_t want[4] = {obs_host ? (size_t)n_cond * plane : 0, area_mean_host ? (size_t)B * RDG_NHOURS : 0,
+                                crps_amean_host ? (size_t)n_cond * RDG_NHOURS : 0, crps_amean_host ? (size_t)cond_per_chunk * plane : 0};
+        for (int i = 0; i < 4; ++i)
+            if (c->st_cap[i] < want[i]) {
+                cudaFree(c->st_buf[i]); c->st_buf[i] = nullptr; c->st_cap[i] = 0;
+                RDG_CUDA(cudaMalloc(&c->st_buf[i], want[i] * 4));
+                c->st_cap[i] = want[i];
+            }
+        if (obs_host) obs_dev = c->st_buf[0];
+        if (area_mean_host) am_dev = c->st_buf[1];
+        if (crps_amean_host) { cr_dev = c->st_buf[2]; crps_tmp = c->st_buf[3]; }
+    }
+    auto cleanup = [&]() {};
 #define RDG_CUDA_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rdg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return (int)e_; } } while (0)
     RDG_CUDA_C(cudaMemsetAsync(c->flag_dev, 0, sizeof(int), c->s_comp));
     RDG_CUDA_C(cudaMemcpyAsync(c->e2e_cond, cond_host, (size_t)n_cond * ncf * 4, cudaMemcpyHostToDevice, c->s_comp));
@@ -516,7 +527,7 @@ extern "C" int rdg_generate_stats_host(rdg_ctx* c, const float* latent_host, con
         int r = gen_forward_chunk(c, c->e2e_lat[k], c->e2e_cond, spc, (int)b0, c->e2e_out[k], n, mode, out_kind, norm_scale,
                                   c->flag_dev, c->s_comp);
         if (!r) r = rdg_stats_chunk(c, c->e2e_out[k], n / spc, spc, obs_dev ? obs_dev + (b0 / spc) * plane : nullptr,
-                                    am_dev ? am_dev + b0 * RDG_NHOURS : nullptr, cr_dev ? cr_dev + (b0 / spc) * RDG_NHOURS : nullptr, c->s_comp);
+                                    am_dev ? am_dev + b0 * RDG_NHOURS : nullptr, crps_tmp, cr_dev ? cr_dev + (b0 / spc) * RDG_NHOURS : nullptr, c->s_comp);
         if (r) { cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_h2d); cleanup(); return r; }
         RDG_CUDA_C(cudaEventRecord(c->ev_comp[k], c->s_comp));
     }

@@ -30,6 +30,8 @@ struct rdg_ctx {
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
     float* e2e_lat[2] = {}; float* e2e_out[2] = {}; float* e2e_cond = nullptr; size_t e2e_cond_cap = 0;
+    // rdg_generate_stats_host staging (grow-only): observations, area means, CRPS area means, per-chunk CRPS field
+    float* st_buf[4] = {}; size_t st_cap[4] = {};
     // instrumentation: kernel launch counter and optional per-layer CUDA-event timing
     long long launches = 0;
     bool prof_on = false;

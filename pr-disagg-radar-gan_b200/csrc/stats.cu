@@ -94,7 +94,7 @@ extern "C" int rdg_ensemble_stats(rdg_ctx* c, const float* fields_dev, int n_con
     return stats_launch(c, fields_dev, n_cond, spc, obs_dev, area_mean_dev, crps_dev, crps_area_mean_dev, (cudaStream_t)stream);
 }
 
-int rdg_stats_chunk(rdg_ctx* c, const float* fields, int n_cond, int spc, const float* obs, float* area_mean, float* crps_amean,
-                    cudaStream_t st) {
-    return stats_launch(c, fields, n_cond, spc, obs, area_mean, nullptr, crps_amean, st);
+int rdg_stats_chunk(rdg_ctx* c, const float* fields, int n_cond, int spc, const float* obs, float* area_mean, float* crps_scratch,
+                    float* crps_amean, cudaStream_t st) {
+    return stats_launch(c, fields, n_cond, spc, obs, area_mean, crps_scratch, crps_amean, st);
 }
