@@ -94,6 +94,15 @@ int  rdg_generate_stats_host(rdg_ctx* ctx, const float* latent_host, const float
                              const float* obs_host, long long B, int mode, int out_kind, float norm_scale,
                              float* area_mean_host, float* crps_area_mean_host);
 
+/* Device-side batch sampler: the preprocessing of generate_real_samples / generate_latent_points
+ * (gan_train_cwgangp_pixelnorm.py:143-174, 177-193) on a radar array resident in HBM.  data_dev [n_days,24,ny,nx] f32 mm/h;
+ * idx_dev [n,3] int32 rows (tidx, yidx, xidx) = indices_all[ixs] (:148); batch_dev [n,24,nd,nd] fractions of the daily sum
+ * (NULL for generate_latent_points, which only needs the condition); cond_dev [n,nd,nd] = daily sum / norm_scale.
+ * flag_dev (optional int32): bit 0 = a fraction is NaN or outside [0,1] (the reference's asserts :167-170), bit 1 = an
+ * index outside the array (:133-136). */
+int  rdg_sample_windows(const float* data_dev, int n_days, int ny, int nx, const int* idx_dev, int n, int nd,
+                        float norm_scale, float* batch_dev, float* cond_dev, int* flag_dev, void* stream);
+
 /* Device-side N(0,1) latent (counter-based Philox4x32-10 + Box-Muller), for throughput runs
  * where the reference would call np.random.normal (raindisagg_gan_pretrained.py:56). */
 int  rdg_fill_normal(float* dst_dev, long long n, uint64_t seed, uint64_t offset, void* stream);

@@ -335,3 +335,23 @@ def crps_ensemble_energy(obs, forecasts):
     n = f.shape[0]
     k = (2 * np.arange(1, n + 1) - n - 1).reshape((n,) + (1,) * (f.ndim - 1))
     return a - (k * fs).sum(axis=0) / (n * n)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batch sampler
+# ---------------------------------------------------------------------------------------------------------
+def sample_windows(data, idcs_batch, ndomain, norm_scale=127.4, with_batch=True):
+    """The numpy statements of generate_real_samples (gan_train_cwgangp_pixelnorm.py:148-163) for given index rows
+    (tidx, yidx, xidx): window gather (view_as_windows :151-152), daily sum (:156), fractions (:159-160), normalised
+    condition (:163).  float32 throughout, as in the reference (data.dtype == float32, :138)."""
+    data = np.asarray(data)
+    assert data.dtype == np.float32
+    batch = np.stack([data[t, :, y:y + ndomain, x:x + ndomain] for t, y, x in np.asarray(idcs_batch)])
+    batch = np.expand_dims(batch, -1)
+    batch_cond = np.sum(batch, axis=1)
+    if with_batch:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            for i in range(len(batch)):
+                batch[i] = batch[i] / batch_cond[i]
+    batch_cond = batch_cond / norm_scale
+    return (batch if with_batch else None), batch_cond

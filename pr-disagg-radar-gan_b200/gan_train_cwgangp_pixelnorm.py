@@ -144,9 +144,13 @@ def synthetic_radar(days=64, ny=64, nx=64, seed=0):
     return (base * prof).astype(np.float32)
 
 
-def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None):
-    """Build what the reference builds at import (:117-140, :360-408)."""
-    global data, indices_all, n_samples, generator, critic, critic_model, generator_model, optimizer, trainer
+sampler = None       # rdg_b200.sampler.DeviceSampler when the batches are drawn on the GPU (setup(device_sampler=True))
+
+
+def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None, device_sampler=None):
+    """Build what the reference builds at import (:117-140, :360-408).  device_sampler (default: env RDG_DEVICE_SAMPLER=1):
+    keep the radar array in HBM and gather / normalise the batches there (replaces the GeneratorEnqueuer workers, :440-449)."""
+    global data, indices_all, n_samples, generator, critic, critic_model, generator_model, optimizer, trainer, sampler
     from rdg_b200.engine import Adam, GanTrainer
     np.random.seed(seed)
     data = synthetic_radar(seed=seed) if data_array is None else np.asarray(data_array, np.float32)
@@ -164,6 +168,12 @@ def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None):
                          seed=seed)
     critic_model = _CriticModel(trainer)
     generator_model = _GeneratorModel(trainer)
+    if device_sampler is None:
+        device_sampler = os.environ.get('RDG_DEVICE_SAMPLER', '0') == '1'
+    sampler = None
+    if device_sampler:
+        from rdg_b200.sampler import DeviceSampler
+        sampler = DeviceSampler(_ctx(), data, indices_all, ndomain, norm_scale)
     return trainer
 
 
@@ -175,6 +185,8 @@ def _windows(ixs):
 
 def generate_real_samples(n_batch):
     """reference :143-174"""
+    if sampler is not None:
+        yield from sampler.real_samples(n_batch)
     while True:
         ixs = np.random.randint(n_samples, size=n_batch)
         batch = _windows(ixs)
@@ -191,6 +203,8 @@ def generate_real_samples(n_batch):
 
 def generate_latent_points(n_batch):
     """reference :177-193"""
+    if sampler is not None:
+        return sampler.latent_points(n_batch, latent_dim)
     latent = np.random.normal(size=(n_batch, latent_dim))
     ixs = np.random.randint(0, n_samples, size=n_batch)
     batch_cond = np.sum(_windows(ixs), axis=1) / norm_scale
@@ -207,6 +221,8 @@ def generate_latent_points_as_generator(n_batch):
 def generate_fake_samples(n_batch):
     """reference :201-206"""
     latent, cond = generate_latent_points(n_batch)
+    if not isinstance(cond, np.ndarray):
+        cond = cond.cpu().numpy()
     return [generator.predict([latent, cond]), cond]
 
 

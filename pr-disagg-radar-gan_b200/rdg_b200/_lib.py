@@ -40,6 +40,8 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "rdg_generate_stats_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong,
                                           C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "rdg_sample_windows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rdg_fill_normal": (C.c_int, [C.c_void_p, C.c_longlong, C.c_uint64, C.c_uint64, C.c_void_p]),
     "rdg_critic_set_weights": (C.c_int, [C.c_void_p, _c_float_pp, _c_size_p, C.c_int]),
     "rdg_critic_get_weights": (C.c_int, [C.c_void_p, _c_float_pp, _c_size_p, C.c_int]),

@@ -110,3 +110,38 @@ def test_nonfinite_latent_is_flagged_in_tensor_core_modes(gen, mode):
     z[3, 7] = np.inf
     with pytest.raises(NonFiniteError):
         g.predict([z, cond], mode=mode)
+
+
+def test_ensemble_scale_properties():
+    """Config #2 shape at 1/10 size (1000 conditions x 100 scenarios, 21 chunks of the default 4736-scenario chunk + a ragged
+    tail): properties that do not need the oracle -- daily-sum conservation for every scenario, finiteness, members of one
+    condition differ, and independence of the chunking (a context with a different chunk size gives the same bits)."""
+    import ctypes as C
+    from rdg_b200 import _lib
+    from rdg_b200.engine import Context, Generator
+    n_cond, spc = 1000, 100
+    B = n_cond * spc
+    gw = W.init_generator_weights(0)
+    rng = np.random.default_rng(354)
+    cond_mm = np.clip(rng.gamma(0.8, 12.0, size=(n_cond, 16, 16, 1)), 0, 200).astype(np.float32)
+    outs = []
+    for chunk in (0, 1000):
+        ctx = Context(16, 1, max_chunk=chunk)
+        try:
+            g = Generator(gw, ctx=ctx, mode="fp16")
+            cond = ctx.dev(cond_mm / np.float32(127.4))
+            n = B if chunk == 0 else 7 * spc
+            z = torch.empty((n, 100), device=cond.device)
+            _lib.check(ctx.lib.rdg_fill_normal(C.c_void_p(z.data_ptr()), n * 100, 77, 0, ctx._stream()))
+            out = g.forward_device(z, cond, scen_per_cond=spc, mode="fp16", out_mm=True)
+            if chunk == 0:
+                assert bool(torch.isfinite(out).all())
+                daily = out.sum(dim=1)
+                want = (cond[:, :, :, 0] * 127.4).repeat_interleave(spc, dim=0)
+                assert float(((daily - want).abs() / want.clamp_min(1e-6)).max()) <= 1e-5
+                assert float((out[0] - out[1]).abs().max()) > 0          # different noise, different scenario
+                assert float(out.min()) >= 0.0
+            outs.append(out[:7 * spc].cpu())
+        finally:
+            ctx.close()
+    assert torch.equal(outs[0], outs[1])
