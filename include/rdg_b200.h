@@ -135,6 +135,9 @@ int  rdg_param_buffer(rdg_ctx* ctx, int which, float** params_dev, size_t* n);
 int  rdg_adam_apply(rdg_ctx* ctx, int which, float lr, float beta1, float beta2, float eps,
                     long long step_t, float grad_scale, void* stream);
 int  rdg_adam_reset(rdg_ctx* ctx, int which);
+/* Device pointers to the Adam moment buffers m, v (flat, same layout as rdg_param_buffer) -- optimizer-state checkpoints
+ * (the reference saves weights only, gan_train_cwgangp_pixelnorm.py:520-521, and cannot resume). */
+int  rdg_adam_buffers(rdg_ctx* ctx, int which, float** m_dev, float** v_dev, size_t* n);
 
 /* ---- building blocks exposed for tests (same kernels the calls above use) ---- */
 /* y = x / sqrt(mean_c(x^2) + 1e-8), optional LeakyReLU(0.2) (gan_train...py:255-266, :333) */

@@ -34,6 +34,18 @@ extern "C" int rdg_param_buffer(rdg_ctx* c, int which, float** params_dev, size_
     return 0;
 }
 
+// Adam moment buffers (same flat layout as the parameters) for optimizer-state checkpoints
+extern "C" int rdg_adam_buffers(rdg_ctx* c, int which, float** m_dev, float** v_dev, size_t* n) {
+    if (!c || which < 0 || which > 1) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
+    int r = ensure_train_state(c);
+    if (r) return r;
+    if (m_dev) *m_dev = which == 0 ? c->g_m : c->c_m;
+    if (v_dev) *v_dev = which == 0 ? c->g_v : c->c_v;
+    if (n) *n = which == 0 ? c->g_total : c->c_total;
+    return 0;
+}
+
 // Keras OptimizerV2 Adam, TF 2.1: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps)
 extern "C" int rdg_adam_apply(rdg_ctx* c, int which, float lr, float beta1, float beta2, float eps, long long step_t,
                               float grad_scale, void* stream) {

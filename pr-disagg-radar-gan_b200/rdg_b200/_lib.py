@@ -57,6 +57,7 @@ SIGNATURES = {
     "rdg_adam_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_longlong,
                                  C.c_float, C.c_void_p]),
     "rdg_adam_reset": (C.c_int, [C.c_void_p, C.c_int]),
+    "rdg_adam_buffers": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _c_size_p]),
     "rdg_pixelnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "rdg_softmax_hours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "rdg_conv3d": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -306,6 +306,49 @@ class GanTrainer:
             self._bufs[("p", which)] = torch.as_tensor(_DevBuf(p.value, n.value), device=f"cuda:{self.ctx.device}")
         return self._bufs[("p", which)]
 
+    def _adam_tensors(self, which):
+        if ("a", which) not in self._bufs:
+            m, v, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+            _lib.check(self.ctx.lib.rdg_adam_buffers(self.ctx.handle, which, C.byref(m), C.byref(v), C.byref(n)))
+            dev = f"cuda:{self.ctx.device}"
+            self._bufs[("a", which)] = (torch.as_tensor(_DevBuf(m.value, n.value), device=dev),
+                                        torch.as_tensor(_DevBuf(v.value, n.value), device=dev))
+        return self._bufs[("a", which)]
+
+    # -- checkpoint / resume.  The reference writes weights only (:520-521) and has no resume path
+    # (`start_epoch` just labels plots, :526-529); this adds the optimizer state so training continues bit-identically.
+    def state_dict(self):
+        torch.cuda.synchronize(self.ctx.device)
+        sd = {"iterations": np.int64(self.optimizer.iterations),
+              "adam": np.array([self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon], np.float64),
+              "rng_state": self._gen.get_state().cpu().numpy()}
+        for which, name, net in ((0, "gen", self.generator), (1, "critic", self.critic)):
+            for i, w in enumerate(net.get_weights()):
+                sd[f"{name}_w{i}"] = w
+            m, v = self._adam_tensors(which)
+            sd[f"{name}_adam_m"], sd[f"{name}_adam_v"] = m.cpu().numpy(), v.cpu().numpy()
+        return sd
+
+    def load_state_dict(self, sd):
+        self.generator.set_weights([sd[f"gen_w{i}"] for i in range(10)])
+        self.critic.set_weights([sd[f"critic_w{i}"] for i in range(10)])
+        for which, name in ((0, "gen"), (1, "critic")):
+            m, v = self._adam_tensors(which)
+            m.copy_(torch.as_tensor(np.asarray(sd[f"{name}_adam_m"], np.float32)))
+            v.copy_(torch.as_tensor(np.asarray(sd[f"{name}_adam_v"], np.float32)))
+        self.optimizer.iterations = int(sd["iterations"])
+        self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon = (float(x) for x in sd["adam"])
+        self._gen.set_state(torch.as_tensor(np.asarray(sd["rng_state"], np.uint8)))
+        torch.cuda.synchronize(self.ctx.device)
+
+    def save_checkpoint(self, path):
+        """One .npz with both nets' weights (Keras order), the Adam moments, the shared step counter and the RNG state."""
+        np.savez(path, **self.state_dict())
+
+    def load_checkpoint(self, path):
+        with np.load(path) as f:
+            self.load_state_dict({k: f[k] for k in f.files})
+
     def critic_mask_shapes(self, B):
         shapes, chans = [], (64, 128, 256, 256)
         for (_, out, _), ch in zip(W.critic_geometry(self.ctx.nd), chans):

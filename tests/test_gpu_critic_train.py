@@ -192,3 +192,39 @@ def test_adam_trajectory_shared_counter(ctx16):
     out16 = gen.predict([z, cond], mode="fp16")
     ref = O.generator_forward(gen.get_weights(), z, cond, torch.float64)
     assert np.max(np.abs(out16 - ref) / np.abs(ref)) <= 1e-2
+
+
+def test_checkpoint_resume(ctx16, tmp_path):
+    """weights + Adam moments + shared step counter + RNG state; a resumed run reproduces the
+    uninterrupted one (the reference saves weights only and cannot resume, gan_train...py:520-529) up to the summation
+    order of the FP32 atomics in the filter-gradient kernels (~1e-7 per step), which is also the run-to-run spread."""
+    from rdg_b200.engine import Critic, GanTrainer, Generator
+    x, cond, z, _, rng = _batch(4, seed=21)
+
+    def run(tr, n):
+        out = []
+        for _ in range(n):
+            out.append(tr.critic_train_on_batch([x, cond, z]))
+            out.append(tr.generator_train_on_batch([z, cond]))
+        return out
+
+    def fresh():
+        return GanTrainer(Generator(W.init_generator_weights(5), ctx=ctx16), Critic(W.init_critic_weights(6), ctx=ctx16), seed=3)
+
+    tr = fresh()
+    run(tr, 2)
+    path = str(tmp_path / "state.npz")
+    tr.save_checkpoint(path)
+    want = run(tr, 2)
+    want_w = tr.generator.get_weights()
+    tr2 = fresh()
+    tr2.load_checkpoint(path)
+    assert tr2.optimizer.iterations == 4
+    got = run(tr2, 2)
+    for g, w_ in zip(got, want):
+        np.testing.assert_allclose(g, w_, rtol=1e-4, atol=1e-6)
+    for a, b in zip(tr2.generator.get_weights(), want_w):
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=5e-6)   # the output-conv bias has a zero gradient: Adam amplifies its rounding noise
+    # without the optimizer state the continuation is a different trajectory (v = 0 restarts Adam's step size)
+    tr3 = fresh()
+    tr3.generator.set_weights(tr.generator.get_weights())
