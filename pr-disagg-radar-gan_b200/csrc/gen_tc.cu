@@ -31,10 +31,14 @@ namespace {
 // SKIP_OOB: offsets whose whole activation tile lies in the zero padding (t+dt outside the grid) are dropped.
 // With weight multicast (cluster > 1) every CTA of the cluster must walk the SAME weight sequence, so the step
 // is kept (oob = true): no activation load, no MMA, but the weight stage is still consumed.
-template <int NPH, bool SKIP_OOB, typename FA, typename FB>
+// The w offsets are walked in the order 0, -1, +1.  MERGE (two w-phases per pass on CTA pairs): the dw = 0 view serves both
+// phases of the pass, so its two weight tiles form ONE N = 2*Cout operand; such a step is reported per 64-channel chunk
+// as on_b(0, tile of phase 0, oob, k, tile of phase 1) with k >= 0 (k = -1: ordinary single-phase stage of kc chunks).
+// Coming first in every (dt, dh) group, the merged step finds both accumulators in the same started / not-started state.
+template <int NPH, bool SKIP_OOB, bool MERGE, typename FA, typename FB>
 __device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk, int kc, FA&& on_a, FB&& on_b) {
     for (int o = 0; o < 27; ++o) {
-        const int dt = o / 9 - 1, dh = (o / 3) % 3 - 1, dw = o % 3 - 1;
+        const int dt = o / 9 - 1, dh = (o / 3) % 3 - 1, dw = (o % 3 == 0) ? 0 : (o % 3 == 1 ? -1 : 1);
         const bool oob = t + dt < 0 || t + dt >= T;   // whole tile in the zero padding
         if (SKIP_OOB && oob) continue;
         uint32_t mask = 0;
@@ -47,12 +51,19 @@ __device__ __forceinline__ void for_each_step(int pass, int t, int T, int nchunk
         if (!mask) continue;
         for (int c = 0; c < nchunk; c += kc) {       // kc consecutive 64-channel chunks per stage
             on_a(dt, dh, dw, c, oob);
+            if (MERGE && mask == 3u) {
+                const int p0 = pass * NPH, p1 = p0 + 1;
+                const int a0 = ((dt + 1 - (p0 >> 2)) << 2) | ((dh + 1 - ((p0 >> 1) & 1)) << 1) | (dw + 1 - (p0 & 1));
+                const int a1 = ((dt + 1 - (p1 >> 2)) << 2) | ((dh + 1 - ((p1 >> 1) & 1)) << 1) | (dw + 1 - (p1 & 1));
+                for (int k = 0; k < kc; ++k) on_b(0, (p0 * 8 + a0) * nchunk + c + k, oob, k, (p1 * 8 + a1) * nchunk + c + k);
+                continue;
+            }
 #pragma unroll
             for (int s = 0; s < NPH; ++s) {
                 if (!(mask & (1u << s))) continue;
                 const int p = pass * NPH + s;
                 const int a = ((dt + 1 - (p >> 2)) << 2) | ((dh + 1 - ((p >> 1) & 1)) << 1) | (dw + 1 - (p & 1));
-                on_b(s, (p * 8 + a) * nchunk + c, oob);
+                on_b(s, (p * 8 + a) * nchunk + c, oob, -1, 0);
             }
         }
     }
@@ -71,7 +82,7 @@ template <int COUT, int NPH, int KC, int CG = 1> struct TcCfg {
     static constexpr int kAccCols = NPH * COUT;
     static constexpr int kAccStages = (kAccCols * 2 <= 512) ? 2 : 1;
     static constexpr int kFuseBytes = COUT == 64 ? kATile + 4096 : 0;
-    static constexpr int kAStages = KC == 1 ? 4 : 3;
+    static constexpr int kAStages = KC == 1 ? (CG == 2 ? 6 : 4) : (CG == 2 ? 4 : 3);   // CTA pairs: half-size weight stages leave room for a deeper activation ring
     static constexpr int kBudget = 218 * 1024 - kFuseBytes - kAStages * kAStage;
     static constexpr int kBStages = kBudget / kBStage > 8 * CG ? 8 * CG : kBudget / kBStage;
     static constexpr int kSmem = 1024 + kAStages * kAStage + kBStages * kBStage + kFuseBytes + COUT * 4 + 512;
@@ -96,6 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w, TcConvArgs args) {
     using Cfg = TcCfg<COUT, NPH, KC, CG>;
     constexpr bool kSkip = true;
+    constexpr bool kMerge = CG == 2 && NPH == 2 && COUT == 128 && KC == 2;   // dw = 0 views as one N = 256 MMA per k16
     const uint32_t cta_rank = CG > 1 ? cluster_ctarank() : 0;
     const bool leader = cta_rank == 0;
     const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;   // a unit = CG tiles (one per CTA of the pair)
@@ -163,7 +175,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
                 const int hblk = unit % n_hblk, t = (unit / n_hblk) % args.T, bblk = unit / (n_hblk * args.T) * CG + (int)cta_rank;
                 const int h0 = hblk * args.Hb, b0 = bblk * args.Bt;
                 for (int pass = 0; pass < 8 / NPH; ++pass) {
-                    for_each_step<NPH, kSkip>(
+                    for_each_step<NPH, kSkip, kMerge>(
                         pass, t, args.T, nchunk, KC,
                         [&](int dt, int dh, int dw, int c, bool oob) {
                             if (oob) return;                  // tile entirely in the zero padding: nothing to load
@@ -183,7 +195,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
                                 }
                             }
                         },
-                        [&](int, int, bool) {});
+                        [&](int, int, bool, int, int) {});
                 }
             }
         }
@@ -195,9 +207,9 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
             for (int unit = unit0; unit < n_units; unit += unit_stride) {
                 const int t = (unit / n_hblk) % args.T;
                 for (int pass = 0; pass < 8 / NPH; ++pass) {
-                    for_each_step<NPH, kSkip>(
+                    for_each_step<NPH, kSkip, kMerge>(
                         pass, t, args.T, nchunk, KC, [&](int, int, int, int, bool) {},
-                        [&](int, int wtile, bool) {
+                        [&](int, int wtile, bool, int mk, int wtile2) {
                             // b_empty[s] completes once the MMA issuers of all CL CTAs released the stage
                             const uint32_t s = bi % Cfg::kBStages, ph = (bi / Cfg::kBStages) & 1;
                             if (!free_next) mbar_wait(&b_empty[s], ph ^ 1);
@@ -212,10 +224,18 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
                                 } else {
                                     // weight image as rows of 128 B, COUT rows per tile: this CTA takes rows rank*COUT/2 .. of each tile
                                     const uint32_t bar = mapa_rank(smem_u32(&b_full[s]), 0);
+                                    if (kMerge && mk >= 0) {
+                                        // merged step: this CTA holds ALL rows of its own phase's tile (rows rank*Cout.. of the N = 2*Cout operand)
+                                        const int row0 = (cta_rank == 0 ? wtile : wtile2) * COUT;
 #pragma unroll
-                                    for (int k = 0; k < KC; ++k)
-                                        tma_load_2d_cg2(b_buf + s * Cfg::kBStage + k * Cfg::kBTile, &tmap_w, bar, 0,
-                                                        (wtile + k) * COUT + (int)cta_rank * (COUT / 2));
+                                        for (int k = 0; k < 2; ++k)
+                                            tma_load_2d_cg2(b_buf + s * Cfg::kBStage + k * (Cfg::kBStage / 2), &tmap_w, bar, 0, row0 + k * (COUT / 2));
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < KC; ++k)
+                                            tma_load_2d_cg2(b_buf + s * Cfg::kBStage + k * Cfg::kBTile, &tmap_w, bar, 0,
+                                                            (wtile + k) * COUT + (int)cta_rank * (COUT / 2));
+                                    }
                                 }
                             }
                         });
@@ -241,7 +261,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
                     uint32_t cur_a = 0;
                     bool have_a = false;
                     uint32_t prev_a_slot = 0;
-                    for_each_step<NPH, kSkip>(
+                    for_each_step<NPH, kSkip, kMerge>(
                         pass, t, args.T, nchunk, KC,
                         [&](int, int, int, int, bool oob) {
                             if (oob) return;
@@ -255,7 +275,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
                             prev_a_slot = s;
                             have_a = true;
                         },
-                        [&](int slot, int, bool oob) {
+                        [&](int slot, int, bool oob, int mk, int) {
                             const uint32_t s = bi % Cfg::kBStages, ph = (bi / Cfg::kBStages) & 1;
                             if (!b_ready) mbar_wait(&b_full[s], ph);
                             ++bi;
@@ -264,7 +284,16 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
                             const uint32_t b_addr = smem_u32(b_buf + s * Cfg::kBStage);
                             const uint32_t acc0 = (started >> slot) & 1u;
                             if (elect_one()) {
-                                if (!oob) {
+                                if (kMerge && mk >= 0) {
+                                    if (!oob) {
+                                        constexpr uint32_t idesc2 = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
+                                                                    ((uint32_t)((2 * COUT) >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+                                        const uint64_t ad = make_sdesc(cur_a + mk * kATile), bd = make_sdesc(b_addr);
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            tc_mma_g<CG>(d_base, ad + 2 * k, bd + 2 * k, idesc2, (started & 1u) | ((mk | k) ? 1u : 0u));
+                                    }
+                                } else if (!oob) {
 #pragma unroll
                                     for (int c = 0; c < KC; ++c) {
                                         const uint64_t ad = make_sdesc(cur_a + c * kATile), bd = make_sdesc(b_addr + c * Cfg::kBTile);
@@ -275,7 +304,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
                                 }
                                 tc_commit_g<CG>(&b_empty[s]);       // CG == 2: releases the stage in both CTAs
                             }
-                            if (!oob) started |= 1u << slot;
+                            if (!oob) started |= (kMerge && mk >= 0) ? 3u : (1u << slot);
                         });
                     if (elect_one()) {
                         if (have_a) tc_commit_g<CG>(&a_empty[prev_a_slot]);
