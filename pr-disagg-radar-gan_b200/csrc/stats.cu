@@ -54,6 +54,43 @@ __global__ void __launch_bounds__(256) crps_ensemble_kernel(const float* __restr
     }
 }
 
+// Large ensembles (spc > 160, e.g. the 1000 members of generate_and_evaluate_crps.py:161-162): bitonic sort of the members of
+// each column in shared memory (padded to a power of two with +inf), then sum_{i<j} |x_i - x_j| = sum_k (2k - n + 1) x_(k):
+// O(n log^2 n) instead of O(n^2) per grid point.
+__global__ void __launch_bounds__(256) crps_ensemble_sort_kernel(const float* __restrict__ fields, const float* __restrict__ obs,
+                                                                 float* __restrict__ crps, int spc, int npad, int cols) {
+    extern __shared__ float tile[];                       // [npad][32]
+    __shared__ double red_pair[8][32], red_abs[8][32];
+    const int cond = blockIdx.x, c0 = blockIdx.y * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float* base = fields + (size_t)cond * spc * cols + c0 + lane;
+    for (int m = w; m < npad; m += 8) tile[m * 32 + lane] = m < spc ? base[(size_t)m * cols] : INFINITY;
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = w; t < npad / 2; t += 8) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const float a = tile[i * 32 + lane], b = tile[l * 32 + lane];
+                const bool asc = (i & k) == 0;
+                if ((a > b) == asc) { tile[i * 32 + lane] = b; tile[l * 32 + lane] = a; }
+            }
+            __syncthreads();
+        }
+    const float y = obs[(size_t)cond * cols + c0 + lane];
+    double pair = 0.0, ab = 0.0;
+    for (int k = w; k < spc; k += 8) {
+        const float x = tile[k * 32 + lane];
+        pair += (double)(2 * k - spc + 1) * (double)x;
+        ab += (double)fabsf(x - y);
+    }
+    red_pair[w][lane] = pair; red_abs[w][lane] = ab;
+    __syncthreads();
+    if (w == 0) {
+        for (int k = 1; k < 8; ++k) { pair += red_pair[k][lane]; ab += red_abs[k][lane]; }
+        crps[(size_t)cond * cols + c0 + lane] = (float)(ab / spc - pair / ((double)spc * spc));
+    }
+}
+
 }  // namespace
 
 static int stats_launch(rdg_ctx* c, const float* fields, int n_cond, int spc, const float* obs, float* area_mean, float* crps,
@@ -71,8 +108,17 @@ static int stats_launch(rdg_ctx* c, const float* fields, int n_cond, int spc, co
         float* tmp = nullptr;
         if (!crps) { RDG_CUDA(cudaMallocAsync(&tmp, (size_t)n_cond * cols * sizeof(float), st)); crps = tmp; }
         static bool attr_set = false;
-        if (!attr_set) { RDG_CUDA(cudaFuncSetAttribute(crps_ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
-        crps_ensemble_kernel<<<dim3(n_cond, cols / 32), 256, smem, st>>>(fields, obs, crps, spc, cols);
+        if (!attr_set) {
+            RDG_CUDA(cudaFuncSetAttribute(crps_ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            RDG_CUDA(cudaFuncSetAttribute(crps_ensemble_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        int npad = 1;
+        while (npad < spc) npad <<= 1;
+        if (spc > 160 && (size_t)npad * 32 * sizeof(float) <= 200 * 1024)
+            crps_ensemble_sort_kernel<<<dim3(n_cond, cols / 32), 256, (size_t)npad * 32 * sizeof(float), st>>>(fields, obs, crps, spc, npad, cols);
+        else
+            crps_ensemble_kernel<<<dim3(n_cond, cols / 32), 256, smem, st>>>(fields, obs, crps, spc, cols);
         RDG_LAUNCH_CHECK();
         c->launches += 1;
         if (crps_amean) {

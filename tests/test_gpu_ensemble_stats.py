@@ -17,7 +17,7 @@ def gen(ctx16):
     return Generator(W.randomize_biases(W.init_generator_weights(0)), ctx=ctx16)
 
 
-@pytest.mark.parametrize("n_cond,spc", [(3, 10), (2, 100), (1, 1), (2, 333)])
+@pytest.mark.parametrize("n_cond,spc", [(3, 10), (2, 100), (1, 1), (2, 160), (2, 333), (1, 1000), (1, 1100)])
 def test_stats_kernels_match_oracle(gen, n_cond, spc):
     rng = np.random.default_rng(spc)
     fields = rng.gamma(0.8, 2.0, size=(n_cond * spc, 24, 16, 16)).astype(np.float32)
