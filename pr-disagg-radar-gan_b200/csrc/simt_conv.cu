@@ -357,9 +357,9 @@ __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ 
     long long r0 = (long long)blockIdx.x * rows_per_block;
     long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = 0.f;
-        for (long long r = r0; r < r1; ++r) s += dy[r * C + c];
-        atomicAdd(&db[c], s);
+        double s = 0.0;        // the fake / real halves of a critic batch nearly cancel: keep the block's partial sum exact
+        for (long long r = r0; r < r1; ++r) s += (double)dy[r * C + c];
+        atomicAdd(&db[c], (float)s);
     }
 }
 

@@ -217,39 +217,69 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
     const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
     size_t max_act = 0, sum_act = 0;
     for (int l = 0; l < 5; ++l) { max_act = std::max(max_act, critic_act_elems(c, l)); sum_act += critic_act_elems(c, l); }
-    const size_t need = ((size_t)B * (3 * (2 * sum_act + 64) + 6 * max_act + 3 * px) + 4096) * 4 + 64 * 256;
+    const size_t need = ((size_t)B * (3 * (2 * sum_act + 64) + 3 * sum_act + 8 * max_act + 3 * px) + 4096) * 4 + 128 * 256;
     TRY(ensure_train_ws(c, need));
     Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
-    CriticActs Af, Ar, Ah;
-    TRY(critic_alloc(c, ws, B, Af)); TRY(critic_alloc(c, ws, B, Ar)); TRY(critic_alloc(c, ws, B, Ah));
+    // The three critic invocations (fake :372, real :373, interpolated :379) run as ONE batch of 3B samples [fake | real | hat]:
+    // every conv sees 3x the rows (the deep critic layers have only 12 / 2 rows per sample), a third of the launches.
+    CriticActs A3;
+    TRY(critic_alloc(c, ws, 3 * B, A3));
+    CriticActs Af = A3, Ar = A3, Ah = A3;                 // views of the three thirds
+    for (int l = 0; l < 5; ++l) {
+        const size_t e = (size_t)B * critic_act_elems(c, l);
+        Ar.h[l] = A3.h[l] + e; Ah.h[l] = A3.h[l] + 2 * e;
+        if (l) { Ar.a[l] = A3.a[l] + e; Ah.a[l] = A3.a[l] + 2 * e; }
+    }
+    Ar.score = A3.score + B; Ah.score = A3.score + 2 * B;
+    const bool use_masks = masks_fake && masks_real && masks_hat;
+    if (!use_masks && (masks_fake || masks_real || masks_hat)) { rdg_set_error("rdg_critic_step_grads: give all three mask sets or none"); return RDG_E_BADARG; }
+    float* masks3_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    const float* masks3[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (use_masks)
+        for (int l = 0; l < 4; ++l) {
+            const size_t e = (size_t)B * critic_act_elems(c, l + 1);
+            masks3_buf[l] = ws.f(3 * e);
+            if (!masks3_buf[l]) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
+            RDG_CUDA(cudaMemcpyAsync(masks3_buf[l], masks_fake[l], e * 4, cudaMemcpyDeviceToDevice, st));
+            RDG_CUDA(cudaMemcpyAsync(masks3_buf[l] + e, masks_real[l], e * 4, cudaMemcpyDeviceToDevice, st));
+            RDG_CUDA(cudaMemcpyAsync(masks3_buf[l] + 2 * e, masks_hat[l], e * 4, cudaMemcpyDeviceToDevice, st));
+            masks3[l] = masks3_buf[l];
+        }
     float* fake_img = ws.f((size_t)B * px);
     float* xhat = ws.f((size_t)B * px);
-    float* t0 = ws.f((size_t)B * max_act); float* t1 = ws.f((size_t)B * max_act);
+    float* t0 = ws.f((size_t)2 * B * max_act); float* t1 = ws.f((size_t)2 * B * max_act);
     float* gbuf = ws.f((size_t)B * max_act);   // first-order gradient g_l of D(xhat)
     float* ubuf = ws.f((size_t)B * max_act);   // second-order cotangent u_l
     float* vbuf = ws.f((size_t)B * max_act);
     float* delta[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int l = 1; l <= 4; ++l) delta[l] = ws.f((size_t)B * critic_act_elems(c, l));
-    float* dscore = ws.f(B); float* norm = ws.f(B); float* lsc = ws.f(8);
+    float* dscore = ws.f(2 * B); float* norm = ws.f(B); float* lsc = ws.f(8);
     if (!lsc || !delta[4]) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
 
     // frozen generator forward (:370, generator.trainable = False :363)
     TRY(rdg_generator_forward(c, latent_dev, cond_dev, 1, fake_img, B, gen_mode, RDG_OUT_FRACTION, 1.f, nullptr, stream));
     RDG_CUDA(cudaMemsetAsync(c->c_grads, 0, c->c_total * 4, st));
 
-    // three critic invocations in graph order: fake (:372), real (:373), interpolated (:379)
-    TRY(critic_fwd_train(c, fake_img, cond_dev, masks_fake, B, Af, st));
-    TRY(critic_fwd_train(c, x_real_dev, cond_dev, masks_real, B, Ar, st));
+    // three critic invocations in graph order: fake (:372), real (:373), interpolated (:379), as one 3B batch
     TRY(ew_interp(x_real_dev, fake_img, alpha_dev, xhat, B, (long long)px, st));
-    TRY(critic_fwd_train(c, xhat, cond_dev, masks_hat, B, Ah, st));
+    TRY(ew_critic_input(fake_img, cond_dev, Af.h[0], B, c->nd, c->ncond, st));
+    TRY(ew_critic_input(x_real_dev, cond_dev, Ar.h[0], B, c->nd, c->ncond, st));
+    TRY(ew_critic_input(xhat, cond_dev, Ah.h[0], B, c->nd, c->ncond, st));
+    for (int l = 0; l < 4; ++l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l, 3 * B);
+        TRY(simt_conv_fwd(A3.h[l], c->c_params + c->c_off[2 * l], c->c_params + c->c_off[2 * l + 1], A3.h[l + 1], g, ACT_LRELU,
+                          masks3[l], 1.f / 0.75f, st, A3.a[l + 1]));
+    }
+    TRY(simt_conv_fwd(A3.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A3.score, rdg_critic_dense_geom(c, 3 * B), ACT_NONE,
+                      nullptr, 1.f, st));
 
-    // Wasserstein terms: l_valid = mean(-D(real)), l_fake = mean(+D(fake))  (:215-216, targets :452-454)
+    // Wasserstein terms: l_valid = mean(-D(real)), l_fake = mean(+D(fake))  (:215-216, targets :452-454); their backward
+    // passes run as one 2B batch [fake | real] with dscore = [+1/B | -1/B]
     TRY(ew_mean_scaled(Ar.score, B, -1.f, lsc + 0, st));
     TRY(ew_mean_scaled(Af.score, B, 1.f, lsc + 1, st));
-    TRY(ew_fill(dscore, B, -1.f / (float)B, st));
-    TRY(critic_bwd(c, Ar, masks_real, dscore, B, c->c_grads, nullptr, t0, t1, st));
     TRY(ew_fill(dscore, B, 1.f / (float)B, st));
-    TRY(critic_bwd(c, Af, masks_fake, dscore, B, c->c_grads, nullptr, t0, t1, st));
+    TRY(ew_fill(dscore + B, B, -1.f / (float)B, st));
+    TRY(critic_bwd(c, A3, use_masks ? masks3 : nullptr, dscore, 2 * B, c->c_grads, nullptr, t0, t1, st));
 
     // gradient penalty (:230-244): first-order backward of sum_b D(xhat_b) to xhat, keeping delta_l
     {
