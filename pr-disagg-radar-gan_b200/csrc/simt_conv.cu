@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(256) conv_bwd_data_smallci_kernel(const float*
 // iteration so that their loads are in flight together (the loop is otherwise one dependent global load per step).
 __global__ void __launch_bounds__(512) conv_bwd_filter_small_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                     float* __restrict__ dw, ConvGeom g, int nslice) {
+    constexpr int kMaxRows = 2048;
+    __shared__ int soff[kMaxRows];           // gather offset of each of the block's rows for this tap (-1: zero padding)
     __shared__ float red[512];
     const int tap = blockIdx.x, slice = blockIdx.y;
     const int kw_ = tap % g.KW, kh_ = (tap / g.KW) % g.KH, kt_ = tap / (g.KW * g.KH);
@@ -280,20 +282,28 @@ __global__ void __launch_bounds__(512) conv_bwd_filter_small_kernel(const float*
     const int pair = threadIdx.x % npair, sub = threadIdx.x / npair;
     const int co = pair % g.Co, ci = pair / g.Co;
     const long long M = (long long)g.B * g.To * g.Ho * g.Wo;
-    const long long per = (M + (long long)nslice * nsub - 1) / ((long long)nslice * nsub);
-    const long long mbeg = ((long long)slice * nsub + sub) * per, mend = mbeg + per < M ? mbeg + per : M;
+    const long long per_blk = (M + nslice - 1) / nslice;           // host guarantees per_blk <= kMaxRows
+    const long long mbeg = (long long)slice * per_blk, mend = mbeg + per_blk < M ? mbeg + per_blk : M;
+    const int rows = mend > mbeg ? (int)(mend - mbeg) : 0;
+    // the index arithmetic is the same for all (ci, co) pairs: do it once per row
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        const PosDec p = decode_pos(mbeg + r, g.To, g.Ho, g.Wo);
+        const int lt = p.t * g.stride + kt_ - g.pt, lh = p.h * g.stride + kh_ - g.ph, lw = p.w * g.stride + kw_ - g.pw;
+        const bool ok = lt >= 0 && lt < g.Ti && lh >= 0 && lh < g.Hi && lw >= 0 && lw < g.Wi;
+        soff[r] = ok ? (int)(((((long long)p.b * g.Ti + lt) * g.Hi + lh) * g.Wi + lw) * g.Ci) : -1;
+    }
+    __syncthreads();
     float acc = 0.f;
-    if (sub < nsub && mbeg < mend) {
-        PosDec p = decode_pos(mbeg, g.To, g.Ho, g.Wo);
-        for (long long m = mbeg; m < mend; m += 4) {
+    if (sub < nsub) {
+        const float* dyb = dy + mbeg * g.Co + co;
+        for (int r = sub; r < rows; r += 4 * nsub) {
             float xv[4], yv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int lt = p.t * g.stride + kt_ - g.pt, lh = p.h * g.stride + kh_ - g.ph, lw = p.w * g.stride + kw_ - g.pw;
-                const bool ok = m + u < mend && lt >= 0 && lt < g.Ti && lh >= 0 && lh < g.Hi && lw >= 0 && lw < g.Wi;
-                xv[u] = ok ? x[((((long long)p.b * g.Ti + lt) * g.Hi + lh) * g.Wi + lw) * g.Ci + ci] : 0.f;
-                yv[u] = ok ? dy[(m + u) * g.Co + co] : 0.f;
-                if (++p.w == g.Wo) { p.w = 0; if (++p.h == g.Ho) { p.h = 0; if (++p.t == g.To) { p.t = 0; ++p.b; } } }
+                const int rr = r + u * nsub;
+                const int off = rr < rows ? soff[rr] : -1;
+                xv[u] = off >= 0 ? x[off + ci] : 0.f;
+                yv[u] = off >= 0 ? dyb[(size_t)rr * g.Co] : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) acc = fmaf(xv[u], yv[u], acc);
@@ -558,8 +568,10 @@ int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, 
     int ntaps = g.KT * g.KH * g.KW;
     if (!g.up && (g.Ci <= 4 || g.Co <= 4) && g.Ci * g.Co <= 256) {
         const int nsub = 512 / (g.Ci * g.Co);
-        int nslice = ceil_div(M, (long long)64 * nsub);             // ~64 rows per thread
+        int nslice = ceil_div(M, (long long)64 * nsub);             // ~64 rows per thread ...
         if (nslice > 128) nslice = 128;
+        if (nslice < ceil_div(M, 2048)) nslice = ceil_div(M, 2048); // ... and at most 2048 rows per block (offset table)
+        if ((long long)g.B * g.Ti * g.Hi * g.Wi * g.Ci >= (1ll << 31)) { rdg_set_error("conv_bwd_filter_small: tensor too large"); return -1; }
         conv_bwd_filter_small_kernel<<<dim3(ntaps, nslice), 512, 0, st>>>(x, dy, dw, g, nslice);
         RDG_LAUNCH_CHECK();
         if (db) return simt_colsum(dy, db, M, g.Co, st);
