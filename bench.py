@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--e2e-group", type=int, default=1000, help="conditions per host-API call in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-iteration timing")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -186,6 +187,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    from rdg_b200.dist import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa else None   # local pinned staging for the e2e legs
 
     n_cond, spc = args.conditions, args.scen_per_cond
     B = n_cond * spc
@@ -364,6 +367,21 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- config #1 (example.py:8-11): cond = 10 mm/day everywhere, n_scenarios = 10, through the Keras-like predict call
+    ex_cond = np.repeat((10.0 * np.ones((1, 16, 16, 1)) / 127.4).astype(np.float32), 10, axis=0)
+    np.random.seed(354)
+    ex_lat = np.random.normal(size=(10, 100)).astype(np.float32)
+    for _ in range(5):
+        ex_out = gen.predict([ex_lat, ex_cond], mode=args.mode)
+    ts = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        ex_out = gen.predict([ex_lat, ex_cond], mode=args.mode)
+        ts.append(time.perf_counter() - t0)
+    example = {"workload": "example.py: cond = 10 mm/day, n_scenarios = 10, gen.predict with host arrays",
+               "latency_us_median": 1e6 * statistics.median(ts), "scenarios_per_s": 10 / statistics.median(ts),
+               "conservation_err": float(np.abs(ex_out.sum(axis=1) - 1).max())}
+
     burst, sustained, hbm, src = load_peaks()
     conv3_ms = ms_sum[5] / max(1, n_l[5])
     units_per_launch = n_u[5] / max(1, n_l[5])
@@ -403,8 +421,8 @@ def main():
             "data": "synthetic",
             "config": dict(workload_config(n_cond, spc), **{"chunk": ctx.max_chunk, "mode": args.mode,
                        "l2": "inputs (410 MB latent+cond) and outputs (24.6 GB) per step exceed the 126 MB L2",
-                       "parallelism": f"shard{world}-independent"}),
-            "e2e": e2e, "e2e_stats": e2e_stats, "train": train, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                       "parallelism": f"shard{world}-independent", "numa_node_rank0": numa}),
+            "e2e": e2e, "e2e_stats": e2e_stats, "train": train, "example": example, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "conservation_rel_err": cons}
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -146,6 +146,7 @@ extern "C" int rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int 
     per32 += (size_t)(d.Ci + d.Co) * 4;
     for (int l = 0; l < 4; ++l) { per16 += gen_act_elems(c, l) * 2; per32 += (l ? gen_act_elems(c, l) * 4 : 0); }
     per16 += gen_act_elems(c, 3) / 64 * 32 * 4;   // f32 tap products P of the fused output conv
+    per32 += gen_act_elems(c, 3) * 4 + 2048;      // phase-major staging of the folded FP32 convs (+ alignment slack)
     c->per_sample16 = per16; c->per_sample32 = per32;
     c->ws_bytes = per16 * (size_t)max_chunk + 4096 * 8;
     RDG_CUDA(cudaMalloc(&c->ws, c->ws_bytes));
@@ -172,6 +173,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     cudaFree(c->c_grads); cudaFree(c->c_m); cudaFree(c->c_v);
     for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) cudaFree(c->g_wpack[k][l]);
     for (int i = 0; i < 4; ++i) cudaFree(c->st_buf[i]);
+    for (int i = 0; i < 3; ++i) cudaFree(c->g_wfold32[i]);
     for (int k = 0; k < 2; ++k) { cudaFree(c->g_w4pack[k]); cudaFree(c->g_wpack_planes[k]); cudaFree(c->g_wpack_dense[k]); }
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->e2e_lat[i]); cudaFree(c->e2e_out[i]);
@@ -204,6 +206,20 @@ static int upload_params(float* dev, const size_t* off, const size_t* size, cons
     for (int i = 0; i < 10; ++i)
         if (sizes[i] != size[i]) { rdg_set_error("%s: tensor %d has %zu elements, expected %zu", what, i, sizes[i], size[i]); return RDG_E_BADARG; }
     for (int i = 0; i < 10; ++i) RDG_CUDA(cudaMemcpy(dev + off[i], tensors[i], size[i] * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// FP32 folded kernels for the SIMT path (FP32 inference mode, training step)
+int rdg_refold32(rdg_ctx* c, cudaStream_t st) {
+    static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
+    if (!c->fold32_stale) return 0;
+    for (int l = 0; l < 3; ++l) {
+        if (!c->g_wfold32[l]) RDG_CUDA(cudaMalloc(&c->g_wfold32[l], folded_weight_elems(cin[l], cout[l]) * sizeof(float)));
+        int r = folded_pack_f32(c->g_params + c->g_off[2 + 2 * l], c->g_wfold32[l], cin[l], cout[l], st);
+        if (r) return r;
+    }
+    c->launches += 3;
+    c->fold32_stale = false;
     return 0;
 }
 
@@ -243,6 +259,7 @@ extern "C" int rdg_generator_set_weights(rdg_ctx* c, const float* const* tensors
     RDG_CUDA(cudaSetDevice(c->device));
     int r = upload_params(c->g_params, c->g_off, c->g_size, tensors, sizes, n, "generator weights");
     if (r) return r;
+    c->fold32_stale = true;
     r = rdg_repack_generator(c, nullptr);
     if (r) return r;
     RDG_CUDA(cudaDeviceSynchronize());
@@ -344,11 +361,13 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
     const float* b4 = c->g_params + c->g_off[9];
     if (mode == RDG_MODE_FP32) {
         const float* cur = d0;
+        if ((r = rdg_refold32(c, st))) return r;
+        float* scratch = (float*)take((size_t)n * gen_act_elems(c, 3) * 4);      // phase-major staging of the largest layer
         for (int l = 0; l < 3; ++l) {
             ConvGeom g = rdg_gen_conv_geom(c, l, n);
             float* y = (float*)take((size_t)n * gen_act_elems(c, l + 1) * 4);
-            { ProfScope ps(c, st, 3 + l, n, 1);
-              if ((r = simt_conv_fwd(cur, c->g_params + c->g_off[2 + 2 * l], c->g_params + c->g_off[3 + 2 * l], y, g, ACT_NONE, nullptr, 1.f, st))) return r; }
+            { ProfScope ps(c, st, 3 + l, n, 1);     // upsample-folded: 8 phase convs with 2^3 taps on the low-res grid
+              if ((r = folded_conv_fwd(cur, c->g_wfold32[l], c->g_params + c->g_off[3 + 2 * l], y, scratch, g, st))) return r; }
             { ProfScope ps(c, st, 7, n, 1);
               if ((r = ew_pixelnorm(y, y, (long long)n * g.To * g.Ho * g.Wo, g.Co, 1, st))) return r; }
             cur = y;

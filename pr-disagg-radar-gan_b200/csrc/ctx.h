@@ -18,6 +18,8 @@ struct rdg_ctx {
     bool conv3_logits = true;       // planes kernel sums the output conv on chip (RDG_CONV3=planes_p: P through HBM)
     void* g_wpack_dense[2] = {};    // Dense kernel as tcgen05 B tiles (nd == 16, ncond == 1 only)
     bool dense_tc = false;
+    float* g_wfold32[3] = {};       // FP32 upsample-folded kernels [8 phases][2,2,2,Ci,Co] of the three upsampled convs (simt_folded.cu)
+    bool fold32_stale = true;
     void* g_w4pack[2] = {};   // output conv as a [32 taps x 64 ch] swizzled 16-bit B tile
     // training state (allocated on first use)
     float* g_grads = nullptr; float* g_m = nullptr; float* g_v = nullptr;
@@ -45,3 +47,4 @@ ConvGeom rdg_gen_dense_geom(const rdg_ctx* c, int B);
 ConvGeom rdg_critic_conv_geom(const rdg_ctx* c, int layer, int B);
 ConvGeom rdg_critic_dense_geom(const rdg_ctx* c, int B);
 int rdg_repack_generator(rdg_ctx* c, cudaStream_t st);
+int rdg_refold32(rdg_ctx* c, cudaStream_t st);      // refresh g_wfold32 if the generator weights changed

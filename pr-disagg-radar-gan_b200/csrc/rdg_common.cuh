@@ -22,7 +22,7 @@ struct ConvGeom {
     int up;
 };
 
-enum { ACT_NONE = 0, ACT_LRELU = 1 };
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ACCUM = 2 /* backward-data only: dst += result */ };
 
 void rdg_set_error(const char* fmt, ...);
 
@@ -53,7 +53,18 @@ int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, c
 // out[c] += sum_r x[r][c]
 int simt_colsum(const float* x, float* out, long long rows, int C, cudaStream_t st);
 // dx = conv_transpose(dy, w): gradient w.r.t. the (logical, i.e. upsampled if g.up) input.
-int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);
+int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st, int accumulate = 0);
+
+// ---- upsample-folded FP32 forms of UpSampling3D(2) + Conv3D(3^3,'same') (simt_folded.cu) ----
+// wf: [8 phases][2,2,2,Ci,Co] folded kernels (f32 sums of the 3^3 kernel's taps); g = the layer's geometry (g.up == 1).
+size_t folded_weight_elems(int Ci, int Co);
+int folded_pack_f32(const float* k, float* wf, int Ci, int Co, cudaStream_t st);
+// y[B,2T,2H,2W,Co] = conv3(upsample2(x)) + bias; scratch: B*2T*2H*2W*Co floats (phase-major staging)
+int folded_conv_fwd(const float* x, const float* wf, const float* bias, float* y, float* scratch, const ConvGeom& g, cudaStream_t st);
+// dyp (out): phase-major copy of dy [8][B,T,H,W,Co]; dx[B,T,H,W,Ci] = gradient w.r.t. the LOW-RES input (upsample backward included)
+int folded_conv_bwd_data(const float* dy, const float* wf, float* dx, float* dyp, const ConvGeom& g, cudaStream_t st);
+// dw[27,Ci,Co] += unfold(sum_p bwd_filter(x, dyp[p])); db[Co] += colsum(dy).  dwf: scratch of folded_weight_elems floats.
+int folded_conv_bwd_filter(const float* x, const float* dy, const float* dyp, float* dwf, float* dw, float* db, const ConvGeom& g, cudaStream_t st);
 // dw += sum_b,pos x (x) dy ; db += sum dy (db may be null). Accumulates (caller zeroes).
 int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, const ConvGeom& g,
                          cudaStream_t st);

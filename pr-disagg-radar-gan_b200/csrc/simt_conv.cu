@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
                 if (pre) pre[m * N + n] = v;            // pre-activation, kept for the backward pass
                 if (act == ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
                 if (mask) v *= mask[m * N + n] * mask_scale;
+            } else if (act == ACT_ACCUM) {
+                v += dst[m * N + n];                    // backward-data of one phase of a folded conv: sum over the phases
             }
             dst[m * N + n] = v;
         }
@@ -166,6 +168,7 @@ __global__ void splitk_epilogue_kernel(const float* __restrict__ part, int nslic
     for (int z = 0; z < nslice; ++z) v += part[(long long)z * MN + i];
     if (bias) v += bias[i % N];
     if (pre) pre[i] = v;
+    if (act == ACT_ACCUM) v += dst[i];
     if (act == ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
     if (mask) v *= mask[i] * mask_scale;
     dst[i] = v;
@@ -501,11 +504,13 @@ int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, c
     return 0;
 }
 
-int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st) {
+int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st, int accumulate) {
     int upf = g.up ? 2 : 1;
     long long M = (long long)g.B * g.Ti * upf * g.Hi * upf * g.Wi * upf;
     if (M == 0) return 0;
     const int ntaps_ = g.KT * g.KH * g.KW;
+    const int act_mode = accumulate ? ACT_ACCUM : ACT_NONE;
+    if (accumulate && (g.stride == 2 || g.Ci <= 4)) { rdg_set_error("simt_conv_bwd_data: accumulate is only supported by the generic path"); return -1; }
     if (!g.up && g.Ci <= 4 && (g.Co & 3) == 0 && (size_t)ntaps_ * g.Ci * g.Co * 4 <= 48 * 1024) {
         conv_bwd_data_smallci_kernel<<<ceil_div(M * g.Ci, 256), 256, (size_t)ntaps_ * g.Ci * g.Co * 4, st>>>(dy, w, dx, g);
         RDG_LAUNCH_CHECK();
@@ -551,12 +556,12 @@ int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeo
         grid.z = nslice;
         conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, ACT_NONE, nullptr, 1.f, nullptr, part);
         RDG_LAUNCH_CHECK();
-        splitk_epilogue_kernel<<<ceil_div(M * g.Ci, 256), 256, 0, st>>>(part, nslice, M * g.Ci, g.Ci, nullptr, dx, ACT_NONE, nullptr, 1.f, nullptr);
+        splitk_epilogue_kernel<<<ceil_div(M * g.Ci, 256), 256, 0, st>>>(part, nslice, M * g.Ci, g.Ci, nullptr, dx, act_mode, nullptr, 1.f, nullptr);
         RDG_LAUNCH_CHECK();
         RDG_CUDA(cudaFreeAsync(part, st));
         return 0;
     }
-    conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, ACT_NONE, nullptr, 1.f, nullptr, nullptr);
+    conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, act_mode, nullptr, 1.f, nullptr, nullptr);
     RDG_LAUNCH_CHECK();
     return 0;
 }

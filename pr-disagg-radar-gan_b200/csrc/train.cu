@@ -62,7 +62,7 @@ extern "C" int rdg_adam_apply(rdg_ctx* c, int which, float lr, float beta1, floa
     size_t n = which == 0 ? c->g_total : c->c_total;
     r = ew_adam(p, g, m, v, (long long)n, (float)lr_t, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
     if (r) return r;
-    if (which == 0) c->gen_packed_stale = true;
+    if (which == 0) { c->gen_packed_stale = true; c->fold32_stale = true; }
     return 0;
 }
 extern "C" int rdg_adam_reset(rdg_ctx* c, int which) {
@@ -187,13 +187,14 @@ int gen_alloc(const rdg_ctx* c, Bump& ws, int B, GenActs& G) {
 }
 
 // FP32 generator forward keeping everything the backward needs (gan_train_cwgangp_pixelnorm.py:319-350)
-int gen_fwd_train(rdg_ctx* c, const float* latent, const float* cond, int B, GenActs& G, cudaStream_t st) {
+int gen_fwd_train(rdg_ctx* c, const float* latent, const float* cond, int B, GenActs& G, float* scratch, cudaStream_t st) {
     ConvGeom dg = rdg_gen_dense_geom(c, B);
+    TRY(rdg_refold32(c, st));
     TRY(ew_assemble_gen_input(latent, cond, 1, 0, G.x0, B, c->nd * c->nd * c->ncond, st));
     TRY(simt_conv_fwd(G.x0, c->g_params + c->g_off[0], c->g_params + c->g_off[1], G.y[0], dg, ACT_LRELU, nullptr, 1.f, st, G.d0_pre));
     for (int l = 0; l < 3; ++l) {
         ConvGeom g = rdg_gen_conv_geom(c, l, B);
-        TRY(simt_conv_fwd(G.y[l], c->g_params + c->g_off[2 + 2 * l], c->g_params + c->g_off[3 + 2 * l], G.cpre[l + 1], g, ACT_NONE, nullptr, 1.f, st));
+        TRY(folded_conv_fwd(G.y[l], c->g_wfold32[l], c->g_params + c->g_off[3 + 2 * l], G.cpre[l + 1], scratch, g, st));
         TRY(ew_pixelnorm(G.cpre[l + 1], G.y[l + 1], (long long)B * g.To * g.Ho * g.Wo, g.Co, 1, st));
     }
     ConvGeom g4 = rdg_gen_conv_geom(c, 3, B);
@@ -324,7 +325,7 @@ extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, con
     for (int l = 0; l < 4; ++l) { gsum += gen_act(c, l); gmax = std::max(gmax, gen_act(c, l)); }
     ConvGeom dg1 = rdg_gen_dense_geom(c, 1);
     const size_t up_max = gmax / 64 * 128 ;   // largest upsampled-input gradient: [24,nd,nd,128]
-    const size_t need = ((size_t)B * (2 * csum + 3 * cmax + 2 * gsum + dg1.Ci + dg1.Co + 4 * px + 2 * gmax + 2 * up_max + 64) + 4096) * 4 + 64 * 256;
+    const size_t need = ((size_t)B * (2 * csum + 3 * cmax + 2 * gsum + dg1.Ci + dg1.Co + 4 * px + 2 * gmax + 2 * up_max + 64) + folded_weight_elems(256, 256) + 4096) * 4 + 64 * 256;
     TRY(ensure_train_ws(c, need));
     Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
     GenActs G; CriticActs A;
@@ -333,11 +334,12 @@ extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, con
     float* dx0 = ws.f((size_t)B * cmax);
     float* dimg = ws.f((size_t)B * px); float* dlog = ws.f((size_t)B * px);
     float* dy = ws.f((size_t)B * gmax); float* dc = ws.f((size_t)B * gmax);
-    float* dup = ws.f((size_t)B * up_max);
+    float* dup = ws.f((size_t)B * up_max);        // phase-major staging (forward) / phase-major dy (backward): >= B * gmax
+    float* dwf = ws.f(folded_weight_elems(256, 256));   // folded filter gradients of one layer
     float* dscore = ws.f(B);
-    if (!dscore || !dup) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
+    if (!dscore || !dup || !dwf) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
 
-    TRY(gen_fwd_train(c, latent_dev, cond_dev, B, G, st));
+    TRY(gen_fwd_train(c, latent_dev, cond_dev, B, G, dup, st));
     TRY(critic_fwd_train(c, G.img, cond_dev, masks, B, A, st));            // critic frozen (:395), dropout active
     TRY(ew_mean_scaled(A.score, B, -1.f, loss_dev, st));                   // wasserstein_loss with target -1 (:408, :452)
     TRY(ew_fill(dscore, B, -1.f / (float)B, st));
@@ -354,9 +356,10 @@ extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, con
         ConvGeom g = rdg_gen_conv_geom(c, l, B);
         const long long rows = (long long)B * g.To * g.Ho * g.Wo;
         TRY(ew_pixelnorm_lrelu_bwd(G.cpre[l + 1], dy, dc, rows, g.Co, st));
-        TRY(simt_conv_bwd_filter(G.y[l], dc, c->g_grads + c->g_off[2 + 2 * l], c->g_grads + c->g_off[3 + 2 * l], g, st));
-        TRY(simt_conv_bwd_data(dc, c->g_params + c->g_off[2 + 2 * l], dup, g, st));        // w.r.t. the upsampled input
-        TRY(ew_upsample_pool(dup, dy, B, g.Ti, g.Hi, g.Wi, g.Ci, st));                     // UpSampling3D backward
+        // upsample-folded backward: straight to the low-res input (the UpSampling3D backward is absorbed), folded filter
+        // gradients un-folded into the 3^3 kernel's gradient
+        TRY(folded_conv_bwd_data(dc, c->g_wfold32[l], dy, dup, g, st));
+        TRY(folded_conv_bwd_filter(G.y[l], dc, dup, dwf, c->g_grads + c->g_off[2 + 2 * l], c->g_grads + c->g_off[3 + 2 * l], g, st));
     }
     {   // dense + lrelu
         ConvGeom dg = rdg_gen_dense_geom(c, B);

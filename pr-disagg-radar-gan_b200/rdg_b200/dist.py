@@ -26,3 +26,37 @@ def allreduce_sum_(flat, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (Linux; best effort, returns the node or None).
+    The host-buffer paths move 24 KB per scenario over PCIe into pinned host memory; with one process per GPU on a two-socket
+    box an unpinned process lands its staging buffers on the remote socket half of the time and the aggregate D2H rate of 8
+    ranks drops to about half.  Call before allocating pinned memory (first touch then places it on the local node)."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        with open(os.path.join(path, "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
