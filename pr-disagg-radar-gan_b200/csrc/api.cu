@@ -129,6 +129,7 @@ extern "C" int rdg_ctx_create(rdg_ctx** out, int device, int nd, int ncond, int 
         c->conv3_logits = !(e && strcmp(e, "planes_p") == 0);   // planes_p: tap products through HBM + gather kernel
         const char* e2 = getenv("RDG_DENSE");
         c->dense_tc = nd == 16 && ncond == 1 && !(e2 && strcmp(e2, "simt") == 0);
+        c->dense_big_tc = !c->dense_tc && !(e2 && strcmp(e2, "simt") == 0);
     }
     gen_shapes(c, c->g_size);
     critic_shapes(c, c->c_size);
@@ -174,6 +175,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) cudaFree(c->g_wpack[k][l]);
     for (int i = 0; i < 4; ++i) cudaFree(c->st_buf[i]);
     for (int i = 0; i < 3; ++i) cudaFree(c->g_wfold32[i]);
+    for (int k = 0; k < 2; ++k) cudaFree(c->g_wpack_dense_big[k]);
     for (int k = 0; k < 2; ++k) { cudaFree(c->g_w4pack[k]); cudaFree(c->g_wpack_planes[k]); cudaFree(c->g_wpack_dense[k]); }
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->e2e_lat[i]); cudaFree(c->e2e_out[i]);
@@ -236,6 +238,13 @@ int rdg_repack_generator(rdg_ctx* c, cudaStream_t st) {
         if (c->conv3_planes) {
             if (!c->g_wpack_planes[k]) RDG_CUDA(cudaMalloc(&c->g_wpack_planes[k], (size_t)64 * 128 * 64 * 2));
             int r2 = pack_folded_weights_planes(hk, c->g_params + c->g_off[6], c->g_wpack_planes[k], st);
+            if (r2) return r2;
+            c->launches += 1;
+        }
+        if (c->dense_big_tc) {
+            const ConvGeom dg = rdg_gen_dense_geom(c, 1);
+            if (!c->g_wpack_dense_big[k]) RDG_CUDA(cudaMalloc(&c->g_wpack_dense_big[k], tc_dense_big_pack_bytes(dg.Ci, dg.Co)));
+            int r2 = pack_dense_big_weights(hk, c->g_params + c->g_off[0], c->g_wpack_dense_big[k], dg.Ci, dg.Co, st);
             if (r2) return r2;
             c->launches += 1;
         }
@@ -349,7 +358,8 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
     float* x0 = nullptr;
     float* d0 = nullptr;
     const bool front_tc = mode != RDG_MODE_FP32 && c->dense_tc;
-    if (!front_tc) {
+    const bool front_big = mode != RDG_MODE_FP32 && c->dense_big_tc;
+    if (!front_tc && !front_big) {
         x0 = (float*)take((size_t)n * dg.Ci * 4);
         d0 = (float*)take((size_t)n * dg.Co * 4);
         { ProfScope ps(c, st, 0, n, 1);
@@ -381,6 +391,11 @@ static int gen_forward_chunk(rdg_ctx* c, const float* latent, const float* cond,
     if (front_tc) {
         ProfScope ps(c, st, 1, n, 1);
         if ((r = tc_dense_lrelu(hk, latent, cond, spc, b_off, c->g_wpack_dense[hk == RDG_HALF_BF16 ? 0 : 1], c->g_params + c->g_off[1], h, n, st))) return r;
+    } else if (front_big) {
+        ProfScope ps(c, st, 1, n, 2);
+        void* x16 = take(tc_dense_big_input_bytes(n, dg.Ci));
+        if ((r = tc_dense_big_lrelu(hk, latent, cond, spc, b_off, c->g_wpack_dense_big[hk == RDG_HALF_BF16 ? 0 : 1], c->g_params + c->g_off[1],
+                                    x16, h, n, dg.Ci, dg.Co, st))) return r;
     } else {
         ProfScope ps(c, st, 2, n, 1);
         if ((r = f32_to_half(hk, d0, h, (long long)n * dg.Co, st))) return r;

@@ -18,6 +18,8 @@ struct rdg_ctx {
     bool conv3_logits = true;       // planes kernel sums the output conv on chip (RDG_CONV3=planes_p: P through HBM)
     void* g_wpack_dense[2] = {};    // Dense kernel as tcgen05 B tiles (nd == 16, ncond == 1 only)
     bool dense_tc = false;
+    void* g_wpack_dense_big[2] = {}; // general tensor-core Dense: 16-bit transpose [N][Kp] (everything dense_tc does not cover)
+    bool dense_big_tc = false;
     float* g_wfold32[3] = {};       // FP32 upsample-folded kernels [8 phases][2,2,2,Ci,Co] of the three upsampled convs (simt_folded.cu)
     bool fold32_stale = true;
     void* g_w4pack[2] = {};   // output conv as a [32 taps x 64 ch] swizzled 16-bit B tile

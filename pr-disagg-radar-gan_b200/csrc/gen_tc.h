@@ -58,3 +58,12 @@ int tc_dense_lrelu(int half_kind, const float* latent, const float* cond, int sp
                    const float* bias, void* out, int B, cudaStream_t st);
 size_t tc_dense_pack_bytes();
 int pack_dense_weights(int half_kind, const float* w, void* dst, cudaStream_t st);
+
+// General Concatenate + Dense + LeakyReLU on tcgen05 (large domain, ncond > 1), gen_dense_big_tc.cu: out[B,N] 16-bit =
+// lrelu([latent | cond[(b_off+b)/spc]] @ W + bias); wT from pack_dense_big_weights ([N][Kp] 16-bit), x16_scratch of
+// tc_dense_big_input_bytes(B, K) bytes.
+size_t tc_dense_big_pack_bytes(int K, int N);
+size_t tc_dense_big_input_bytes(int B, int K);
+int pack_dense_big_weights(int half_kind, const float* w, void* dst, int K, int N, cudaStream_t st);
+int tc_dense_big_lrelu(int half_kind, const float* latent, const float* cond, int spc, int b_off, const void* wT, const float* bias,
+                       void* x16_scratch, void* out, int B, int K, int N, cudaStream_t st);

@@ -34,6 +34,16 @@ for B in (32, 1024):
     res[f"gen_B{B}"] = {"ms": ms, "scenarios_per_s": B / ms * 1e3, "executed_tflops": B * 2 * MAC_FOLDED / ms / 1e9,
                          "direct_form_tflops": B * 2 * MAC_DIRECT / ms / 1e9}
     want = cond[:, :, :, 0] * 127.4
+    if B > 100:
+        import ctypes as C
+        ctx.lib.rdg_profile_enable(ctx.handle, 1)
+        gen.forward_device(z, cond, mode="fp16", out_mm=True, out=out, check=False)
+        torch.cuda.synchronize()
+        ctx.lib.rdg_profile_enable(ctx.handle, 0)
+        ms_sum, n_l, n_u = (C.c_double * 8)(), (C.c_longlong * 8)(), (C.c_longlong * 8)()
+        ctx.lib.rdg_profile_collect(ctx.handle, ms_sum, n_l, n_u)
+        names = ["concat", "dense", "cvt16", "upconv256", "upconv128", "upconv64", "out_conv_softmax", "pixelnorm"]
+        res[f"gen_B{B}"]["layer_ms"] = {names[i]: round(ms_sum[i], 3) for i in range(8) if n_l[i]}
     res[f"gen_B{B}"]["conservation_rel_err"] = float(((out.sum(dim=1) - want).abs() / want.clamp_min(1e-6)).max().item())
 B = 32
 tr = GanTrainer(gen, crit, gen_mode="fp16", seed=1)
