@@ -112,7 +112,7 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
     const bool leader = cta_rank == 0;
     const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;   // a unit = CG tiles (one per CTA of the pair)
     static_assert(!FUSE || COUT == 64, "fused output conv needs Cout == 64");
-    static_assert(!FUSE || CG == 1, "the fused output conv is single-CTA only");
+
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;
@@ -128,7 +128,8 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
     uint64_t* acc_full = b_empty + Cfg::kBStages;
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* p_full = acc_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
+    uint64_t* y_ready = p_full + 1;          // FUSE on CTA pairs, leader: both CTAs' activation tiles are in shared memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_ready + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = args.Cin / 64;
@@ -137,13 +138,15 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
 
     for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = args.bias[i];
     if (FUSE) {
-        const uint4* src = reinterpret_cast<const uint4*>(args.w4tile);
+        // CG == 2: this CTA holds tap rows rank*16 .. rank*16+15 of the [32 x 64] tile (N = 32 split over the pair)
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(args.w4tile) + cta_rank * (4096 / CG));
         uint4* dst = reinterpret_cast<uint4*>(w4_tile);
-        for (int i = threadIdx.x; i < 4096 / 16; i += kThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 4096 / CG / 16; i += kThreads) dst[i] = src[i];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (MMA)
     }
     if (threadIdx.x == 0) {
         mbar_init(p_full, 1);
+        mbar_init(y_ready, CG);
         for (int i = 0; i < Cfg::kAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         // CG == 2: one arrive per CTA (elected epilogue thread after the group's named barrier)
@@ -379,15 +382,23 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         tc_fence_before();
                         asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (warp == 3 && elect_one()) {
-                            tc_fence_after();
-                            constexpr uint32_t idesc_p = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
-                                                         ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-                            const uint64_t yd = make_sdesc(smem_u32(y_tile)), wd = make_sdesc(smem_u32(w4_tile));
-                            const uint32_t d_p = tmem_base + as * Cfg::kAccCols + s * COUT;   // reuse the consumed accumulator
+                        if (warp == 3) {
+                            if (CG > 1) {
+                                if (elect_one()) mbar_arrive_cluster(mapa_rank(smem_u32(y_ready), 0));
+                                __syncwarp();
+                                if (leader) mbar_wait_cluster(y_ready, p_it & 1);
+                            }
+                            if (leader && elect_one()) {
+                                tc_fence_after();
+                                constexpr uint32_t idesc_p = (1u << 4) | (HalfOps<HT>::kFmt << 7) | (HalfOps<HT>::kFmt << 10) |
+                                                             ((uint32_t)(32 >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+                                const uint64_t yd = make_sdesc(smem_u32(y_tile)), wd = make_sdesc(smem_u32(w4_tile));
+                                const uint32_t d_p = tmem_base + as * Cfg::kAccCols + s * COUT;   // reuse the consumed accumulator
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) tc_mma_f16(d_p, yd + 2 * k, wd + 2 * k, idesc_p, k > 0 ? 1u : 0u);
-                            tc_commit(p_full);
+                                for (int k = 0; k < 4; ++k) tc_mma_g<CG>(d_p, yd + 2 * k, wd + 2 * k, idesc_p, k > 0 ? 1u : 0u);
+                                tc_commit_g<CG>(p_full);
+                            }
+                            __syncwarp();
                         }
                         mbar_wait(p_full, p_it & 1);
                         ++p_it;
@@ -719,11 +730,11 @@ int launch_upconv_cg(const void* x, const void* wpack, const float* bias, void* 
 template <typename HT, int COUT, int NPH, int KC, bool FUSE>
 int launch_upconv(const void* x, const void* wpack, const float* bias, void* y, const void* w4tile, float* p_out, int B,
                   int T, int H, int W, int Cin, int sm_count, cudaStream_t st) {
-    // CTA pairs (cta_group::2) for the layers without the fused output conv; RDG_CG=1 forces single-CTA MMAs.
+    // CTA pairs (cta_group::2); RDG_CG=1 forces single-CTA MMAs.
     // (An earlier weight-multicast cluster variant of the single-CTA kernel measured no gain and was removed.)
     static const int cg = getenv("RDG_CG") ? atoi(getenv("RDG_CG")) : 2;
-    if (!FUSE && cg == 2)
-        return launch_upconv_cg<HT, COUT, NPH, KC, FUSE, FUSE ? 1 : 2>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
+    if (cg == 2)
+        return launch_upconv_cg<HT, COUT, NPH, KC, FUSE, 2>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
     return launch_upconv_cg<HT, COUT, NPH, KC, FUSE, 1>(x, wpack, bias, y, w4tile, p_out, B, T, H, W, Cin, sm_count, st);
 }
 
