@@ -415,9 +415,10 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": "scenarios/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp16": "f16 operands, f32 accumulate (tcgen05 kind::f16)",
-                                           "bf16": "bf16 operands, f32 accumulate (tcgen05 kind::f16)",
-                                           "fp32": "f32"}[args.mode],
+            "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.mode],
+            "dtype_detail": {"fp16": "f16 operands, f32 accumulate in TMEM (tcgen05 kind::f16); PixelNorm / softmax in f32",
+                             "bf16": "bf16 operands, f32 accumulate in TMEM (tcgen05 kind::f16); PixelNorm / softmax in f32",
+                             "fp32": "f32 SIMT, upsample-folded"}[args.mode],
             "data": "synthetic",
             "config": dict(workload_config(n_cond, spc), **{"chunk": ctx.max_chunk, "mode": args.mode,
                        "l2": "inputs (410 MB latent+cond) and outputs (24.6 GB) per step exceed the 126 MB L2",
