@@ -134,7 +134,9 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = args.Cin / 64;
     const int n_hblk = args.H / args.Hb;
-    const int n_units = args.n_tiles / CG;           // host pads the sample-block count to a multiple of CG
+    const int n_units = args.n_tiles / CG * args.pass_split;   // host pads the sample-block count to a multiple of CG
+    // small launches: the 8 / NPH passes (output phases) of a tile are spread over pass_split CTAs (pairs) to cut latency
+    const int pass_per = (8 / NPH) / args.pass_split;
 
     for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = args.bias[i];
     if (FUSE) {
@@ -175,9 +177,10 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
             uint32_t free_next = mbar_test(&a_empty[0], 1);
             for (int unit = unit0; unit < n_units; unit += unit_stride) {
                 // the CTAs of a pair share (t, h block) and take sample blocks CG*k + rank (may be past B: TMA zero-fills, epilogue masks)
-                const int hblk = unit % n_hblk, t = (unit / n_hblk) % args.T, bblk = unit / (n_hblk * args.T) * CG + (int)cta_rank;
+                const int tu = unit / args.pass_split, pass0 = (unit % args.pass_split) * pass_per;
+                const int hblk = tu % n_hblk, t = (tu / n_hblk) % args.T, bblk = tu / (n_hblk * args.T) * CG + (int)cta_rank;
                 const int h0 = hblk * args.Hb, b0 = bblk * args.Bt;
-                for (int pass = 0; pass < 8 / NPH; ++pass) {
+                for (int pass = pass0; pass < pass0 + pass_per; ++pass) {
                     for_each_step<NPH, kSkip, kMerge>(
                         pass, t, args.T, nchunk, KC,
                         [&](int dt, int dh, int dw, int c, bool oob) {
@@ -208,8 +211,9 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
             uint32_t bi = 0;
             uint32_t free_next = mbar_test(&b_empty[0], 1);
             for (int unit = unit0; unit < n_units; unit += unit_stride) {
-                const int t = (unit / n_hblk) % args.T;
-                for (int pass = 0; pass < 8 / NPH; ++pass) {
+                const int tu = unit / args.pass_split, pass0 = (unit % args.pass_split) * pass_per;
+                const int t = (tu / n_hblk) % args.T;
+                for (int pass = pass0; pass < pass0 + pass_per; ++pass) {
                     for_each_step<NPH, kSkip, kMerge>(
                         pass, t, args.T, nchunk, KC, [&](int, int, int, int, bool) {},
                         [&](int, int wtile, bool, int mk, int wtile2) {
@@ -253,8 +257,9 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
             uint32_t ai = 0, bi = 0, acc_it = 0;
             uint32_t a_ready = 0, b_ready = 0;       // results of early probes of the next full barriers
             for (int unit = unit0; unit < n_units; unit += unit_stride) {
-                const int t = (unit / n_hblk) % args.T;
-                for (int pass = 0; pass < 8 / NPH; ++pass, ++acc_it) {
+                const int tu = unit / args.pass_split, pass0 = (unit % args.pass_split) * pass_per;
+                const int t = (tu / n_hblk) % args.T;
+                for (int pass = pass0; pass < pass0 + pass_per; ++pass, ++acc_it) {
                     const uint32_t as = acc_it % Cfg::kAccStages, aph = (acc_it / Cfg::kAccStages) & 1;
                     if (CG == 1) mbar_wait(&acc_empty[as], aph ^ 1);
                     else mbar_wait_cluster(&acc_empty[as], aph ^ 1);
@@ -325,10 +330,11 @@ tc_upconv_pixelnorm_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
         HT* out = reinterpret_cast<HT*>(args.out);
         uint32_t acc_it = 0, p_it = 0;
         for (int unit = unit0; unit < n_units; unit += unit_stride) {
-            const int hblk = unit % n_hblk, t = (unit / n_hblk) % args.T, bblk = unit / (n_hblk * args.T) * CG + (int)cta_rank;
+            const int tu = unit / args.pass_split, pass0 = (unit % args.pass_split) * pass_per;
+            const int hblk = tu % n_hblk, t = (tu / n_hblk) % args.T, bblk = tu / (n_hblk * args.T) * CG + (int)cta_rank;
             const int b = bblk * args.Bt + bl, h = hblk * args.Hb + hl;
             const bool valid = b < args.B;
-            for (int pass = 0; pass < 8 / NPH; ++pass, ++acc_it) {
+            for (int pass = pass0; pass < pass0 + pass_per; ++pass, ++acc_it) {
                 const uint32_t as = acc_it % Cfg::kAccStages, aph = (acc_it / Cfg::kAccStages) & 1;
                 mbar_wait(&acc_full[as], aph);
                 tc_fence_after();
@@ -714,8 +720,10 @@ int launch_upconv_cg(const void* x, const void* wpack, const float* bias, void* 
         RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
         attr_set = true;
     }
-    const int units = a.n_tiles / CG;
     const int max_clusters = sm_count / CG;
+    a.pass_split = 1;
+    while (a.pass_split * 2 <= 8 / NPH && a.n_tiles / CG * a.pass_split * 2 <= max_clusters) a.pass_split *= 2;
+    const int units = a.n_tiles / CG * a.pass_split;
     const int grid = (units < max_clusters ? units : max_clusters) * CG;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;

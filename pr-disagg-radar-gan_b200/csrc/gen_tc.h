@@ -15,6 +15,7 @@ struct TcConvArgs {
     int Cin;
     int Hb, Bt;         // TMA box: Bt samples x Hb rows x W columns = 128 accumulator rows
     int n_tiles;
+    int pass_split;     // generic kernel: CTAs (pairs) sharing the 8 / NPH passes of one tile (1 unless the launch is small)
     const void* wpack;  // [8 phases][8 taps][Cin/64][Cout rows x 64 k] 16-bit, rows pre-swizzled (128B)
     const float* bias;
     void* out;          // [B,2T,2H,2W,Cout] 16-bit (unused when the output conv is fused)

@@ -364,15 +364,27 @@ __global__ void __launch_bounds__(256) conv_fwd_smallco_kernel(const float* __re
     y[idx] = v;
 }
 
-// db[c] += sum_m dy[m][c]
-__global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, long long M, int C,
-                              long long rows_per_block) {
-    long long r0 = (long long)blockIdx.x * rows_per_block;
-    long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double s = 0.0;        // the fake / real halves of a critic batch nearly cancel: keep the block's partial sum exact
-        for (long long r = r0; r < r1; ++r) s += (double)dy[r * C + c];
-        atomicAdd(&db[c], (float)s);
+// db[c] += sum_m dy[m][c]: a block sums rows_per_block rows; 8 row groups (warps) x 32 channel lanes, partial sums in double
+// (the fake / real halves of a critic batch nearly cancel), reduced over the row groups in shared memory, one float atomic per
+// channel and block.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, long long M, int C,
+                                                     long long rows_per_block) {
+    __shared__ double red[8][33];
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        double s = 0.0;
+        if (c < C)
+            for (long long r = r0 + grp; r < r1; r += 8) s += (double)dy[r * C + c];
+        red[grp][lane] = s;
+        __syncthreads();
+        if (grp == 0 && c < C) {
+            for (int k = 1; k < 8; ++k) s += red[k][lane];
+            atomicAdd(&db[c], (float)s);
+        }
+        __syncthreads();
     }
 }
 
@@ -595,7 +607,7 @@ int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, 
 int simt_colsum(const float* x, float* out, long long rows, int C, cudaStream_t st) {
     if (rows <= 0) return 0;
     long long rpb = 256;
-    colsum_kernel<<<ceil_div(rows, rpb), 128, 0, st>>>(x, out, rows, C, rpb);
+    colsum_kernel<<<ceil_div(rows, rpb), 256, 0, st>>>(x, out, rows, C, rpb);
     RDG_LAUNCH_CHECK();
     return 0;
 }
