@@ -185,6 +185,9 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     }
     cudaFree(c->e2e_cond);
     cudaFree(c->train_ws);
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);

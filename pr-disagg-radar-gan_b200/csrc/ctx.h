@@ -32,6 +32,8 @@ struct rdg_ctx {
     int* flag_dev = nullptr;
     // host-buffer pipeline
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    // training: filter gradients run on a side stream next to the backward-data chain (train.cu)
+    cudaStream_t s_aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
     float* e2e_lat[2] = {}; float* e2e_out[2] = {}; float* e2e_cond = nullptr; size_t e2e_cond_cap = 0;
     // rdg_generate_stats_host staging (grow-only): observations, area means, CRPS area means, per-chunk CRPS field

@@ -63,6 +63,9 @@ int folded_pack_f32(const float* k, float* wf, int Ci, int Co, cudaStream_t st);
 int folded_conv_fwd(const float* x, const float* wf, const float* bias, float* y, float* scratch, const ConvGeom& g, cudaStream_t st);
 // dyp (out): phase-major copy of dy [8][B,T,H,W,Co]; dx[B,T,H,W,Ci] = gradient w.r.t. the LOW-RES input (upsample backward included)
 int folded_conv_bwd_data(const float* dy, const float* wf, float* dx, float* dyp, const ConvGeom& g, cudaStream_t st);
+// the two halves of folded_conv_bwd_data, for callers that overlap the filter gradient with the second one
+int folded_deinterleave(const float* dy, float* dyp, const ConvGeom& g, cudaStream_t st);
+int folded_conv_bwd_data_phases(const float* dyp, const float* wf, float* dx, const ConvGeom& g, cudaStream_t st);
 // dw[27,Ci,Co] += unfold(sum_p bwd_filter(x, dyp[p])); db[Co] += colsum(dy).  dwf: scratch of folded_weight_elems floats.
 int folded_conv_bwd_filter(const float* x, const float* dy, const float* dyp, float* dwf, float* dw, float* db, const ConvGeom& g, cudaStream_t st);
 // dw += sum_b,pos x (x) dy ; db += sum dy (db may be null). Accumulates (caller zeroes).

@@ -100,17 +100,28 @@ int folded_conv_fwd(const float* x, const float* wf, const float* bias, float* y
     return 0;
 }
 
-int folded_conv_bwd_data(const float* dy, const float* wf, float* dx, float* dyp, const ConvGeom& g, cudaStream_t st) {
-    if (!g.up || (g.Co & 3)) { rdg_set_error("folded_conv_bwd_data: needs an upsampled conv with Co %% 4 == 0"); return -1; }
-    const size_t per_phase = (size_t)g.B * g.Ti * g.Hi * g.Wi * g.Co, wper = (size_t)8 * g.Ci * g.Co;
+int folded_deinterleave(const float* dy, float* dyp, const ConvGeom& g, cudaStream_t st) {
+    if (!g.up || (g.Co & 3)) { rdg_set_error("folded_deinterleave: needs an upsampled conv with Co %% 4 == 0"); return -1; }
+    const size_t per_phase = (size_t)g.B * g.Ti * g.Hi * g.Wi * g.Co;
     const long long n4 = (long long)8 * per_phase / 4;
     phase_shuffle_kernel<false><<<ceil_div(n4, 256), 256, 0, st>>>(const_cast<float*>(dy), dyp, g.B, g.Ti, g.Hi, g.Wi, g.Co / 4);
     RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int folded_conv_bwd_data_phases(const float* dyp, const float* wf, float* dx, const ConvGeom& g, cudaStream_t st) {
+    const size_t per_phase = (size_t)g.B * g.Ti * g.Hi * g.Wi * g.Co, wper = (size_t)8 * g.Ci * g.Co;
     for (int p = 0; p < 8; ++p) {
         int r = simt_conv_bwd_data(dyp + p * per_phase, wf + p * wper, dx, phase_geom(g, p), st, p > 0);
         if (r) return r;
     }
     return 0;
+}
+
+int folded_conv_bwd_data(const float* dy, const float* wf, float* dx, float* dyp, const ConvGeom& g, cudaStream_t st) {
+    int r = folded_deinterleave(dy, dyp, g, st);
+    if (r) return r;
+    return folded_conv_bwd_data_phases(dyp, wf, dx, g, st);
 }
 
 int folded_conv_bwd_filter(const float* x, const float* dy, const float* dyp, float* dwf, float* dw, float* db, const ConvGeom& g,

@@ -111,6 +111,24 @@ struct CriticActs {
 
 #define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
 
+// Side stream for work that is independent of the backward-data chain (filter gradients, which only accumulate into the
+// gradient buffer with atomics).  fork(): the side stream may start once everything queued on `main` so far has run;
+// join(): `main` continues only after everything queued on the side stream.
+struct SideStream {
+    rdg_ctx* c; cudaStream_t main;
+    int init() {
+        if (!c->s_aux) {
+            RDG_CUDA(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+            RDG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            RDG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    cudaStream_t aux() const { return c->s_aux; }
+    int fork() { RDG_CUDA(cudaEventRecord(c->ev_fork, main)); RDG_CUDA(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); return 0; }
+    int join() { RDG_CUDA(cudaEventRecord(c->ev_join, c->s_aux)); RDG_CUDA(cudaStreamWaitEvent(main, c->ev_join, 0)); return 0; }
+};
+
 int critic_alloc(const rdg_ctx* c, Bump& ws, int B, CriticActs& A) {
     for (int l = 0; l < 5; ++l) {
         A.h[l] = ws.f((size_t)B * critic_act_elems(c, l));
@@ -140,18 +158,26 @@ int critic_fwd_train(rdg_ctx* c, const float* sample, const float* cond, const f
 int critic_bwd(rdg_ctx* c, const CriticActs& A, const float* const* masks, const float* dscore, int B, float* grads,
                float* dx0, float* tmp0, float* tmp1, cudaStream_t st) {
     ConvGeom d = rdg_critic_dense_geom(c, B);
-    if (grads) TRY(simt_conv_bwd_filter(A.h[4], dscore, grads + c->c_off[8], grads + c->c_off[9], d, st));
+    SideStream ss{c, st};
+    TRY(ss.init());
+    // filter gradients on the side stream, each next to the backward-data conv of the same layer
+    if (grads) { TRY(ss.fork()); TRY(simt_conv_bwd_filter(A.h[4], dscore, grads + c->c_off[8], grads + c->c_off[9], d, ss.aux())); }
     float* dh = tmp0;   // gradient w.r.t. h[l]
     float* da = tmp1;   // gradient w.r.t. a[l]
     TRY(simt_conv_bwd_data(dscore, c->c_params + c->c_off[8], dh, d, st));
     for (int l = 4; l >= 1; --l) {
         ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
         const long long n = (long long)B * critic_act_elems(c, l);
+        if (grads) TRY(ss.join());                    // the previous layer's filter gradient still reads da
         TRY(ew_lrelu_bwd(A.a[l], dh, da, n, masks ? masks[l - 1] : nullptr, 1.f / 0.75f, st));
-        if (grads) TRY(simt_conv_bwd_filter(A.h[l - 1], da, grads + c->c_off[2 * (l - 1)], grads + c->c_off[2 * (l - 1) + 1], g, st));
+        if (grads) {
+            TRY(ss.fork());
+            TRY(simt_conv_bwd_filter(A.h[l - 1], da, grads + c->c_off[2 * (l - 1)], grads + c->c_off[2 * (l - 1) + 1], g, ss.aux()));
+        }
         if (l > 1) TRY(simt_conv_bwd_data(da, c->c_params + c->c_off[2 * (l - 1)], dh, g, st));
         else if (dx0) TRY(simt_conv_bwd_data(da, c->c_params + c->c_off[0], dx0, g, st));
     }
+    if (grads) TRY(ss.join());
     return 0;
 }
 
@@ -298,10 +324,14 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
         // cotangent of 10 * mean((n-1)^2) w.r.t. g_0 (sample channel only)
         TRY(ew_gp_cotangent(gbuf, norm, 10.f * 2.f / (float)B, ubuf, C0, B, (long long)px, st));
         // second-order pass: g_{l-1} = convT_l(delta_l) is bilinear in (W_l, delta_l); LeakyReLU'' = 0
+        SideStream ss{c, st};
+        TRY(ss.init());
         for (int l = 1; l <= 4; ++l) {
             ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
-            TRY(simt_conv_bwd_filter(ubuf, delta[l], c->c_grads + c->c_off[2 * (l - 1)], nullptr, g, st));      // d/dW_l
+            TRY(ss.fork());                                                                                        // side stream:
+            TRY(simt_conv_bwd_filter(ubuf, delta[l], c->c_grads + c->c_off[2 * (l - 1)], nullptr, g, ss.aux()));   // d/dW_l
             TRY(simt_conv_fwd(ubuf, c->c_params + c->c_off[2 * (l - 1)], nullptr, vbuf, g, ACT_NONE, nullptr, 1.f, st));   // d/d delta_l
+            TRY(ss.join());                                                                                        // ubuf is rewritten next
             TRY(ew_lrelu_bwd(Ah.a[l], vbuf, ubuf, (long long)B * critic_act_elems(c, l), masks_hat ? masks_hat[l - 1] : nullptr, 1.f / 0.75f, st));
         }
         TRY(simt_colsum(ubuf, c->c_grads + c->c_off[8], B, (int)critic_act_elems(c, 4), st));                   // d/dW5
@@ -347,20 +377,27 @@ extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, con
     TRY(ew_extract_channel0(dx0, dimg, (long long)B * px, 1 + c->ncond, st));
     RDG_CUDA(cudaMemsetAsync(c->g_grads, 0, c->g_total * 4, st));
     TRY(ew_softmax_hours_bwd(G.img, dimg, dlog, B, c->nd * c->nd, st));
-    {   // output conv
+    SideStream ss{c, st};
+    TRY(ss.init());
+    {   // output conv: filter gradient on the side stream next to the backward-data conv
         ConvGeom g4 = rdg_gen_conv_geom(c, 3, B);
-        TRY(simt_conv_bwd_filter(G.y[3], dlog, c->g_grads + c->g_off[8], c->g_grads + c->g_off[9], g4, st));
+        TRY(ss.fork());
+        TRY(simt_conv_bwd_filter(G.y[3], dlog, c->g_grads + c->g_off[8], c->g_grads + c->g_off[9], g4, ss.aux()));
         TRY(simt_conv_bwd_data(dlog, c->g_params + c->g_off[8], dy, g4, st));
     }
     for (int l = 2; l >= 0; --l) {   // upsample + conv + pixelnorm + lrelu blocks
         ConvGeom g = rdg_gen_conv_geom(c, l, B);
         const long long rows = (long long)B * g.To * g.Ho * g.Wo;
+        TRY(ss.join());                               // the previous block's filter gradient still reads dc / dup
         TRY(ew_pixelnorm_lrelu_bwd(G.cpre[l + 1], dy, dc, rows, g.Co, st));
         // upsample-folded backward: straight to the low-res input (the UpSampling3D backward is absorbed), folded filter
-        // gradients un-folded into the 3^3 kernel's gradient
-        TRY(folded_conv_bwd_data(dc, c->g_wfold32[l], dy, dup, g, st));
-        TRY(folded_conv_bwd_filter(G.y[l], dc, dup, dwf, c->g_grads + c->g_off[2 + 2 * l], c->g_grads + c->g_off[3 + 2 * l], g, st));
+        // gradients (side stream) un-folded into the 3^3 kernel's gradient
+        TRY(folded_deinterleave(dc, dup, g, st));
+        TRY(ss.fork());
+        TRY(folded_conv_bwd_filter(G.y[l], dc, dup, dwf, c->g_grads + c->g_off[2 + 2 * l], c->g_grads + c->g_off[3 + 2 * l], g, ss.aux()));
+        TRY(folded_conv_bwd_data_phases(dup, c->g_wfold32[l], dy, g, st));
     }
+    TRY(ss.join());
     {   // dense + lrelu
         ConvGeom dg = rdg_gen_dense_geom(c, B);
         TRY(ew_lrelu_bwd(G.d0_pre, dy, dc, (long long)B * dg.Co, nullptr, 1.f, st));
