@@ -185,9 +185,11 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     }
     cudaFree(c->e2e_cond);
     cudaFree(c->train_ws);
-    if (c->s_aux) cudaStreamDestroy(c->s_aux);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (int i = 0; i < 3; ++i) {
+        if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
+        if (c->ev_fork[i]) cudaEventDestroy(c->ev_fork[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);

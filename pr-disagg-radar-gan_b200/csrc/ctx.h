@@ -33,7 +33,8 @@ struct rdg_ctx {
     // host-buffer pipeline
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     // training: filter gradients run on a side stream next to the backward-data chain (train.cu)
-    cudaStream_t s_aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // [0] filter gradients of the main chain, [1] the gradient-penalty chain of the critic step, [2] its filter gradients
+    cudaStream_t s_aux[3] = {}; cudaEvent_t ev_fork[3] = {}, ev_join[3] = {};
     cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
     float* e2e_lat[2] = {}; float* e2e_out[2] = {}; float* e2e_cond = nullptr; size_t e2e_cond_cap = 0;
     // rdg_generate_stats_host staging (grow-only): observations, area means, CRPS area means, per-chunk CRPS field

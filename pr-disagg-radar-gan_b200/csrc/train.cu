@@ -115,18 +115,18 @@ struct CriticActs {
 // gradient buffer with atomics).  fork(): the side stream may start once everything queued on `main` so far has run;
 // join(): `main` continues only after everything queued on the side stream.
 struct SideStream {
-    rdg_ctx* c; cudaStream_t main;
+    rdg_ctx* c; cudaStream_t main; int k;       // k: which of the context's side streams (see ctx.h)
     int init() {
-        if (!c->s_aux) {
-            RDG_CUDA(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
-            RDG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-            RDG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        if (!c->s_aux[k]) {
+            RDG_CUDA(cudaStreamCreateWithFlags(&c->s_aux[k], cudaStreamNonBlocking));
+            RDG_CUDA(cudaEventCreateWithFlags(&c->ev_fork[k], cudaEventDisableTiming));
+            RDG_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
         }
         return 0;
     }
-    cudaStream_t aux() const { return c->s_aux; }
-    int fork() { RDG_CUDA(cudaEventRecord(c->ev_fork, main)); RDG_CUDA(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); return 0; }
-    int join() { RDG_CUDA(cudaEventRecord(c->ev_join, c->s_aux)); RDG_CUDA(cudaStreamWaitEvent(main, c->ev_join, 0)); return 0; }
+    cudaStream_t aux() const { return c->s_aux[k]; }
+    int fork() { RDG_CUDA(cudaEventRecord(c->ev_fork[k], main)); RDG_CUDA(cudaStreamWaitEvent(c->s_aux[k], c->ev_fork[k], 0)); return 0; }
+    int join() { RDG_CUDA(cudaEventRecord(c->ev_join[k], c->s_aux[k])); RDG_CUDA(cudaStreamWaitEvent(main, c->ev_join[k], 0)); return 0; }
 };
 
 int critic_alloc(const rdg_ctx* c, Bump& ws, int B, CriticActs& A) {
@@ -158,7 +158,7 @@ int critic_fwd_train(rdg_ctx* c, const float* sample, const float* cond, const f
 int critic_bwd(rdg_ctx* c, const CriticActs& A, const float* const* masks, const float* dscore, int B, float* grads,
                float* dx0, float* tmp0, float* tmp1, cudaStream_t st) {
     ConvGeom d = rdg_critic_dense_geom(c, B);
-    SideStream ss{c, st};
+    SideStream ss{c, st, 0};
     TRY(ss.init());
     // filter gradients on the side stream, each next to the backward-data conv of the same layer
     if (grads) { TRY(ss.fork()); TRY(simt_conv_bwd_filter(A.h[4], dscore, grads + c->c_off[8], grads + c->c_off[9], d, ss.aux())); }
@@ -280,7 +280,7 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
     float* vbuf = ws.f((size_t)B * max_act);
     float* delta[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int l = 1; l <= 4; ++l) delta[l] = ws.f((size_t)B * critic_act_elems(c, l));
-    float* dscore = ws.f(2 * B); float* norm = ws.f(B); float* lsc = ws.f(8);
+    float* dscore = ws.f(2 * B); float* dscore_gp = ws.f(B); float* norm = ws.f(B); float* lsc = ws.f(8);
     if (!lsc || !delta[4]) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
 
     // frozen generator forward (:370, generator.trainable = False :363)
@@ -300,6 +300,12 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
     TRY(simt_conv_fwd(A3.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A3.score, rdg_critic_dense_geom(c, 3 * B), ACT_NONE,
                       nullptr, 1.f, st));
 
+    cudaStream_t main_st = st;
+    {   // the gradient-penalty chain (further down) may start as soon as the forward pass is done
+        SideStream gp0{c, main_st, 1};
+        TRY(gp0.init());
+        TRY(gp0.fork());
+    }
     // Wasserstein terms: l_valid = mean(-D(real)), l_fake = mean(+D(fake))  (:215-216, targets :452-454); their backward
     // passes run as one 2B batch [fake | real] with dscore = [+1/B | -1/B]
     TRY(ew_mean_scaled(Ar.score, B, -1.f, lsc + 0, st));
@@ -308,11 +314,14 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
     TRY(ew_fill(dscore + B, B, -1.f / (float)B, st));
     TRY(critic_bwd(c, A3, use_masks ? masks3 : nullptr, dscore, 2 * B, c->c_grads, nullptr, t0, t1, st));
 
-    // gradient penalty (:230-244): first-order backward of sum_b D(xhat_b) to xhat, keeping delta_l
+    // gradient penalty (:230-244): first-order backward of sum_b D(xhat_b) to xhat, keeping delta_l.  Independent of the
+    // Wasserstein backward above (separate buffers; both only ADD into the gradient buffer), so it runs on its own stream.
+    SideStream gp{c, main_st, 1};
     {
+        cudaStream_t st = gp.aux();               // shadows the caller's stream inside this block
         ConvGeom d = rdg_critic_dense_geom(c, B);
-        TRY(ew_fill(dscore, B, 1.f, st));
-        TRY(simt_conv_bwd_data(dscore, c->c_params + c->c_off[8], gbuf, d, st));          // g_4 = W5 broadcast
+        TRY(ew_fill(dscore_gp, B, 1.f, st));
+        TRY(simt_conv_bwd_data(dscore_gp, c->c_params + c->c_off[8], gbuf, d, st));          // g_4 = W5 broadcast
         for (int l = 4; l >= 1; --l) {
             ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
             TRY(ew_lrelu_bwd(Ah.a[l], gbuf, delta[l], (long long)B * critic_act_elems(c, l), masks_hat ? masks_hat[l - 1] : nullptr, 1.f / 0.75f, st));
@@ -324,7 +333,7 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
         // cotangent of 10 * mean((n-1)^2) w.r.t. g_0 (sample channel only)
         TRY(ew_gp_cotangent(gbuf, norm, 10.f * 2.f / (float)B, ubuf, C0, B, (long long)px, st));
         // second-order pass: g_{l-1} = convT_l(delta_l) is bilinear in (W_l, delta_l); LeakyReLU'' = 0
-        SideStream ss{c, st};
+        SideStream ss{c, st, 2};
         TRY(ss.init());
         for (int l = 1; l <= 4; ++l) {
             ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
@@ -336,6 +345,7 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
         }
         TRY(simt_colsum(ubuf, c->c_grads + c->c_off[8], B, (int)critic_act_elems(c, 4), st));                   // d/dW5
     }
+    TRY(gp.join());
     TRY(ew_combine_losses(lsc + 0, lsc + 1, lsc + 2, 10.f, losses4_dev, st));
     return 0;
 }
@@ -377,7 +387,7 @@ extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, con
     TRY(ew_extract_channel0(dx0, dimg, (long long)B * px, 1 + c->ncond, st));
     RDG_CUDA(cudaMemsetAsync(c->g_grads, 0, c->g_total * 4, st));
     TRY(ew_softmax_hours_bwd(G.img, dimg, dlog, B, c->nd * c->nd, st));
-    SideStream ss{c, st};
+    SideStream ss{c, st, 0};
     TRY(ss.init());
     {   // output conv: filter gradient on the side stream next to the backward-data conv
         ConvGeom g4 = rdg_gen_conv_geom(c, 3, B);
