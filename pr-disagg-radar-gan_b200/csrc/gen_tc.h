@@ -22,6 +22,7 @@ struct TcConvArgs {
     const void* w4tile; // fused output conv: [32 taps x 64 ch] 16-bit swizzled tile (taps >= 27 zero)
     float* p_out;       // fused output conv: [B,2T,2H,2W,32] f32 per-tap partial products
     int* logit_out;     // planes kernel only: fused output conv summed on chip -> [B,2T,16,16] fixed-point logits (no bias)
+    int sup_split;      // planes kernel: 1 = one work item per (sample-pair group, super-tile) (small launches)
     int* nonfinite;     // planes kernel, logit mode: set to 1 if any activation is Inf / NaN
     int dbg;            // experiments only (RDG_DBG): 1 = epilogue does not touch TMEM, 2 = no output-conv MMA, 4 = skip N=64 MMAs
 };

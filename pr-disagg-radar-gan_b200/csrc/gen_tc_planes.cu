@@ -138,14 +138,22 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     tc_fence_after();
     const int grp0 = blockIdx.x / CG, grp_stride = gridDim.x / CG;   // a group = CG consecutive units, one per CTA of the pair
     const int n_groups = (n_units + CG - 1) / CG;
+    // Work item = (group, range of super-tiles).  Large launches: one item per group (all n_super super-tiles).  Small launches
+    // (args.sup_split): one item per (group, super-tile), so a few sample pairs still spread over many SMs; an item then loads
+    // planes 2sup-1 .. 2sup+2, and in the on-chip-logit mode flushes ALL the hours it touched with global integer atomics
+    // (the neighbouring items add the rest; the host zeroes the buffer first).
+    const int sup_per = args.sup_split ? 1 : n_super;
+    const int items_per_grp = n_super / sup_per, n_items = n_groups * items_per_grp;
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ================= plane producer: one haloed box per plane and 64-channel chunk =================
         uint32_t li = 0;
-        for (int grp = grp0; grp < n_groups; grp += grp_stride) {
+        for (int item = grp0; item < n_items; item += grp_stride) {
+            const int grp = item / items_per_grp, sup_lo = (item % items_per_grp) * sup_per, sup_hi = sup_lo + sup_per;
+            const int p_lo = 2 * sup_lo - 1 < 0 ? 0 : 2 * sup_lo - 1, p_hi = 2 * sup_hi > T - 1 ? T - 1 : 2 * sup_hi;
             const int b0 = (grp * CG + (int)rank) * 2;            // may be >= B (odd tail): TMA zero-fills, epilogue masks
-            for (int p = 0; p < T; ++p, ++li) {
+            for (int p = p_lo; p <= p_hi; ++p, ++li) {
                 const uint32_t s = li % kSlots, ph = (li / kSlots) & 1;
                 mbar_wait(&a_empty[s], ph ^ 1);
                 if (elect_one()) {
@@ -163,8 +171,8 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
         // ================= weight producer: the 1 MB stage sequence of a super-tile, streamed in order =================
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(args.wpack);
         uint32_t bi = 0;
-        for (int grp = grp0; grp < n_groups; grp += grp_stride)
-            for (int sup = 0; sup < n_super; ++sup)
+        for (int item = grp0; item < n_items; item += grp_stride)
+            for (int sup = 0; sup < sup_per; ++sup)
                 for (int st = 0; st < 4 * kStagesPerPass; ++st, ++bi) {
                     const uint32_t s = bi % kBStages, ph = (bi / kBStages) & 1;
                     mbar_wait(&b_empty[s], ph ^ 1);
@@ -196,9 +204,11 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
         const uint32_t a_base = smem_u32(a_reg), b_base = smem_u32(b_buf);
         uint32_t bi = 0, acc_it = 0, li0 = 0;        // li0 = plane-load index of plane 0 of the current unit
         uint32_t b_ready = 0;
-        for (int grp = grp0; grp < n_groups; grp += grp_stride, li0 += T) {
-            int ready = -1;                          // highest plane of this unit known to have landed
-            for (int sup = 0; sup < n_super; ++sup)
+        for (int item = grp0; item < n_items; item += grp_stride) {
+            const int sup_lo = (item % items_per_grp) * sup_per, sup_hi = sup_lo + sup_per;
+            const int p_lo = 2 * sup_lo - 1 < 0 ? 0 : 2 * sup_lo - 1, p_hi = 2 * sup_hi > T - 1 ? T - 1 : 2 * sup_hi;
+            int ready = p_lo - 1;                    // highest plane of this item known to have landed
+            for (int sup = sup_lo; sup < sup_hi; ++sup)
                 for (int pass = 0; pass < 4; ++pass, ++acc_it) {
                     const int pt = pass >> 1, ph = pass & 1;
                     const int w = 2 * sup + pt;      // window: planes w-1, w, w+1
@@ -215,11 +225,11 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
                         // activation view of this M tile for (dt, dh, chunk); the plane may lie outside [0,T) (zero padding in t)
                         const int plane = 2 * sup + m + pt - 1 + at;
                         const bool a_ok = plane >= 0 && plane < T;
-                        const uint32_t l = li0 + (uint32_t)(a_ok ? plane : 0);
+                        const uint32_t l = li0 + (uint32_t)(a_ok ? plane - p_lo : 0);     // ring position: planes of an item load in order
                         if (a_ok) {
                             while (ready < plane) {
                                 ++ready;
-                                const uint32_t lr = li0 + (uint32_t)ready;
+                                const uint32_t lr = li0 + (uint32_t)(ready - p_lo);
                                 mbar_wait(&a_full[lr % kSlots], (lr / kSlots) & 1);
                             }
                         }
@@ -268,21 +278,20 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
                             __syncwarp();
                         }
                         // plane w-1 is read for the last time by the at = 0 half of the ph = 1 pass of window w
-                        if (g == 3 && ph == 1 && w >= 1) {
-                            const uint32_t lw = li0 + (uint32_t)(w - 1);
+                        if (g == 3 && ph == 1 && w - 1 >= p_lo) {
+                            const uint32_t lw = li0 + (uint32_t)(w - 1 - p_lo);
                             if (elect_one()) tc_commit_g<CG>(&a_empty[lw % kSlots]);
                             __syncwarp();
                         }
                     }
                     if (elect_one()) {
-                        if (sup == n_super - 1 && pass == 3) {            // last pass of the unit: plane T-1 is done too
-                            const uint32_t lw = li0 + (uint32_t)(T - 1);
-                            tc_commit_g<CG>(&a_empty[lw % kSlots]);
-                        }
+                        if (sup == sup_hi - 1 && pass == 3)               // last pass of the item: its remaining planes are done too
+                            for (int pl = 2 * sup_hi - 1; pl <= p_hi; ++pl) tc_commit_g<CG>(&a_empty[(li0 + (uint32_t)(pl - p_lo)) % kSlots]);
                         tc_commit_g<CG>(&acc_full[as * 2 + m]);
                     }
                     __syncwarp();
                 }
+            li0 += (uint32_t)(p_hi - p_lo + 1);
         }
       }
     } else {
@@ -305,11 +314,12 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
         const int et = threadIdx.x - 128;       // 0..255 over both epilogue groups
         const float fx_scale = logit_mode ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(args.w4tile) + kW4Tile)[0] : 0.f;
         bool bad = false;
-        for (int grp = grp0; grp < n_groups; grp += grp_stride) {
+        for (int item = grp0; item < n_items; item += grp_stride) {
+            const int grp = item / items_per_grp, sup_lo = (item % items_per_grp) * sup_per, sup_hi = sup_lo + sup_per;
             const int unit = grp * CG + (int)rank;
             const int b = unit * 2 + bl;
             const bool valid = b < args.B;
-            for (int sup = 0; sup < n_super; ++sup)
+            for (int sup = sup_lo; sup < sup_hi; ++sup)
                 for (int pass = 0; pass < 4; ++pass, ++acc_it) {
                     const int pt = pass >> 1, ph = pass & 1;
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
@@ -422,7 +432,7 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
                         // finishes in place) and clear the ring slots for reuse.
                         asm volatile("bar.sync 3, 256;" ::: "memory");
                         const int h_lo = sup == 0 ? 0 : 4 * sup - 1;
-                        const int h_hi = sup == n_super - 1 ? T2 - 1 : 4 * sup + 2;
+                        const int h_hi = sup == sup_hi - 1 ? (4 * sup + 4 > T2 - 1 ? T2 - 1 : 4 * sup + 4) : 4 * sup + 2;
                         const int n = (h_hi - h_lo + 1) * 512;
                         for (int i = et; i < n; i += 256) {
                             const int hour = h_lo + (i >> 9), s2 = (i >> 8) & 1, pix = i & 255;
@@ -430,7 +440,10 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
                             const int v = *rp;
                             *rp = 0;
                             const int bb = unit * 2 + s2;
-                            if (bb < args.B) args.logit_out[((size_t)bb * T2 + hour) * 256 + pix] = v;
+                            if (bb < args.B) {
+                                int* dst = args.logit_out + ((size_t)bb * T2 + hour) * 256 + pix;
+                                if (args.sup_split) atomicAdd(dst, v); else *dst = v;      // split items share their border hours
+                            }
                         }
                         asm volatile("bar.sync 3, 256;" ::: "memory");
                     }
@@ -503,6 +516,9 @@ int launch_planes(const void* x, const void* wpack, const float* bias, void* y, 
         if (r != CUDA_SUCCESS) { rdg_set_error("cuTensorMapEncodeTiled (planes weights) failed: %d", (int)r); return RDG_TC_E_DRIVER; }
     }
     const int n_units = (B + 1) / 2;
+    // small launches: one work item per (group of units, super-tile) instead of per group (latency of a few samples)
+    a.sup_split = ((n_units + 1) / 2) * 2 <= sm_count / 2 ? 1 : 0;
+    if (a.sup_split && logit_out) RDG_CUDA(cudaMemsetAsync(logit_out, 0, (size_t)B * 2 * T * 256 * sizeof(int), st));
     // CTA pairs (cta_group::2) halve the weight-operand reads and weight writes per SM; RDG_PLANES_CG=1: one CTA per unit
     static const int cg = getenv("RDG_PLANES_CG") ? atoi(getenv("RDG_PLANES_CG")) : 2;
     if (cg == 2 && n_units >= 2) {
@@ -513,8 +529,9 @@ int launch_planes(const void* x, const void* wpack, const float* bias, void* y, 
             attr_set = true;
         }
         const int n_groups = (n_units + 1) / 2, max_clusters = sm_count / 2;
+        const int n_items = n_groups * (a.sup_split ? T / 2 : 1);
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * (n_groups < max_clusters ? n_groups : max_clusters));
+        cfg.gridDim = dim3(2 * (n_items < max_clusters ? n_items : max_clusters));
         cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -529,7 +546,8 @@ int launch_planes(const void* x, const void* wpack, const float* bias, void* y, 
         RDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set = true;
     }
-    const int grid = n_units < sm_count ? n_units : sm_count;
+    const int n_items1 = n_units * (a.sup_split ? T / 2 : 1);
+    const int grid = n_items1 < sm_count ? n_items1 : sm_count;
     kern<<<grid, kThreads, kSmem, st>>>(tmap, tmap_w, a);
     RDG_LAUNCH_CHECK();
     return 0;
