@@ -162,3 +162,29 @@ def test_small_launch_split_is_bit_identical(gen):
     finally:
         big.close(); small.close()
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("factor", [30.0, 1e-3])
+def test_fixed_point_scale_follows_the_output_conv_weights(factor):
+    """The on-chip output-conv sum is int32 fixed point with a power-of-two scale derived from the weights at pack time
+    (PixelNorm bounds |y|_2 <= 8, so 16 * sum_tap |w_tap|_2 bounds every partial sum).  Scaling the output conv by 30x / 0.001x
+    must neither overflow nor lose resolution: compare with the f32 tap-product path (same MMAs, RDG_CONV3=planes_p)."""
+    import os
+    from rdg_b200.engine import Context, Generator
+    gw = W.randomize_biases(W.init_generator_weights(2))
+    gw[8] = (gw[8] * np.float32(factor)).astype(np.float32)
+    z, cond = _inputs(12, seed=77)
+    ctx_a = Context(16, 1, max_chunk=64)
+    os.environ["RDG_CONV3"] = "planes_p"
+    try:
+        ctx_b = Context(16, 1, max_chunk=64)
+    finally:
+        os.environ.pop("RDG_CONV3", None)
+    try:
+        a = Generator(gw, ctx=ctx_a).predict([z, cond], mode="fp16").astype(np.float64)
+        b = Generator(gw, ctx=ctx_b).predict([z, cond], mode="fp16").astype(np.float64)
+    finally:
+        ctx_a.close(); ctx_b.close()
+    assert np.isfinite(a).all() and np.max(np.abs(a.sum(axis=1) - 1)) <= 1e-5
+    big = b > 1e-12
+    assert np.max(np.abs(a[big] - b[big]) / b[big]) <= 2e-4
