@@ -48,8 +48,10 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
                                                        const float* __restrict__ bias, float* __restrict__ dst,
                                                        ConvGeom g, int act, const float* __restrict__ mask,
                                                        float mask_scale, float* __restrict__ pre, float* __restrict__ part) {
-    __shared__ __align__(16) float As[BK][BM + 4];
-    __shared__ __align__(16) float Bs[BK][BN + 4];
+    // double-buffered tiles: while the FMAs of step s run, the global loads of step s+1 are in flight in registers
+    // (one __syncthreads per step; small grids are bound by the load latency of the step chain, not by FLOPs)
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int upf = g.up ? 2 : 1;
     const int LT = g.Ti * upf, LH = g.Hi * upf, LW = g.Wi * upf;   // logical input dims
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
     const int a_m = tid >> 2, a_k = (tid & 3) * 4;
     const long long am = m0 + a_m;
     const bool am_ok = am < M;
-    PosDec ap = decode_pos(am_ok ? am : 0, MT, MH, MW);
+    const PosDec ap = decode_pos(am_ok ? am : 0, MT, MH, MW);
 
     float acc[4][4];
 #pragma unroll
@@ -77,10 +79,15 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
     const int per_slice = (total_steps + (int)gridDim.z - 1) / (int)gridDim.z;
     const int step_beg = (int)blockIdx.z * per_slice;
     const int step_end = step_beg + per_slice < total_steps ? step_beg + per_slice : total_steps;
-    for (int tap = step_beg / nck; tap * nck < step_end; ++tap) {
+
+    // gather state of the current tap for this thread's A row
+    int cur_tap = -1;
+    bool ok = false;
+    long long base = 0;
+    auto set_tap = [&](int tap) {
+        cur_tap = tap;
         const int kw_ = tap % g.KW, kh_ = (tap / g.KW) % g.KH, kt_ = tap / (g.KW * g.KH);
-        bool ok = am_ok;
-        long long base = 0;
+        ok = am_ok;
         if (MODE == 0) {
             int lt = ap.t * g.stride + kt_ - g.pt, lh = ap.h * g.stride + kh_ - g.ph, lw = ap.w * g.stride + kw_ - g.pw;
             ok = ok && lt >= 0 && lt < LT && lh >= 0 && lh < LH && lw >= 0 && lw < LW;
@@ -94,44 +101,62 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
             ok = ok && nt < g.To && nh < g.Ho && nw < g.Wo;
             base = ((((long long)ap.b * g.To + nt) * g.Ho + nh) * g.Wo + nw) * g.Co;
         }
-        const int ck_beg = tap * nck < step_beg ? step_beg - tap * nck : 0;
-        const int ck_end = (tap + 1) * nck > step_end ? step_end - tap * nck : nck;
-        for (int c0 = ck_beg * BK; c0 < ck_end * BK; c0 += BK) {
-            // A tile: 64 positions x 16 reduction channels
-            float av[4] = {0.f, 0.f, 0.f, 0.f};
-            if (ok) {
-                const float* p = src + base + c0 + a_k;
-                if (c0 + a_k + 3 < KC && ((KC & 3) == 0)) {
-                    float4 v = *reinterpret_cast<const float4*>(p);
-                    av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (c0 + a_k + j < KC) av[j] = p[j];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) As[a_k + j][a_m] = av[j];
-            // B tile: 16 reduction channels x 64 outputs
-            if (MODE == 0) {
-                const int bk = tid >> 4, bn = (tid & 15) * 4;
-                const int ci = c0 + bk;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int n = n0 + bn + j;
-                    Bs[bk][bn + j] = (ci < g.Ci && n < g.Co) ? w[((long long)tap * g.Ci + ci) * g.Co + n] : 0.f;
-                }
+    };
+    float av[4], bv[4];
+    // global -> registers for reduction step `step` (A: 64 positions x 16 channels, B: 16 channels x 64 outputs)
+    auto load_step = [&](int step) {
+        const int tap = step / nck, c0 = (step - tap * nck) * BK;
+        if (tap != cur_tap) set_tap(tap);
+        av[0] = av[1] = av[2] = av[3] = 0.f;
+        if (ok) {
+            const float* p = src + base + c0 + a_k;
+            if (c0 + a_k + 3 < KC && ((KC & 3) == 0)) {
+                const float4 v = *reinterpret_cast<const float4*>(p);
+                av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
             } else {
-                const int bk = tid & 15;
-                const int co = c0 + bk;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int nn = (tid >> 4) + j * 16;
-                    int ci = n0 + nn;
-                    Bs[bk][nn] = (co < g.Co && ci < g.Ci) ? w[((long long)tap * g.Ci + ci) * g.Co + co] : 0.f;
-                }
+                for (int j = 0; j < 4; ++j) if (c0 + a_k + j < KC) av[j] = p[j];
             }
-            __syncthreads();
-            fma_tile(acc, As, Bs, ty, tx);
+        }
+        if (MODE == 0) {
+            const int bk = tid >> 4, bn = (tid & 15) * 4, ci = c0 + bk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + bn + j;
+                bv[j] = (ci < g.Ci && n < g.Co) ? w[((long long)tap * g.Ci + ci) * g.Co + n] : 0.f;
+            }
+        } else {
+            const int bk = tid & 15, co = c0 + bk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = n0 + (tid >> 4) + j * 16;
+                bv[j] = (co < g.Co && ci < g.Ci) ? w[((long long)tap * g.Ci + ci) * g.Co + co] : 0.f;
+            }
+        }
+    };
+    auto store_step = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) As[buf][a_k + j][a_m] = av[j];
+        if (MODE == 0) {
+            const int bk = tid >> 4, bn = (tid & 15) * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Bs[buf][bk][bn + j] = bv[j];
+        } else {
+            const int bk = tid & 15;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Bs[buf][bk][(tid >> 4) + j * 16] = bv[j];
+        }
+    };
+    if (step_beg < step_end) {
+        load_step(step_beg);
+        store_step(0);
+        __syncthreads();
+        for (int step = step_beg; step < step_end; ++step) {
+            const int buf = (step - step_beg) & 1;
+            const bool more = step + 1 < step_end;
+            if (more) load_step(step + 1);                 // in flight during the FMAs below
+            fma_tile(acc, As[buf], Bs[buf], ty, tx);
+            if (more) store_step(buf ^ 1);                 // the other buffer was last read before the previous barrier
             __syncthreads();
         }
     }
@@ -299,17 +324,18 @@ __global__ void __launch_bounds__(512) conv_bwd_filter_small_kernel(const float*
     float acc = 0.f;
     if (sub < nsub) {
         const float* dyb = dy + mbeg * g.Co + co;
-        for (int r = sub; r < rows; r += 4 * nsub) {
-            float xv[4], yv[4];
+        constexpr int U = 16;                 // rows in flight per thread: the loop is bound by the latency of its loads
+        for (int r = sub; r < rows; r += U * nsub) {
+            float xv[U], yv[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int rr = r + u * nsub;
                 const int off = rr < rows ? soff[rr] : -1;
                 xv[u] = off >= 0 ? x[off + ci] : 0.f;
                 yv[u] = off >= 0 ? dyb[(size_t)rr * g.Co] : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc = fmaf(xv[u], yv[u], acc);
+            for (int u = 0; u < U; ++u) acc = fmaf(xv[u], yv[u], acc);
         }
     }
     red[threadIdx.x] = acc;
