@@ -158,3 +158,12 @@ def test_data_parallel_gradients_match_single_rank_gloo():
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert err <= 1e-12
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    """bind_to_gpu_numa_node must never raise (no GPU here, single-node VMs on the GPU boxes) and must not shrink the CPU set."""
+    import os
+    from rdg_b200.dist import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
