@@ -82,14 +82,16 @@ def _PixelNormalization():
     return P
 
 
+_CTXS = {}
+
+
 def _ctx():
-    global _CTX
-    try:
-        return _CTX
-    except NameError:
+    """One context per (ndomain, n_channel): the additional-input and large-domain variants only change these two."""
+    key = (ndomain, n_channel)
+    if key not in _CTXS:
         from rdg_b200.engine import Context
-        _CTX = Context(ndomain, n_channel)
-        return _CTX
+        _CTXS[key] = Context(ndomain, n_channel)
+    return _CTXS[key]
 
 
 def create_discriminator():
@@ -145,13 +147,50 @@ def synthetic_radar(days=64, ny=64, nx=64, seed=0):
 
 
 sampler = None       # rdg_b200.sampler.DeviceSampler when the batches are drawn on the GPU (setup(device_sampler=True))
+extra_inputs = None  # None | 'doy' | 'lon': the additional-input variants of revision1/additional_inputs/
+timelist_all = None  # 'doy': day of year of every day of `data` (..._doy.py:128)
+min_lonidx = max_lonidx = 0   # 'lon': normalisation of the x index (..._lon.py:127-129)
 
 
-def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None, device_sampler=None):
+def _extra_channels(idcs_batch):
+    """Extra condition channels of the additional-input variants, (n, ndomain, ndomain, k) or None:
+    'doy' -> sin / cos of the day of year (gan_train_cwgangp_pixelnorm_doy.py:175-185),
+    'lon' -> x index normalised with the min / max over the valid indices (..._lon.py:176-185)."""
+    if extra_inputs is None:
+        return None
+    if extra_inputs == 'doy':
+        batch_doy = timelist_all[idcs_batch[:, 0]]
+        batch_doy = np.tile(batch_doy, (1, ndomain, ndomain, 1)).T
+        return np.concatenate([np.sin(2 * np.pi * batch_doy / 365), np.cos(2 * np.pi * batch_doy / 365)], axis=-1)
+    batch_lon = (idcs_batch[:, 2] - min_lonidx) / max_lonidx
+    return np.tile(batch_lon, (1, ndomain, ndomain, 1)).T
+
+
+def _with_extra(batch_cond, idcs_batch):
+    extra = _extra_channels(idcs_batch)
+    if extra is None:
+        return batch_cond
+    if isinstance(batch_cond, np.ndarray):
+        return np.concatenate([batch_cond, extra], axis=-1)
+    import torch
+    return torch.cat([batch_cond, torch.as_tensor(extra, dtype=batch_cond.dtype, device=batch_cond.device)], dim=-1)
+
+
+def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None, device_sampler=None, extra=None, timelist=None,
+          domain=None):
     """Build what the reference builds at import (:117-140, :360-408).  device_sampler (default: env RDG_DEVICE_SAMPLER=1):
-    keep the radar array in HBM and gather / normalise the batches there (replaces the GeneratorEnqueuer workers, :440-449)."""
+    keep the radar array in HBM and gather / normalise the batches there (replaces the GeneratorEnqueuer workers, :440-449).
+    extra = 'doy' (with timelist = day of year per day) or 'lon': the additional-input variants (n_channel = 3 / 2);
+    domain = 64: the large-domain variant (alternative_domains/gan_train_cwgangp_pixelnorm_largedomain.py:59)."""
     global data, indices_all, n_samples, generator, critic, critic_model, generator_model, optimizer, trainer, sampler
+    global extra_inputs, timelist_all, min_lonidx, max_lonidx, n_channel, ndomain
     from rdg_b200.engine import Adam, GanTrainer
+    if extra not in (None, 'doy', 'lon'):
+        raise ValueError("extra must be None, 'doy' or 'lon'")
+    extra_inputs = extra
+    n_channel = {None: 1, 'doy': 3, 'lon': 2}[extra]
+    if domain is not None:
+        ndomain = int(domain)
     np.random.seed(seed)
     data = synthetic_radar(seed=seed) if data_array is None else np.asarray(data_array, np.float32)
     assert data.ndim == 4 and data.shape[1] == nhours
@@ -161,6 +200,11 @@ def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None, device_sam
                          for x in range(0, nx - ndomain + 1, stride)]
     indices_all = np.array(valid_indices)
     n_samples = len(indices_all)
+    if extra == 'doy':
+        timelist_all = np.arange(data.shape[0]) % 365 + 1 if timelist is None else np.asarray(timelist)
+        assert len(timelist_all) == data.shape[0]
+    if extra == 'lon':
+        min_lonidx, max_lonidx = np.min(indices_all[:, 2]), np.max(indices_all[:, 2])
     generator = create_generator()        # generator first, like the reference (:361-362)
     critic = create_discriminator()
     optimizer = Adam(lr=0.0001, beta_1=0, beta_2=0.9)     # reference :385
@@ -185,8 +229,10 @@ def _windows(ixs):
 
 def generate_real_samples(n_batch):
     """reference :143-174"""
-    if sampler is not None:
-        yield from sampler.real_samples(n_batch)
+    while sampler is not None:
+        ixs = np.random.randint(n_samples, size=n_batch)                       # same draw as below (:147)
+        batch, batch_cond = sampler.gather(ixs)
+        yield [batch, _with_extra(batch_cond, indices_all[ixs])]
     while True:
         ixs = np.random.randint(n_samples, size=n_batch)
         batch = _windows(ixs)
@@ -194,8 +240,9 @@ def generate_real_samples(n_batch):
         for i in range(n_batch):
             batch[i] = batch[i] / batch_cond[i]
         batch_cond = batch_cond / norm_scale
+        batch_cond = _with_extra(batch_cond, indices_all[ixs])
         assert batch.shape == (n_batch, nhours, ndomain, ndomain, 1)
-        assert batch_cond.shape == (n_batch, ndomain, ndomain, 1)
+        assert batch_cond.shape == (n_batch, ndomain, ndomain, n_channel)
         assert ~np.any(np.isnan(batch)) and ~np.any(np.isnan(batch_cond))
         assert np.max(batch) <= 1 and np.min(batch) >= 0
         yield [batch, batch_cond]
@@ -203,12 +250,14 @@ def generate_real_samples(n_batch):
 
 def generate_latent_points(n_batch):
     """reference :177-193"""
-    if sampler is not None:
-        return sampler.latent_points(n_batch, latent_dim)
     latent = np.random.normal(size=(n_batch, latent_dim))
     ixs = np.random.randint(0, n_samples, size=n_batch)
+    if sampler is not None:
+        _, batch_cond = sampler.gather(ixs, with_batch=False)
+        return [latent, _with_extra(batch_cond, indices_all[ixs])]
     batch_cond = np.sum(_windows(ixs), axis=1) / norm_scale
-    assert batch_cond.shape == (n_batch, ndomain, ndomain, 1)
+    batch_cond = _with_extra(batch_cond, indices_all[ixs])
+    assert batch_cond.shape == (n_batch, ndomain, ndomain, n_channel)
     assert ~np.any(np.isnan(batch_cond))
     return [latent, batch_cond]
 

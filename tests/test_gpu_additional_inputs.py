@@ -111,3 +111,39 @@ def test_training_steps_match_oracle(nets):
         if i < 9:
             assert _rel_l2(gg[off:off + n].reshape(shp), rg) <= 1e-2, f"generator grad tensor {i}"
         off += (n + 3) // 4 * 4
+
+
+@pytest.mark.parametrize("extra,nch", [("doy", 3), ("lon", 2)])
+def test_dropin_training_module_variants(extra, nch):
+    """revision1/additional_inputs/gan_train_cwgangp_pixelnorm_{doy,lon}.py through the drop-in module: the extra condition
+    channels (sin / cos of the day of year, :175-185; normalised x index, ..._lon.py:176-185) are appended to the daily-sum
+    condition, on the host path and on the device-sampler path alike, and both training steps run."""
+    import gan_train_cwgangp_pixelnorm as m
+    try:
+        m.setup(seed=2, extra=extra, device_sampler=False)
+        assert m.n_channel == nch and m.generator.ncond == nch
+        np.random.seed(5)
+        rb, rc = next(m.generate_real_samples(4))
+        rl, rcc = m.generate_latent_points(3)
+        assert rc.shape == (4, 16, 16, nch) and rcc.shape == (3, 16, 16, nch)
+        # literal restatement of the reference's channel construction for the first sample
+        np.random.seed(5)
+        ixs = np.random.randint(m.n_samples, size=4)
+        t, y, x = m.indices_all[ixs[0]]
+        if extra == "doy":
+            d = m.timelist_all[t]
+            assert np.allclose(rc[0, :, :, 1], np.sin(2 * np.pi * d / 365)) and np.allclose(rc[0, :, :, 2], np.cos(2 * np.pi * d / 365))
+        else:
+            assert np.allclose(rc[0, :, :, 1], (x - m.min_lonidx) / m.max_lonidx)
+        m.setup(seed=2, extra=extra, device_sampler=True)
+        np.random.seed(5)
+        db, dc = next(m.generate_real_samples(4))
+        dl, dcc = m.generate_latent_points(3)
+        assert np.array_equal(db.cpu().numpy(), rb)
+        np.testing.assert_allclose(dc.cpu().numpy(), rc.astype(np.float32), rtol=0, atol=0)
+        np.testing.assert_allclose(dcc.cpu().numpy(), rcc.astype(np.float32), rtol=0, atol=0)
+        losses = m.critic_model.train_on_batch([db, dc, np.random.normal(size=(4, 100))])
+        g_loss = m.generator_model.train_on_batch([dl, dcc], None)
+        assert len(losses) == 4 and np.isfinite(losses).all() and np.isfinite(g_loss)
+    finally:
+        m.setup(seed=0, extra=None, device_sampler=False)
