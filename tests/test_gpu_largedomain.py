@@ -62,3 +62,21 @@ def test_critic_forward_and_step(big):
         n = int(np.prod(shp)); mine = g[off:off + n].reshape(shp); off += (n + 3) // 4 * 4
         rel = np.linalg.norm(mine - rg) / (np.linalg.norm(rg) + 1e-30)
         assert rel <= 1e-3, f"critic grad {i}: {rel:.2e}"      # loose: LeakyReLU sign flips, see test_gpu_critic_train.py
+
+
+def test_dropin_training_module_large_domain(tmp_path, monkeypatch):
+    """alternative_domains/gan_train_cwgangp_pixelnorm_largedomain.py through the drop-in module: setup(domain=64), one
+    iteration of train() (5 critic steps + 1 generator step, :463-491) at batch 2 on synthetic radar-shaped data."""
+    import gan_train_cwgangp_pixelnorm as m
+    monkeypatch.chdir(tmp_path)
+    try:
+        m.setup(seed=1, domain=64, device_sampler=True)
+        assert m.ndomain == 64 and m.generator.get_weights()[0].shape == (100 + 64 * 64, 49152)
+        m.hist['d_loss'].clear(); m.hist['g_loss'].clear()
+        m.train(1, 2, bat_per_epo=1, save=False)
+        assert len(m.hist['g_loss']) == 1 and np.isfinite(m.hist['g_loss'][0]) and np.isfinite(m.hist['d_loss'][0])
+        fake, cond = m.generate_fake_samples(2)
+        assert fake.shape == (2, 24, 64, 64, 1) and np.max(np.abs(fake.sum(axis=1) - 1)) <= 1e-5
+    finally:
+        m.ndomain = 16
+        m.setup(seed=0, extra=None, device_sampler=False)
