@@ -115,6 +115,12 @@ int  rdg_critic_get_weights(rdg_ctx* ctx, float* const* tensors, const size_t* s
 int  rdg_critic_forward(rdg_ctx* ctx, const float* sample_dev, const float* cond_dev,
                         const float* const* masks_dev, float* score_dev, int B, void* stream);
 
+/* critic([sample, cond]) in the 16-bit tensor-core scoring mode (mode = RDG_MODE_FP16 / RDG_MODE_BF16; inference, Dropout is
+ * identity): the stride-2 convs D2..D4 (gan_train_cwgangp_pixelnorm.py:291-301) run as tcgen05 implicit GEMMs fed by TMA boxes
+ * with element stride 2, the 2-channel first conv (:286-288) and the final Dense (:303-304) on CUDA cores. */
+int  rdg_critic_forward_tc(rdg_ctx* ctx, const float* sample_dev, const float* cond_dev, float* score_dev, int B, int mode,
+                           void* stream);
+
 /* ---- training steps (gan_train_cwgangp_pixelnorm.py:365-408, 468-482) ----
  * Evaluate the losses and the gradient of the step's loss w.r.t. the trainable net, leaving
  * the gradients in the context's gradient buffers (for an allreduce between ranks), then

@@ -176,6 +176,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     for (int i = 0; i < 4; ++i) cudaFree(c->st_buf[i]);
     for (int i = 0; i < 3; ++i) cudaFree(c->g_wfold32[i]);
     for (int k = 0; k < 2; ++k) cudaFree(c->g_wpack_dense_big[k]);
+    for (int k = 0; k < 2; ++k) for (int l = 0; l < 3; ++l) cudaFree(c->c_wpack[k][l]);
     for (int k = 0; k < 2; ++k) { cudaFree(c->g_w4pack[k]); cudaFree(c->g_wpack_planes[k]); cudaFree(c->g_wpack_dense[k]); }
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->e2e_lat[i]); cudaFree(c->e2e_out[i]);
@@ -301,6 +302,7 @@ extern "C" int rdg_critic_set_weights(rdg_ctx* c, const float* const* tensors, c
     int r = upload_params(c->c_params, c->c_off, c->c_size, tensors, sizes, n, "critic weights");
     if (r) return r;
     c->critic_ready = true;
+    c->critic_packed_stale = true;
     return 0;
 }
 extern "C" int rdg_critic_get_weights(rdg_ctx* c, float* const* tensors, const size_t* sizes, int n) {
@@ -617,6 +619,50 @@ extern "C" int rdg_critic_forward(rdg_ctx* c, const float* sample_dev, const flo
         }
         ConvGeom d = rdg_critic_dense_geom(c, n);
         if ((r = simt_conv_fwd(cur, c->c_params + c->c_off[8], c->c_params + c->c_off[9], score_dev + b0, d, ACT_NONE, nullptr, 1.f, st))) return r;
+    }
+    return 0;
+}
+
+// critic([sample, cond]) in the 16-bit tensor-core scoring mode (inference: Dropout is identity)
+extern "C" int rdg_critic_forward_tc(rdg_ctx* c, const float* sample_dev, const float* cond_dev, float* score_dev, int B, int mode,
+                                     void* stream) {
+    if (!c || B < 0 || (mode != RDG_MODE_BF16 && mode != RDG_MODE_FP16)) { rdg_set_error("rdg_critic_forward_tc: bad arguments"); return RDG_E_BADARG; }
+    if (!c->critic_ready) { rdg_set_error("critic weights not set"); return RDG_E_NOWEIGHT; }
+    RDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int r;
+    if (c->critic_packed_stale) {
+        for (int k = 0; k < 2; ++k)
+            for (int l = 1; l < 4; ++l) {
+                ConvGeom g = rdg_critic_conv_geom(c, l, 1);
+                if (!c->c_wpack[k][l - 1]) RDG_CUDA(cudaMalloc(&c->c_wpack[k][l - 1], (size_t)27 * g.Ci * g.Co * 2));
+                if ((r = pack_critic_weights(k == 0 ? RDG_HALF_BF16 : RDG_HALF_FP16, c->c_params + c->c_off[2 * l], c->c_wpack[k][l - 1], g.Ci, g.Co, st))) return r;
+            }
+        c->launches += 6;
+        c->critic_packed_stale = false;
+    }
+    const int hk = mode == RDG_MODE_BF16 ? RDG_HALF_BF16 : RDG_HALF_FP16, wk = hk == RDG_HALF_BF16 ? 0 : 1;
+    size_t per = 0;
+    for (int l = 0; l < 4; ++l) { ConvGeom g = rdg_critic_conv_geom(c, l, 1); per += (size_t)g.To * g.Ho * g.Wo * g.Co * 2 + 256; }
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((c->ws_bytes - 4096) / per, 1 << 20));
+    const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int n = std::min(chunk, B - b0);
+        uint8_t* p = reinterpret_cast<uint8_t*>(c->ws);
+        auto take = [&](size_t bytes) { void* q = p; p += (bytes + 255) / 256 * 256; return q; };
+        ConvGeom g0 = rdg_critic_conv_geom(c, 0, n);
+        void* cur = take((size_t)n * g0.To * g0.Ho * g0.Wo * g0.Co * 2);
+        if ((r = critic_first_conv(hk, sample_dev + (size_t)b0 * px, cond_dev + (size_t)b0 * c->nd * c->nd * c->ncond, c->c_params + c->c_off[0],
+                                   c->c_params + c->c_off[1], cur, n, c->nd, c->ncond, g0, st))) return r;
+        for (int l = 1; l < 4; ++l) {
+            ConvGeom g = rdg_critic_conv_geom(c, l, n);
+            void* y = take((size_t)n * g.To * g.Ho * g.Wo * g.Co * 2);
+            if ((r = tc_critic_conv(hk, cur, c->c_wpack[wk][l - 1], c->c_params + c->c_off[2 * l + 1], y, g, c->sm_count, st))) return r;
+            cur = y;
+        }
+        ConvGeom d = rdg_critic_dense_geom(c, n);
+        if ((r = critic_dense_score(hk, cur, c->c_params + c->c_off[8], c->c_params + c->c_off[9], score_dev + b0, n, d.Ci, st))) return r;
+        c->launches += 5;
     }
     return 0;
 }

@@ -22,6 +22,8 @@ struct rdg_ctx {
     bool dense_big_tc = false;
     float* g_wfold32[3] = {};       // FP32 upsample-folded kernels [8 phases][2,2,2,Ci,Co] of the three upsampled convs (simt_folded.cu)
     bool fold32_stale = true;
+    void* c_wpack[2][3] = {};       // critic D2..D4 kernels as tcgen05 B tiles ([0] = bf16, [1] = fp16), critic_tc.cu
+    bool critic_packed_stale = true;
     void* g_w4pack[2] = {};   // output conv as a [32 taps x 64 ch] swizzled 16-bit B tile
     // training state (allocated on first use)
     float* g_grads = nullptr; float* g_m = nullptr; float* g_v = nullptr;

@@ -69,3 +69,12 @@ size_t tc_dense_big_input_bytes(int B, int K);
 int pack_dense_big_weights(int half_kind, const float* w, void* dst, int K, int N, cudaStream_t st);
 int tc_dense_big_lrelu(int half_kind, const float* latent, const float* cond, int spc, int b_off, const void* wT, const float* bias,
                        void* x16_scratch, void* out, int B, int K, int N, cudaStream_t st);
+
+// Critic forward on the tensor cores (critic_tc.cu): stride-2 Conv3D + LeakyReLU layers D2..D4 as tcgen05 implicit GEMMs
+// (g = rdg_critic_conv_geom of the layer; x, y 16-bit channels-last), the 2-channel first conv and the final Dense on CUDA cores.
+struct ConvGeom;
+int tc_critic_conv(int half_kind, const void* x, const void* wpack, const float* bias, void* y, const ConvGeom& g, int sm_count, cudaStream_t st);
+int pack_critic_weights(int half_kind, const float* k, void* dst, int Cin, int Cout, cudaStream_t st);
+int critic_first_conv(int half_kind, const float* sample, const float* cond, const float* w, const float* bias, void* out, int B, int nd,
+                      int ncond, const ConvGeom& g, cudaStream_t st);
+int critic_dense_score(int half_kind, const void* h4, const float* w5, const float* b5, float* score, int B, int K, cudaStream_t st);

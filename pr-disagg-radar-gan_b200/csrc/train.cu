@@ -63,6 +63,7 @@ extern "C" int rdg_adam_apply(rdg_ctx* c, int which, float lr, float beta1, floa
     r = ew_adam(p, g, m, v, (long long)n, (float)lr_t, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
     if (r) return r;
     if (which == 0) { c->gen_packed_stale = true; c->fold32_stale = true; }
+    else c->critic_packed_stale = true;
     return 0;
 }
 extern "C" int rdg_adam_reset(rdg_ctx* c, int which) {

@@ -47,6 +47,7 @@ SIGNATURES = {
     "rdg_critic_get_weights": (C.c_int, [C.c_void_p, _c_float_pp, _c_size_p, C.c_int]),
     "rdg_critic_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_int,
                                      C.c_void_p]),
+    "rdg_critic_forward_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "rdg_critic_step_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
                                         C.c_int, C.c_void_p, C.c_void_p]),

@@ -222,11 +222,18 @@ class Critic:
         _lib.check(self.ctx.lib.rdg_critic_get_weights(self.ctx.handle, ptrs, sizes, len(ws)))
         return ws
 
-    def forward_device(self, sample, cond, masks=None):
-        """sample [B,24,nd,nd(,1)] cuda f32, cond [B,nd,nd,ncond] cuda f32 -> scores [B] cuda f32."""
+    def forward_device(self, sample, cond, masks=None, mode="fp32"):
+        """sample [B,24,nd,nd(,1)] cuda f32, cond [B,nd,nd,ncond] cuda f32 -> scores [B] cuda f32.
+        mode "fp16" / "bf16": tensor-core scoring (inference only, no dropout masks)."""
         ctx = self.ctx
         B = int(sample.shape[0])
         score = torch.empty((B,), device=sample.device, dtype=torch.float32)
+        if mode != "fp32":
+            if masks is not None:
+                raise ValueError("the tensor-core critic mode is inference only (no dropout masks)")
+            _lib.check(ctx.lib.rdg_critic_forward_tc(ctx.handle, C.c_void_p(sample.data_ptr()), C.c_void_p(cond.data_ptr()),
+                                                     C.c_void_p(score.data_ptr()), B, _lib.MODES[mode], ctx._stream()))
+            return score
         mp = None
         if masks is not None:
             mp = (C.c_void_p * 4)(*[C.c_void_p(m.data_ptr()) for m in masks])
@@ -234,13 +241,13 @@ class Critic:
                                               mp, C.c_void_p(score.data_ptr()), B, ctx._stream()))
         return score
 
-    def predict(self, inputs, masks=None):
+    def predict(self, inputs, masks=None, mode="fp32"):
         """critic.predict([sample, cond]) -> (B,1) float32."""
         sample, cond = inputs
         s = self.ctx.dev(sample)
         c = self.ctx.dev(cond)
         m = None if masks is None else [self.ctx.dev(x) for x in masks]
-        out = self.forward_device(s, c, m)
+        out = self.forward_device(s, c, m, mode=mode)
         torch.cuda.synchronize(self.ctx.device)
         return out.cpu().numpy().reshape(-1, 1)
 

@@ -233,3 +233,19 @@ def test_checkpoint_resume(ctx16, tmp_path):
     # without the optimizer state the continuation is a different trajectory (v = 0 restarts Adam's step size)
     tr3 = fresh()
     tr3.generator.set_weights(tr.generator.get_weights())
+
+
+@pytest.mark.parametrize("mode,tol", [("fp16", 5e-3), ("bf16", 4e-2)])
+@pytest.mark.parametrize("B", [1, 9, 200])
+def test_critic_forward_tensor_core_mode(nets, B, mode, tol):
+    """Scoring mode on tcgen05 (stride-2 convs via TMA boxes with element stride 2, TF 'same' padding = OOB zero fill):
+    scores against the FP64 oracle; tolerance relative to the score spread (16-bit operands through four conv layers)."""
+    gen, crit, gw, cw = nets
+    x, cond, _, _, _ = _batch(B, seed=17)
+    ref = O.critic_forward(cw, x, cond, None, torch.float64)
+    out = crit.predict([x, cond], mode=mode)
+    assert out.shape == (B, 1) and np.isfinite(out).all()
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.max(np.abs(out - ref)) <= tol * scale
+    f32 = crit.predict([x, cond])
+    assert np.max(np.abs(out - f32)) <= tol * scale
