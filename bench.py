@@ -360,6 +360,23 @@ def main():
                  "config": "cWGAN-GP, 5 critic steps (3 critic passes + gradient penalty, frozen generator forward on tensor cores) "
                            "+ 1 generator step, batch 32 per GPU, FP32 SIMT gradients, one flat-gradient all-reduce per optimizer step",
                  "finite": bool(np.isfinite(losses).all() and np.isfinite(gl))}
+        # critic scoring (config #3, forward only): synthetic hourly fraction fields, tensor-core scoring mode vs the FP32 path
+        CB = 20000
+        cx = torch.rand((CB, 24, 16, 16), device=dev); cx = cx / cx.sum(dim=1, keepdim=True)
+        cc = torch.as_tensor(synth_conditions(CB, 16, 77 + rank), device=dev)
+        critic_rates = {}
+        for cmode in ("fp16", "fp32"):
+            for _ in range(2):
+                tcrit.forward_device(cx, cc, mode=cmode)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                tcrit.forward_device(cx, cc, mode=cmode)
+            c1.record(); torch.cuda.synchronize()
+            critic_rates[cmode] = CB / (c0.elapsed_time(c1) / 3 / 1e3)
+        train["critic_scoring_samples_per_s_per_gpu"] = critic_rates
+        del cx, cc
         tctx.close()
 
     if rank != 0:

@@ -241,6 +241,7 @@ def test_critic_forward_tensor_core_mode(nets, B, mode, tol):
     """Scoring mode on tcgen05 (stride-2 convs via TMA boxes with element stride 2, TF 'same' padding = OOB zero fill):
     scores against the FP64 oracle; tolerance relative to the score spread (16-bit operands through four conv layers)."""
     gen, crit, gw, cw = nets
+    crit.set_weights(cw)        # the training tests above share the context and leave their own weights in it
     x, cond, _, _, _ = _batch(B, seed=17)
     ref = O.critic_forward(cw, x, cond, None, torch.float64)
     out = crit.predict([x, cond], mode=mode)
