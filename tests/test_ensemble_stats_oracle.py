@@ -31,3 +31,17 @@ def test_crps_cdf_form_equals_energy_form():
 def test_area_mean():
     x = np.arange(2 * 24 * 4 * 4, dtype=np.float64).reshape(2, 24, 4, 4)
     np.testing.assert_allclose(O.area_mean(x)[1, 3], x[1, 3].mean())
+
+
+def test_sample_windows_hand_case():
+    """Oracle restatement of generate_real_samples' preprocessing (gan_train_cwgangp_pixelnorm.py:148-163) on a 2x2 window."""
+    data = np.zeros((2, 24, 3, 3), np.float32)
+    data[1, :, 1:, 1:] = np.arange(1, 25, dtype=np.float32)[:, None, None]        # hour h carries h mm at every pixel
+    batch, cond = O.sample_windows(data, np.array([[1, 1, 1]]), 2, norm_scale=127.4)
+    assert batch.shape == (1, 24, 2, 2, 1) and cond.shape == (1, 2, 2, 1)
+    assert batch.dtype == np.float32 and cond.dtype == np.float32
+    np.testing.assert_allclose(cond[0, :, :, 0], np.float32(300.0) / np.float32(127.4))       # 1 + 2 + ... + 24 = 300
+    np.testing.assert_allclose(batch[0, :, 0, 0, 0], np.arange(1, 25, dtype=np.float32) / np.float32(300.0))
+    assert abs(float(batch[0].sum(axis=0).max()) - 1) < 1e-6
+    none, cond2 = O.sample_windows(data, np.array([[1, 1, 1]]), 2, with_batch=False)
+    assert none is None and np.array_equal(cond, cond2)
