@@ -3,6 +3,7 @@
 #include "rdg_common.cuh"
 #include "gen_tc.h"
 #include "ctx.h"
+#include "tcg.h"
 #include "../../include/rdg_b200.h"
 
 #include <cstdarg>
@@ -683,6 +684,40 @@ extern "C" int rdg_conv3d(int op, const int* geom17, const float* a, const float
     if (op == 0) return simt_conv_fwd(a, b, bias, out, g, act, nullptr, 1.f, st);
     if (op == 1) return simt_conv_bwd_data(a, b, out, g, st);
     if (op == 2) return simt_conv_bwd_filter(a, b, out, out2, g, st);
+    // 10..12: the same three on the tensor cores (tcgen05 kind::tf32, tcg_gemm.cu); g.up selects the upsample-folded forms
+    if (op >= 10 && op <= 12) {
+        const size_t wn = (size_t)g.KT * g.KH * g.KW * g.Ci * g.Co;
+        int r = 0;
+        if (!g.up) {
+            if (op == 10) {
+                float* wT = nullptr;
+                RDG_CUDA(cudaMallocAsync(&wT, wn * 4, st));
+                if (!(r = tcg_transpose_blocks(b, wT, g.KT * g.KH * g.KW, g.Ci, g.Co, st))) r = tcg_conv_fwd(a, wT, bias, out, g, act, nullptr, 1.f, st);
+                RDG_CUDA(cudaFreeAsync(wT, st));
+                return r;
+            }
+            if (op == 11) return tcg_conv_bwd_data(a, b, out, g, st);
+            if ((r = tcg_conv_bwd_filter(a, b, out, g, st))) return r;
+            return out2 ? simt_colsum(b, out2, (long long)g.B * g.To * g.Ho * g.Wo, g.Co, st) : 0;
+        }
+        const size_t fn = folded_weight_elems(g.Ci, g.Co);
+        float* wf = nullptr; float* wfT = nullptr;
+        RDG_CUDA(cudaMallocAsync(&wf, fn * 4, st));
+        RDG_CUDA(cudaMallocAsync(&wfT, fn * 4, st));
+        if (op == 10) {
+            if (!(r = folded_pack_f32(b, wf, g.Ci, g.Co, st)) && !(r = tcg_transpose_blocks(wf, wfT, 64, g.Ci, g.Co, st)))
+                r = tcg_folded_fwd(a, wfT, bias, out, g, st);
+        } else if (op == 11) {   // `out` = gradient w.r.t. the LOW-RES input
+            if (!(r = folded_pack_f32(b, wf, g.Ci, g.Co, st))) r = tcg_folded_bwd_data(a, wf, out, g, st);
+        } else {
+            RDG_CUDA(cudaMemsetAsync(wf, 0, fn * 4, st));
+            if (!(r = tcg_folded_bwd_filter(a, b, wf, g, st))) r = folded_unfold_grad(wf, out, g.Ci, g.Co, st);
+            if (!r && out2) r = simt_colsum(b, out2, (long long)8 * g.B * g.Ti * g.Hi * g.Wi, g.Co, st);
+        }
+        RDG_CUDA(cudaFreeAsync(wf, st));
+        RDG_CUDA(cudaFreeAsync(wfT, st));
+        return r;
+    }
     return RDG_E_BADARG;
 }
 

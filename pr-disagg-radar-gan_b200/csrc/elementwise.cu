@@ -178,6 +178,60 @@ __global__ void fill_normal_kernel(float* __restrict__ dst, long long n, uint64_
     for (int j = 0; j < 4; ++j) if (q * 4 + j < n) dst[q * 4 + j] = z[j];
 }
 
+// ---- device-resident training state: lets a captured CUDA graph of a training step be replayed (the Philox counter and the
+// Adam step live in device memory and are advanced by kernels inside the graph instead of being baked into kernel arguments)
+__global__ void train_tick_kernel(RdgTrainState* s) { s->rng_ctr += 1ull; }
+__global__ void adam_prepare_kernel(RdgTrainState* s, float lr, float b1, float b2) {
+    const long long t = ++s->adam_t;      // shared step counter of the one optimizer object (gan_train_cwgangp_pixelnorm.py:385)
+    s->lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n4, const RdgTrainState* __restrict__ s, float b1, float b2, float eps, float gs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float lr_t = s->lr_t;
+    float4 gi = reinterpret_cast<const float4*>(g)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+    float4 pi = reinterpret_cast<float4*>(p)[i];
+    float* G = &gi.x; float* M = &mi.x; float* V = &vi.x; float* P = &pi.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float gj = G[j] * gs;
+        M[j] = b1 * M[j] + (1.f - b1) * gj;
+        V[j] = b2 * V[j] + (1.f - b2) * gj * gj;
+        P[j] = P[j] - lr_t * M[j] / (sqrtf(V[j]) + eps);
+    }
+    reinterpret_cast<float4*>(m)[i] = mi; reinterpret_cast<float4*>(v)[i] = vi; reinterpret_cast<float4*>(p)[i] = pi;
+}
+// kind 0: N(0,1) (Box-Muller), 1: U[0,1), 2: Bernoulli(keep) as 0/1 floats.  Philox counter = (quad index, stream id, step counter)
+__global__ void fill_random_dev_kernel(float* __restrict__ dst, long long n, uint64_t seed, const RdgTrainState* __restrict__ s,
+                                       uint32_t stream_id, int kind, float keep) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 4 >= n) return;
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)((uint64_t)q >> 32), stream_id, (uint32_t)s->rng_ctr};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    float z[4];
+    if (kind == 0) {
+        float u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = ((float)c[j] + 0.5f) * 2.3283064365386963e-10f;
+        const float r0 = sqrtf(-2.f * logf(u[0])), r1 = sqrtf(-2.f * logf(u[2]));
+        float s0, c0, s1, c1;
+        sincospif(2.f * u[1], &s0, &c0);
+        sincospif(2.f * u[3], &s1, &c1);
+        z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float u = (float)(c[j] >> 8) * 5.9604644775390625e-08f;     // [0,1) with 24 bits
+            z[j] = kind == 1 ? u : (u < keep ? 1.f : 0.f);
+        }
+    }
+    if (q * 4 + 3 < n) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(z[0], z[1], z[2], z[3]);
+    else for (int j = 0; q * 4 + j < n; ++j) dst[q * 4 + j] = z[j];
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
                             float gs) {
@@ -320,6 +374,30 @@ int ew_adam(float* p, const float* g, float* m, float* v, long long n, float lr_
             float eps, float grad_scale, cudaStream_t st) {
     if (!n) return 0;
     adam_kernel<<<EW_GRID(n)>>>(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int ew_train_tick(RdgTrainState* s, cudaStream_t st) {
+    train_tick_kernel<<<1, 1, 0, st>>>(s);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_adam_dev(float* p, const float* g, float* m, float* v, long long n, RdgTrainState* s, float lr, float beta1, float beta2,
+                float eps, float grad_scale, cudaStream_t st) {
+    if (!n) return 0;
+    if (n & 3) { rdg_set_error("ew_adam_dev: parameter count must be a multiple of 4 (flat buffers are padded)"); return -1; }
+    adam_prepare_kernel<<<1, 1, 0, st>>>(s, lr, beta1, beta2);
+    RDG_LAUNCH_CHECK();
+    adam_dev_kernel<<<EW_GRID(n / 4)>>>(p, g, m, v, n / 4, s, beta1, beta2, eps, grad_scale);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_fill_random_dev(float* dst, long long n, uint64_t seed, const RdgTrainState* s, uint32_t stream_id, int kind, float keep,
+                       cudaStream_t st) {
+    if (!n) return 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) != 0) { rdg_set_error("ew_fill_random_dev: destination must be 16-byte aligned"); return -1; }
+    fill_random_dev_kernel<<<EW_GRID((n + 3) / 4)>>>(dst, n, seed, s, stream_id, kind, keep);
     RDG_LAUNCH_CHECK();
     return 0;
 }

@@ -24,7 +24,6 @@ struct TcConvArgs {
     int* logit_out;     // planes kernel only: fused output conv summed on chip -> [B,2T,16,16] fixed-point logits (no bias)
     int sup_split;      // planes kernel: 1 = one work item per (sample-pair group, super-tile) (small launches)
     int* nonfinite;     // planes kernel, logit mode: set to 1 if any activation is Inf / NaN
-    int dbg;            // experiments only (RDG_DBG): 1 = epilogue does not touch TMEM, 2 = no output-conv MMA, 4 = skip N=64 MMAs
 };
 
 // y[B,2T,2H,2W,Cout] = LeakyReLU(PixelNorm(conv3x3x3(upsample2(x[B,T,H,W,Cin])) + bias))

@@ -263,7 +263,7 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
                             tc_fence_after();
                             const uint32_t b_addr = b_base + s * kBStage;
                             if (elect_one()) {
-                                if (a_ok && !(args.dbg & 4)) {
+                                if (a_ok) {
                                     const uint64_t al = make_sdesc_sbo(a_view - kRow, kSboA), ar = make_sdesc_sbo(a_view + kRow, kSboA);
                                     const uint64_t b0d = make_sdesc(b_addr), b1d = make_sdesc(b_addr + kBStage / 2);
 #pragma unroll
@@ -327,7 +327,7 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
                     tc_fence_after();
                     const size_t o_row = (((size_t)b * T2 + (2 * (2 * sup + m) + pt)) * H2 + (2 * h + ph)) * W2 + 2 * wq;
                     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccCols + m * 128;
-                    if (!(args.dbg & 1)) {
+                    {
 #pragma unroll 1
                         for (int pw = 0; pw < 2; ++pw) {
                             const uint32_t taddr = lane_base + pw * 64;
@@ -358,7 +358,7 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
                                 tc_st32(taddr, pk);                        // y as the A operand of the tap product
                                 tc_fence_before();
                                 asm volatile("bar.sync %0, 128;" ::"r"(1 + m) : "memory");
-                                if (q == 0 && !(args.dbg & 2)) {
+                                if (q == 0) {
                                     if (CG > 1) {
                                         // both CTAs' y tiles must be in TMEM before the leader issues the pair's product
                                         if (elect_one()) mbar_arrive_cluster(mapa_rank(smem_u32(&y_ready[m * 2 + pw]), 0));
@@ -381,7 +381,7 @@ tc_upconv64_planes_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
                                     dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                             }
                         }
-                        if (fuse && !(args.dbg & 2)) {
+                        if (fuse) {
 #pragma unroll 1
                             for (int pw = 0; pw < 2; ++pw) {
                                 mbar_wait(&p_full[m * 2 + pw], p_it & 1);
@@ -489,8 +489,6 @@ int launch_planes(const void* x, const void* wpack, const float* bias, void* y, 
     TcConvArgs a{};
     a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin;
     a.wpack = wpack; a.bias = bias; a.out = y; a.w4tile = w4tile; a.p_out = p_out; a.logit_out = logit_out; a.nonfinite = nonfinite;
-    static const int dbg = getenv("RDG_DBG") ? atoi(getenv("RDG_DBG")) : 0;
-    a.dbg = dbg;
 
     // tensor dims ordered (C, W, B, H, T) so that the box lands as [h'][sample][w'][64 ch] rows
     CUtensorMap tmap;

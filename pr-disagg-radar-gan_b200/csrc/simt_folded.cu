@@ -137,3 +137,9 @@ int folded_conv_bwd_filter(const float* x, const float* dy, const float* dyp, fl
     if (db) return simt_colsum(dy, db, (long long)8 * g.B * g.Ti * g.Hi * g.Wi, g.Co, st);
     return 0;
 }
+
+int folded_unfold_grad(const float* dwf, float* dw, int Ci, int Co, cudaStream_t st) {
+    fold_unpack_grad_kernel<<<ceil_div((long long)27 * Ci * Co, 256), 256, 0, st>>>(dwf, dw, Ci * Co);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,32 @@
+// Training-path implicit GEMMs on the 5th-generation tensor cores (tcg_gemm.cu): every contraction of the cWGAN-GP step
+// (gan_train_cwgangp_pixelnorm.py:272-357 forward, :230-244 gradient penalty, :387-408 gradients) as tcgen05.mma kind::tf32
+// with FP32 accumulators in TMEM.  Operands are the FP32 training tensors themselves (rounded to tf32 on the way into shared
+// memory), so the tensor-core mode shares every buffer, mask and pre-activation with the FP32 SIMT parity mode.
+// Same argument meaning as the simt_* / folded_* primitives of rdg_common.cuh.
+#pragma once
+#include "rdg_common.cuh"
+
+#define RDG_TCG_E_SHAPE (-12)   // geometry the tensor-core training kernels do not cover (callers fall back to nothing: it is an error)
+
+// [nblk][R][C] -> [nblk][C][R]
+int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, cudaStream_t st);
+
+// y = act(conv(x, w) + bias) [* mask * mask_scale]; wT = the kernel with its last two axes swapped: (KT,KH,KW,Co,Ci).
+// g.up must be 0 (the generator's upsampled convs go through the folded entry points below).
+int tcg_conv_fwd(const float* x, const float* wT, const float* bias, float* y, const ConvGeom& g, int act, const float* mask,
+                 float mask_scale, cudaStream_t st, float* pre = nullptr);
+// dx = conv_transpose(dy, w); w in the Keras layout (KT,KH,KW,Ci,Co).  stride 1 or 2, g.up == 0.
+int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);
+// dw += sum_{b,pos} x (x) dy (accumulates with atomics; caller zeroes).  No bias gradient (use simt_colsum).
+int tcg_conv_bwd_filter(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st);
+
+// Upsample-folded forms of UpSampling3D(2) + Conv3D(3^3,'same'); g = the layer's geometry (g.up == 1).
+// wfT: [8 phases][8 taps][Co][Ci] (tcg_transpose_blocks of folded_pack_f32's output); wf: [8][8][Ci][Co].
+// y[B,2T,2H,2W,Co] = conv3(upsample2(x)) + bias
+int tcg_folded_fwd(const float* x, const float* wfT, const float* bias, float* y, const ConvGeom& g, cudaStream_t st);
+// dx[B,T,H,W,Ci] = gradient w.r.t. the LOW-RES input (upsample backward absorbed); dy interleaved [B,2T,2H,2W,Co]
+int tcg_folded_bwd_data(const float* dy, const float* wf, float* dx, const ConvGeom& g, cudaStream_t st);
+// dwf[8][8][Ci][Co] += folded filter gradients (atomics; caller zeroes, then un-folds with folded_unfold_grad)
+int tcg_folded_bwd_filter(const float* x, const float* dy, float* dwf, const ConvGeom& g, cudaStream_t st);
+// dw[27][Ci][Co] += unfold(dwf)   (simt_folded.cu)
+int folded_unfold_grad(const float* dwf, float* dw, int Ci, int Co, cudaStream_t st);

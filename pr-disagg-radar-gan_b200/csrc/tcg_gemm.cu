@@ -1,0 +1,649 @@
+// Training-path implicit GEMMs on tcgen05 (kind::tf32, FP32 accumulate in TMEM) -- see tcg.h.
+//
+// Two kernels cover every contraction of the training step:
+//
+//  tcg_rowgemm_kernel   D[row, n] = sum_{tap, c} SRC[pos(row) (+) tap][c] * W[tap][n][c]
+//      rows = output positions (forward convs: critic stride-2 'same'/'valid', Dense, the 8 phase convs of an upsample-folded
+//      block) or input positions (backward-data: stride-2 transposed convs by parity class, the folded block's backward straight
+//      to the low-res grid).  All of them are the same thing after the host has split the row set into CLASSES (parity classes /
+//      output phases): inside a class the source coordinate is an affine map a*t + c_tap of the class-local coordinate, the set
+//      of contributing taps is the same for every row, and the output coordinate is o + os*t.  128 rows per CTA (UMMA M = 128),
+//      N <= 256 accumulator columns, K streamed in 32-element (128-byte) blocks through a shared-memory ring.
+//
+//  tcg_filtergrad_kernel   dW[tap][ci][co] += sum_pos X[pos (+) tap][ci] * DY[pos][co]
+//      the contraction runs over positions, which are NOT contiguous in the channels-last tensors: the producer warps read 16-byte
+//      channel vectors per position and scatter them transposed into the K-major operand tiles (lane = position: conflict-free).
+//
+// Both: 8 producer warps gather operands global -> registers (cvt.rna.tf32) -> 128-byte-swizzled K-major shared memory
+// (fence.proxy.async, mbarrier full/empty ring), one elected thread of warp 8 issues tcgen05.mma, the producer warps turn into the
+// epilogue (tcgen05.ld 32x32b: thread = accumulator row).  Split-K: deterministic partial slices + splitk reduction (row GEMM),
+// vector red.global.add (filter gradients, which accumulate into the shared gradient buffer anyway).
+#include "tc_ptx.cuh"
+#include "tcg.h"
+#include <algorithm>
+
+namespace {
+using namespace rdg_tc;
+
+constexpr int TCG_THREADS = 288;
+constexpr int MAX_STAGES = 8;
+
+struct TcgTap { int8_t ct, ch, cw, pad_; int32_t widx; };
+struct TcgClass { int Tc, Hc, Wc, rows, tile_begin, ot, oh, ow, tap_begin, tap_count; };
+
+struct TcgRowArgs {
+    const float* src; const float* w; float* out; float* part;
+    const float* bias; float* pre; const float* mask;
+    float mask_scale; int act;
+    int a, os;                // source coordinate scale, output coordinate step
+    int Ts, Hs, Ws, Cs;       // source tensor (channels-last)
+    int To, Ho, Wo, Nt;       // output tensor
+    int N;                    // accumulator columns of one CTA (divides Nt)
+    int Kc, kchunks;          // contraction channels per tap, 32-element blocks per tap
+    int wrow;                 // weight elements between consecutive n
+    long long wtap;           // weight elements per tap block
+    long long out_elems;      // elements of the output tensor (stride between split-K slices)
+    int nclass, nslice, nstages;
+    TcgClass cls[8];
+    TcgTap taps[64];
+};
+
+struct TcgFTap { int8_t xt, xh, xw, yt, yh, yw; int16_t widx; };
+struct TcgFilterArgs {
+    const float* x; const float* dy; float* dw;
+    int Tc, Hc, Wc, rows;     // iteration grid per sample; rows = B*Tc*Hc*Wc positions
+    int ax, Tx, Hx, Wx, Ci;
+    int ay, Ty, Hy, Wy, Co;
+    int Mt, N, ksplit, nstages;
+    long long wblk;           // dw elements per tap block (Ci*Co)
+    TcgFTap taps[64];
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void sts4_tf32(uint8_t* dst, float4 v) {
+    float4 r = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    *reinterpret_cast<float4*>(dst) = r;
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_cols_for(int N) { return N <= 32 ? 32u : N <= 64 ? 64u : N <= 128 ? 128u : 256u; }
+__device__ __forceinline__ uint32_t idesc_tf32(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);   // F32 accum, tf32 x tf32, K-major, M = 128
+}
+
+// MMA issuer loop shared by both kernels: stage s holds A (128 rows) at +0 and B (N rows) at +16384
+__device__ __forceinline__ void mma_issue_loop(uint8_t* smem, uint32_t stage_bytes, int nst, int nkb, int N, uint32_t tmem,
+                                               uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_bar) {
+    const uint32_t idesc = idesc_tf32(N);
+    for (int i = 0; i < nkb; ++i) {
+        const int s = i % nst;
+        mbar_wait(&full_bar[s], (uint32_t)(i / nst) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint64_t ad = make_sdesc(smem_u32(smem + (size_t)s * stage_bytes));
+            const uint64_t bd = make_sdesc(smem_u32(smem + (size_t)s * stage_bytes + 16384));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (i | k) ? 1u : 0u);
+            tc_commit(&empty_bar[s]);
+            if (i == nkb - 1) tc_commit(acc_bar);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ row GEMM
+__global__ void __launch_bounds__(TCG_THREADS, 1) tcg_rowgemm_kernel(const __grid_constant__ TcgRowArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N, nst = p.nstages;
+    const uint32_t stage_bytes = 16384u + (uint32_t)N * 128u;
+
+    int ci = 0;
+    for (int i = 1; i < p.nclass; ++i)
+        if ((int)blockIdx.x >= p.cls[i].tile_begin) ci = i;
+    const TcgClass cl = p.cls[ci];
+    const int row0 = ((int)blockIdx.x - cl.tile_begin) * 128;
+    const int n0 = blockIdx.y * N;
+    const int nkb_all = cl.tap_count * p.kchunks;
+    const int kb_lo = (int)((long long)blockIdx.z * nkb_all / p.nslice);
+    const int nkb = (int)((long long)(blockIdx.z + 1) * nkb_all / p.nslice) - kb_lo;
+
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(&tmem_slot, tmem_cols_for(N));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 8) {
+        mma_issue_loop(smem, stage_bytes, nst, nkb, N, tmem, full_bar, empty_bar, &acc_bar);
+    } else {
+        // ---- producers: thread = (row sub-index rsub, 16-byte chunk) of every 32-row slab of the A and B tiles
+        const int chunk = tid & 7, rsub = tid >> 3;
+        int rbase[4], rcoord[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = row0 + rsub + 32 * j;
+            rbase[j] = -1; rcoord[j] = 0;
+            if (r < cl.rows) {
+                int q = r;
+                const int w2 = q % cl.Wc; q /= cl.Wc;
+                const int h2 = q % cl.Hc; q /= cl.Hc;
+                const int t2 = q % cl.Tc; const int b = q / cl.Tc;
+                const int ts = p.a * t2, hs = p.a * h2, ws = p.a * w2;
+                rbase[j] = (((b * p.Ts + ts) * p.Hs + hs) * p.Ws + ws) * p.Cs;
+                rcoord[j] = ts | (hs << 10) | (ws << 20);
+            }
+        }
+        const uint32_t sw_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)(rsub & 7) * 128u + (uint32_t)((chunk ^ (rsub & 7)) << 4);
+        const int nb = N >> 5;     // 32-row slabs of the B tile
+        for (int i = 0; i < nkb; ++i) {
+            const int kb = kb_lo + i;
+            const int te = kb / p.kchunks, kc = kb - te * p.kchunks;
+            const TcgTap tp = p.taps[cl.tap_begin + te];
+            const int s = i % nst;
+            const int k0 = kc * 32 + chunk * 4;
+            const bool kval = k0 < p.Kc;
+            const int doff = ((tp.ct * p.Hs + tp.ch) * p.Ws + tp.cw) * p.Cs + k0;
+            float4 va[4], vb[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ts = (rcoord[j] & 1023) + tp.ct, hs = ((rcoord[j] >> 10) & 1023) + tp.ch, ws = (rcoord[j] >> 20) + tp.cw;
+                const bool ok = kval && rbase[j] >= 0 && (unsigned)ts < (unsigned)p.Ts && (unsigned)hs < (unsigned)p.Hs &&
+                                (unsigned)ws < (unsigned)p.Ws;
+                va[j] = ok ? ldg4(p.src + rbase[j] + doff) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float* wb = p.w + (long long)tp.widx * p.wtap + (long long)(n0 + rsub) * p.wrow + k0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nb) vb[j] = kval ? ldg4(wb + (long long)(32 * j) * p.wrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i >= nst) mbar_wait(&empty_bar[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
+            uint8_t* sa = smem + (size_t)s * stage_bytes + sw_off;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sts4_tf32(sa + j * 4096, va[j]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nb) sts4_tf32(sa + 16384 + j * 4096, vb[j]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
+        // ---- epilogue: warp = (lane quarter q, column half)
+        if (nkb > 0) {        // an empty K slice (class with fewer taps than slices) contributes zeros and never touches TMEM
+            mbar_wait(&acc_bar, 0);
+            tc_fence_after();
+        }
+        const int q = warp & 3, half = warp >> 2;
+        const int cph = N >= 64 ? N / 2 : 32;
+        const int c_lo = half * cph, c_hi = min(N, c_lo + cph);
+        const int r = row0 + q * 32 + lane;
+        long long off = -1;
+        if (r < cl.rows) {
+            int qq = r;
+            const int w2 = qq % cl.Wc; qq /= cl.Wc;
+            const int h2 = qq % cl.Hc; qq /= cl.Hc;
+            const int t2 = qq % cl.Tc; const int b = qq / cl.Tc;
+            off = ((((long long)b * p.To + cl.ot + p.os * t2) * p.Ho + cl.oh + p.os * h2) * p.Wo + cl.ow + p.os * w2) * p.Nt + n0;
+        }
+        for (int c = c_lo; c < c_hi; c += 32) {
+            uint32_t v[32];
+            if (nkb > 0) tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (off < 0) continue;
+            if (p.part) {
+                float* dst = p.part + (long long)blockIdx.z * p.out_elems + off + c;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float x[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        x[e] = __uint_as_float(v[j + e]);
+                        if (p.bias) x[e] += __ldg(p.bias + n0 + c + j + e);
+                    }
+                    if (p.pre) *reinterpret_cast<float4*>(p.pre + off + c + j) = make_float4(x[0], x[1], x[2], x[3]);
+                    if (p.act == ACT_LRELU) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x[e] = x[e] > 0.f ? x[e] : 0.2f * x[e];
+                    }
+                    if (p.mask) {
+                        const float4 m = ldg4(p.mask + off + c + j);
+                        x[0] *= m.x * p.mask_scale; x[1] *= m.y * p.mask_scale; x[2] *= m.z * p.mask_scale; x[3] *= m.w * p.mask_scale;
+                    }
+                    *reinterpret_cast<float4*>(p.out + off + c + j) = make_float4(x[0], x[1], x[2], x[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols_for(N)); }
+}
+
+// out = act(sum of slices + bias) [* mask]; same contract as the SIMT split-K epilogue
+__global__ void tcg_splitk_epilogue_kernel(const float* __restrict__ part, int nslice, long long MN4, int N, const float* __restrict__ bias,
+                                           float* __restrict__ y, int act, const float* __restrict__ mask, float mask_scale,
+                                           float* __restrict__ pre) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MN4) return;
+    float4 s = reinterpret_cast<const float4*>(part)[i];
+    for (int z = 1; z < nslice; ++z) {
+        const float4 t = reinterpret_cast<const float4*>(part)[(long long)z * MN4 + i];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    if (bias) {
+        const float4 b = ldg4(bias + (int)((i * 4) % N));
+        s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+    }
+    if (pre) reinterpret_cast<float4*>(pre)[i] = s;
+    if (act == ACT_LRELU) {
+        s.x = s.x > 0.f ? s.x : 0.2f * s.x; s.y = s.y > 0.f ? s.y : 0.2f * s.y;
+        s.z = s.z > 0.f ? s.z : 0.2f * s.z; s.w = s.w > 0.f ? s.w : 0.2f * s.w;
+    }
+    if (mask) {
+        const float4 m = reinterpret_cast<const float4*>(mask)[i];
+        s.x *= m.x * mask_scale; s.y *= m.y * mask_scale; s.z *= m.z * mask_scale; s.w *= m.w * mask_scale;
+    }
+    reinterpret_cast<float4*>(y)[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ filter gradient
+__global__ void __launch_bounds__(TCG_THREADS, 1) tcg_filtergrad_kernel(const __grid_constant__ TcgFilterArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N, nst = p.nstages;
+    const uint32_t stage_bytes = 16384u + (uint32_t)N * 128u;
+    const TcgFTap tp = p.taps[blockIdx.x];
+    const int mt = (int)blockIdx.y % p.Mt, nt = (int)blockIdx.y / p.Mt;
+    const int m0 = mt * 128, n0 = nt * N;
+    const int nkb_all = (p.rows + 31) >> 5;
+    const int kb_lo = (int)((long long)blockIdx.z * nkb_all / p.ksplit);
+    const int nkb = (int)((long long)(blockIdx.z + 1) * nkb_all / p.ksplit) - kb_lo;
+
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(&tmem_slot, tmem_cols_for(N));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 8) {
+        mma_issue_loop(smem, stage_bytes, nst, nkb, N, tmem, full_bar, empty_bar, &acc_bar);
+    } else {
+        // ---- producers: lane = position (k index) of the 32-position block; warp = channel group.
+        // A rows [16 warp, +16) = input channels m0 + ..; B rows [cpw warp, +cpw) = output channels n0 + .., cpw = N / 8
+        const int cpw = N >> 3;                 // 4 .. 32 channels of B per warp
+        const int nvb = cpw >> 2;               // float4 loads per lane for B
+        const bool a_on = m0 + 16 * warp < p.Ci;
+        const uint32_t kcol = (uint32_t)(lane & 3) * 4u;
+        const uint32_t kch = (uint32_t)(lane >> 2);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % nst;
+            const int pos = (kb_lo + i) * 32 + lane;
+            bool xok = false, yok = false;
+            long long xoff = 0, yoff = 0;
+            if (pos < p.rows) {
+                int q = pos;
+                const int w2 = q % p.Wc; q /= p.Wc;
+                const int h2 = q % p.Hc; q /= p.Hc;
+                const int t2 = q % p.Tc; const int b = q / p.Tc;
+                const int xt = p.ax * t2 + tp.xt, xh = p.ax * h2 + tp.xh, xw = p.ax * w2 + tp.xw;
+                xok = (unsigned)xt < (unsigned)p.Tx && (unsigned)xh < (unsigned)p.Hx && (unsigned)xw < (unsigned)p.Wx;
+                xoff = ((((long long)b * p.Tx + xt) * p.Hx + xh) * p.Wx + xw) * p.Ci + m0 + 16 * warp;
+                const int yt = p.ay * t2 + tp.yt, yh = p.ay * h2 + tp.yh, yw = p.ay * w2 + tp.yw;
+                yok = xok && (unsigned)yt < (unsigned)p.Ty && (unsigned)yh < (unsigned)p.Hy && (unsigned)yw < (unsigned)p.Wy;
+                yoff = ((((long long)b * p.Ty + yt) * p.Hy + yh) * p.Wy + yw) * p.Co + n0 + cpw * warp;
+            }
+            float4 va[4], vb[8];
+            if (a_on) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) va[j] = xok ? ldg4(p.x + xoff + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nvb) vb[j] = yok ? ldg4(p.dy + yoff + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i >= nst) mbar_wait(&empty_bar[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            if (a_on) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float e[4] = {va[j].x, va[j].y, va[j].z, va[j].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t row = (uint32_t)(16 * warp + 4 * j + u);
+                        *reinterpret_cast<float*>(sa + (row >> 3) * 1024u + (row & 7u) * 128u + ((kch ^ (row & 7u)) << 4) + kcol) = to_tf32(e[u]);
+                    }
+                }
+            }
+            uint8_t* sb = sa + 16384;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < nvb) {
+                    const float e[4] = {vb[j].x, vb[j].y, vb[j].z, vb[j].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t row = (uint32_t)(cpw * warp + 4 * j + u);
+                        *reinterpret_cast<float*>(sb + (row >> 3) * 1024u + (row & 7u) * 128u + ((kch ^ (row & 7u)) << 4) + kcol) = to_tf32(e[u]);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
+        // ---- epilogue: accumulator row = input channel, columns = output channels -> dw[tap][ci][co] += D
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3, half = warp >> 2;
+        const int cph = N >= 64 ? N / 2 : 32;
+        const int c_lo = half * cph, c_hi = min(N, c_lo + cph);
+        const int ci = m0 + q * 32 + lane;
+        float* dst = p.dw + (long long)tp.widx * p.wblk + (long long)ci * p.Co + n0;
+        for (int c = c_lo; c < c_hi; c += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (ci >= p.Ci) continue;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols_for(N)); }
+}
+
+__global__ void transpose_blocks_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
+    __shared__ float tile[32][33];
+    const float* s = src + (size_t)blockIdx.z * R * C;
+    float* d = dst + (size_t)blockIdx.z * R * C;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[j][threadIdx.x] = s[(size_t)r * C + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < R && c < C) d[(size_t)c * R + r] = tile[threadIdx.x][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int pick_stages(int N) {
+    const int stage = 16384 + N * 128;
+    int n = (200 * 1024) / stage;
+    return std::max(2, std::min(n, 6));
+}
+size_t smem_bytes(int N, int nst) { return (size_t)nst * (16384 + N * 128) + 1024; }
+
+int tile_n_for(int Nt, int mtiles) {
+    // widest accumulator that still leaves enough CTAs; Nt is a multiple of 32
+    for (int N : {256, 128, 64, 32})
+        if (Nt % N == 0 && (N <= 64 || (long long)mtiles * (Nt / N) >= 96)) return N;
+    return 0;
+}
+
+int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const float* bias, float* y, int act, const float* mask,
+                   float mask_scale, float* pre) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        RDG_CUDA(cudaFuncSetAttribute(tcg_rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+        attr_done = true;
+    }
+    a.nstages = pick_stages(a.N);
+    const int ctas = mtiles * (a.Nt / a.N);
+    int nslice = 1;
+    if (ctas < 148 && max_kb >= 8) {
+        nslice = (296 + ctas - 1) / ctas;
+        nslice = std::min(nslice, max_kb / 4);
+        nslice = std::max(nslice, 1);
+    }
+    a.nslice = nslice;
+    dim3 grid(mtiles, a.Nt / a.N, nslice);
+    if (nslice > 1) {
+        float* part = nullptr;
+        RDG_CUDA(cudaMallocAsync(&part, (size_t)nslice * a.out_elems * sizeof(float), st));
+        a.part = part; a.bias = nullptr; a.pre = nullptr; a.mask = nullptr; a.act = ACT_NONE;
+        tcg_rowgemm_kernel<<<grid, TCG_THREADS, smem_bytes(a.N, a.nstages), st>>>(a);
+        RDG_LAUNCH_CHECK();
+        const long long mn4 = a.out_elems / 4;
+        tcg_splitk_epilogue_kernel<<<ceil_div(mn4, 256), 256, 0, st>>>(part, nslice, mn4, a.Nt, bias, y, act, mask, mask_scale, pre);
+        RDG_LAUNCH_CHECK();
+        RDG_CUDA(cudaFreeAsync(part, st));
+        return 0;
+    }
+    a.part = nullptr; a.bias = bias; a.pre = pre; a.mask = mask; a.mask_scale = mask_scale; a.act = act;
+    tcg_rowgemm_kernel<<<grid, TCG_THREADS, smem_bytes(a.N, a.nstages), st>>>(a);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+bool fits_i32(long long v) { return v < (1ll << 31); }
+
+}  // namespace
+
+int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, cudaStream_t st) {
+    dim3 grid(ceil_div(C, 32), ceil_div(R, 32), nblk);
+    transpose_blocks_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, R, C);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int tcg_conv_fwd(const float* x, const float* wT, const float* bias, float* y, const ConvGeom& g, int act, const float* mask,
+                 float mask_scale, cudaStream_t st, float* pre) {
+    if (g.up || (g.Ci & 3) || (g.Co & 31) || g.KT * g.KH * g.KW > 64) { rdg_set_error("tcg_conv_fwd: unsupported geometry"); return RDG_TCG_E_SHAPE; }
+    const long long rows = (long long)g.B * g.To * g.Ho * g.Wo;
+    if (rows == 0) return 0;
+    if (!fits_i32((long long)g.B * g.Ti * g.Hi * g.Wi * g.Ci) || !fits_i32(rows * g.Co)) { rdg_set_error("tcg_conv_fwd: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgRowArgs a{};
+    a.src = x; a.w = wT; a.out = y;
+    a.a = g.stride; a.os = 1;
+    a.Ts = g.Ti; a.Hs = g.Hi; a.Ws = g.Wi; a.Cs = g.Ci;
+    a.To = g.To; a.Ho = g.Ho; a.Wo = g.Wo; a.Nt = g.Co;
+    a.Kc = g.Ci; a.kchunks = ceil_div(g.Ci, 32); a.wrow = g.Ci; a.wtap = (long long)g.Co * g.Ci;
+    a.out_elems = rows * g.Co;
+    const int mtiles = ceil_div(rows, 128);
+    a.N = tile_n_for(g.Co, mtiles);
+    a.nclass = 1;
+    a.cls[0] = TcgClass{g.To, g.Ho, g.Wo, (int)rows, 0, 0, 0, 0, 0, g.KT * g.KH * g.KW};
+    int n = 0;
+    for (int kt = 0; kt < g.KT; ++kt)
+        for (int kh = 0; kh < g.KH; ++kh)
+            for (int kw = 0; kw < g.KW; ++kw, ++n) a.taps[n] = TcgTap{(int8_t)(kt - g.pt), (int8_t)(kh - g.ph), (int8_t)(kw - g.pw), 0, n};
+    return launch_rowgemm(a, mtiles, n * a.kchunks, st, bias, y, act, mask, mask_scale, pre);
+}
+
+int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st) {
+    if (g.up || (g.Co & 3) || (g.Ci & 31) || (g.stride != 1 && g.stride != 2) || g.KT * g.KH * g.KW > 64) {
+        rdg_set_error("tcg_conv_bwd_data: unsupported geometry"); return RDG_TCG_E_SHAPE;
+    }
+    const long long rows = (long long)g.B * g.Ti * g.Hi * g.Wi;
+    if (rows == 0) return 0;
+    if (!fits_i32((long long)g.B * g.To * g.Ho * g.Wo * g.Co) || !fits_i32(rows * g.Ci)) { rdg_set_error("tcg_conv_bwd_data: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgRowArgs a{};
+    a.src = dy; a.w = w; a.out = dx;
+    a.a = 1; a.os = g.stride;
+    a.Ts = g.To; a.Hs = g.Ho; a.Ws = g.Wo; a.Cs = g.Co;
+    a.To = g.Ti; a.Ho = g.Hi; a.Wo = g.Wi; a.Nt = g.Ci;
+    a.Kc = g.Co; a.kchunks = ceil_div(g.Co, 32); a.wrow = g.Co; a.wtap = (long long)g.Ci * g.Co;
+    a.out_elems = rows * g.Ci;
+    const int s = g.stride;
+    int ncls = 0, ntap = 0, tiles = 0, max_taps = 0;
+    for (int qt = 0; qt < s; ++qt)
+        for (int qh = 0; qh < s; ++qh)
+            for (int qw = 0; qw < s; ++qw) {
+                const int Tc = (g.Ti - qt + s - 1) / s, Hc = (g.Hi - qh + s - 1) / s, Wc = (g.Wi - qw + s - 1) / s;
+                if (Tc <= 0 || Hc <= 0 || Wc <= 0) continue;
+                TcgClass c{Tc, Hc, Wc, g.B * Tc * Hc * Wc, tiles, qt, qh, qw, ntap, 0};
+                for (int kt = 0; kt < g.KT; ++kt) {
+                    if ((qt + g.pt - kt) % s) continue;
+                    for (int kh = 0; kh < g.KH; ++kh) {
+                        if ((qh + g.ph - kh) % s) continue;
+                        for (int kw = 0; kw < g.KW; ++kw) {
+                            if ((qw + g.pw - kw) % s) continue;
+                            a.taps[ntap++] = TcgTap{(int8_t)((qt + g.pt - kt) / s), (int8_t)((qh + g.ph - kh) / s), (int8_t)((qw + g.pw - kw) / s), 0,
+                                                    (kt * g.KH + kh) * g.KW + kw};
+                            ++c.tap_count;
+                        }
+                    }
+                }
+                if (c.tap_count == 0) {   // positions no output reads: the gradient is zero; one all-invalid tap keeps the tile well-formed
+                    a.taps[ntap++] = TcgTap{(int8_t)-128, (int8_t)-128, (int8_t)-128, 0, 0};
+                    c.tap_count = 1;
+                }
+                max_taps = std::max(max_taps, c.tap_count);
+                tiles += ceil_div(c.rows, 128);
+                a.cls[ncls++] = c;
+            }
+    a.nclass = ncls;
+    a.N = tile_n_for(g.Ci, tiles);
+    return launch_rowgemm(a, tiles, max_taps * a.kchunks, st, nullptr, dx, ACT_NONE, nullptr, 1.f, nullptr);
+}
+
+int tcg_folded_fwd(const float* x, const float* wfT, const float* bias, float* y, const ConvGeom& g, cudaStream_t st) {
+    if (!g.up || (g.Ci & 31) || (g.Co & 31)) { rdg_set_error("tcg_folded_fwd: unsupported geometry"); return RDG_TCG_E_SHAPE; }
+    const long long rows = (long long)g.B * g.Ti * g.Hi * g.Wi;
+    if (rows == 0) return 0;
+    if (!fits_i32(rows * g.Ci) || !fits_i32(rows * 8 * g.Co)) { rdg_set_error("tcg_folded_fwd: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgRowArgs a{};
+    a.src = x; a.w = wfT; a.out = y;
+    a.a = 1; a.os = 2;
+    a.Ts = g.Ti; a.Hs = g.Hi; a.Ws = g.Wi; a.Cs = g.Ci;
+    a.To = 2 * g.Ti; a.Ho = 2 * g.Hi; a.Wo = 2 * g.Wi; a.Nt = g.Co;
+    a.Kc = g.Ci; a.kchunks = g.Ci / 32; a.wrow = g.Ci; a.wtap = (long long)g.Co * g.Ci;
+    a.out_elems = rows * 8 * g.Co;
+    const int tpc = ceil_div(rows, 128);
+    for (int p = 0; p < 8; ++p) {
+        const int pt = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+        a.cls[p] = TcgClass{g.Ti, g.Hi, g.Wi, (int)rows, p * tpc, pt, ph, pw, p * 8, 8};
+        for (int t = 0; t < 8; ++t) {
+            const int at = t >> 2, ah = (t >> 1) & 1, aw = t & 1;
+            a.taps[p * 8 + t] = TcgTap{(int8_t)(at - 1 + pt), (int8_t)(ah - 1 + ph), (int8_t)(aw - 1 + pw), 0, p * 8 + t};
+        }
+    }
+    a.nclass = 8;
+    a.N = tile_n_for(g.Co, 8 * tpc);
+    return launch_rowgemm(a, 8 * tpc, 8 * a.kchunks, st, bias, y, ACT_NONE, nullptr, 1.f, nullptr);
+}
+
+int tcg_folded_bwd_data(const float* dy, const float* wf, float* dx, const ConvGeom& g, cudaStream_t st) {
+    if (!g.up || (g.Ci & 31) || (g.Co & 31)) { rdg_set_error("tcg_folded_bwd_data: unsupported geometry"); return RDG_TCG_E_SHAPE; }
+    const long long rows = (long long)g.B * g.Ti * g.Hi * g.Wi;
+    if (rows == 0) return 0;
+    if (!fits_i32(rows * g.Ci) || !fits_i32(rows * 8 * g.Co)) { rdg_set_error("tcg_folded_bwd_data: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgRowArgs a{};
+    a.src = dy; a.w = wf; a.out = dx;
+    a.a = 2; a.os = 1;
+    a.Ts = 2 * g.Ti; a.Hs = 2 * g.Hi; a.Ws = 2 * g.Wi; a.Cs = g.Co;
+    a.To = g.Ti; a.Ho = g.Hi; a.Wo = g.Wi; a.Nt = g.Ci;
+    a.Kc = g.Co; a.kchunks = g.Co / 32; a.wrow = g.Co; a.wtap = (long long)g.Ci * g.Co;
+    a.out_elems = rows * g.Ci;
+    const int mtiles = ceil_div(rows, 128);
+    a.cls[0] = TcgClass{g.Ti, g.Hi, g.Wi, (int)rows, 0, 0, 0, 0, 0, 64};
+    for (int p = 0; p < 8; ++p) {
+        const int pt = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+        for (int t = 0; t < 8; ++t) {
+            const int at = t >> 2, ah = (t >> 1) & 1, aw = t & 1;
+            // x[q] feeds output 2(q - d) + phase with d = a - 1 + phase  ->  source offset phase - 2d on the high-res grid
+            a.taps[p * 8 + t] = TcgTap{(int8_t)(pt - 2 * (at - 1 + pt)), (int8_t)(ph - 2 * (ah - 1 + ph)), (int8_t)(pw - 2 * (aw - 1 + pw)), 0, p * 8 + t};
+        }
+    }
+    a.nclass = 1;
+    a.N = tile_n_for(g.Ci, mtiles);
+    return launch_rowgemm(a, mtiles, 64 * a.kchunks, st, nullptr, dx, ACT_NONE, nullptr, 1.f, nullptr);
+}
+
+namespace {
+int launch_filtergrad(TcgFilterArgs& a, int ntap, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        RDG_CUDA(cudaFuncSetAttribute(tcg_filtergrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+        attr_done = true;
+    }
+    a.Mt = ceil_div(a.Ci, 128);
+    int N = 0;
+    for (int n : {256, 128, 64, 32})
+        if (a.Co % n == 0 && (n <= 64 || (long long)ntap * a.Mt * (a.Co / n) >= 96)) { N = n; break; }
+    if (!N) { rdg_set_error("tcg filter gradient: Co must be a multiple of 32"); return RDG_TCG_E_SHAPE; }
+    a.N = N;
+    a.nstages = pick_stages(N);
+    const int ctas = ntap * a.Mt * (a.Co / N);
+    const int nkb = (a.rows + 31) / 32;
+    int ks = (296 + ctas - 1) / ctas;
+    ks = std::max(1, std::min(ks, nkb / 4));
+    a.ksplit = ks;
+    dim3 grid(ntap, a.Mt * (a.Co / N), ks);
+    tcg_filtergrad_kernel<<<grid, TCG_THREADS, smem_bytes(N, a.nstages), st>>>(a);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+}  // namespace
+
+int tcg_conv_bwd_filter(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st) {
+    if (g.up || (g.Ci & 15) || (g.Co & 31) || g.KT * g.KH * g.KW > 64) { rdg_set_error("tcg_conv_bwd_filter: unsupported geometry"); return RDG_TCG_E_SHAPE; }
+    const long long rows = (long long)g.B * g.To * g.Ho * g.Wo;
+    if (rows == 0) return 0;
+    if (!fits_i32(rows)) { rdg_set_error("tcg_conv_bwd_filter: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgFilterArgs a{};
+    a.x = x; a.dy = dy; a.dw = dw;
+    a.Tc = g.To; a.Hc = g.Ho; a.Wc = g.Wo; a.rows = (int)rows;
+    a.ax = g.stride; a.Tx = g.Ti; a.Hx = g.Hi; a.Wx = g.Wi; a.Ci = g.Ci;
+    a.ay = 1; a.Ty = g.To; a.Hy = g.Ho; a.Wy = g.Wo; a.Co = g.Co;
+    a.wblk = (long long)g.Ci * g.Co;
+    int n = 0;
+    for (int kt = 0; kt < g.KT; ++kt)
+        for (int kh = 0; kh < g.KH; ++kh)
+            for (int kw = 0; kw < g.KW; ++kw, ++n)
+                a.taps[n] = TcgFTap{(int8_t)(kt - g.pt), (int8_t)(kh - g.ph), (int8_t)(kw - g.pw), 0, 0, 0, (int16_t)n};
+    return launch_filtergrad(a, n, st);
+}
+
+int tcg_folded_bwd_filter(const float* x, const float* dy, float* dwf, const ConvGeom& g, cudaStream_t st) {
+    if (!g.up || (g.Ci & 15) || (g.Co & 31)) { rdg_set_error("tcg_folded_bwd_filter: unsupported geometry"); return RDG_TCG_E_SHAPE; }
+    const long long rows = (long long)g.B * g.Ti * g.Hi * g.Wi;
+    if (rows == 0) return 0;
+    if (!fits_i32(rows)) { rdg_set_error("tcg_folded_bwd_filter: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgFilterArgs a{};
+    a.x = x; a.dy = dy; a.dw = dwf;
+    a.Tc = g.Ti; a.Hc = g.Hi; a.Wc = g.Wi; a.rows = (int)rows;
+    a.ax = 1; a.Tx = g.Ti; a.Hx = g.Hi; a.Wx = g.Wi; a.Ci = g.Ci;
+    a.ay = 2; a.Ty = 2 * g.Ti; a.Hy = 2 * g.Hi; a.Wy = 2 * g.Wi; a.Co = g.Co;
+    a.wblk = (long long)g.Ci * g.Co;
+    for (int p = 0; p < 8; ++p) {
+        const int pt = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+        for (int t = 0; t < 8; ++t) {
+            const int at = t >> 2, ah = (t >> 1) & 1, aw = t & 1;
+            a.taps[p * 8 + t] = TcgFTap{(int8_t)(at - 1 + pt), (int8_t)(ah - 1 + ph), (int8_t)(aw - 1 + pw), (int8_t)pt, (int8_t)ph, (int8_t)pw,
+                                        (int16_t)(p * 8 + t)};
+        }
+    }
+    return launch_filtergrad(a, 64, st);
+}

@@ -32,18 +32,25 @@ def _pad8(n):
 # ============================================================================ reader
 class _Reader:
     def __init__(self, buf):
-        self.b = buf
-        if buf[:8] != SIG:
-            raise ValueError("not an HDF5 file (bad signature)")
-        ver = buf[8]
+        # The superblock sits at offset 0 or, after a user block, at 512, 1024, 2048, ... (HDF5 spec III.A); every file
+        # address is relative to the superblock's base address, which is the user-block size for files libhdf5 writes.
+        sb = 0
+        while buf[sb:sb + 8] != SIG:
+            sb = 512 if sb == 0 else sb * 2
+            if sb + 8 > len(buf):
+                raise ValueError("not an HDF5 file (bad signature)")
+        ver = buf[sb + 8]
         if ver not in (0, 1):
             raise NotImplementedError(f"HDF5 superblock version {ver} (only 0/1: libver='earliest')")
-        so, sl = buf[13], buf[14]
+        so, sl = buf[sb + 13], buf[sb + 14]
         if so != 8 or sl != 8:
             raise NotImplementedError("HDF5 files with offset/length size != 8")
-        pos = 24 if ver == 0 else 28
+        pos = sb + (24 if ver == 0 else 28)
         self.base = struct.unpack_from("<Q", buf, pos)[0]
-        root_entry = pos + 32
+        if self.base > sb:
+            raise ValueError("HDF5 base address beyond the superblock")
+        self.b = buf[self.base:] if self.base else buf      # addresses below index this view directly
+        root_entry = pos - self.base + 32
         self.root = self._symtab_entry(root_entry)
 
     # -- low level
@@ -238,7 +245,6 @@ class _Reader:
         if kind == "contig":
             if off == UNDEF:
                 return np.zeros(shape, dt["np"])
-            off += self.base
         return self._decode(dt, shape, off)
 
 

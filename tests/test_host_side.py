@@ -101,6 +101,43 @@ def test_hdf5_generic_tree_and_errors(tmp_path):
         hdf5.load_keras_weights(_write(tmp_path, {"children": {"x": np.zeros(3, np.float32)}}))
 
 
+def test_hdf5_reads_a_libhdf5_written_file_with_user_block():
+    """External fixture, NOT produced by this repo's writer: scipy's MATLAB-v7.3 test file (written by libhdf5 through MATLAB 7.4
+    on GLNX86; copied from scipy/io/matlab/tests/data/testhdf5_7.4_GLNX86.mat).  512-byte user block -> superblock at 512,
+    base address 512, v0 superblock, symbol-table root group, v1 object headers, contiguous float64 dataset, string attribute."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "external_libhdf5_userblock.mat")
+    raw = open(path, "rb").read()
+    assert raw[:6] == b"MATLAB" and raw[512:520] == hdf5.SIG          # the signature is NOT at offset 0
+    f = hdf5.H5File(path)
+    assert f.keys() == ["testdouble"]
+    x = f["testdouble"]
+    assert x.dtype == np.float64 and x.shape == (9, 1)
+    np.testing.assert_allclose(x[:, 0], np.arange(9) * np.pi / 4, rtol=0, atol=1e-15)
+    leaf = f._r.children(f._r.root["ohdr"])["testdouble"]
+    assert f._r.attributes(leaf)["MATLAB_class"] == b"double"
+    # the same bytes with the user block cut off and the base address patched to 0 read identically
+    cut = bytearray(raw[512:]); cut[24:32] = (0).to_bytes(8, "little")
+    np.testing.assert_array_equal(hdf5.H5File(bytes(cut))["testdouble"], x)
+
+
+def test_hdf5_own_file_behind_a_user_block(tmp_path):
+    gw = W.init_critic_weights(3)
+    p = str(tmp_path / "c.h5")
+    hdf5.save_keras_weights(p, gw, "critic")
+    raw = bytearray(open(p, "rb").read())
+    ver = raw[8]
+    pos = 24 if ver == 0 else 28
+    raw[pos:pos + 8] = (1024).to_bytes(8, "little")                     # base address = user-block size
+    blob = bytes(1024) + bytes(raw)
+    f = hdf5.H5File(blob)
+    names = [x.decode() for x in f["model_weights"].attrs["layer_names"]]
+    seq = [n for n in names if n.startswith("sequential")][0]
+    wn = [x.decode() for x in f["model_weights"][seq].attrs["weight_names"]]
+    np.testing.assert_array_equal(f["model_weights/" + seq + "/" + wn[0]], gw[0])
+    with pytest.raises(ValueError):
+        bad = bytearray(blob); bad[1024 + pos:1024 + pos + 8] = (4096).to_bytes(8, "little")
+        hdf5.H5File(bytes(bad))
+
 def _write(tmp_path, tree):
     p = str(tmp_path / "t.h5")
     hdf5.write_h5(p, tree)
