@@ -145,6 +145,27 @@ int  rdg_adam_reset(rdg_ctx* ctx, int which);
  * (the reference saves weights only, gan_train_cwgangp_pixelnorm.py:520-521, and cannot resume). */
 int  rdg_adam_buffers(rdg_ctx* ctx, int which, float** m_dev, float** v_dev, size_t* n);
 
+/* ---- tensor-core training mode and replayable steps ----
+ * rdg_set_train_mode(ctx, 1): the two step evaluations above run every wide contraction (critic convs forward / transposed /
+ * filter gradients, the gradient-penalty second-order pass :230-244, the generator's upsample-folded convs and Dense, forward and
+ * backward :387-408) as tcgen05.mma kind::tf32 implicit GEMMs with FP32 accumulation in TMEM (gradients <= 1e-2 relative L2 of
+ * the FP64 oracle; measured ~1e-3).  Mode 0 (default) is the FP32 SIMT parity mode (<= 2e-5). */
+int  rdg_set_train_mode(rdg_ctx* ctx, int mode);
+/* The same evaluations with the step's random inputs drawn on the device (Philox: key = seed, counter = element / stream / a step
+ * counter that lives in device memory): latent ~ N(0,1) (:470, :177-193), alpha ~ U[0,1) (:223), Dropout(0.25) keep masks
+ * (:289-301; dropout = 0 disables them).  No host value enters the launch arguments, so the calls of a whole 5 + 1 iteration
+ * (plus rdg_adam_apply_dev and the gradient all-reduce) can be captured in one CUDA graph and replayed.  Need train mode 1. */
+int  rdg_critic_step_dev(rdg_ctx* ctx, const float* x_real_dev, const float* cond_dev, int B, int gen_mode,
+                         unsigned long long seed, int dropout, float* losses4_dev, void* stream);
+int  rdg_generator_step_dev(rdg_ctx* ctx, const float* cond_dev, int B, unsigned long long seed, int dropout,
+                            float* loss_dev, void* stream);
+/* rdg_adam_apply with the shared step counter kept (and incremented) in device memory, followed by the refresh of the derived
+ * weight images the next step reads; gen_mode = the mode of the frozen generator forward in the critic step. */
+int  rdg_adam_apply_dev(rdg_ctx* ctx, int which, float lr, float beta1, float beta2, float eps, float grad_scale,
+                        int gen_mode, void* stream);
+/* set = 0: read, set = 1: write the device-resident counters (Adam step, Philox step); synchronises the device. */
+int  rdg_train_state(rdg_ctx* ctx, int set, long long* adam_t, unsigned long long* rng_ctr);
+
 /* ---- building blocks exposed for tests (same kernels the calls above use) ---- */
 /* y = x / sqrt(mean_c(x^2) + 1e-8), optional LeakyReLU(0.2) (gan_train...py:255-266, :333) */
 int  rdg_pixelnorm(const float* x_dev, float* y_dev, long long rows, int C, int lrelu, void* stream);
@@ -154,7 +175,9 @@ int  rdg_softmax_hours(const float* logits_dev, float* out_dev, long long B, int
 /* The FP32 SIMT Conv3D primitives behind the critic / training path (Keras Conv3D semantics,
  * gan_train_cwgangp_pixelnorm.py:286-301, :331-345).  geom17 = {B, Ti,Hi,Wi,Ci, To,Ho,Wo,Co, KT,KH,KW, stride,
  * pad_before_t,h,w, upsample_input}.  op 0: out = act(conv(a, w=b) + bias); op 1: out = d/d(input) given
- * dy=a, w=b (w.r.t. the upsampled input if upsample_input); op 2: out += d/dw given x=a, dy=b, out2 += d/dbias. */
+ * dy=a, w=b (w.r.t. the upsampled input if upsample_input); op 2: out += d/dw given x=a, dy=b, out2 += d/dbias.
+ * op 10 / 11 / 12: the same three on the tensor cores (tcgen05 kind::tf32, the training mode's kernels); with upsample_input
+ * they take the upsample-folded forms and op 11 returns the gradient w.r.t. the LOW-RES input. */
 int  rdg_conv3d(int op, const int* geom17, const float* a, const float* b, const float* bias, float* out,
                 float* out2, int act, void* stream);
 

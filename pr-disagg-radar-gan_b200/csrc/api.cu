@@ -187,6 +187,8 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     }
     cudaFree(c->e2e_cond);
     cudaFree(c->train_ws);
+    cudaFree(c->c_wT); cudaFree(c->c_w1p); cudaFree(c->g_denseT); cudaFree(c->g_w4p); cudaFree(c->tstate); cudaFree(c->rnd_buf);
+    for (int i = 0; i < 3; ++i) cudaFree(c->g_wfoldT[i]);
     for (int i = 0; i < 3; ++i) {
         if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
         if (c->ev_fork[i]) cudaEventDestroy(c->ev_fork[i]);
@@ -233,9 +235,10 @@ int rdg_refold32(rdg_ctx* c, cudaStream_t st) {
 }
 
 // (Re)build the folded + swizzled 16-bit operand tiles from the f32 master weights, on the device.
-int rdg_repack_generator(rdg_ctx* c, cudaStream_t st) {
+int rdg_repack_generator(rdg_ctx* c, cudaStream_t st, int kinds) {
     static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
     for (int k = 0; k < 2; ++k) {
+        if (!(kinds & (1 << k))) continue;
         const int hk = k == 0 ? RDG_HALF_BF16 : RDG_HALF_FP16;
         for (int l = 0; l < 3; ++l) {
             if (!c->g_wpack[k][l]) RDG_CUDA(cudaMalloc(&c->g_wpack[k][l], (size_t)64 * cin[l] * cout[l] * 2));
@@ -266,7 +269,7 @@ int rdg_repack_generator(rdg_ctx* c, cudaStream_t st) {
         if (r) return r;
     }
     c->launches += 10;
-    c->gen_packed_stale = false;
+    c->gen_stale_kinds &= ~kinds;
     return 0;
 }
 
@@ -275,8 +278,8 @@ extern "C" int rdg_generator_set_weights(rdg_ctx* c, const float* const* tensors
     RDG_CUDA(cudaSetDevice(c->device));
     int r = upload_params(c->g_params, c->g_off, c->g_size, tensors, sizes, n, "generator weights");
     if (r) return r;
-    c->fold32_stale = true;
-    r = rdg_repack_generator(c, nullptr);
+    c->fold32_stale = true; c->g_tcw_stale = true; c->gen_stale_kinds = 3;
+    r = rdg_repack_generator(c, nullptr, 3);
     if (r) return r;
     RDG_CUDA(cudaDeviceSynchronize());
     c->gen_ready = true;
@@ -303,7 +306,7 @@ extern "C" int rdg_critic_set_weights(rdg_ctx* c, const float* const* tensors, c
     int r = upload_params(c->c_params, c->c_off, c->c_size, tensors, sizes, n, "critic weights");
     if (r) return r;
     c->critic_ready = true;
-    c->critic_packed_stale = true;
+    c->critic_packed_stale = true; c->c_wT_stale = true;
     return 0;
 }
 extern "C" int rdg_critic_get_weights(rdg_ctx* c, float* const* tensors, const size_t* sizes, int n) {
@@ -447,7 +450,7 @@ extern "C" int rdg_generator_forward(rdg_ctx* c, const float* latent_dev, const 
     if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
     RDG_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (c->gen_packed_stale && mode != RDG_MODE_FP32) { int r = rdg_repack_generator(c, st); if (r) return r; }
+    if (mode != RDG_MODE_FP32 && (c->gen_stale_kinds & rdg_kind_bit(mode))) { int r = rdg_repack_generator(c, st, rdg_kind_bit(mode)); if (r) return r; }
     const int chunk = chunk_for_mode(c, mode);
     const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
     for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -465,7 +468,7 @@ extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const flo
     if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
     if (B == 0) return 0;
     RDG_CUDA(cudaSetDevice(c->device));
-    if (c->gen_packed_stale && mode != RDG_MODE_FP32) { int r = rdg_repack_generator(c, c->s_comp); if (r) return r; }
+    if (mode != RDG_MODE_FP32 && (c->gen_stale_kinds & rdg_kind_bit(mode))) { int r = rdg_repack_generator(c, c->s_comp, rdg_kind_bit(mode)); if (r) return r; }
     const int chunk = chunk_for_mode(c, mode);
     const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
     const size_t ncf = (size_t)c->nd * c->nd * c->ncond;
@@ -522,7 +525,7 @@ extern "C" int rdg_generate_stats_host(rdg_ctx* c, const float* latent_host, con
     if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
     if (B == 0) return 0;
     RDG_CUDA(cudaSetDevice(c->device));
-    if (c->gen_packed_stale && mode != RDG_MODE_FP32) { int r = rdg_repack_generator(c, c->s_comp); if (r) return r; }
+    if (mode != RDG_MODE_FP32 && (c->gen_stale_kinds & rdg_kind_bit(mode))) { int r = rdg_repack_generator(c, c->s_comp, rdg_kind_bit(mode)); if (r) return r; }
     const int chunk_max = chunk_for_mode(c, mode);
     if (spc > chunk_max) { rdg_set_error("rdg_generate_stats_host: %d members per condition exceed the chunk of %d samples", spc, chunk_max); return RDG_E_BADARG; }
     const int cond_per_chunk = chunk_max / spc, chunk = cond_per_chunk * spc;
@@ -684,15 +687,31 @@ extern "C" int rdg_conv3d(int op, const int* geom17, const float* a, const float
     if (op == 0) return simt_conv_fwd(a, b, bias, out, g, act, nullptr, 1.f, st);
     if (op == 1) return simt_conv_bwd_data(a, b, out, g, st);
     if (op == 2) return simt_conv_bwd_filter(a, b, out, out2, g, st);
-    // 10..12: the same three on the tensor cores (tcgen05 kind::tf32, tcg_gemm.cu); g.up selects the upsample-folded forms
-    if (op >= 10 && op <= 12) {
+    // 10..12: the same three on the tensor cores (tcgen05 kind::tf32, tcg_gemm.cu); g.up selects the upsample-folded forms;
+    // 13: forward with 3xTF32 operand splitting (the training mode's forward passes)
+    if (op >= 10 && op <= 13) {
         const size_t wn = (size_t)g.KT * g.KH * g.KW * g.Ci * g.Co;
+        const int precise = op == 13;
+        if (op == 13) op = 10;
         int r = 0;
+        if (!g.up && g.Ci <= 4) {          // few-channel input (critic's first conv)
+            const int taps = g.KT * g.KH * g.KW;
+            if (op == 10) {
+                float* wp = nullptr;
+                RDG_CUDA(cudaMallocAsync(&wp, (size_t)g.Co * tcg_smallci_kpad(taps, g.Ci) * 4, st));
+                if (!(r = tcg_pack_smallci_weights(b, wp, taps, g.Ci, g.Co, st))) r = tcg_conv_fwd_smallci(a, wp, bias, out, g, act, nullptr, 1.f, st, nullptr, precise);
+                RDG_CUDA(cudaFreeAsync(wp, st));
+                return r;
+            }
+            if (op == 11) return simt_conv_bwd_data(a, b, out, g, st);
+            if ((r = tcg_conv_bwd_filter_smallci(a, b, out, g, st))) return r;
+            return out2 ? simt_colsum(b, out2, (long long)g.B * g.To * g.Ho * g.Wo, g.Co, st) : 0;
+        }
         if (!g.up) {
             if (op == 10) {
                 float* wT = nullptr;
                 RDG_CUDA(cudaMallocAsync(&wT, wn * 4, st));
-                if (!(r = tcg_transpose_blocks(b, wT, g.KT * g.KH * g.KW, g.Ci, g.Co, st))) r = tcg_conv_fwd(a, wT, bias, out, g, act, nullptr, 1.f, st);
+                if (!(r = tcg_transpose_blocks(b, wT, g.KT * g.KH * g.KW, g.Ci, g.Co, st))) r = tcg_conv_fwd(a, wT, bias, out, g, act, nullptr, 1.f, st, nullptr, precise);
                 RDG_CUDA(cudaFreeAsync(wT, st));
                 return r;
             }
@@ -706,7 +725,7 @@ extern "C" int rdg_conv3d(int op, const int* geom17, const float* a, const float
         RDG_CUDA(cudaMallocAsync(&wfT, fn * 4, st));
         if (op == 10) {
             if (!(r = folded_pack_f32(b, wf, g.Ci, g.Co, st)) && !(r = tcg_transpose_blocks(wf, wfT, 64, g.Ci, g.Co, st)))
-                r = tcg_folded_fwd(a, wfT, bias, out, g, st);
+                r = tcg_folded_fwd(a, wfT, bias, out, g, st, precise);
         } else if (op == 11) {   // `out` = gradient w.r.t. the LOW-RES input
             if (!(r = folded_pack_f32(b, wf, g.Ci, g.Co, st))) r = tcg_folded_bwd_data(a, wf, out, g, st);
         } else {

@@ -10,7 +10,8 @@ struct rdg_ctx {
     // FP32 master parameters, Keras tensor order, concatenated (each tensor 16-byte aligned)
     float* g_params = nullptr; size_t g_off[10] = {}, g_size[10] = {}, g_total = 0;
     float* c_params = nullptr; size_t c_off[10] = {}, c_size[10] = {}, c_total = 0;
-    bool gen_ready = false, critic_ready = false, gen_packed_stale = false;
+    bool gen_ready = false, critic_ready = false;
+    int gen_stale_kinds = 0;        // 16-bit operand images older than the master weights: bit 0 = bf16, bit 1 = fp16
     // folded + swizzled 16-bit operand tiles of the three upsampled convs: [0]=bf16, [1]=fp16
     void* g_wpack[2][3] = {};
     void* g_wpack_planes[2] = {};   // 128 -> 64 layer in the stage order of the resident-plane kernel (nd == 16 only)
@@ -29,6 +30,16 @@ struct rdg_ctx {
     float* g_grads = nullptr; float* g_m = nullptr; float* g_v = nullptr;
     float* c_grads = nullptr; float* c_m = nullptr; float* c_v = nullptr;
     void* train_ws = nullptr; size_t train_ws_bytes = 0;
+    // tensor-core training mode (tcg_gemm.cu, train_tc.cu): 0 = FP32 SIMT (<= 1e-5 parity mode), 1 = tcgen05 kind::tf32
+    int train_mode = 0;
+    float* c_w1p = nullptr;                          // critic first conv packed [Co][Kpad] (k = tap * Ci + channel), tcg_pack_smallci_weights
+    float* c_wT = nullptr; bool c_wT_stale = true;   // critic conv kernels D2..D4 with (Ci, Co) swapped, at the offsets of c_params
+    float* g_wfoldT[3] = {};                         // folded generator kernels transposed: [8 phases][8 taps][Co][Ci]
+    float* g_denseT = nullptr;                       // Dense kernel transposed [N][K]
+    float* g_w4p = nullptr;                          // output conv: [32 taps (27 + zeros)][64] followed by its transpose [64][32]
+    bool g_tcw_stale = true;
+    RdgTrainState* tstate = nullptr;                 // device-resident Philox / Adam step counters (replayable CUDA graphs)
+    float* rnd_buf = nullptr; size_t rnd_cap = 0;    // latent / alpha / dropout masks drawn on the device (rdg_*_step_dev)
     // forward workspace
     void* ws = nullptr; size_t ws_bytes = 0; size_t per_sample16 = 0, per_sample32 = 0;
     int* flag_dev = nullptr;
@@ -53,5 +64,6 @@ ConvGeom rdg_gen_conv_geom(const rdg_ctx* c, int layer, int B);
 ConvGeom rdg_gen_dense_geom(const rdg_ctx* c, int B);
 ConvGeom rdg_critic_conv_geom(const rdg_ctx* c, int layer, int B);
 ConvGeom rdg_critic_dense_geom(const rdg_ctx* c, int B);
-int rdg_repack_generator(rdg_ctx* c, cudaStream_t st);
+int rdg_repack_generator(rdg_ctx* c, cudaStream_t st, int kinds);   // kinds: bit 0 = bf16, bit 1 = fp16
+static inline int rdg_kind_bit(int mode) { return mode == 1 /* RDG_MODE_BF16 */ ? 1 : 2; }
 int rdg_refold32(rdg_ctx* c, cudaStream_t st);      // refresh g_wfold32 if the generator weights changed

@@ -251,6 +251,71 @@ __global__ void interp_kernel(const float* __restrict__ xr, const float* __restr
     const float a = alpha[i / per];
     xh[i] = a * xr[i] + (1.f - a) * xf[i];          // RandomWeightedAverage, gan_train_cwgangp_pixelnorm.py:221-224
 }
+// ---- output conv Conv3D(64->1,'same') through per-tap products (training, tensor-core mode): P[pos][tap] = y[pos] . w4[tap]
+// logits[b,t,h,w] = b4 + sum_tap P[(t+kt-1, h+kh-1, w+kw-1)][tap]       (gan_train_cwgangp_pixelnorm.py:345)
+__global__ void tap_gather_logits_kernel(const float* __restrict__ P, const float* __restrict__ b4, float* __restrict__ logits,
+                                         int B, int nd) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)B * RDG_NHOURS * nd * nd;
+    if (i >= n) return;
+    const int w = (int)(i % nd), h = (int)((i / nd) % nd), t = (int)((i / ((long long)nd * nd)) % RDG_NHOURS);
+    float s = b4[0];
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+        const int tt = t + kt - 1;
+        if ((unsigned)tt >= (unsigned)RDG_NHOURS) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hh = h + kh - 1;
+            if ((unsigned)hh >= (unsigned)nd) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ww = w + kw - 1;
+                if ((unsigned)ww >= (unsigned)nd) continue;
+                const long long q = i + ((long long)(kt - 1) * nd + (kh - 1)) * nd + (kw - 1);
+                s += P[q * 32 + (kt * 3 + kh) * 3 + kw];
+            }
+        }
+    }
+    logits[i] = s;
+}
+// its transpose: Gd[pos][tap] = dlogits[pos - (k - 1)] (0 outside the grid, taps 27..31 zero) so that
+// dy = Gd . w4 and dw4 = Gd^T . y are plain GEMMs
+__global__ void tap_scatter_dlogits_kernel(const float* __restrict__ dl, float* __restrict__ Gd, int B, int nd) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (position, tap quad)
+    const long long n = (long long)B * RDG_NHOURS * nd * nd;
+    if (i >= n * 8) return;
+    const long long pos = i >> 3;
+    const int tq = (int)(i & 7);
+    const int w = (int)(pos % nd), h = (int)((pos / nd) % nd), t = (int)((pos / ((long long)nd * nd)) % RDG_NHOURS);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int tap = tq * 4 + j;
+        v[j] = 0.f;
+        if (tap < 27) {
+            const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+            const int tt = t - (kt - 1), hh = h - (kh - 1), ww = w - (kw - 1);
+            if ((unsigned)tt < (unsigned)RDG_NHOURS && (unsigned)hh < (unsigned)nd && (unsigned)ww < (unsigned)nd)
+                v[j] = dl[pos - (((long long)(kt - 1) * nd + (kh - 1)) * nd + (kw - 1))];
+        }
+    }
+    *reinterpret_cast<float4*>(Gd + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+// w4 (27,64,1) -> w4p [32][64] (rows 27..31 zero) and, behind it, w4pT [64][32]
+__global__ void pad_w4_kernel(const float* __restrict__ w4, float* __restrict__ w4p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 32 * 64) return;
+    const int tap = i >> 6, ch = i & 63;
+    const float v = tap < 27 ? w4[tap * 64 + ch] : 0.f;
+    w4p[i] = v;
+    w4p[2048 + ch * 32 + tap] = v;
+}
+// three constant segments of n each (the cotangents of the merged [fake | real | interpolated] critic backward)
+__global__ void fill3_kernel(float* __restrict__ d, int n, float a, float b, float c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n) d[i] = i < n ? a : (i < 2 * n ? b : c);
+}
 __global__ void fill_kernel(float* __restrict__ d, long long n, float v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = v;
@@ -398,6 +463,32 @@ int ew_fill_random_dev(float* dst, long long n, uint64_t seed, const RdgTrainSta
     if (!n) return 0;
     if ((reinterpret_cast<uintptr_t>(dst) & 15) != 0) { rdg_set_error("ew_fill_random_dev: destination must be 16-byte aligned"); return -1; }
     fill_random_dev_kernel<<<EW_GRID((n + 3) / 4)>>>(dst, n, seed, s, stream_id, kind, keep);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int ew_tap_gather_logits(const float* P, const float* b4, float* logits, int B, int nd, cudaStream_t st) {
+    const long long n = (long long)B * RDG_NHOURS * nd * nd;
+    if (!n) return 0;
+    tap_gather_logits_kernel<<<EW_GRID(n)>>>(P, b4, logits, B, nd);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_tap_scatter_dlogits(const float* dl, float* Gd, int B, int nd, cudaStream_t st) {
+    const long long n = (long long)B * RDG_NHOURS * nd * nd * 8;
+    if (!n) return 0;
+    tap_scatter_dlogits_kernel<<<EW_GRID(n)>>>(dl, Gd, B, nd);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_pad_w4(const float* w4, float* w4p, cudaStream_t st) {
+    pad_w4_kernel<<<8, 256, 0, st>>>(w4, w4p);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_fill3(float* dst, int n, float a, float b, float c, cudaStream_t st) {
+    if (!n) return 0;
+    fill3_kernel<<<EW_GRID(3 * n)>>>(dst, n, a, b, c);
     RDG_LAUNCH_CHECK();
     return 0;
 }

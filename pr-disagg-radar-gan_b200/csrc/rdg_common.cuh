@@ -103,6 +103,10 @@ int ew_fill_random_dev(float* dst, long long n, uint64_t seed, const RdgTrainSta
                        cudaStream_t st);
 
 // training-step helpers
+int ew_tap_gather_logits(const float* P, const float* b4, float* logits, int B, int nd, cudaStream_t st);   // P [B,24,nd,nd,32]
+int ew_tap_scatter_dlogits(const float* dl, float* Gd, int B, int nd, cudaStream_t st);                      // Gd [B,24,nd,nd,32]
+int ew_pad_w4(const float* w4, float* w4p, cudaStream_t st);     // -> [32][64] then [64][32]
+int ew_fill3(float* dst, int n, float a, float b, float c, cudaStream_t st);
 int ew_interp(const float* xr, const float* xf, const float* alpha, float* xhat, int B, long long per, cudaStream_t st);
 int ew_fill(float* dst, long long n, float v, cudaStream_t st);
 int ew_mean_scaled(const float* x, long long n, float scale, float* out, cudaStream_t st);   // out = scale * mean(x)

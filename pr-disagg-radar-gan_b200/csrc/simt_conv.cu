@@ -399,18 +399,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        const int c = c0 + lane;
-        double s = 0.0;
-        if (c < C)
-            for (long long r = r0 + grp; r < r1; r += 8) s += (double)dy[r * C + c];
-        red[grp][lane] = s;
-        __syncthreads();
-        if (grp == 0 && c < C) {
-            for (int k = 1; k < 8; ++k) s += red[k][lane];
-            atomicAdd(&db[c], (float)s);
-        }
-        __syncthreads();
+    const int c = blockIdx.y * 32 + lane;           // one 32-channel block per blockIdx.y
+    double s = 0.0;
+    if (c < C)
+        for (long long r = r0 + grp; r < r1; r += 8) s += (double)dy[r * C + c];
+    red[grp][lane] = s;
+    __syncthreads();
+    if (grp == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) s += red[k][lane];
+        atomicAdd(&db[c], (float)s);
     }
 }
 
@@ -633,7 +630,7 @@ int simt_conv_bwd_filter(const float* x, const float* dy, float* dw, float* db, 
 int simt_colsum(const float* x, float* out, long long rows, int C, cudaStream_t st) {
     if (rows <= 0) return 0;
     long long rpb = 256;
-    colsum_kernel<<<ceil_div(rows, rpb), 256, 0, st>>>(x, out, rows, C, rpb);
+    colsum_kernel<<<dim3(ceil_div(rows, rpb), ceil_div(C, 32)), 256, 0, st>>>(x, out, rows, C, rpb);
     RDG_LAUNCH_CHECK();
     return 0;
 }

@@ -13,8 +13,18 @@ int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, c
 
 // y = act(conv(x, w) + bias) [* mask * mask_scale]; wT = the kernel with its last two axes swapped: (KT,KH,KW,Co,Ci).
 // g.up must be 0 (the generator's upsampled convs go through the folded entry points below).
+// precise: 3xTF32 (operands split into tf32 high + low parts, three MMAs per k step: FP32-grade products).  Forward passes use it:
+// LeakyReLU's derivative is discontinuous, so a pre-activation that changes sign under tf32 rounding changes every upstream
+// gradient; backward passes are linear in their operands and run single-pass tf32.
 int tcg_conv_fwd(const float* x, const float* wT, const float* bias, float* y, const ConvGeom& g, int act, const float* mask,
-                 float mask_scale, cudaStream_t st, float* pre = nullptr);
+                 float mask_scale, cudaStream_t st, float* pre = nullptr, int precise = 0);
+// few input channels (Ci <= 4: the critic's first conv, gan_train_cwgangp_pixelnorm.py:286-287): K = taps * Ci, gathered per element.
+// wTp = tcg_pack_smallci_weights(w): [Co][Kpad], Kpad = tcg_smallci_kpad(taps, Ci), zero beyond taps * Ci.
+int tcg_smallci_kpad(int taps, int Ci);
+int tcg_pack_smallci_weights(const float* w, float* wTp, int taps, int Ci, int Co, cudaStream_t st);
+int tcg_conv_fwd_smallci(const float* x, const float* wTp, const float* bias, float* y, const ConvGeom& g, int act, const float* mask,
+                         float mask_scale, cudaStream_t st, float* pre = nullptr, int precise = 0);
+int tcg_conv_bwd_filter_smallci(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st);
 // dx = conv_transpose(dy, w); w in the Keras layout (KT,KH,KW,Ci,Co).  stride 1 or 2, g.up == 0.
 int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);
 // dw += sum_{b,pos} x (x) dy (accumulates with atomics; caller zeroes).  No bias gradient (use simt_colsum).
@@ -23,7 +33,7 @@ int tcg_conv_bwd_filter(const float* x, const float* dy, float* dw, const ConvGe
 // Upsample-folded forms of UpSampling3D(2) + Conv3D(3^3,'same'); g = the layer's geometry (g.up == 1).
 // wfT: [8 phases][8 taps][Co][Ci] (tcg_transpose_blocks of folded_pack_f32's output); wf: [8][8][Ci][Co].
 // y[B,2T,2H,2W,Co] = conv3(upsample2(x)) + bias
-int tcg_folded_fwd(const float* x, const float* wfT, const float* bias, float* y, const ConvGeom& g, cudaStream_t st);
+int tcg_folded_fwd(const float* x, const float* wfT, const float* bias, float* y, const ConvGeom& g, cudaStream_t st, int precise = 0);
 // dx[B,T,H,W,Ci] = gradient w.r.t. the LOW-RES input (upsample backward absorbed); dy interleaved [B,2T,2H,2W,Co]
 int tcg_folded_bwd_data(const float* dy, const float* wf, float* dx, const ConvGeom& g, cudaStream_t st);
 // dwf[8][8][Ci][Co] += folded filter gradients (atomics; caller zeroes, then un-folds with folded_unfold_grad)

@@ -44,6 +44,7 @@ struct TcgRowArgs {
     long long wtap;           // weight elements per tap block
     long long out_elems;      // elements of the output tensor (stride between split-K slices)
     int nclass, nslice, nstages;
+    int ksmall;               // > 0: few-channel input, k = tap * Cs + channel runs over ksmall = taps * Cs valid elements (Kc = padded)
     TcgClass cls[8];
     TcgTap taps[64];
 };
@@ -55,6 +56,7 @@ struct TcgFilterArgs {
     int ax, Tx, Hx, Wx, Ci;
     int ay, Ty, Hy, Wy, Co;
     int Mt, N, ksplit, nstages;
+    int ksmall;               // > 0: few-channel input: A rows = (tap, channel), ksmall = taps * Ci of them, one launch for all taps
     long long wblk;           // dw elements per tap block (Ci*Co)
     TcgFTap taps[64];
 };
@@ -77,19 +79,29 @@ __device__ __forceinline__ uint32_t idesc_tf32(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);   // F32 accum, tf32 x tf32, K-major, M = 128
 }
 
-// MMA issuer loop shared by both kernels: stage s holds A (128 rows) at +0 and B (N rows) at +16384
+// MMA issuer loop shared by both kernels.  Stage layout: A (128 rows) at +0, B (32 NB rows) at +16384; SPLIT (3xTF32): the low parts
+// A_lo / B_lo follow in the second half of the stage and every k step issues hi*hi + lo*hi + hi*lo.
+template <bool SPLIT>
 __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, uint32_t stage_bytes, int nst, int nkb, int N, uint32_t tmem,
                                                uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_bar) {
     const uint32_t idesc = idesc_tf32(N);
+    const uint32_t half = SPLIT ? stage_bytes / 2 : 0;
     for (int i = 0; i < nkb; ++i) {
         const int s = i % nst;
         mbar_wait(&full_bar[s], (uint32_t)(i / nst) & 1u);
         tc_fence_after();
         if (elect_one()) {
-            const uint64_t ad = make_sdesc(smem_u32(smem + (size_t)s * stage_bytes));
-            const uint64_t bd = make_sdesc(smem_u32(smem + (size_t)s * stage_bytes + 16384));
+            const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint64_t ad = make_sdesc(base), bd = make_sdesc(base + 16384);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (i | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+                tc_mma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (i | k) ? 1u : 0u);
+                if (SPLIT) {
+                    const uint64_t al = make_sdesc(base + half), bl = make_sdesc(base + half + 16384);
+                    tc_mma_tf32(tmem, al + 2 * k, bd + 2 * k, idesc, 1u);
+                    tc_mma_tf32(tmem, ad + 2 * k, bl + 2 * k, idesc, 1u);
+                }
+            }
             tc_commit(&empty_bar[s]);
             if (i == nkb - 1) tc_commit(acc_bar);
         }
@@ -97,15 +109,26 @@ __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, uint32_t stage_byt
     }
 }
 
+template <bool SPLIT>
+__device__ __forceinline__ void sts4_op(uint8_t* dst, uint32_t lo_off, float4 v) {
+    const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    *reinterpret_cast<float4*>(dst) = h;
+    if (SPLIT) *reinterpret_cast<float4*>(dst + lo_off) = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+}
+
 // ------------------------------------------------------------------------------------------------ row GEMM
-__global__ void __launch_bounds__(TCG_THREADS, 1) tcg_rowgemm_kernel(const __grid_constant__ TcgRowArgs p) {
+// NB = N / 32 (32-row slabs of the B tile); SPLIT = 3xTF32 (forward passes: FP32-grade pre-activations keep the LeakyReLU slope
+// pattern of the FP64 oracle); two CTAs per SM where the register / shared-memory budget allows.
+template <int NB, bool SPLIT>
+__global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 : 1) tcg_rowgemm_kernel(const __grid_constant__ TcgRowArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = p.N, nst = p.nstages;
-    const uint32_t stage_bytes = 16384u + (uint32_t)N * 128u;
+    constexpr int N = NB * 32;
+    const int nst = p.nstages;
+    constexpr uint32_t stage_bytes = (16384u + (uint32_t)N * 128u) * (SPLIT ? 2u : 1u);
 
     int ci = 0;
     for (int i = 1; i < p.nclass; ++i)
@@ -113,7 +136,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_rowgemm_kernel(const __gri
     const TcgClass cl = p.cls[ci];
     const int row0 = ((int)blockIdx.x - cl.tile_begin) * 128;
     const int n0 = blockIdx.y * N;
-    const int nkb_all = cl.tap_count * p.kchunks;
+    const int nkb_all = p.ksmall ? p.kchunks : cl.tap_count * p.kchunks;
     const int kb_lo = (int)((long long)blockIdx.z * nkb_all / p.nslice);
     const int nkb = (int)((long long)(blockIdx.z + 1) * nkb_all / p.nslice) - kb_lo;
 
@@ -129,7 +152,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_rowgemm_kernel(const __gri
     const uint32_t tmem = tmem_slot;
 
     if (warp == 8) {
-        mma_issue_loop(smem, stage_bytes, nst, nkb, N, tmem, full_bar, empty_bar, &acc_bar);
+        mma_issue_loop<SPLIT>(smem, stage_bytes, nst, nkb, N, tmem, full_bar, empty_bar, &acc_bar);
     } else {
         // ---- producers: thread = (row sub-index rsub, 16-byte chunk) of every 32-row slab of the A and B tiles
         const int chunk = tid & 7, rsub = tid >> 3;
@@ -149,37 +172,76 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_rowgemm_kernel(const __gri
             }
         }
         const uint32_t sw_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)(rsub & 7) * 128u + (uint32_t)((chunk ^ (rsub & 7)) << 4);
-        const int nb = N >> 5;     // 32-row slabs of the B tile
-        for (int i = 0; i < nkb; ++i) {
+
+        auto load = [&](int i, float4 (&va)[4], float4 (&vb)[NB]) {
             const int kb = kb_lo + i;
-            const int te = kb / p.kchunks, kc = kb - te * p.kchunks;
+            int te = 0, kc = kb;
+            if (!p.ksmall) { te = kb / p.kchunks; kc = kb - te * p.kchunks; }
             const TcgTap tp = p.taps[cl.tap_begin + te];
-            const int s = i % nst;
             const int k0 = kc * 32 + chunk * 4;
             const bool kval = k0 < p.Kc;
-            const int doff = ((tp.ct * p.Hs + tp.ch) * p.Ws + tp.cw) * p.Cs + k0;
-            float4 va[4], vb[8];
+            const float* wb = p.w + (long long)(p.ksmall ? 0 : tp.widx) * p.wtap + (long long)(n0 + rsub) * p.wrow + k0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ts = (rcoord[j] & 1023) + tp.ct, hs = ((rcoord[j] >> 10) & 1023) + tp.ch, ws = (rcoord[j] >> 20) + tp.cw;
-                const bool ok = kval && rbase[j] >= 0 && (unsigned)ts < (unsigned)p.Ts && (unsigned)hs < (unsigned)p.Hs &&
-                                (unsigned)ws < (unsigned)p.Ws;
-                va[j] = ok ? ldg4(p.src + rbase[j] + doff) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < NB; ++j) vb[j] = kval ? ldg4(wb + (long long)(32 * j) * p.wrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!p.ksmall) {
+                const int doff = ((tp.ct * p.Hs + tp.ch) * p.Ws + tp.cw) * p.Cs + k0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ts = (rcoord[j] & 1023) + tp.ct, hs = ((rcoord[j] >> 10) & 1023) + tp.ch, ws = (rcoord[j] >> 20) + tp.cw;
+                    const bool ok = kval && rbase[j] >= 0 && (unsigned)ts < (unsigned)p.Ts && (unsigned)hs < (unsigned)p.Hs &&
+                                    (unsigned)ws < (unsigned)p.Ws;
+                    va[j] = ok ? ldg4(p.src + rbase[j] + doff) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                // few input channels (the critic's first conv, Cs = 1 + ncond): k = tap * Cs + channel, element-wise gather
+                int eo[4], ect[4], ech[4], ecw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u;
+                    eo[u] = -1; ect[u] = ech[u] = ecw[u] = 0;
+                    if (k < p.ksmall) {
+                        const int tap = k / p.Cs, c = k - tap * p.Cs;
+                        const TcgTap tq = p.taps[cl.tap_begin + tap];
+                        ect[u] = tq.ct; ech[u] = tq.ch; ecw[u] = tq.cw;
+                        eo[u] = ((tq.ct * p.Hs + tq.ch) * p.Ws + tq.cw) * p.Cs + c;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ts = (rcoord[j] & 1023) + ect[u], hs = ((rcoord[j] >> 10) & 1023) + ech[u], ws = (rcoord[j] >> 20) + ecw[u];
+                        const bool ok = eo[u] != -1 && rbase[j] >= 0 && (unsigned)ts < (unsigned)p.Ts && (unsigned)hs < (unsigned)p.Hs &&
+                                        (unsigned)ws < (unsigned)p.Ws;
+                        e[u] = ok ? __ldg(p.src + rbase[j] + eo[u]) : 0.f;
+                    }
+                    va[j] = make_float4(e[0], e[1], e[2], e[3]);
+                }
             }
-            const float* wb = p.w + (long long)tp.widx * p.wtap + (long long)(n0 + rsub) * p.wrow + k0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nb) vb[j] = kval ? ldg4(wb + (long long)(32 * j) * p.wrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto store = [&](int i, const float4 (&va)[4], const float4 (&vb)[NB]) {
+            const int s = i % nst;
             if (i >= nst) mbar_wait(&empty_bar[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
             uint8_t* sa = smem + (size_t)s * stage_bytes + sw_off;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sts4_tf32(sa + j * 4096, va[j]);
+            for (int j = 0; j < 4; ++j) sts4_op<SPLIT>(sa + j * 4096, stage_bytes / 2, va[j]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nb) sts4_tf32(sa + 16384 + j * 4096, vb[j]);
+            for (int j = 0; j < NB; ++j) sts4_op<SPLIT>(sa + 16384 + j * 4096, stage_bytes / 2, vb[j]);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
+        };
+        // software pipeline: the loads of k-block i+1 are in flight while k-block i is rounded and stored
+        float4 a0[4], b0[NB], a1[4], b1[NB];
+        if (nkb > 0) load(0, a0, b0);
+        for (int i = 0; i < nkb; i += 2) {
+            if (i + 1 < nkb) load(i + 1, a1, b1);
+            store(i, a0, b0);
+            if (i + 1 < nkb) {
+                if (i + 2 < nkb) load(i + 2, a0, b0);
+                store(i + 1, a1, b1);
+            }
         }
         // ---- epilogue: warp = (lane quarter q, column half)
         if (nkb > 0) {        // an empty K slice (class with fewer taps than slices) contributes zeros and never touches TMEM
@@ -187,7 +249,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_rowgemm_kernel(const __gri
             tc_fence_after();
         }
         const int q = warp & 3, half = warp >> 2;
-        const int cph = N >= 64 ? N / 2 : 32;
+        constexpr int cph = N >= 64 ? N / 2 : 32;
         const int c_lo = half * cph, c_hi = min(N, c_lo + cph);
         const int r = row0 + q * 32 + lane;
         long long off = -1;
@@ -268,14 +330,20 @@ __global__ void tcg_splitk_epilogue_kernel(const float* __restrict__ part, int n
 }
 
 // ------------------------------------------------------------------------------------------------ filter gradient
-__global__ void __launch_bounds__(TCG_THREADS, 1) tcg_filtergrad_kernel(const __grid_constant__ TcgFilterArgs p) {
+// NVB = float4 loads per lane and k-block for the B tile (N = 32 NVB).  Producer warp w owns input channels [16 w, +16) of the A
+// tile and output channels [4 NVB w, +4 NVB) of the B tile.  Lanes pair up on a position (lane = (position sub-index, channel
+// half)): a load instruction covers 16 positions x 32 contiguous bytes (full sectors), the transposed scalar stores of a warp hit
+// 32 different banks (row = channel, column = position).  p.ksmall: few-channel input (critic's first conv): A rows = (tap, channel).
+template <int NVB>
+__global__ void __launch_bounds__(TCG_THREADS, NVB <= 4 ? 2 : 1) tcg_filtergrad_kernel(const __grid_constant__ TcgFilterArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = p.N, nst = p.nstages;
-    const uint32_t stage_bytes = 16384u + (uint32_t)N * 128u;
+    constexpr int N = NVB * 32;
+    const int nst = p.nstages;
+    constexpr uint32_t stage_bytes = 16384u + (uint32_t)N * 128u;
     const TcgFTap tp = p.taps[blockIdx.x];
     const int mt = (int)blockIdx.y % p.Mt, nt = (int)blockIdx.y / p.Mt;
     const int m0 = mt * 128, n0 = nt * N;
@@ -295,81 +363,137 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_filtergrad_kernel(const __
     const uint32_t tmem = tmem_slot;
 
     if (warp == 8) {
-        mma_issue_loop(smem, stage_bytes, nst, nkb, N, tmem, full_bar, empty_bar, &acc_bar);
+        mma_issue_loop<false>(smem, stage_bytes, nst, nkb, N, tmem, full_bar, empty_bar, &acc_bar);
     } else {
-        // ---- producers: lane = position (k index) of the 32-position block; warp = channel group.
-        // A rows [16 warp, +16) = input channels m0 + ..; B rows [cpw warp, +cpw) = output channels n0 + .., cpw = N / 8
-        const int cpw = N >> 3;                 // 4 .. 32 channels of B per warp
-        const int nvb = cpw >> 2;               // float4 loads per lane for B
-        const bool a_on = m0 + 16 * warp < p.Ci;
-        const uint32_t kcol = (uint32_t)(lane & 3) * 4u;
-        const uint32_t kch = (uint32_t)(lane >> 2);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % nst;
-            const int pos = (kb_lo + i) * 32 + lane;
-            bool xok = false, yok = false;
-            long long xoff = 0, yoff = 0;
-            if (pos < p.rows) {
-                int q = pos;
-                const int w2 = q % p.Wc; q /= p.Wc;
-                const int h2 = q % p.Hc; q /= p.Hc;
-                const int t2 = q % p.Tc; const int b = q / p.Tc;
-                const int xt = p.ax * t2 + tp.xt, xh = p.ax * h2 + tp.xh, xw = p.ax * w2 + tp.xw;
-                xok = (unsigned)xt < (unsigned)p.Tx && (unsigned)xh < (unsigned)p.Hx && (unsigned)xw < (unsigned)p.Wx;
-                xoff = ((((long long)b * p.Tx + xt) * p.Hx + xh) * p.Wx + xw) * p.Ci + m0 + 16 * warp;
-                const int yt = p.ay * t2 + tp.yt, yh = p.ay * h2 + tp.yh, yw = p.ay * w2 + tp.yw;
-                yok = xok && (unsigned)yt < (unsigned)p.Ty && (unsigned)yh < (unsigned)p.Hy && (unsigned)yw < (unsigned)p.Wy;
-                yoff = ((((long long)b * p.Ty + yt) * p.Hy + yh) * p.Wy + yw) * p.Co + n0 + cpw * warp;
+        constexpr int CPW = 4 * NVB;                       // B channels per warp
+        constexpr bool B_PAIR = CPW >= 8;                  // lanes pair up on a position (else lane = position)
+        const int psub = lane >> 1, cq = lane & 1;
+        const bool a_on = p.ksmall ? 16 * warp < p.ksmall : m0 + 16 * warp < p.Ci;
+        // one position of this lane: offsets of its x / dy rows, or -1
+        auto locate = [&](int pos, long long& xoff, long long& yoff) {
+            xoff = -1; yoff = -1;
+            if (pos >= p.rows) return;
+            int q = pos;
+            const int w2 = q % p.Wc; q /= p.Wc;
+            const int h2 = q % p.Hc; q /= p.Hc;
+            const int t2 = q % p.Tc; const int b = q / p.Tc;
+            const int yt = p.ay * t2 + tp.yt, yh = p.ay * h2 + tp.yh, yw = p.ay * w2 + tp.yw;
+            const bool yok = (unsigned)yt < (unsigned)p.Ty && (unsigned)yh < (unsigned)p.Hy && (unsigned)yw < (unsigned)p.Wy;
+            if (p.ksmall) {          // per-tap validity is resolved per element below; xoff = the tap-free base
+                xoff = ((((long long)b * p.Tx + p.ax * t2) * p.Hx + p.ax * h2) * p.Wx + p.ax * w2) * p.Ci;
+                xoff = (xoff << 30) | ((long long)(p.ax * t2) << 20) | ((long long)(p.ax * h2) << 10) | (long long)(p.ax * w2);
+                if (yok) yoff = ((((long long)b * p.Ty + yt) * p.Hy + yh) * p.Wy + yw) * p.Co + n0;
+                return;
             }
-            float4 va[4], vb[8];
+            const int xt = p.ax * t2 + tp.xt, xh = p.ax * h2 + tp.xh, xw = p.ax * w2 + tp.xw;
+            const bool xok = (unsigned)xt < (unsigned)p.Tx && (unsigned)xh < (unsigned)p.Hx && (unsigned)xw < (unsigned)p.Wx;
+            if (xok && yok) {
+                xoff = ((((long long)b * p.Tx + xt) * p.Hx + xh) * p.Wx + xw) * p.Ci + m0;
+                yoff = ((((long long)b * p.Ty + yt) * p.Hy + yh) * p.Wy + yw) * p.Co + n0;
+            }
+        };
+        // A: 16 channels per warp = 2 position halves x 2 channel groups of 8 (lane pair: 2 x float4); va[2 h + g]
+        // B: CPW channels per warp; B_PAIR: 2 halves x (CPW / 8) groups, vb[(CPW / 8) h + g]; else lane = position, vb[0]
+        auto load = [&](int i, float4 (&va)[4], float4 (&vb)[NVB]) {
+            const int pos0 = (kb_lo + i) * 32;
+            long long xo[2], yo[2];
+            locate(pos0 + psub, xo[0], yo[0]);
+            locate(pos0 + 16 + psub, xo[1], yo[1]);
             if (a_on) {
+                if (!p.ksmall) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) va[j] = xok ? ldg4(p.x + xoff + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+                            va[2 * h + g] = xo[h] >= 0 ? ldg4(p.x + xo[h] + 16 * warp + 8 * g + 4 * cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            float e[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int m = 16 * warp + 8 * g + 4 * cq + u;      // row = tap * Ci + channel
+                                e[u] = 0.f;
+                                if (m < p.ksmall && xo[h] >= 0 && yo[h] >= 0) {
+                                    const int tap = m / p.Ci, c = m - tap * p.Ci;
+                                    const TcgFTap tq = p.taps[tap];
+                                    const int xt = (int)((xo[h] >> 20) & 1023) + tq.xt, xh = (int)((xo[h] >> 10) & 1023) + tq.xh, xw = (int)(xo[h] & 1023) + tq.xw;
+                                    if ((unsigned)xt < (unsigned)p.Tx && (unsigned)xh < (unsigned)p.Hx && (unsigned)xw < (unsigned)p.Wx)
+                                        e[u] = __ldg(p.x + (xo[h] >> 30) + ((long long)(tq.xt * p.Hx + tq.xh) * p.Wx + tq.xw) * p.Ci + c);
+                                }
+                            }
+                            va[2 * h + g] = make_float4(e[0], e[1], e[2], e[3]);
+                        }
+                }
             }
+            if (B_PAIR) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nvb) vb[j] = yok ? ldg4(p.dy + yoff + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int g = 0; g < CPW / 8; ++g)
+                        vb[(CPW / 8) * h + g] = yo[h] >= 0 ? ldg4(p.dy + yo[h] + CPW * warp + 8 * g + 4 * cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                long long x1, y1;
+                locate(pos0 + lane, x1, y1);
+                vb[0] = y1 >= 0 ? ldg4(p.dy + y1 + CPW * warp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto sts_t = [&](uint8_t* tile, int row0, int k, float4 v) {       // 4 consecutive rows (channels), column k
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t row = (uint32_t)(row0 + u);
+                *reinterpret_cast<float*>(tile + (row >> 3) * 1024u + (row & 7u) * 128u + ((((uint32_t)k >> 2) ^ (row & 7u)) << 4) + ((uint32_t)k & 3u) * 4u) =
+                    to_tf32(e[u]);
+            }
+        };
+        auto store = [&](int i, const float4 (&va)[4], const float4 (&vb)[NVB]) {
+            const int s = i % nst;
             if (i >= nst) mbar_wait(&empty_bar[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
             uint8_t* sa = smem + (size_t)s * stage_bytes;
             if (a_on) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float e[4] = {va[j].x, va[j].y, va[j].z, va[j].w};
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t row = (uint32_t)(16 * warp + 4 * j + u);
-                        *reinterpret_cast<float*>(sa + (row >> 3) * 1024u + (row & 7u) * 128u + ((kch ^ (row & 7u)) << 4) + kcol) = to_tf32(e[u]);
-                    }
-                }
+                    for (int g = 0; g < 2; ++g) sts_t(sa, 16 * warp + 8 * g + 4 * cq, 16 * h + psub, va[2 * h + g]);
             }
-            uint8_t* sb = sa + 16384;
+            if (B_PAIR) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < nvb) {
-                    const float e[4] = {vb[j].x, vb[j].y, vb[j].z, vb[j].w};
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t row = (uint32_t)(cpw * warp + 4 * j + u);
-                        *reinterpret_cast<float*>(sb + (row >> 3) * 1024u + (row & 7u) * 128u + ((kch ^ (row & 7u)) << 4) + kcol) = to_tf32(e[u]);
-                    }
-                }
+                    for (int g = 0; g < CPW / 8; ++g) sts_t(sa + 16384, CPW * warp + 8 * g + 4 * cq, 16 * h + psub, vb[(CPW / 8) * h + g]);
+            } else {
+                sts_t(sa + 16384, CPW * warp, lane, vb[0]);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
+        };
+        float4 a0[4], b0[NVB], a1[4], b1[NVB];
+        if (nkb > 0) load(0, a0, b0);
+        for (int i = 0; i < nkb; i += 2) {
+            if (i + 1 < nkb) load(i + 1, a1, b1);
+            store(i, a0, b0);
+            if (i + 1 < nkb) {
+                if (i + 2 < nkb) load(i + 2, a0, b0);
+                store(i + 1, a1, b1);
+            }
         }
-        // ---- epilogue: accumulator row = input channel, columns = output channels -> dw[tap][ci][co] += D
+        // ---- epilogue: accumulator row = input channel (or (tap, channel)), columns = output channels -> dw += D
         mbar_wait(&acc_bar, 0);
         tc_fence_after();
         const int q = warp & 3, half = warp >> 2;
-        const int cph = N >= 64 ? N / 2 : 32;
+        constexpr int cph = N >= 64 ? N / 2 : 32;
         const int c_lo = half * cph, c_hi = min(N, c_lo + cph);
-        const int ci = m0 + q * 32 + lane;
-        float* dst = p.dw + (long long)tp.widx * p.wblk + (long long)ci * p.Co + n0;
+        const int row = m0 + q * 32 + lane;
+        const int row_lim = p.ksmall ? p.ksmall : p.Ci;
+        float* dst = p.dw + (long long)tp.widx * p.wblk + (long long)row * p.Co + n0;
         for (int c = c_lo; c < c_hi; c += 32) {
             uint32_t v[32];
             tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            if (ci >= p.Ci) continue;
+            if (row >= row_lim) continue;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
                 red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
@@ -397,12 +521,14 @@ __global__ void transpose_blocks_kernel(const float* __restrict__ src, float* __
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-int pick_stages(int N) {
-    const int stage = 16384 + N * 128;
-    int n = (200 * 1024) / stage;
+// shared-memory ring depth: two CTAs per SM (about 100 KB each) where the kernel's launch bounds allow it, else one
+int pick_stages(int N, bool split) {
+    const int stage = (16384 + N * 128) * (split ? 2 : 1);
+    const bool two = (N / 32) * (split ? 2 : 1) <= 4;
+    const int n = ((two ? 104 : 208) * 1024) / stage;
     return std::max(2, std::min(n, 6));
 }
-size_t smem_bytes(int N, int nst) { return (size_t)nst * (16384 + N * 128) + 1024; }
+size_t smem_bytes(int N, int nst, bool split) { return (size_t)nst * (16384 + N * 128) * (split ? 2 : 1) + 1024; }
 
 int tile_n_for(int Nt, int mtiles) {
     // widest accumulator that still leaves enough CTAs; Nt is a multiple of 32
@@ -411,14 +537,32 @@ int tile_n_for(int Nt, int mtiles) {
     return 0;
 }
 
-int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const float* bias, float* y, int act, const float* mask,
-                   float mask_scale, float* pre) {
+template <int NB, bool SPLIT>
+int launch_rowgemm_t(const TcgRowArgs& a, dim3 grid, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        RDG_CUDA(cudaFuncSetAttribute(tcg_rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+        RDG_CUDA(cudaFuncSetAttribute(tcg_rowgemm_kernel<NB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
         attr_done = true;
     }
-    a.nstages = pick_stages(a.N);
+    tcg_rowgemm_kernel<NB, SPLIT><<<grid, TCG_THREADS, smem_bytes(NB * 32, a.nstages, SPLIT), st>>>(a);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int launch_rowgemm_n(const TcgRowArgs& a, dim3 grid, bool split, cudaStream_t st) {
+    switch (a.N) {
+        case 32:  return split ? launch_rowgemm_t<1, true>(a, grid, st) : launch_rowgemm_t<1, false>(a, grid, st);
+        case 64:  return split ? launch_rowgemm_t<2, true>(a, grid, st) : launch_rowgemm_t<2, false>(a, grid, st);
+        case 128: return split ? launch_rowgemm_t<4, true>(a, grid, st) : launch_rowgemm_t<4, false>(a, grid, st);
+        case 256: return split ? launch_rowgemm_t<8, true>(a, grid, st) : launch_rowgemm_t<8, false>(a, grid, st);
+    }
+    rdg_set_error("tcg row GEMM: the output channel count must be a multiple of 32");
+    return RDG_TCG_E_SHAPE;
+}
+
+int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const float* bias, float* y, int act, const float* mask,
+                   float mask_scale, float* pre, bool split = false) {
+    if (split && a.N > 128) a.N = 128;           // the 3xTF32 stage is twice as large
+    a.nstages = pick_stages(a.N, split);
     const int ctas = mtiles * (a.Nt / a.N);
     int nslice = 1;
     if (ctas < 148 && max_kb >= 8) {
@@ -432,8 +576,8 @@ int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const
         float* part = nullptr;
         RDG_CUDA(cudaMallocAsync(&part, (size_t)nslice * a.out_elems * sizeof(float), st));
         a.part = part; a.bias = nullptr; a.pre = nullptr; a.mask = nullptr; a.act = ACT_NONE;
-        tcg_rowgemm_kernel<<<grid, TCG_THREADS, smem_bytes(a.N, a.nstages), st>>>(a);
-        RDG_LAUNCH_CHECK();
+        int r = launch_rowgemm_n(a, grid, split, st);
+        if (r) return r;
         const long long mn4 = a.out_elems / 4;
         tcg_splitk_epilogue_kernel<<<ceil_div(mn4, 256), 256, 0, st>>>(part, nslice, mn4, a.Nt, bias, y, act, mask, mask_scale, pre);
         RDG_LAUNCH_CHECK();
@@ -441,9 +585,7 @@ int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const
         return 0;
     }
     a.part = nullptr; a.bias = bias; a.pre = pre; a.mask = mask; a.mask_scale = mask_scale; a.act = act;
-    tcg_rowgemm_kernel<<<grid, TCG_THREADS, smem_bytes(a.N, a.nstages), st>>>(a);
-    RDG_LAUNCH_CHECK();
-    return 0;
+    return launch_rowgemm_n(a, grid, split, st);
 }
 
 bool fits_i32(long long v) { return v < (1ll << 31); }
@@ -458,7 +600,7 @@ int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, c
 }
 
 int tcg_conv_fwd(const float* x, const float* wT, const float* bias, float* y, const ConvGeom& g, int act, const float* mask,
-                 float mask_scale, cudaStream_t st, float* pre) {
+                 float mask_scale, cudaStream_t st, float* pre, int precise) {
     if (g.up || (g.Ci & 3) || (g.Co & 31) || g.KT * g.KH * g.KW > 64) { rdg_set_error("tcg_conv_fwd: unsupported geometry"); return RDG_TCG_E_SHAPE; }
     const long long rows = (long long)g.B * g.To * g.Ho * g.Wo;
     if (rows == 0) return 0;
@@ -478,7 +620,52 @@ int tcg_conv_fwd(const float* x, const float* wT, const float* bias, float* y, c
     for (int kt = 0; kt < g.KT; ++kt)
         for (int kh = 0; kh < g.KH; ++kh)
             for (int kw = 0; kw < g.KW; ++kw, ++n) a.taps[n] = TcgTap{(int8_t)(kt - g.pt), (int8_t)(kh - g.ph), (int8_t)(kw - g.pw), 0, n};
-    return launch_rowgemm(a, mtiles, n * a.kchunks, st, bias, y, act, mask, mask_scale, pre);
+    return launch_rowgemm(a, mtiles, n * a.kchunks, st, bias, y, act, mask, mask_scale, pre, precise != 0);
+}
+
+// ---- few-channel input (the critic's first conv: Ci = 1 + ncond): K = taps * Ci elements gathered one by one
+int tcg_smallci_kpad(int taps, int Ci) { return (taps * Ci + 31) / 32 * 32; }
+
+namespace {
+__global__ void pack_smallci_kernel(const float* __restrict__ w, float* __restrict__ wTp, int K, int Kpad, int Co) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Co * Kpad) return;
+    const int n = i / Kpad, k = i - n * Kpad;
+    wTp[i] = k < K ? w[(size_t)k * Co + n] : 0.f;
+}
+}  // namespace
+
+int tcg_pack_smallci_weights(const float* w, float* wTp, int taps, int Ci, int Co, cudaStream_t st) {
+    const int Kpad = tcg_smallci_kpad(taps, Ci);
+    pack_smallci_kernel<<<ceil_div((long long)Co * Kpad, 256), 256, 0, st>>>(w, wTp, taps * Ci, Kpad, Co);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int tcg_conv_fwd_smallci(const float* x, const float* wTp, const float* bias, float* y, const ConvGeom& g, int act, const float* mask,
+                         float mask_scale, cudaStream_t st, float* pre, int precise) {
+    const int taps = g.KT * g.KH * g.KW;
+    if (g.up || g.Ci > 4 || (g.Co & 31) || taps > 64 || taps * g.Ci > 128) { rdg_set_error("tcg_conv_fwd_smallci: unsupported geometry"); return RDG_TCG_E_SHAPE; }
+    const long long rows = (long long)g.B * g.To * g.Ho * g.Wo;
+    if (rows == 0) return 0;
+    if (!fits_i32((long long)g.B * g.Ti * g.Hi * g.Wi * g.Ci) || !fits_i32(rows * g.Co)) { rdg_set_error("tcg_conv_fwd_smallci: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgRowArgs a{};
+    a.src = x; a.w = wTp; a.out = y;
+    a.a = g.stride; a.os = 1;
+    a.Ts = g.Ti; a.Hs = g.Hi; a.Ws = g.Wi; a.Cs = g.Ci;
+    a.To = g.To; a.Ho = g.Ho; a.Wo = g.Wo; a.Nt = g.Co;
+    a.ksmall = taps * g.Ci;
+    a.Kc = tcg_smallci_kpad(taps, g.Ci); a.kchunks = a.Kc / 32; a.wrow = a.Kc; a.wtap = 0;
+    a.out_elems = rows * g.Co;
+    const int mtiles = ceil_div(rows, 128);
+    a.N = tile_n_for(g.Co, mtiles);
+    a.nclass = 1;
+    a.cls[0] = TcgClass{g.To, g.Ho, g.Wo, (int)rows, 0, 0, 0, 0, 0, taps};
+    int n = 0;
+    for (int kt = 0; kt < g.KT; ++kt)
+        for (int kh = 0; kh < g.KH; ++kh)
+            for (int kw = 0; kw < g.KW; ++kw, ++n) a.taps[n] = TcgTap{(int8_t)(kt - g.pt), (int8_t)(kh - g.ph), (int8_t)(kw - g.pw), 0, 0};
+    return launch_rowgemm(a, mtiles, a.kchunks, st, bias, y, act, mask, mask_scale, pre, precise != 0);
 }
 
 int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st) {
@@ -528,7 +715,7 @@ int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom
     return launch_rowgemm(a, tiles, max_taps * a.kchunks, st, nullptr, dx, ACT_NONE, nullptr, 1.f, nullptr);
 }
 
-int tcg_folded_fwd(const float* x, const float* wfT, const float* bias, float* y, const ConvGeom& g, cudaStream_t st) {
+int tcg_folded_fwd(const float* x, const float* wfT, const float* bias, float* y, const ConvGeom& g, cudaStream_t st, int precise) {
     if (!g.up || (g.Ci & 31) || (g.Co & 31)) { rdg_set_error("tcg_folded_fwd: unsupported geometry"); return RDG_TCG_E_SHAPE; }
     const long long rows = (long long)g.B * g.Ti * g.Hi * g.Wi;
     if (rows == 0) return 0;
@@ -551,7 +738,7 @@ int tcg_folded_fwd(const float* x, const float* wfT, const float* bias, float* y
     }
     a.nclass = 8;
     a.N = tile_n_for(g.Co, 8 * tpc);
-    return launch_rowgemm(a, 8 * tpc, 8 * a.kchunks, st, bias, y, ACT_NONE, nullptr, 1.f, nullptr);
+    return launch_rowgemm(a, 8 * tpc, 8 * a.kchunks, st, bias, y, ACT_NONE, nullptr, 1.f, nullptr, precise != 0);
 }
 
 int tcg_folded_bwd_data(const float* dy, const float* wf, float* dx, const ConvGeom& g, cudaStream_t st) {
@@ -582,30 +769,60 @@ int tcg_folded_bwd_data(const float* dy, const float* wf, float* dx, const ConvG
 }
 
 namespace {
-int launch_filtergrad(TcgFilterArgs& a, int ntap, cudaStream_t st) {
+template <int NVB>
+int launch_filtergrad_t(const TcgFilterArgs& a, dim3 grid, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        RDG_CUDA(cudaFuncSetAttribute(tcg_filtergrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+        RDG_CUDA(cudaFuncSetAttribute(tcg_filtergrad_kernel<NVB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
         attr_done = true;
     }
-    a.Mt = ceil_div(a.Ci, 128);
+    tcg_filtergrad_kernel<NVB><<<grid, TCG_THREADS, smem_bytes(NVB * 32, a.nstages, false), st>>>(a);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int launch_filtergrad(TcgFilterArgs& a, int ntap, cudaStream_t st) {
+    a.Mt = a.ksmall ? 1 : ceil_div(a.Ci, 128);
     int N = 0;
     for (int n : {256, 128, 64, 32})
         if (a.Co % n == 0 && (n <= 64 || (long long)ntap * a.Mt * (a.Co / n) >= 96)) { N = n; break; }
     if (!N) { rdg_set_error("tcg filter gradient: Co must be a multiple of 32"); return RDG_TCG_E_SHAPE; }
     a.N = N;
-    a.nstages = pick_stages(N);
+    a.nstages = pick_stages(N, false);
     const int ctas = ntap * a.Mt * (a.Co / N);
     const int nkb = (a.rows + 31) / 32;
-    int ks = (296 + ctas - 1) / ctas;
+    int ks = (592 + ctas - 1) / ctas;
     ks = std::max(1, std::min(ks, nkb / 4));
     a.ksplit = ks;
     dim3 grid(ntap, a.Mt * (a.Co / N), ks);
-    tcg_filtergrad_kernel<<<grid, TCG_THREADS, smem_bytes(N, a.nstages), st>>>(a);
-    RDG_LAUNCH_CHECK();
-    return 0;
+    switch (N) {
+        case 32:  return launch_filtergrad_t<1>(a, grid, st);
+        case 64:  return launch_filtergrad_t<2>(a, grid, st);
+        case 128: return launch_filtergrad_t<4>(a, grid, st);
+        default:  return launch_filtergrad_t<8>(a, grid, st);
+    }
 }
 }  // namespace
+
+int tcg_conv_bwd_filter_smallci(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st) {
+    const int taps = g.KT * g.KH * g.KW;
+    if (g.up || g.Ci > 4 || (g.Co & 31) || taps > 64 || taps * g.Ci > 128) { rdg_set_error("tcg_conv_bwd_filter_smallci: unsupported geometry"); return RDG_TCG_E_SHAPE; }
+    const long long rows = (long long)g.B * g.To * g.Ho * g.Wo;
+    if (rows == 0) return 0;
+    if (!fits_i32(rows) || !fits_i32((long long)g.B * g.Ti * g.Hi * g.Wi * g.Ci)) { rdg_set_error("tcg_conv_bwd_filter_smallci: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgFilterArgs a{};
+    a.x = x; a.dy = dy; a.dw = dw;
+    a.Tc = g.To; a.Hc = g.Ho; a.Wc = g.Wo; a.rows = (int)rows;
+    a.ax = g.stride; a.Tx = g.Ti; a.Hx = g.Hi; a.Wx = g.Wi; a.Ci = g.Ci;
+    a.ay = 1; a.Ty = g.To; a.Hy = g.Ho; a.Wy = g.Wo; a.Co = g.Co;
+    a.ksmall = taps * g.Ci;
+    a.wblk = 0;
+    int n = 0;
+    for (int kt = 0; kt < g.KT; ++kt)
+        for (int kh = 0; kh < g.KH; ++kh)
+            for (int kw = 0; kw < g.KW; ++kw, ++n)
+                a.taps[n] = TcgFTap{(int8_t)(kt - g.pt), (int8_t)(kh - g.ph), (int8_t)(kw - g.pw), 0, 0, 0, 0};
+    return launch_filtergrad(a, 1, st);
+}
 
 int tcg_conv_bwd_filter(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st) {
     if (g.up || (g.Ci & 15) || (g.Co & 31) || g.KT * g.KH * g.KW > 64) { rdg_set_error("tcg_conv_bwd_filter: unsupported geometry"); return RDG_TCG_E_SHAPE; }

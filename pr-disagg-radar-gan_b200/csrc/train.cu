@@ -62,8 +62,8 @@ extern "C" int rdg_adam_apply(rdg_ctx* c, int which, float lr, float beta1, floa
     size_t n = which == 0 ? c->g_total : c->c_total;
     r = ew_adam(p, g, m, v, (long long)n, (float)lr_t, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
     if (r) return r;
-    if (which == 0) { c->gen_packed_stale = true; c->fold32_stale = true; }
-    else c->critic_packed_stale = true;
+    if (which == 0) { c->gen_stale_kinds = 3; c->fold32_stale = true; c->g_tcw_stale = true; }
+    else { c->critic_packed_stale = true; c->c_wT_stale = true; }
     return 0;
 }
 extern "C" int rdg_adam_reset(rdg_ctx* c, int which) {
@@ -231,6 +231,13 @@ int gen_fwd_train(rdg_ctx* c, const float* latent, const float* cond, int B, Gen
 
 }  // namespace
 
+namespace {
+int critic_step_tc_masks(rdg_ctx* c, const float* x_real, const float* cond, const float* latent, const float* alpha,
+                         const float* const* mf, const float* const* mr, const float* const* mh, int B, int gen_mode, float* losses4,
+                         cudaStream_t st);
+int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const float* const* masks, int B, float* loss_dev, cudaStream_t st);
+}
+
 // critic_model.train_on_batch evaluation without the optimizer update
 // (gan_train_cwgangp_pixelnorm.py:365-392, 472): losses4 = [total, l_valid, l_fake, l_gp]; gradients of
 // `total` w.r.t. the critic weights are left in the critic gradient buffer.
@@ -242,6 +249,7 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
     RDG_CUDA(cudaSetDevice(c->device));
     TRY(ensure_train_state(c));
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->train_mode == 1) return critic_step_tc_masks(c, x_real_dev, cond_dev, latent_dev, alpha_dev, masks_fake, masks_real, masks_hat, B, gen_mode, losses4_dev, st);
     const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
     size_t max_act = 0, sum_act = 0;
     for (int l = 0; l < 5; ++l) { max_act = std::max(max_act, critic_act_elems(c, l)); sum_act += critic_act_elems(c, l); }
@@ -360,6 +368,7 @@ extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, con
     RDG_CUDA(cudaSetDevice(c->device));
     TRY(ensure_train_state(c));
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->train_mode == 1) return generator_step_tc(c, latent_dev, cond_dev, masks, B, loss_dev, st);
     const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
     size_t cmax = 0, csum = 0, gsum = 0, gmax = 0;
     for (int l = 0; l < 5; ++l) { cmax = std::max(cmax, critic_act_elems(c, l)); csum += critic_act_elems(c, l); }
@@ -414,5 +423,393 @@ extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, con
         TRY(ew_lrelu_bwd(G.d0_pre, dy, dc, (long long)B * dg.Co, nullptr, 1.f, st));
         TRY(simt_conv_bwd_filter(G.x0, dc, c->g_grads + c->g_off[0], c->g_grads + c->g_off[1], dg, st));
     }
+    return 0;
+}
+
+// ================================================================================================================
+// Tensor-core training mode (train_mode 1): the same two steps with every wide contraction on tcgen05 kind::tf32
+// (tcg_gemm.cu) and a shorter dependency chain:
+//  * the Wasserstein backward (fake | real) and the first-order gradient-penalty backward (interpolated) are ONE 3B backward-data
+//    chain with cotangents [+1/B | -1/B | 1] (the same linear operator, per-sample masks);
+//  * the second-order cotangents u_l overwrite the interpolated third of the saved activations h_l, so the Wasserstein filter
+//    gradient bwd_filter(h_{l-1}, da_l) and the penalty's bwd_filter(u_{l-1}, delta_l) are ONE contraction over 3B samples;
+//  * the generator's Conv3D(64->1) runs as per-tap products P = y . w4^T (N = 32) + a gather, its backward as two plain GEMMs
+//    on the gathered cotangent matrix.
+// The 2-channel first critic conv (K = 54) and the Dense(1) stay on the CUDA cores.
+// ================================================================================================================
+#include "tcg.h"
+
+namespace {
+
+int refresh_critic_wT(rdg_ctx* c, cudaStream_t st) {
+    ConvGeom g0 = rdg_critic_conv_geom(c, 0, 1);
+    if (!c->c_wT) RDG_CUDA(cudaMalloc(&c->c_wT, c->c_total * 4));
+    if (!c->c_w1p) RDG_CUDA(cudaMalloc(&c->c_w1p, (size_t)g0.Co * tcg_smallci_kpad(27, g0.Ci) * 4));
+    if (!c->c_wT_stale) return 0;
+    TRY(tcg_pack_smallci_weights(c->c_params + c->c_off[0], c->c_w1p, 27, g0.Ci, g0.Co, st));
+    for (int l = 1; l < 4; ++l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l, 1);
+        TRY(tcg_transpose_blocks(c->c_params + c->c_off[2 * l], c->c_wT + c->c_off[2 * l], 27, g.Ci, g.Co, st));
+    }
+    c->c_wT_stale = false;
+    return 0;
+}
+
+int refresh_gen_tcw(rdg_ctx* c, cudaStream_t st) {
+    static const int cin[3] = {256, 256, 128}, cout[3] = {256, 128, 64};
+    TRY(rdg_refold32(c, st));
+    ConvGeom dg = rdg_gen_dense_geom(c, 1);
+    for (int l = 0; l < 3; ++l)
+        if (!c->g_wfoldT[l]) RDG_CUDA(cudaMalloc(&c->g_wfoldT[l], folded_weight_elems(cin[l], cout[l]) * sizeof(float)));
+    if (!c->g_denseT) RDG_CUDA(cudaMalloc(&c->g_denseT, (size_t)dg.Ci * dg.Co * 4));
+    if (!c->g_w4p) RDG_CUDA(cudaMalloc(&c->g_w4p, 2 * 2048 * 4));
+    if (!c->g_tcw_stale) return 0;
+    for (int l = 0; l < 3; ++l) TRY(tcg_transpose_blocks(c->g_wfold32[l], c->g_wfoldT[l], 64, cin[l], cout[l], st));
+    TRY(tcg_transpose_blocks(c->g_params + c->g_off[0], c->g_denseT, 1, dg.Ci, dg.Co, st));
+    TRY(ew_pad_w4(c->g_params + c->g_off[8], c->g_w4p, st));
+    c->g_tcw_stale = false;
+    return 0;
+}
+
+bool tc_layer_ok(const ConvGeom& g) { return (g.Ci & 31) == 0 && (g.Co & 31) == 0; }
+
+// critic conv layer l (0..3) forward on the tensor cores; precise = 3xTF32 (real forward passes), 0 for the linear second-order pass
+int critic_conv_fwd_tc(rdg_ctx* c, int l, const float* x, const float* bias, float* y, const ConvGeom& g, int act, const float* mask,
+                       cudaStream_t st, float* pre, int precise) {
+    if (l == 0 && g.Ci <= 4) return tcg_conv_fwd_smallci(x, c->c_w1p, bias, y, g, act, mask, 1.f / 0.75f, st, pre, precise);
+    if (l && tc_layer_ok(g)) return tcg_conv_fwd(x, c->c_wT + c->c_off[2 * l], bias, y, g, act, mask, 1.f / 0.75f, st, pre, precise);
+    return simt_conv_fwd(x, c->c_params + c->c_off[2 * l], bias, y, g, act, mask, 1.f / 0.75f, st, pre);
+}
+
+// masks3: per layer ONE buffer of 3B samples [fake | real | interpolated] (or all null)
+int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const float* latent, const float* alpha, const float* const* masks3,
+                   int B, int gen_mode, float* losses4, cudaStream_t st) {
+    const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
+    size_t max_act = 0, sum_act = 0;
+    for (int l = 0; l < 5; ++l) { max_act = std::max(max_act, critic_act_elems(c, l)); sum_act += critic_act_elems(c, l); }
+    const size_t need = ((size_t)B * (3 * (3 * sum_act + 64) + 6 * max_act + 3 * px) + 8192) * 4 + 128 * 256;
+    TRY(ensure_train_ws(c, need));
+    Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
+    CriticActs A3;
+    TRY(critic_alloc(c, ws, 3 * B, A3));
+    float* hat_h[5]; float* hat_a[5];
+    for (int l = 0; l < 5; ++l) {
+        const size_t e = (size_t)B * critic_act_elems(c, l);
+        hat_h[l] = A3.h[l] + 2 * e;
+        hat_a[l] = l ? A3.a[l] + 2 * e : nullptr;
+    }
+    float* fake_img = ws.f((size_t)B * px);
+    float* xhat = ws.f((size_t)B * px);
+    float* dh = ws.f((size_t)3 * B * max_act);
+    float* da[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int l = 1; l <= 4; ++l) da[l] = ws.f((size_t)3 * B * critic_act_elems(c, l));
+    float* g0 = ws.f((size_t)B * critic_act_elems(c, 0));
+    float* vbuf = ws.f((size_t)B * max_act);
+    float* dscore3 = ws.f(3 * B); float* norm = ws.f(B); float* lsc = ws.f(8);
+    if (!lsc || !vbuf || !da[4]) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
+    TRY(refresh_critic_wT(c, st));
+    const float ms = 1.f / 0.75f;
+
+    // frozen generator forward (:370, generator.trainable = False :363)
+    TRY(rdg_generator_forward(c, latent, cond, 1, fake_img, B, gen_mode, RDG_OUT_FRACTION, 1.f, nullptr, st));
+    RDG_CUDA(cudaMemsetAsync(c->c_grads, 0, c->c_total * 4, st));
+    TRY(ew_interp(x_real, fake_img, alpha, xhat, B, (long long)px, st));                    // RandomWeightedAverage :221-224
+    TRY(ew_critic_input(fake_img, cond, A3.h[0], B, c->nd, c->ncond, st));
+    TRY(ew_critic_input(x_real, cond, A3.h[0] + (size_t)B * critic_act_elems(c, 0), B, c->nd, c->ncond, st));
+    TRY(ew_critic_input(xhat, cond, hat_h[0], B, c->nd, c->ncond, st));
+    // critic forward on [fake | real | interpolated] (:372, :373, :379)
+    for (int l = 0; l < 4; ++l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l, 3 * B);
+        TRY(critic_conv_fwd_tc(c, l, A3.h[l], c->c_params + c->c_off[2 * l + 1], A3.h[l + 1], g, ACT_LRELU, masks3 ? masks3[l] : nullptr, st,
+                               A3.a[l + 1], 1));
+    }
+    TRY(simt_conv_fwd(A3.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A3.score, rdg_critic_dense_geom(c, 3 * B), ACT_NONE,
+                      nullptr, 1.f, st));
+    TRY(ew_mean_scaled(A3.score + B, B, -1.f, lsc + 0, st));      // l_valid = mean(-D(real))  (:215-216, targets :452-454)
+    TRY(ew_mean_scaled(A3.score, B, 1.f, lsc + 1, st));           // l_fake  = mean(+D(fake))
+
+    // one backward-data chain for the three thirds: cotangents of the scores [+1/B | -1/B | 1]
+    SideStream ss{c, st, 0};
+    TRY(ss.init());
+    TRY(ew_fill3(dscore3, B, 1.f / (float)B, -1.f / (float)B, 1.f, st));
+    TRY(ss.fork());
+    TRY(simt_conv_bwd_filter(A3.h[4], dscore3, c->c_grads + c->c_off[8], c->c_grads + c->c_off[9], rdg_critic_dense_geom(c, 2 * B), ss.aux()));
+    TRY(simt_conv_bwd_data(dscore3, c->c_params + c->c_off[8], dh, rdg_critic_dense_geom(c, 3 * B), st));
+    for (int l = 4; l >= 1; --l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l - 1, 3 * B);
+        TRY(ew_lrelu_bwd(A3.a[l], dh, da[l], (long long)3 * B * critic_act_elems(c, l), masks3 ? masks3[l - 1] : nullptr, ms, st));
+        TRY(ss.fork());       // bias gradients of the Wasserstein terms: the first 2B samples
+        TRY(simt_colsum(da[l], c->c_grads + c->c_off[2 * (l - 1) + 1], (long long)2 * B * (critic_act_elems(c, l) / g.Co), g.Co, ss.aux()));
+        if (l > 1) {
+            if (tc_layer_ok(g)) TRY(tcg_conv_bwd_data(da[l], c->c_params + c->c_off[2 * (l - 1)], dh, g, st));
+            else TRY(simt_conv_bwd_data(da[l], c->c_params + c->c_off[2 * (l - 1)], dh, g, st));
+        } else {              // only the penalty needs the gradient w.r.t. the critic input: interpolated third
+            ConvGeom g1 = rdg_critic_conv_geom(c, 0, B);
+            TRY(simt_conv_bwd_data(da[1] + (size_t)2 * B * critic_act_elems(c, 1), c->c_params + c->c_off[0], g0, g1, st));
+        }
+    }
+    // gradient penalty (:230-244): norm of the input gradient, 'mse' against zeros, cotangent of 10 * mean((n-1)^2)
+    const int C0 = 1 + c->ncond;
+    TRY(ew_gp_norm(g0, C0, B, (long long)px, norm, st));
+    TRY(ew_gp_loss(norm, B, lsc + 2, st));
+    TRY(ew_gp_cotangent(g0, norm, 10.f * 2.f / (float)B, hat_h[0], C0, B, (long long)px, st));     // u_0 replaces h_0 of the third
+    // second-order pass (LeakyReLU'' = 0): u_l = S_l (.) conv_l(u_{l-1}); filter gradients of BOTH loss parts in one contraction
+    for (int l = 1; l <= 4; ++l) {
+        ConvGeom g3 = rdg_critic_conv_geom(c, l - 1, 3 * B);
+        ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
+        TRY(ss.fork());
+        if (l > 1 && tc_layer_ok(g3)) TRY(tcg_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], g3, ss.aux()));
+        else if (l == 1 && g3.Ci <= 4) TRY(tcg_conv_bwd_filter_smallci(A3.h[0], da[1], c->c_grads + c->c_off[0], g3, ss.aux()));
+        else TRY(simt_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], nullptr, g3, ss.aux()));
+        TRY(critic_conv_fwd_tc(c, l - 1, hat_h[l - 1], nullptr, vbuf, g, ACT_NONE, nullptr, st, nullptr, 0));
+        TRY(ew_lrelu_bwd(hat_a[l], vbuf, hat_h[l], (long long)B * critic_act_elems(c, l),
+                         masks3 ? masks3[l - 1] + (size_t)2 * B * critic_act_elems(c, l) : nullptr, ms, st));
+    }
+    TRY(simt_colsum(hat_h[4], c->c_grads + c->c_off[8], B, (int)critic_act_elems(c, 4), st));      // d/dW5 of the penalty
+    TRY(ss.join());
+    TRY(ew_combine_losses(lsc + 0, lsc + 1, lsc + 2, 10.f, losses4, st));
+    return 0;
+}
+
+int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const float* const* masks, int B, float* loss_dev, cudaStream_t st) {
+    const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
+    size_t cmax = 0, csum = 0, gsum = 0, gmax = 0;
+    for (int l = 0; l < 5; ++l) { cmax = std::max(cmax, critic_act_elems(c, l)); csum += critic_act_elems(c, l); }
+    for (int l = 0; l < 4; ++l) { gsum += gen_act(c, l); gmax = std::max(gmax, gen_act(c, l)); }
+    ConvGeom dg1 = rdg_gen_dense_geom(c, 1);
+    const size_t need = ((size_t)B * (2 * csum + 3 * cmax + 2 * gsum + dg1.Ci + dg1.Co + 4 * px + 2 * gmax + 32 * px + 64) +
+                         folded_weight_elems(256, 256) + 8192) * 4 + 64 * 256;
+    TRY(ensure_train_ws(c, need));
+    Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
+    GenActs G; CriticActs A;
+    TRY(gen_alloc(c, ws, B, G)); TRY(critic_alloc(c, ws, B, A));
+    float* t0 = ws.f((size_t)B * cmax); float* t1 = ws.f((size_t)B * cmax);
+    float* dx0 = ws.f((size_t)B * cmax);
+    float* dimg = ws.f((size_t)B * px); float* dlog = ws.f((size_t)B * px);
+    float* dy = ws.f((size_t)B * gmax); float* dc = ws.f((size_t)B * gmax);
+    float* ptap = ws.f((size_t)B * px * 32);          // per-tap products P (forward), gathered cotangents Gd (backward)
+    float* dwf = ws.f(folded_weight_elems(256, 256));
+    float* dw4 = ws.f(2048);
+    float* dscore = ws.f(B);
+    if (!dscore || !dwf || !ptap) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
+    TRY(refresh_gen_tcw(c, st));
+    TRY(refresh_critic_wT(c, st));
+    const float ms = 1.f / 0.75f;
+
+    // ---- generator forward keeping what the backward needs (:319-350)
+    ConvGeom dg = rdg_gen_dense_geom(c, B);
+    TRY(ew_assemble_gen_input(latent, cond, 1, 0, G.x0, B, c->nd * c->nd * c->ncond, st));
+    TRY(tcg_conv_fwd(G.x0, c->g_denseT, c->g_params + c->g_off[1], G.y[0], dg, ACT_LRELU, nullptr, 1.f, st, G.d0_pre, 1));
+    for (int l = 0; l < 3; ++l) {
+        ConvGeom g = rdg_gen_conv_geom(c, l, B);
+        TRY(tcg_folded_fwd(G.y[l], c->g_wfoldT[l], c->g_params + c->g_off[3 + 2 * l], G.cpre[l + 1], g, st, 1));
+        TRY(ew_pixelnorm(G.cpre[l + 1], G.y[l + 1], (long long)B * g.To * g.Ho * g.Wo, g.Co, 1, st));
+    }
+    ConvGeom gp{};       // the output conv's tap products as a 1x1x1 "conv" 64 -> 32 over the 24 x nd x nd grid
+    gp.B = B; gp.Ti = gp.To = RDG_NHOURS; gp.Hi = gp.Ho = c->nd; gp.Wi = gp.Wo = c->nd; gp.Ci = 64; gp.Co = 32;
+    gp.KT = gp.KH = gp.KW = 1; gp.stride = 1;
+    TRY(tcg_conv_fwd(G.y[3], c->g_w4p, nullptr, ptap, gp, ACT_NONE, nullptr, 1.f, st, nullptr, 1));
+    TRY(ew_tap_gather_logits(ptap, c->g_params + c->g_off[9], G.logits, B, c->nd, st));
+    TRY(ew_softmax_hours(G.logits, G.img, B, c->nd * c->nd, nullptr, 1, 1, 1.f, 0, nullptr, st));
+
+    // ---- critic on the generated sample (critic frozen :395, dropout active) and its backward to the image
+    TRY(ew_critic_input(G.img, cond, A.h[0], B, c->nd, c->ncond, st));
+    for (int l = 0; l < 4; ++l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l, B);
+        TRY(critic_conv_fwd_tc(c, l, A.h[l], c->c_params + c->c_off[2 * l + 1], A.h[l + 1], g, ACT_LRELU, masks ? masks[l] : nullptr, st, A.a[l + 1], 1));
+    }
+    TRY(simt_conv_fwd(A.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A.score, rdg_critic_dense_geom(c, B), ACT_NONE, nullptr, 1.f, st));
+    TRY(ew_mean_scaled(A.score, B, -1.f, loss_dev, st));                   // wasserstein_loss with target -1 (:408, :452)
+    TRY(ew_fill(dscore, B, -1.f / (float)B, st));
+    TRY(simt_conv_bwd_data(dscore, c->c_params + c->c_off[8], t0, rdg_critic_dense_geom(c, B), st));
+    for (int l = 4; l >= 1; --l) {
+        ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
+        TRY(ew_lrelu_bwd(A.a[l], t0, t1, (long long)B * critic_act_elems(c, l), masks ? masks[l - 1] : nullptr, ms, st));
+        if (l > 1 && tc_layer_ok(g)) TRY(tcg_conv_bwd_data(t1, c->c_params + c->c_off[2 * (l - 1)], t0, g, st));
+        else TRY(simt_conv_bwd_data(t1, c->c_params + c->c_off[2 * (l - 1)], l > 1 ? t0 : dx0, g, st));
+    }
+    TRY(ew_extract_channel0(dx0, dimg, (long long)B * px, 1 + c->ncond, st));
+    RDG_CUDA(cudaMemsetAsync(c->g_grads, 0, c->g_total * 4, st));
+    TRY(ew_softmax_hours_bwd(G.img, dimg, dlog, B, c->nd * c->nd, st));
+
+    // ---- generator backward
+    SideStream ss{c, st, 0};
+    TRY(ss.init());
+    {   // output conv: Gd[pos][tap] = dlogits[pos - offset(tap)]; dy3 = Gd . w4, dw4 = Gd^T . y3, db4 = sum dlogits
+        TRY(ew_tap_scatter_dlogits(dlog, ptap, B, c->nd, st));
+        ConvGeom gb = gp; gb.Ci = 32; gb.Co = 64;
+        TRY(ss.fork());
+        RDG_CUDA(cudaMemsetAsync(dw4, 0, 2048 * 4, ss.aux()));
+        TRY(tcg_conv_bwd_filter(ptap, G.y[3], dw4, gb, ss.aux()));
+        RDG_CUDA(cudaMemcpyAsync(c->g_grads + c->g_off[8], dw4, 27 * 64 * 4, cudaMemcpyDeviceToDevice, ss.aux()));
+        TRY(simt_colsum(dlog, c->g_grads + c->g_off[9], (long long)B * px, 1, ss.aux()));
+        TRY(tcg_conv_fwd(ptap, c->g_w4p + 2048, nullptr, dy, gb, ACT_NONE, nullptr, 1.f, st));
+    }
+    for (int l = 2; l >= 0; --l) {   // upsample + conv + pixelnorm + lrelu blocks
+        ConvGeom g = rdg_gen_conv_geom(c, l, B);
+        const long long rows = (long long)B * g.To * g.Ho * g.Wo;
+        TRY(ss.join());                               // the previous block's filter gradient still reads dc
+        TRY(ew_pixelnorm_lrelu_bwd(G.cpre[l + 1], dy, dc, rows, g.Co, st));
+        TRY(ss.fork());
+        RDG_CUDA(cudaMemsetAsync(dwf, 0, folded_weight_elems(g.Ci, g.Co) * 4, ss.aux()));
+        TRY(tcg_folded_bwd_filter(G.y[l], dc, dwf, g, ss.aux()));
+        TRY(folded_unfold_grad(dwf, c->g_grads + c->g_off[2 + 2 * l], g.Ci, g.Co, ss.aux()));
+        TRY(simt_colsum(dc, c->g_grads + c->g_off[3 + 2 * l], rows, g.Co, ss.aux()));
+        TRY(tcg_folded_bwd_data(dc, c->g_wfold32[l], dy, g, st));
+    }
+    TRY(ss.join());
+    {   // dense + lrelu
+        TRY(ew_lrelu_bwd(G.d0_pre, dy, dc, (long long)B * dg.Co, nullptr, 1.f, st));
+        TRY(simt_conv_bwd_filter(G.x0, dc, c->g_grads + c->g_off[0], c->g_grads + c->g_off[1], dg, st));
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- entry points
+namespace {
+
+size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
+
+int ensure_rnd(rdg_ctx* c, size_t floats) {
+    if (c->rnd_cap >= floats) return 0;
+    if (c->rnd_buf) { RDG_CUDA(cudaDeviceSynchronize()); RDG_CUDA(cudaFree(c->rnd_buf)); c->rnd_buf = nullptr; c->rnd_cap = 0; }
+    RDG_CUDA(cudaMalloc(&c->rnd_buf, floats * 4));
+    c->rnd_cap = floats;
+    return 0;
+}
+int ensure_tstate(rdg_ctx* c) {
+    if (c->tstate) return 0;
+    RDG_CUDA(cudaMalloc(&c->tstate, sizeof(RdgTrainState)));
+    RDG_CUDA(cudaMemset(c->tstate, 0, sizeof(RdgTrainState)));
+    return 0;
+}
+// layout of the per-step random inputs in rnd_buf: latent [B,100] | alpha [B] | masks of the 4 critic layers, `reps` samples sets each
+struct RndLayout { size_t latent, alpha, mask[4], total; };
+RndLayout rnd_layout(const rdg_ctx* c, int B, int reps) {
+    RndLayout L{};
+    size_t o = 0;
+    L.latent = o; o += pad4((size_t)B * RDG_LATENT);
+    L.alpha = o; o += pad4(B);
+    for (int l = 0; l < 4; ++l) { L.mask[l] = o; o += pad4((size_t)reps * B * critic_act_elems(c, l + 1)); }
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+namespace {
+int critic_step_tc_masks(rdg_ctx* c, const float* x_real, const float* cond, const float* latent, const float* alpha,
+                         const float* const* mf, const float* const* mr, const float* const* mh, int B, int gen_mode, float* losses4,
+                         cudaStream_t st) {
+    const bool use = mf && mr && mh;
+    if (!use && (mf || mr || mh)) { rdg_set_error("rdg_critic_step_grads: give all three mask sets or none"); return RDG_E_BADARG; }
+    const float* masks3[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (use) {
+        const RndLayout L = rnd_layout(c, B, 3);
+        TRY(ensure_rnd(c, L.total));
+        for (int l = 0; l < 4; ++l) {
+            const size_t e = (size_t)B * critic_act_elems(c, l + 1);
+            float* d = c->rnd_buf + L.mask[l];
+            RDG_CUDA(cudaMemcpyAsync(d, mf[l], e * 4, cudaMemcpyDeviceToDevice, st));
+            RDG_CUDA(cudaMemcpyAsync(d + e, mr[l], e * 4, cudaMemcpyDeviceToDevice, st));
+            RDG_CUDA(cudaMemcpyAsync(d + 2 * e, mh[l], e * 4, cudaMemcpyDeviceToDevice, st));
+            masks3[l] = d;
+        }
+    }
+    return critic_step_tc(c, x_real, cond, latent, alpha, use ? masks3 : nullptr, B, gen_mode, losses4, st);
+}
+}  // namespace
+
+extern "C" int rdg_set_train_mode(rdg_ctx* c, int mode) {
+    if (!c || (mode != 0 && mode != 1)) return RDG_E_BADARG;
+    c->train_mode = mode;
+    return 0;
+}
+
+// The two step evaluations with latent noise, interpolation weights and dropout masks drawn ON THE DEVICE from the context's
+// Philox state (key = seed, counter = (element, stream, step counter in device memory)): no host work between the calls, so a
+// whole 5 + 1 iteration can be captured in one CUDA graph and replayed (the step counter advances inside the graph).
+extern "C" int rdg_critic_step_dev(rdg_ctx* c, const float* x_real_dev, const float* cond_dev, int B, int gen_mode,
+                                   unsigned long long seed, int dropout, float* losses4_dev, void* stream) {
+    if (!c || B < 1 || !x_real_dev || !cond_dev || !losses4_dev) { rdg_set_error("rdg_critic_step_dev: bad arguments"); return RDG_E_BADARG; }
+    if (!c->gen_ready || !c->critic_ready) { rdg_set_error("weights not set"); return RDG_E_NOWEIGHT; }
+    if (c->train_mode != 1) { rdg_set_error("rdg_critic_step_dev needs the tensor-core training mode (rdg_set_train_mode(ctx, 1))"); return RDG_E_BADARG; }
+    RDG_CUDA(cudaSetDevice(c->device));
+    TRY(ensure_train_state(c)); TRY(ensure_tstate(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const RndLayout L = rnd_layout(c, B, 3);
+    TRY(ensure_rnd(c, L.total));
+    TRY(ew_train_tick(c->tstate, st));
+    TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 0, 0.f, st));   // np.random.normal :470
+    TRY(ew_fill_random_dev(c->rnd_buf + L.alpha, B, seed, c->tstate, 2, 1, 0.f, st));                              // tf.random.uniform :223
+    const float* masks3[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (dropout) {        // Dropout(0.25) of the three critic invocations (:289-301): one draw over the four 3B mask tensors
+        TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 3, 2, 0.75f, st));
+        for (int l = 0; l < 4; ++l) masks3[l] = c->rnd_buf + L.mask[l];
+    }
+    return critic_step_tc(c, x_real_dev, cond_dev, c->rnd_buf + L.latent, c->rnd_buf + L.alpha, dropout ? masks3 : nullptr, B, gen_mode,
+                          losses4_dev, st);
+}
+
+extern "C" int rdg_generator_step_dev(rdg_ctx* c, const float* cond_dev, int B, unsigned long long seed, int dropout, float* loss_dev,
+                                      void* stream) {
+    if (!c || B < 1 || !cond_dev || !loss_dev) { rdg_set_error("rdg_generator_step_dev: bad arguments"); return RDG_E_BADARG; }
+    if (!c->gen_ready || !c->critic_ready) { rdg_set_error("weights not set"); return RDG_E_NOWEIGHT; }
+    if (c->train_mode != 1) { rdg_set_error("rdg_generator_step_dev needs the tensor-core training mode (rdg_set_train_mode(ctx, 1))"); return RDG_E_BADARG; }
+    RDG_CUDA(cudaSetDevice(c->device));
+    TRY(ensure_train_state(c)); TRY(ensure_tstate(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const RndLayout L = rnd_layout(c, B, 1);
+    TRY(ensure_rnd(c, rnd_layout(c, B, 3).total));      // same buffer as the critic step: size it once
+    TRY(ew_train_tick(c->tstate, st));
+    TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 0, 0.f, st));   // generate_latent_points :177-193
+    const float* masks[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (dropout) {
+        TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 3, 2, 0.75f, st));
+        for (int l = 0; l < 4; ++l) masks[l] = c->rnd_buf + L.mask[l];
+    }
+    return generator_step_tc(c, c->rnd_buf + L.latent, cond_dev, dropout ? masks : nullptr, B, loss_dev, st);
+}
+
+// Keras-Adam with the shared step counter in device memory (incremented by the call), followed by the refresh of every derived
+// weight image the next step reads (transposed / folded / 16-bit packed), so the context is consistent at step boundaries and the
+// call sequence of an iteration does not depend on host-side staleness flags (graph capture).
+extern "C" int rdg_adam_apply_dev(rdg_ctx* c, int which, float lr, float beta1, float beta2, float eps, float grad_scale, int gen_mode,
+                                  void* stream) {
+    if (!c || which < 0 || which > 1) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
+    TRY(ensure_train_state(c)); TRY(ensure_tstate(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* p = which == 0 ? c->g_params : c->c_params;
+    float* g = which == 0 ? c->g_grads : c->c_grads;
+    float* m = which == 0 ? c->g_m : c->c_m;
+    float* v = which == 0 ? c->g_v : c->c_v;
+    const size_t n = which == 0 ? c->g_total : c->c_total;
+    TRY(ew_adam_dev(p, g, m, v, (long long)n, c->tstate, lr, beta1, beta2, eps, grad_scale, st));
+    if (which == 0) {
+        c->gen_stale_kinds = 3; c->fold32_stale = true; c->g_tcw_stale = true;
+        if (gen_mode != RDG_MODE_FP32) TRY(rdg_repack_generator(c, st, rdg_kind_bit(gen_mode)));
+        if (c->train_mode == 1) TRY(refresh_gen_tcw(c, st));
+    } else {
+        c->critic_packed_stale = true; c->c_wT_stale = true;
+        if (c->train_mode == 1) TRY(refresh_critic_wT(c, st));
+    }
+    return 0;
+}
+
+// host <-> device copy of the training counters (checkpoints; keeping `optimizer.iterations` in step with replayed graphs)
+extern "C" int rdg_train_state(rdg_ctx* c, int set, long long* adam_t, unsigned long long* rng_ctr) {
+    if (!c || !adam_t || !rng_ctr) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
+    TRY(ensure_tstate(c));
+    RdgTrainState s{};
+    RDG_CUDA(cudaDeviceSynchronize());
+    RDG_CUDA(cudaMemcpy(&s, c->tstate, sizeof(s), cudaMemcpyDeviceToHost));
+    if (set) {
+        s.adam_t = *adam_t; s.rng_ctr = *rng_ctr;
+        RDG_CUDA(cudaMemcpy(c->tstate, &s, sizeof(s), cudaMemcpyHostToDevice));
+    } else { *adam_t = s.adam_t; *rng_ctr = s.rng_ctr; }
     return 0;
 }

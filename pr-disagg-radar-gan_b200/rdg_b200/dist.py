@@ -28,6 +28,14 @@ def allreduce_sum_(flat, group=None):
     return flat
 
 
+def broadcast_(t, src=0, group=None):
+    """In-place broadcast of a tensor from rank `src` (replica initialisation of data-parallel training)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(t, src=src, group=group)
+    return t
+
+
 def bind_to_gpu_numa_node(device_index: int):
     """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (Linux; best effort, returns the node or None).
     The host-buffer paths move 24 KB per scenario over PCIe into pinned host memory; with one process per GPU on a two-socket

@@ -282,16 +282,67 @@ class GanTrainer:
 
     WHICH_GEN, WHICH_CRITIC = 0, 1
 
-    def __init__(self, generator, critic, optimizer=None, gen_mode="fp32", seed=0, process_group=None):
+    def __init__(self, generator, critic, optimizer=None, gen_mode="fp32", seed=0, process_group=None, train_mode=None,
+                 dropout=True):
+        """train_mode "fp32": FP32 SIMT gradients (<= 2e-5 parity mode); "tf32": every wide contraction on tcgen05 kind::tf32
+        (default: env RDG_TRAIN_MODE or "fp32").  Under torch.distributed the replicas are made identical here (weights and
+        Adam moments broadcast from rank 0) and every rank gets its own random stream (seed + rank) for noise / alpha / masks."""
         assert generator.ctx is critic.ctx, "generator and critic must share one Context"
         self.ctx, self.generator, self.critic = generator.ctx, generator, critic
         self.optimizer = optimizer or Adam()
         self.gen_mode = gen_mode
         self.pg = process_group
+        self.train_mode = train_mode or os.environ.get("RDG_TRAIN_MODE", "fp32")
+        if self.train_mode not in ("fp32", "tf32"):
+            raise ValueError("train_mode must be 'fp32' or 'tf32'")
+        self.dropout = bool(dropout)
+        self.rank = self._rank()
+        self.seed = int(seed)
         self._gen = torch.Generator(device=f"cuda:{self.ctx.device}")
-        self._gen.manual_seed(seed)
+        self._gen.manual_seed(self.seed + self.rank)
+        self.profile_comm = False
+        self._comm_events = []
         self.last_comm_ms = 0.0
         self._bufs = {}
+        self._graph = None
+        self._set_mode()
+        self._push_counters(self.optimizer.iterations, 0)
+        if self._world() > 1:
+            self.sync_replicas()
+
+    def _set_mode(self):
+        _lib.check(self.ctx.lib.rdg_set_train_mode(self.ctx.handle, 1 if self.train_mode == "tf32" else 0))
+
+    def _rank(self):
+        import torch.distributed as dist
+        return dist.get_rank(self.pg) if dist.is_available() and dist.is_initialized() else 0
+
+    def _push_counters(self, adam_t, rng_ctr):
+        a, r = C.c_longlong(int(adam_t)), C.c_ulonglong(int(rng_ctr))
+        _lib.check(self.ctx.lib.rdg_train_state(self.ctx.handle, 1, C.byref(a), C.byref(r)))
+
+    def _pull_counters(self):
+        a, r = C.c_longlong(0), C.c_ulonglong(0)
+        _lib.check(self.ctx.lib.rdg_train_state(self.ctx.handle, 0, C.byref(a), C.byref(r)))
+        return int(a.value), int(r.value)
+
+    def sync_replicas(self, src=0):
+        """Make every rank's weights and optimizer state those of `src` (data-parallel replicas must start identical: the
+        gradient exchange only keeps them identical).  Derived weight images are rebuilt by the set_weights calls."""
+        from .dist import broadcast_
+        torch.cuda.synchronize(self.ctx.device)
+        for which, net in ((0, self.generator), (1, self.critic)):
+            broadcast_(self.param_tensor(which), src, self.pg)
+            m, v = self._adam_tensors(which)
+            broadcast_(m, src, self.pg)
+            broadcast_(v, src, self.pg)
+        it = torch.tensor([self.optimizer.iterations], device=f"cuda:{self.ctx.device}", dtype=torch.int64)
+        broadcast_(it, src, self.pg)
+        torch.cuda.synchronize(self.ctx.device)
+        self.optimizer.iterations = int(it.item())
+        self.generator.set_weights(self.generator.get_weights())     # re-derive the packed / folded images from the new master
+        self.critic.set_weights(self.critic.get_weights())
+        self._push_counters(self.optimizer.iterations, self._pull_counters()[1])
 
     # -- helpers
     def _world(self):
@@ -326,7 +377,9 @@ class GanTrainer:
     # (`start_epoch` just labels plots, :526-529); this adds the optimizer state so training continues bit-identically.
     def state_dict(self):
         torch.cuda.synchronize(self.ctx.device)
-        sd = {"iterations": np.int64(self.optimizer.iterations),
+        adam_t, rng_ctr = self._pull_counters()
+        assert adam_t == self.optimizer.iterations, "host / device Adam step counters diverged"
+        sd = {"iterations": np.int64(self.optimizer.iterations), "rng_ctr": np.uint64(rng_ctr),
               "adam": np.array([self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon], np.float64),
               "rng_state": self._gen.get_state().cpu().numpy()}
         for which, name, net in ((0, "gen", self.generator), (1, "critic", self.critic)):
@@ -346,6 +399,7 @@ class GanTrainer:
         self.optimizer.iterations = int(sd["iterations"])
         self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon = (float(x) for x in sd["adam"])
         self._gen.set_state(torch.as_tensor(np.asarray(sd["rng_state"], np.uint8)))
+        self._push_counters(self.optimizer.iterations, int(sd.get("rng_ctr", 0)))
         torch.cuda.synchronize(self.ctx.device)
 
     def save_checkpoint(self, path):
@@ -374,19 +428,79 @@ class GanTrainer:
         return (C.c_void_p * 4)(*[C.c_void_p(m.data_ptr()) for m in masks])
 
     def _apply(self, which):
+        """Gradient exchange (SUM over ranks, 1/world folded into Adam) + Keras-Adam update with the shared step counter, which
+        lives in device memory (rdg_adam_apply_dev) so that the same call sequence can be captured in a CUDA graph."""
         from .dist import allreduce_sum_
         world = self._world()
         if world > 1:
             g = self.grad_tensor(which)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            if self.profile_comm:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             allreduce_sum_(g, self.pg)           # 1/world is folded into the fused Adam kernel (grad_scale)
-            e1.record()
-            self._comm_events = getattr(self, "_comm_events", []) + [(e0, e1)]
+            if self.profile_comm:
+                e1.record()
+                self._comm_events.append((e0, e1))
         opt = self.optimizer
         opt.iterations += 1
-        _lib.check(self.ctx.lib.rdg_adam_apply(self.ctx.handle, which, opt.lr, opt.beta_1, opt.beta_2, opt.epsilon,
-                                               opt.iterations, 1.0 / world, self.ctx._stream()))
+        _lib.check(self.ctx.lib.rdg_adam_apply_dev(self.ctx.handle, which, opt.lr, opt.beta_1, opt.beta_2, opt.epsilon,
+                                                   1.0 / world, _lib.MODES[self.gen_mode], self.ctx._stream()))
+
+    # -- device-resident steps (tensor-core mode): noise / alpha / dropout masks drawn on the GPU, nothing read back
+    def critic_step_device(self, x_real, cond, losses_out):
+        """One critic step (gradients + exchange + update) on device tensors; losses_out: cuda float32 [4]."""
+        ctx = self.ctx
+        self._set_mode()
+        _lib.check(ctx.lib.rdg_critic_step_dev(ctx.handle, C.c_void_p(x_real.data_ptr()), C.c_void_p(cond.data_ptr()),
+                                               int(x_real.shape[0]), _lib.MODES[self.gen_mode], self.seed + self.rank,
+                                               int(self.dropout), C.c_void_p(losses_out.data_ptr()), ctx._stream()))
+        self._apply(self.WHICH_CRITIC)
+
+    def generator_step_device(self, cond, loss_out):
+        ctx = self.ctx
+        self._set_mode()
+        _lib.check(ctx.lib.rdg_generator_step_dev(ctx.handle, C.c_void_p(cond.data_ptr()), int(cond.shape[0]),
+                                                  self.seed + self.rank, int(self.dropout), C.c_void_p(loss_out.data_ptr()),
+                                                  ctx._stream()))
+        self._apply(self.WHICH_GEN)
+
+    def capture_iteration(self, batch, n_critic=5):
+        """Capture one training iteration (n_critic critic steps + 1 generator step, reference :468-482, with the gradient
+        exchange and the Adam updates) in a CUDA graph.  Returns an IterationGraph: fill `x_real` [n_critic,B,24,nd,nd,1],
+        `cond` [n_critic,B,nd,nd,ncond] and `cond_gen` [B,nd,nd,ncond] (static device tensors) and call replay();
+        `d_losses` [n_critic,4] and `g_loss` [1] are device tensors read whenever the caller wants (no sync per step)."""
+        if self.train_mode != "tf32":
+            raise RuntimeError("capture_iteration needs train_mode='tf32' (device-resident step inputs)")
+        dev = f"cuda:{self.ctx.device}"
+        nd, nc = self.ctx.nd, self.ctx.ncond
+        ig = IterationGraph()
+        ig.n_critic, ig.trainer = n_critic, self
+        ig.x_real = torch.zeros((n_critic, batch, W.NHOURS, nd, nd, 1), device=dev)
+        ig.cond = torch.zeros((n_critic, batch, nd, nd, nc), device=dev)
+        ig.cond_gen = torch.zeros((batch, nd, nd, nc), device=dev)
+        ig.d_losses = torch.zeros((n_critic, 4), device=dev)
+        ig.g_loss = torch.zeros((1,), device=dev)
+        ig.x_real[:] = 1.0 / W.NHOURS
+
+        def body():
+            for k in range(n_critic):
+                self.critic_step_device(ig.x_real[k], ig.cond[k], ig.d_losses[k])
+            self.generator_step_device(ig.cond_gen, ig.g_loss)
+
+        it0 = self.optimizer.iterations
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(self.ctx.device))
+        with torch.cuda.stream(s):
+            body()                      # eager pass: allocations, attribute calls and weight images happen outside the capture
+        torch.cuda.current_stream(self.ctx.device).wait_stream(s)
+        torch.cuda.synchronize(self.ctx.device)
+        ig.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ig.graph):
+            body()
+        torch.cuda.synchronize(self.ctx.device)
+        # the eager pass was a real iteration; the capture itself launches nothing, only the host mirror moved
+        self.optimizer.iterations = it0 + n_critic + 1
+        return ig
 
     # -- the two train_on_batch calls
     def critic_grads(self, x_real, cond, latent, alpha=None, masks3="draw"):
@@ -402,6 +516,7 @@ class GanTrainer:
         mf, mr, mh = (None, None, None) if masks3 is None else [[ctx.dev(m) for m in ms] for ms in masks3]
         losses = torch.empty(4, device=xr.device, dtype=torch.float32)
         self._keep = (xr, c, z, al, mf, mr, mh)
+        self._set_mode()
         _lib.check(ctx.lib.rdg_critic_step_grads(
             ctx.handle, C.c_void_p(xr.data_ptr()), C.c_void_p(c.data_ptr()), C.c_void_p(z.data_ptr()),
             C.c_void_p(al.data_ptr()), self._maskptrs(mf), self._maskptrs(mr), self._maskptrs(mh), B,
@@ -426,6 +541,7 @@ class GanTrainer:
         m = None if masks is None else [ctx.dev(x) for x in masks]
         loss = torch.empty(1, device=z.device, dtype=torch.float32)
         self._keep = (z, c, m)
+        self._set_mode()
         _lib.check(ctx.lib.rdg_generator_step_grads(ctx.handle, C.c_void_p(z.data_ptr()), C.c_void_p(c.data_ptr()),
                                                     self._maskptrs(m), B, C.c_void_p(loss.data_ptr()), ctx._stream()))
         return loss
@@ -438,9 +554,16 @@ class GanTrainer:
         return float(loss.item())
 
     def comm_ms(self):
-        """Sum of the all-reduce durations recorded so far (device time), then reset."""
-        ev = getattr(self, "_comm_events", [])
+        """Sum of the all-reduce durations recorded while `profile_comm` was set (device time), then reset."""
         torch.cuda.synchronize(self.ctx.device)
-        ms = sum(a.elapsed_time(b) for a, b in ev)
+        ms = sum(a.elapsed_time(b) for a, b in self._comm_events)
         self._comm_events = []
         return ms
+
+
+class IterationGraph:
+    """A captured training iteration (GanTrainer.capture_iteration)."""
+
+    def replay(self):
+        self.graph.replay()
+        self.trainer.optimizer.iterations += self.n_critic + 1

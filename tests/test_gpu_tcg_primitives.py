@@ -30,6 +30,10 @@ CASES = [  # name, B, (Ti,Hi,Wi), Ci, Co, k, stride, pads((before,after) per axi
     ("gen_up3", 3, (12, 8, 8), 128, 64, 3, 1, ((1, 1),) * 3, 1),
     ("gen_up3_b32", 32, (12, 8, 8), 128, 64, 3, 1, ((1, 1),) * 3, 1),
     ("gen_dense", 32, (1, 1, 1), 356, 3072, 1, 1, ((0, 0),) * 3, 0),
+    ("critic1_valid", 4, (24, 16, 16), 2, 64, 3, 2, ((0, 0),) * 3, 0),
+    ("critic1_valid_b96", 96, (24, 16, 16), 2, 64, 3, 2, ((0, 0),) * 3, 0),
+    ("critic1_valid_ncond3", 3, (24, 16, 16), 4, 64, 3, 2, ((0, 0),) * 3, 0),
+    ("critic1_valid_ncond2", 3, (24, 16, 16), 3, 64, 3, 2, ((0, 0),) * 3, 0),
 ]
 
 
@@ -66,6 +70,10 @@ def test_tcg_primitives(ctx16, case):
     _lib.check(lib.rdg_conv3d(10, geom, P(xd), P(wd), P(bd), P(yd), None, 0, None))
     torch.cuda.synchronize()
     assert rel(yd.cpu().numpy(), y_ref) <= TOL
+    yd.fill_(float("nan"))
+    _lib.check(lib.rdg_conv3d(13, geom, P(xd), P(wd), P(bd), P(yd), None, 0, None))      # 3xTF32: FP32-grade forward
+    torch.cuda.synchronize()
+    assert rel(yd.cpu().numpy(), y_ref) <= 2e-5
     if Ci % 32 == 0:
         _lib.check(lib.rdg_conv3d(11, geom, P(dyd), P(wd), None, P(dxd), None, 0, None))
         torch.cuda.synchronize()

@@ -1,8 +1,13 @@
 #!/usr/bin/env python
-"""Training-step timing (BASELINE.json configs #3 / #4): cWGAN-GP iterations/s of the gan_train_cwgangp_pixelnorm.py
-step (5 critic steps + 1 generator step, batch 32 per GPU, :70-78,463-491) on synthetic radar-shaped data resident in
-HBM.  Single GPU: `python tools/bench_train.py`; data-parallel: `python -m torch.distributed.run --nproc-per-node N
---master-addr 127.0.0.1 tools/bench_train.py` (one NCCL all-reduce of the flat FP32 gradient buffer per optimizer step).
+"""Training-step timing (BASELINE.json configs #3 / #4): one cWGAN-GP iteration of gan_train_cwgangp_pixelnorm.py
+(5 critic steps + 1 generator step, batch 32 per GPU, :70-78, :463-491) on synthetic radar-shaped data resident in HBM.
+
+  keras   : critic_model.train_on_batch / generator_model.train_on_batch surface (losses read back every step)
+  device  : rdg_*_step_dev calls issued eagerly (noise / alpha / masks drawn on the GPU, nothing read back)
+  graph   : the same call sequence captured once in a CUDA graph and replayed
+
+Single GPU: `python tools/bench_train.py`; data-parallel: `python -m torch.distributed.run --nproc-per-node N
+--master-addr 127.0.0.1 tools/bench_train.py` (gradient all-reduce per optimizer step, inside the graph).
 Prints one JSON line (rank 0).  Secondary bench: the headline metric stays bench.py's scenarios/s."""
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,11 +18,14 @@ import torch
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--gen-mode", default="fp32", choices=["fp32", "fp16", "bf16"],
+    ap.add_argument("--nd", type=int, default=16)
+    ap.add_argument("--gen-mode", default="fp16", choices=["fp32", "fp16", "bf16"],
                     help="precision of the FROZEN generator forward inside the critic step")
+    ap.add_argument("--paths", default="keras_fp32,keras_tf32,device,graph")
+    ap.add_argument("--profile-steps", action="store_true", help="CUDA-event time of one critic step and one generator step (device path)")
     args = ap.parse_args()
     from rdg_b200 import weights as W
     from rdg_b200.engine import Context, Generator, Critic, GanTrainer
@@ -28,46 +36,76 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    ctx = Context(16, 1, device=local, max_chunk=1024)
-    gen = Generator(W.init_generator_weights(0), ctx=ctx)
-    crit = Critic(W.init_critic_weights(1), ctx=ctx)
-    tr = GanTrainer(gen, crit, gen_mode=args.gen_mode, seed=100 + rank)
+    nd = args.nd
+    ctx = Context(nd, 1, device=local, max_chunk=1024 if nd == 16 else 64)
+    gen = Generator(W.init_generator_weights(0, nd), ctx=ctx, mode=args.gen_mode)
+    crit = Critic(W.init_critic_weights(1, nd), ctx=ctx)
     B = args.batch
     rng = np.random.default_rng(7 + rank)
-    logits = rng.standard_normal((B, 24, 16, 16, 1)).astype(np.float32) * 2
-    e = np.exp(logits - logits.max(axis=1, keepdims=True))
-    x_real = ctx.dev((e / e.sum(axis=1, keepdims=True)).astype(np.float32))
-    cond = ctx.dev((np.clip(rng.gamma(0.8, 12.0, size=(B, 16, 16, 1)), 0, 200) / 127.4).astype(np.float32))
+    logits = rng.standard_normal((5, B, 24, nd, nd, 1)).astype(np.float32) * 2
+    e = np.exp(logits - logits.max(axis=2, keepdims=True))
+    x_real = ctx.dev((e / e.sum(axis=2, keepdims=True)).astype(np.float32))
+    cond = ctx.dev((np.clip(rng.gamma(0.8, 12.0, size=(5, B, nd, nd, 1)), 0, 200) / 127.4).astype(np.float32))
     dev = x_real.device
     g = torch.Generator(device=dev); g.manual_seed(5 + rank)
 
-    def iteration():
-        out = None
-        for _ in range(5):
-            z = torch.randn((B, 100), device=dev, generator=g)
-            out = tr.critic_train_on_batch([x_real, cond, z])
-        z = torch.randn((B, 100), device=dev, generator=g)
-        gl = tr.generator_train_on_batch([z, cond])
-        return out, gl
+    def timed(fn, iters):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist: dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / iters
+        if dist: dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / iters, wall * 1e3], device=dev, dtype=torch.float64)
+        if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item())
 
-    for _ in range(args.warmup):
-        out, gl = iteration()
-    torch.cuda.synchronize()
-    if dist: dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.iters):
-        out, gl = iteration()
-    torch.cuda.synchronize()
-    if dist: dist.barrier()
-    dt = (time.perf_counter() - t0) / args.iters
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {}
+    paths = args.paths.split(",")
+    for name in paths:
+        if name.startswith("keras"):
+            tr = GanTrainer(gen, crit, gen_mode=args.gen_mode, seed=100, train_mode=name.split("_")[1])
+
+            def iteration():
+                for k in range(5):
+                    z = torch.randn((B, 100), device=dev, generator=g)
+                    out = tr.critic_train_on_batch([x_real[k], cond[k], z])
+                z = torch.randn((B, 100), device=dev, generator=g)
+                return out, tr.generator_train_on_batch([z, cond[0]])
+            res[name] = timed(iteration, max(3, args.iters // 4))
+        elif name == "device":
+            tr = GanTrainer(gen, crit, gen_mode=args.gen_mode, seed=100, train_mode="tf32")
+            dl = torch.zeros((5, 4), device=dev); gl = torch.zeros(1, device=dev)
+
+            def iteration():
+                for k in range(5):
+                    tr.critic_step_device(x_real[k], cond[k], dl[k])
+                tr.generator_step_device(cond[0], gl)
+            res[name] = timed(iteration, args.iters)
+            if args.profile_steps:
+                res["critic_step_ms"] = timed(lambda: tr.critic_step_device(x_real[0], cond[0], dl[0]), args.iters * 5)[0]
+                res["generator_step_ms"] = timed(lambda: tr.generator_step_device(cond[0], gl), args.iters * 5)[0]
+            res["losses_last"] = {"critic": dl[-1].cpu().tolist(), "generator": float(gl.item())}
+        elif name == "graph":
+            tr = GanTrainer(gen, crit, gen_mode=args.gen_mode, seed=100, train_mode="tf32")
+            tr.profile_comm = False
+            ig = tr.capture_iteration(B)
+            ig.x_real.copy_(x_real); ig.cond.copy_(cond); ig.cond_gen.copy_(cond[0])
+            res[name] = timed(ig.replay, args.iters)
+            res["graph_losses_last"] = {"critic": ig.d_losses[-1].cpu().tolist(), "generator": float(ig.g_loss.item())}
     if rank == 0:
-        print(json.dumps({"metric": "cWGAN-GP training iterations/s (5 critic + 1 generator step, batch 32 per GPU)",
-                          "value": 1.0 / float(t.item()), "unit": "iterations/s", "n_gpus": world, "ms_per_iteration": 1e3 * float(t.item()),
-                          "samples_per_s": world * B / float(t.item()), "scaling": "weak", "gen_mode": args.gen_mode,
-                          "comm_ms_last_step": tr.comm_ms() if hasattr(tr, "comm_ms") else None,
-                          "losses_last": {"critic": out, "generator": gl}}))
+        best = min(v[0] for k, v in res.items() if isinstance(v, tuple))
+        print(json.dumps({"metric": "cWGAN-GP training iteration (5 critic + 1 generator step, batch %d per GPU, nd %d)" % (B, nd),
+                          "ms_per_iteration": {k: {"device_ms": v[0], "wall_ms": v[1]} for k, v in res.items() if isinstance(v, tuple)},
+                          "best_ms": best, "samples_per_s": world * B / (best * 1e-3), "n_gpus": world, "scaling": "weak",
+                          "gen_mode": args.gen_mode, **{k: v for k, v in res.items() if not isinstance(v, tuple)}}))
     if dist: dist.destroy_process_group()
 
 
