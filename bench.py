@@ -12,8 +12,13 @@ full ensemble, no data-path collective), seeded random-init generator of the ref
            LeakyReLU + fused output-conv tap products), CUDA-event duration on the launch stream inside the
            timed steps, algorithmic FLOPs; `traffic` = DRAM bytes of one launch from the committed
            ncu --set full capture (profiles/r1h_ncu_planes_cg2_summary.md), scaled to the units of a launch
-  cpu_baseline / --impl reference: the oracle (torch-CPU restatement of the Keras graph; TensorFlow
-           is not installed in this image) on a bounded sample of the same workload.
+  cpu_baseline / --impl reference: BASELINE.md section 3: `import tensorflow` + the shipped .h5 if both exist (kind "tf"),
+           else the oracle (torch-CPU restatement of the Keras graph, kind "port") on a bounded sample of the same workload;
+           the cpu_baseline sample is the FIRST 32 conditions x 100 scenarios of the timed workload with the same latent
+           noise, and its output is also the parity check of the timed GPU output (`parity`).
+  train / dp: one cWGAN-GP iteration (5 critic + 1 generator step, batch 32 per GPU) replayed from a CUDA graph in the
+           tensor-core training mode; at N > 1 the N-rank averaged gradients are compared with rank 0 running the gathered batch.
+The JSON line is ordered so that `e2e_stats`, `train` and `dp` come last (the driver keeps the tail of stdout).
 """
 import argparse
 import ctypes as C
@@ -91,8 +96,9 @@ def synth_conditions(n_cond, nd, seed):
     return cond_mm / np.float32(127.4)
 
 
-def cpu_reference_rate(n_cond, spc, threads, reps=1):
-    """Oracle (torch-CPU FP32 restatement of gen.predict + rescale) on n_cond x spc scenarios."""
+def cpu_reference_rate(n_cond, spc, threads, reps=1, latent=None, cond=None, keep=False):
+    """Oracle (torch-CPU FP32 restatement of gen.predict + rescale) on n_cond x spc scenarios.  latent [n_cond*spc,100] / cond
+    [n_cond,16,16,1] given: that sample (the head of the timed GPU workload); keep: also return the mm/h fields."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import torch
@@ -100,19 +106,55 @@ def cpu_reference_rate(n_cond, spc, threads, reps=1):
     from rdg_b200 import weights as W
     torch.set_num_threads(threads)
     gw = W.init_generator_weights(0)
-    cond = synth_conditions(n_cond, 16, 354)
+    if cond is None:
+        cond = synth_conditions(n_cond, 16, 354)
     rng = np.random.default_rng(1)
-    best = None
+    best, fields = None, None
     for _ in range(reps):
+        outs = []
         t0 = time.perf_counter()
         for i in range(n_cond):   # one predict per condition, like generate_and_evaluate_crps.py:177-188
-            z = rng.standard_normal((spc, 100)).astype(np.float32)
+            z = rng.standard_normal((spc, 100)).astype(np.float32) if latent is None else latent[i * spc:(i + 1) * spc]
             cb = np.repeat(cond[i:i + 1], spc, axis=0)
             out = O.generator_forward(gw, z, cb, torch.float32)
-            _ = out[..., 0] * cond[i, :, :, 0] * np.float32(127.4)
+            mm = out[..., 0] * cond[i, :, :, 0] * np.float32(127.4)
+            if keep:
+                outs.append(mm)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
+        fields = outs
+    if keep:
+        return n_cond * spc / best, best, np.concatenate(fields)
     return n_cond * spc / best, best
+
+
+def tf_reference_rate(n_cond, spc):
+    """the reference's own TensorFlow generate_scenarios, if TensorFlow and the shipped
+    trained_models/*.h5 exist on this box (they do not in the build image; the attempt is made at every run)."""
+    try:
+        import tensorflow  # noqa: F401
+    except Exception as e:          # ImportError, or a broken install
+        return None, f"tensorflow not importable ({type(e).__name__})"
+    import glob
+    import numpy as np
+    ref_dirs = [os.path.join(ROOT, "baseline", "_ref"), "/root/reference"]
+    for d in ref_dirs:
+        if glob.glob(os.path.join(d, "trained_models", "gen_*.h5")) and os.path.exists(os.path.join(d, "raindisagg_gan_pretrained.py")):
+            cwd = os.getcwd()
+            try:
+                os.chdir(d)
+                sys.path.insert(0, d)
+                import raindisagg_gan_pretrained as ref
+                cond = synth_conditions(n_cond, 16, 354) * np.float32(127.4)
+                ref.generate_scenarios(cond[0], spc)
+                t0 = time.perf_counter()
+                for i in range(n_cond):
+                    ref.generate_scenarios(cond[i], spc)
+                dt = time.perf_counter() - t0
+                return n_cond * spc / dt, dt
+            finally:
+                os.chdir(cwd)
+    return None, "tensorflow imports but trained_models/gen_*.h5 is not shipped"
 
 
 def workload_config(n_cond, spc):
@@ -129,8 +171,13 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     n_cond = args.ref_conditions
     times = []
+    tf_rate, tf_note = tf_reference_rate(1, SCEN_PER_COND)
+    kind = "tf" if tf_rate is not None else "port"
     for i in range(args.warmup + args.steps):
-        rate, dt = cpu_reference_rate(n_cond, SCEN_PER_COND, threads)
+        if kind == "tf":
+            rate, dt = tf_reference_rate(n_cond, SCEN_PER_COND)
+        else:
+            rate, dt = cpu_reference_rate(n_cond, SCEN_PER_COND, threads)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
@@ -141,8 +188,9 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args.conditions, args.scen_per_cond), sample=sample,
                            note="each step is a bounded sample of the workload; rate = sample scenarios / sample time"),
-            "cpu_baseline": {"value": value, "unit": "scenarios/s", "cores": threads, "kind": "port", "sample": sample,
-                             "note": "torch-CPU FP32 restatement of the Keras generator; TensorFlow is not installed"},
+            "cpu_baseline": {"value": value, "unit": "scenarios/s", "cores": threads, "kind": kind, "sample": sample,
+                             "note": "reference TensorFlow generate_scenarios" if kind == "tf" else
+                                     f"torch-CPU FP32 restatement of the Keras generator ({tf_note})"},
             "e2e": {"value": value, "unit": "scenarios/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -158,7 +206,8 @@ def main():
     ap.add_argument("--scen-per-cond", type=int, default=SCEN_PER_COND)
     ap.add_argument("--chunk", type=int, default=0, help="samples per internal pass (0 = library default)")
     ap.add_argument("--ref-conditions", type=int, default=10, help="conditions per step of the CPU reference arm")
-    ap.add_argument("--cpu-conditions", type=int, default=40, help="conditions of the cpu_baseline sample")
+    ap.add_argument("--cpu-conditions", type=int, default=32, help="conditions of the cpu_baseline / parity sample (x100 scenarios)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the bf16 rate and the large-domain block")
     ap.add_argument("--e2e-group", type=int, default=1000, help="conditions per host-API call in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -246,6 +295,9 @@ def main():
     chk = out[:spc * 4].sum(dim=1)
     want = (cond[:4, :, :, 0] * 127.4).repeat_interleave(spc, dim=0)
     cons = float(((chk - want).abs() / want.clamp_min(1e-6)).max().item())
+    n_par = min(n_cond, args.cpu_conditions)
+    head_out = out[:n_par * spc].cpu().numpy()          # first conditions of the LAST TIMED step, checked against the oracle below
+    head_lat = latent[:n_par * spc].cpu().numpy()
 
     # ---- end-to-end through the host-buffer C-ABI call
     e2e = None
@@ -281,7 +333,7 @@ def main():
         e2e = {"value": world * B / float(t.item()), "unit": "scenarios/s",
                "h2d_bytes_per_step": int(lat_h.numel() * 4 + cond_p.numel() * 4),
                "d2h_bytes_per_step": int(B * 24 * 16 * 16 * 4), "steps": n_e2e,
-               "api": f"rdg_generate_host (pinned host buffers, 3-stream chunk pipeline), {grp_cond} conditions per call"}
+               "api": f"rdg_generate_host, pinned buffers, {grp_cond} conditions per call"}
         # the last group's e2e result equals the device-resident result
         last0 = ((n_cond - 1) // grp_cond) * grp_cond * spc
         assert torch.equal(out_h[:1000], out[last0:last0 + 1000].cpu()), "e2e output differs from device-resident output"
@@ -321,45 +373,96 @@ def main():
         e2e_stats = {"value": world * B / float(t.item()), "unit": "scenarios/s",
                      "h2d_bytes_per_step": int(lat_h.numel() * 4 + cond_p.numel() * 4 + n_cond * 24 * 256 * 4),
                      "d2h_bytes_per_step": int(B * 24 * 4 + n_cond * 24 * 4),
-                     "api": f"rdg_generate_stats_host: generation + on-device area means and ensemble CRPS, {grp_cond} conditions per call"}
+                     "api": "rdg_generate_stats_host (area means + CRPS on device)"}
         del lat_h
 
-    # ---- training iteration (configs #3/#4): 5 critic steps + 1 generator step, batch 32 per GPU, data-parallel over the ranks
-    train = None
+    # ---- training (configs #3/#4): one cWGAN-GP iteration = 5 critic steps + 1 generator step, batch 32 per GPU, data-parallel over
+    # the ranks; tensor-core training mode (tcgen05 kind::tf32), the whole iteration replayed from one CUDA graph
+    train = dp = None
     if not args.no_train:
         from rdg_b200.engine import Critic, GanTrainer
         tctx = Context(16, 1, device=local, max_chunk=1024)
-        tgen = Generator(W.init_generator_weights(0), ctx=tctx)
+        tgen = Generator(W.init_generator_weights(0), ctx=tctx, mode="fp16")
         tcrit = Critic(W.init_critic_weights(1), ctx=tctx)
-        tr = GanTrainer(tgen, tcrit, gen_mode="fp16", seed=100 + rank)
         TB = 32
         rng = np.random.default_rng(7 + rank)
-        lg = rng.standard_normal((TB, 24, 16, 16, 1)).astype(np.float32) * 2
-        ex = np.exp(lg - lg.max(axis=1, keepdims=True))
-        x_real = tctx.dev((ex / ex.sum(axis=1, keepdims=True)).astype(np.float32))
-        tcond = tctx.dev(synth_conditions(TB, 16, 1000 + rank))
+        lg = rng.standard_normal((5, TB, 24, 16, 16, 1)).astype(np.float32) * 2
+        ex = np.exp(lg - lg.max(axis=2, keepdims=True))
+        x_real = tctx.dev((ex / ex.sum(axis=2, keepdims=True)).astype(np.float32))
+        tcond = tctx.dev(synth_conditions(5 * TB, 16, 1000 + rank).reshape(5, TB, 16, 16, 1))
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / n], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        tr = GanTrainer(tgen, tcrit, gen_mode="fp16", seed=100, train_mode="tf32")
+        ig = tr.capture_iteration(TB)
+        ig.x_real.copy_(x_real); ig.cond.copy_(tcond); ig.cond_gen.copy_(tcond[0])
+        ms_graph = timed(ig.replay, 20)
+        losses, gl = ig.d_losses.cpu().numpy(), float(ig.g_loss.item())
+        dl, gls = torch.zeros((5, 4), device=dev), torch.zeros(1, device=dev)
+        ms_crit = timed(lambda: tr.critic_step_device(x_real[0], tcond[0], dl[0]), 20)
+        ms_gen = timed(lambda: tr.generator_step_device(tcond[0], gls), 20)
         tg = torch.Generator(device=dev); tg.manual_seed(5 + rank)
+        tr32 = GanTrainer(tgen, tcrit, gen_mode="fp16", seed=100, train_mode="fp32")
 
-        def iteration():
-            for _ in range(5):
-                losses = tr.critic_train_on_batch([x_real, tcond, torch.randn((TB, 100), device=dev, generator=tg)])
-            return losses, tr.generator_train_on_batch([torch.randn((TB, 100), device=dev, generator=tg), tcond])
-
-        for _ in range(3):
-            iteration()
-        barrier()
-        n_it = 5
-        t0 = time.perf_counter()
-        for _ in range(n_it):
-            losses, gl = iteration()
-        barrier()
-        t = torch.tensor([(time.perf_counter() - t0) / n_it], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        train = {"ms_per_iteration": 1e3 * float(t.item()), "samples_per_s": world * TB / float(t.item()),
-                 "config": "cWGAN-GP, 5 critic steps (3 critic passes + gradient penalty, frozen generator forward on tensor cores) "
-                           "+ 1 generator step, batch 32 per GPU, FP32 SIMT gradients, one flat-gradient all-reduce per optimizer step",
+        def keras_iteration():
+            for k in range(5):
+                tr32.critic_train_on_batch([x_real[k], tcond[k], torch.randn((TB, 100), device=dev, generator=tg)])
+            tr32.generator_train_on_batch([torch.randn((TB, 100), device=dev, generator=tg), tcond[0]])
+        ms_fp32 = timed(keras_iteration, 3)
+        flop_iter = 40.2e9 * TB          # direct-form work of one iteration per sample
+        train = {"ms_per_iteration": ms_graph, "samples_per_s": world * TB / (ms_graph * 1e-3), "critic_step_ms": ms_crit,
+                 "generator_step_ms": ms_gen, "fp32_simt_ms_per_iteration": ms_fp32,
+                 "direct_form_tflops_per_gpu": flop_iter / (ms_graph * 1e-3) / 1e12,
+                 "mode": "tcgen05 kind::tf32 (3xTF32 forward), CUDA-graph replay, batch 32/GPU, device Philox noise/alpha/dropout",
                  "finite": bool(np.isfinite(losses).all() and np.isfinite(gl))}
+        if world > 1:
+            # data-parallel parity: N-rank averaged gradients == rank 0 on the gathered N*32 batch, FP32 mode,
+            # explicit inputs, no dropout; and the share of the gradient exchange in an eagerly issued iteration
+            z = torch.randn((TB, 100), device=dev, generator=tg)
+            al = torch.rand((TB,), device=dev, generator=tg)
+            errs = {}
+            for which, name in ((1, "critic"), (0, "generator")):
+                if which == 1:
+                    tr32.critic_grads(x_real[0], tcond[0], z, al, None)
+                else:
+                    tr32.generator_grads(z, tcond[0], None)
+                g = tr32.grad_tensor(which).clone()
+                dist.all_reduce(g)
+                g /= world
+                parts = [torch.empty_like(t) for t in (x_real[0], tcond[0], z, al) for _ in range(world)]
+                gathered = []
+                for i, t in enumerate((x_real[0], tcond[0], z, al)):
+                    lst = parts[i * world:(i + 1) * world]
+                    dist.all_gather(lst, t.contiguous())
+                    gathered.append(torch.cat(lst))
+                if rank == 0:
+                    if which == 1:
+                        tr32.critic_grads(gathered[0], gathered[1], gathered[2], gathered[3], None)
+                    else:
+                        tr32.generator_grads(gathered[2], gathered[1], None)
+                    ref = tr32.grad_tensor(which)
+                    errs[name] = float(((g - ref).norm() / ref.norm()).item())
+                barrier()
+            tr.profile_comm = True
+            tr.comm_ms()
+            ms_eager = timed(lambda: [tr.critic_step_device(x_real[k], tcond[k], dl[k]) for k in range(5)] + [tr.generator_step_device(tcond[0], gls)], 10)
+            comm = tr.comm_ms() / 13.0
+            tr.profile_comm = False
+            dp = {"ranks": world, "grad_parity_rel_l2": errs, "allreduce_ms_per_iteration": comm,
+                  "allreduce_share_of_eager_iteration": comm / ms_eager, "exchange": "NCCL all-reduce of the flat FP32 gradient buffer inside the graph"}
         # critic scoring (config #3, forward only): synthetic hourly fraction fields, tensor-core scoring mode vs the FP32 path
         CB = 20000
         cx = torch.rand((CB, 24, 16, 16), device=dev); cx = cx / cx.sum(dim=1, keepdim=True)
@@ -374,9 +477,9 @@ def main():
             for _ in range(3):
                 tcrit.forward_device(cx, cc, mode=cmode)
             c1.record(); torch.cuda.synchronize()
-            critic_rates[cmode] = CB / (c0.elapsed_time(c1) / 3 / 1e3)
+            critic_rates[cmode] = round(CB / (c0.elapsed_time(c1) / 3 / 1e3))
         train["critic_scoring_samples_per_s_per_gpu"] = critic_rates
-        del cx, cc
+        del cx, cc, ig
         tctx.close()
 
     if rank != 0:
@@ -399,49 +502,85 @@ def main():
                "latency_us_median": 1e6 * statistics.median(ts), "scenarios_per_s": 10 / statistics.median(ts),
                "conservation_err": float(np.abs(ex_out.sum(axis=1) - 1).max())}
 
+    # ---- extras: the bf16 operand mode's rate on the same workload, and the large-domain variant (config #5)
+    extras = {}
+    if not args.no_extras and world == 1:
+        for _ in range(2):
+            gen.forward_device(latent, cond, scen_per_cond=spc, mode="bf16", out_mm=True, out=out, check=False)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(2):
+            gen.forward_device(latent, cond, scen_per_cond=spc, mode="bf16", out_mm=True, out=out, check=False)
+        b1.record(); torch.cuda.synchronize()
+        extras["bf16_scenarios_per_s"] = round(B / (b0.elapsed_time(b1) / 2 / 1e3))
+        del out, latent
+        torch.cuda.empty_cache()
+        lctx = Context(64, 1, device=local)
+        lgen = Generator(W.init_generator_weights(0, 64), ctx=lctx, mode="fp16")
+        ld = {}
+        for LB in (32, 1024):
+            lc = lctx.dev(synth_conditions(LB, 64, 3))
+            lz = torch.randn((LB, 100), device=dev)
+            lo = torch.empty((LB, 24, 64, 64), device=dev)
+            for _ in range(2):
+                lgen.forward_device(lz, lc, mode="fp16", out_mm=True, out=lo, check=False)
+            torch.cuda.synchronize()
+            b0.record()
+            nrep = 3 if LB > 100 else 10
+            for _ in range(nrep):
+                lgen.forward_device(lz, lc, mode="fp16", out_mm=True, out=lo, check=False)
+            b1.record(); torch.cuda.synchronize()
+            ms = b0.elapsed_time(b1) / nrep
+            ld[f"B{LB}"] = {"scenarios_per_s": round(LB / ms * 1e3, 1), "executed_tflops": round(LB * 2 * 10.845e9 / ms / 1e9, 1)}
+        extras["largedomain_nd64"] = ld
+        lctx.close()
+
     burst, sustained, hbm, src = load_peaks()
     conv3_ms = ms_sum[5] / max(1, n_l[5])
     units_per_launch = n_u[5] / max(1, n_l[5])
-    ach = units_per_launch * 2 * MAC_CONV3 / (conv3_ms * 1e-3) / 1e12 if conv3_ms > 0 else 0.0
+    direct = units_per_launch * 2 * MAC_CONV3 / (conv3_ms * 1e-3) / 1e12 if conv3_ms > 0 else 0.0
+    executed = direct * MAC_CONV3_FOLDED / MAC_CONV3
+    issued = executed * (1.0 - 16.0 / 384.0)      # the hour-boundary taps (16 of 384 M-tile steps) are skipped, not issued
     layer_names = ["concat", "dense_front", "cvt16", "upconv256", "upconv128", "upconv64_planes", "softmax_hours", "pixelnorm"]
-    shares = {layer_names[i]: round(ms_sum[i] / args.steps, 3) for i in range(8) if n_l[i]}
-    roofline = {"bound": "tensor", "kernel": "tc_upconv64_planes_kernel (UpSampling3D + Conv3D 128->64 + PixelNorm + LeakyReLU "
-                                              "+ fused Conv3D 64->1 summed on chip; resident-plane tcgen05 cta_group::2 kernel)",
-                "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
-                "peak_kind": f"{src} sustained bf16 cuBLAS (burst {burst})", "frac_of_burst": ach / burst,
-                "executed_tflops": ach * MAC_CONV3_FOLDED / MAC_CONV3,
-                "executed_frac": ach * MAC_CONV3_FOLDED / MAC_CONV3 / sustained,
-                "note": "achieved counts the reference graph's direct-form FLOPs (SURVEY 8d); the kernel executes the exact "
-                        "upsample-folded form (3.375x fewer MACs), so achieved may exceed the cuBLAS peak; executed_* counts "
-                        "the MACs actually issued to the tensor pipe",
+    shares = {layer_names[i]: round(ms_sum[i] / args.steps, 2) for i in range(8) if n_l[i]}
+    roofline = {"bound": "tensor", "kernel": "tc_upconv64_planes_kernel",
+                "achieved": issued, "peak": sustained, "unit": "TFLOP/s", "frac": issued / sustained,
+                "peak_kind": f"{src} sustained bf16 cuBLAS (burst {burst})", "frac_of_burst": issued / burst,
+                "counts": "MACs issued to the tensor pipe (upsample-folded form, skipped boundary taps excluded)",
+                "direct_form_tflops": direct, "fold_factor": MAC_CONV3 / MAC_CONV3_FOLDED,
                 "ms_per_launch": conv3_ms, "units_per_launch": units_per_launch,
-                "flop_per_unit": 2 * MAC_CONV3, "traffic": CONV3_DRAM_BYTES_PER_UNIT * units_per_launch,
-                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1h_ncu_planes_cg2_summary.md)",
+                "traffic": CONV3_DRAM_BYTES_PER_UNIT * units_per_launch,
                 "algorithmic_bytes_per_launch": units_per_launch * (12 * 64 * 128 * 2 + 24 * 256 * 4),
                 "layer_ms_per_step": shares,
-                "whole_path_frac": value / world * 2 * MAC_TOTAL / 1e12 / sustained,
                 "whole_path_executed_frac": value / world * 2 * MAC_TOTAL_FOLDED / 1e12 / sustained}
 
-    cpu = None
+    # ---- CPU baseline + parity: the oracle on the first conditions of the timed workload, same latent noise
+    cpu = parity = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
-        rate, dt = cpu_reference_rate(args.cpu_conditions, spc, threads)
+        tf_rate, tf_note = tf_reference_rate(1, spc)
+        rate, dt, ref = cpu_reference_rate(n_par, spc, threads, latent=head_lat, cond=cond_h[:n_par], keep=True)
         cpu = {"value": rate, "unit": "scenarios/s", "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_conditions} conditions x {spc} scenarios ({dt:.1f} s) of the {n_cond} x {spc} workload",
-               "note": "torch-CPU FP32 restatement (oracle/rdg_oracle.py); TensorFlow not installable here"}
+               "sample": f"first {n_par} conditions x {spc} scenarios ({dt:.1f} s) of the {n_cond} x {spc} workload, same noise as the GPU run",
+               "note": f"torch-CPU FP32 restatement (oracle/rdg_oracle.py); {tf_note}"}
+        if tf_rate is not None:
+            cpu["tf_reference_scenarios_per_s"] = tf_rate
+        ok = ref > 1e-12
+        rel = np.abs(head_out.astype(np.float64) - ref)[ok] / ref[ok]
+        parity = {"checked_scenarios": int(n_par * spc), "max_rel_err": float(rel.max()), "rms_rel_err": float(np.sqrt(np.mean(rel ** 2))),
+                  "bound": {"fp16": 1e-2, "bf16": 4e-2, "fp32": 1e-5}[args.mode], "against": "FP32 CPU oracle, first scenarios of the last timed step"}
+        parity["ok"] = bool(parity["max_rel_err"] <= parity["bound"])
 
     line = {"metric": METRIC, "value": value, "unit": "scenarios/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.mode],
-            "dtype_detail": {"fp16": "f16 operands, f32 accumulate in TMEM (tcgen05 kind::f16); PixelNorm / softmax in f32",
-                             "bf16": "bf16 operands, f32 accumulate in TMEM (tcgen05 kind::f16); PixelNorm / softmax in f32",
-                             "fp32": "f32 SIMT, upsample-folded"}[args.mode],
-            "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.mode], "data": "synthetic",
             "config": dict(workload_config(n_cond, spc), **{"chunk": ctx.max_chunk, "mode": args.mode,
-                       "l2": "inputs (410 MB latent+cond) and outputs (24.6 GB) per step exceed the 126 MB L2",
+                       "l2": "inputs (410 MB) and outputs (24.6 GB) per step exceed the 126 MB L2",
                        "parallelism": f"shard{world}-independent", "numa_node_rank0": numa}),
-            "e2e": e2e, "e2e_stats": e2e_stats, "train": train, "example": example, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "conservation_rel_err": cons}
+            "gpu_launches": int(launches), "clocks": clocks, "conservation_rel_err": cons, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "example": example, "extras": extras,
+            "e2e": e2e, "e2e_stats": e2e_stats, "train": train, "dp": dp}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -57,10 +57,15 @@ struct TcgFilterArgs {
     int ay, Ty, Hy, Wy, Co;
     int Mt, N, ksplit, nstages;
     int ksmall;               // > 0: few-channel input: A rows = (tap, channel), ksmall = taps * Ci of them, one launch for all taps
+    unsigned long long mW, mH, mT;   // fast_div multipliers of Wc, Hc, Tc
+    int cpa;                  // 16-byte channel chunks per position of this launch's A tile: min(Ci, 128) / 4, a power of two
     long long wblk;           // dw elements per tap block (Ci*Co)
     TcgFTap taps[64];
 };
 
+// x / d for 0 <= x < 2^24, 1 <= d < 256 with the host-computed multiplier ceil(2^40 / d): exact (x d^2 < 2^40), 4 instructions
+// instead of the ~35 of a runtime integer division (the producers decompose two positions per k-block)
+__device__ __forceinline__ int fast_div(int x, unsigned long long m) { return (int)(((unsigned long long)(unsigned)x * m) >> 40); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void sts4_tf32(uint8_t* dst, float4 v) {
     float4 r = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
@@ -89,6 +94,7 @@ __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, uint32_t stage_byt
     for (int i = 0; i < nkb; ++i) {
         const int s = i % nst;
         mbar_wait(&full_bar[s], (uint32_t)(i / nst) & 1u);
+        if (!SPLIT) fence_proxy_async_smem();      // cp.async producers: the landed (generic-proxy) writes -> async proxy
         tc_fence_after();
         if (elect_one()) {
             const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
     const int nkb = (int)((long long)(blockIdx.z + 1) * nkb_all / p.nslice) - kb_lo;
 
     if (tid == 0) {
-        for (int s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < nst; ++s) { mbar_init(&full_bar[s], SPLIT ? 8 : 256); mbar_init(&empty_bar[s], 1); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -232,15 +238,66 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
         };
-        // software pipeline: the loads of k-block i+1 are in flight while k-block i is rounded and stored
-        float4 a0[4], b0[NB], a1[4], b1[NB];
-        if (nkb > 0) load(0, a0, b0);
-        for (int i = 0; i < nkb; i += 2) {
-            if (i + 1 < nkb) load(i + 1, a1, b1);
-            store(i, a0, b0);
-            if (i + 1 < nkb) {
-                if (i + 2 < nkb) load(i + 2, a0, b0);
-                store(i + 1, a1, b1);
+        if (SPLIT) {
+            // register path (operands are split into tf32 high + low parts on the way): software pipeline, the loads of k-block
+            // i+1 are in flight while k-block i is rounded and stored
+            float4 a0[4], b0[NB], a1[4], b1[NB];
+            if (nkb > 0) load(0, a0, b0);
+            for (int i = 0; i < nkb; i += 2) {
+                if (i + 1 < nkb) load(i + 1, a1, b1);
+                store(i, a0, b0);
+                if (i + 1 < nkb) {
+                    if (i + 2 < nkb) load(i + 2, a0, b0);
+                    store(i + 1, a1, b1);
+                }
+            }
+        } else {
+            // asynchronous path: cp.async straight into the swizzled tiles (the tensor core truncates FP32 bit patterns to tf32),
+            // completion arrives on the stage's full barrier; the producers only wait for free stages, so `nstages` k-blocks
+            // are in flight per CTA
+            for (int i = 0; i < nkb; ++i) {
+                const int kb = kb_lo + i;
+                int te = 0, kc = kb;
+                if (!p.ksmall) { te = kb / p.kchunks; kc = kb - te * p.kchunks; }
+                const TcgTap tp = p.taps[cl.tap_begin + te];
+                const int k0 = kc * 32 + chunk * 4;
+                const bool kval = k0 < p.Kc;
+                const int s = i % nst;
+                if (i >= nst) mbar_wait(&empty_bar[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes + sw_off);
+                const float* wb = p.w + (long long)(p.ksmall ? 0 : tp.widx) * p.wtap + (long long)(n0 + rsub) * p.wrow + (kval ? k0 : 0);
+#pragma unroll
+                for (int j = 0; j < NB; ++j) cp_async16(sa + 16384 + j * 4096, wb + (long long)(32 * j) * p.wrow, kval ? 16u : 0u);
+                if (!p.ksmall) {
+                    const int doff = ((tp.ct * p.Hs + tp.ch) * p.Ws + tp.cw) * p.Cs + k0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ts = (rcoord[j] & 1023) + tp.ct, hs = ((rcoord[j] >> 10) & 1023) + tp.ch, ws = (rcoord[j] >> 20) + tp.cw;
+                        const bool ok = kval && rbase[j] >= 0 && (unsigned)ts < (unsigned)p.Ts && (unsigned)hs < (unsigned)p.Hs &&
+                                        (unsigned)ws < (unsigned)p.Ws;
+                        cp_async16(sa + j * 4096, ok ? p.src + rbase[j] + doff : p.src, ok ? 16u : 0u);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + u;
+                        int eo = -1, ect = 0, ech = 0, ecw = 0;
+                        if (k < p.ksmall) {
+                            const int tap = k / p.Cs, c = k - tap * p.Cs;
+                            const TcgTap tq = p.taps[cl.tap_begin + tap];
+                            ect = tq.ct; ech = tq.ch; ecw = tq.cw;
+                            eo = ((tq.ct * p.Hs + tq.ch) * p.Ws + tq.cw) * p.Cs + c;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int ts = (rcoord[j] & 1023) + ect, hs = ((rcoord[j] >> 10) & 1023) + ech, ws = (rcoord[j] >> 20) + ecw;
+                            const bool ok = eo != -1 && rbase[j] >= 0 && (unsigned)ts < (unsigned)p.Ts && (unsigned)hs < (unsigned)p.Hs &&
+                                            (unsigned)ws < (unsigned)p.Ws;
+                            cp_async4(sa + j * 4096 + 4 * u, ok ? p.src + rbase[j] + eo : p.src, ok ? 4u : 0u);
+                        }
+                    }
+                }
+                cp_async_mbar_arrive_noinc(&full_bar[s]);
             }
         }
         // ---- epilogue: warp = (lane quarter q, column half)
@@ -330,11 +387,25 @@ __global__ void tcg_splitk_epilogue_kernel(const float* __restrict__ part, int n
 }
 
 // ------------------------------------------------------------------------------------------------ filter gradient
-// NVB = float4 loads per lane and k-block for the B tile (N = 32 NVB).  Producer warp w owns input channels [16 w, +16) of the A
-// tile and output channels [4 NVB w, +4 NVB) of the B tile.  Lanes pair up on a position (lane = (position sub-index, channel
-// half)): a load instruction covers 16 positions x 32 contiguous bytes (full sectors), the transposed scalar stores of a warp hit
-// 32 different banks (row = channel, column = position).  p.ksmall: few-channel input (critic's first conv): A rows = (tap, channel).
-template <int NVB>
+// dW[tap][ci][co] += sum_pos X[pos (+) tap][ci] * DY[pos][co]: the contraction index (positions) is the SLOW index of the
+// channels-last tensors, so both operands are staged MN-major (tcgen05 reads either major for tf32; the only MN-major tf32 layout
+// is SWIZZLE_128B_BASE32B: 512-byte atoms of 4 positions x 32 channels, the four 32-byte chunks of a 128-byte row XOR-ed with the
+// row index): a position's channels are one contiguous 16-byte-vector copy (coalesced LDG.128 -> STS.128, no transposition).
+// Tile = [8 k-atoms][channel atoms][4 positions][128 B], LBO = atom stride along channels, SBO = along positions; K = 8 per MMA
+// = two k-atoms.
+// NVB = N / 32 (channel atoms of the B tile).  KSMALL (critic's first conv: rows = (tap, channel), gathered per element) keeps a
+// K-major A tile (row = (tap, channel), 32 positions per 128-byte row).
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+template <int NVB, bool KSMALL>
 __global__ void __launch_bounds__(TCG_THREADS, NVB <= 4 ? 2 : 1) tcg_filtergrad_kernel(const __grid_constant__ TcgFilterArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -352,7 +423,7 @@ __global__ void __launch_bounds__(TCG_THREADS, NVB <= 4 ? 2 : 1) tcg_filtergrad_
     const int nkb = (int)((long long)(blockIdx.z + 1) * nkb_all / p.ksplit) - kb_lo;
 
     if (tid == 0) {
-        for (int s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 256); mbar_init(&empty_bar[s], 1); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -363,23 +434,37 @@ __global__ void __launch_bounds__(TCG_THREADS, NVB <= 4 ? 2 : 1) tcg_filtergrad_
     const uint32_t tmem = tmem_slot;
 
     if (warp == 8) {
-        mma_issue_loop<false>(smem, stage_bytes, nst, nkb, N, tmem, full_bar, empty_bar, &acc_bar);
+        // A: MN-major [4 k-atoms][4 channel atoms] (KSMALL: K-major, k step = 32 bytes inside the row); B: MN-major [4][NVB]
+        const uint32_t idesc = idesc_tf32(N) | (KSMALL ? 0u : (1u << 15)) | (1u << 16);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % nst;
+            mbar_wait(&full_bar[s], (uint32_t)(i / nst) & 1u);
+            fence_proxy_async_smem();      // the landed cp.async (generic-proxy) writes -> async proxy
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = KSMALL ? make_sdesc(base) + 2 * k : make_sdesc_mn(base + k * 4096, 512, 2048);
+                    const uint64_t bd = make_sdesc_mn(base + 16384 + k * (NVB * 1024), 512, NVB * 512);
+                    tc_mma_tf32(tmem, ad, bd, idesc, (i | k) ? 1u : 0u);
+                }
+                tc_commit(&empty_bar[s]);
+                if (i == nkb - 1) tc_commit(&acc_bar);
+            }
+            __syncwarp();
+        }
     } else {
-        constexpr int CPW = 4 * NVB;                       // B channels per warp
-        constexpr bool B_PAIR = CPW >= 8;                  // lanes pair up on a position (else lane = position)
-        const int psub = lane >> 1, cq = lane & 1;
-        const bool a_on = p.ksmall ? 16 * warp < p.ksmall : m0 + 16 * warp < p.Ci;
-        // one position of this lane: offsets of its x / dy rows, or -1
+        // one position: element offsets of its x / dy rows (channel 0 of this CTA's tiles), or -1
         auto locate = [&](int pos, long long& xoff, long long& yoff) {
             xoff = -1; yoff = -1;
             if (pos >= p.rows) return;
-            int q = pos;
-            const int w2 = q % p.Wc; q /= p.Wc;
-            const int h2 = q % p.Hc; q /= p.Hc;
-            const int t2 = q % p.Tc; const int b = q / p.Tc;
+            const int q1 = fast_div(pos, p.mW), w2 = pos - q1 * p.Wc;
+            const int q2 = fast_div(q1, p.mH), h2 = q1 - q2 * p.Hc;
+            const int b = fast_div(q2, p.mT), t2 = q2 - b * p.Tc;
             const int yt = p.ay * t2 + tp.yt, yh = p.ay * h2 + tp.yh, yw = p.ay * w2 + tp.yw;
             const bool yok = (unsigned)yt < (unsigned)p.Ty && (unsigned)yh < (unsigned)p.Hy && (unsigned)yw < (unsigned)p.Wy;
-            if (p.ksmall) {          // per-tap validity is resolved per element below; xoff = the tap-free base
+            if (KSMALL) {          // per-tap validity is resolved per element; xoff packs the tap-free base and the coordinates
                 xoff = ((((long long)b * p.Tx + p.ax * t2) * p.Hx + p.ax * h2) * p.Wx + p.ax * w2) * p.Ci;
                 xoff = (xoff << 30) | ((long long)(p.ax * t2) << 20) | ((long long)(p.ax * h2) << 10) | (long long)(p.ax * w2);
                 if (yok) yoff = ((((long long)b * p.Ty + yt) * p.Hy + yh) * p.Wy + yw) * p.Co + n0;
@@ -392,94 +477,71 @@ __global__ void __launch_bounds__(TCG_THREADS, NVB <= 4 ? 2 : 1) tcg_filtergrad_
                 yoff = ((((long long)b * p.Ty + yt) * p.Hy + yh) * p.Wy + yw) * p.Co + n0;
             }
         };
-        // A: 16 channels per warp = 2 position halves x 2 channel groups of 8 (lane pair: 2 x float4); va[2 h + g]
-        // B: CPW channels per warp; B_PAIR: 2 halves x (CPW / 8) groups, vb[(CPW / 8) h + g]; else lane = position, vb[0]
-        auto load = [&](int i, float4 (&va)[4], float4 (&vb)[NVB]) {
+        // work items = (position, 16-byte channel chunk); a thread's items are tid, tid + 256, ...
+        constexpr int CPB = 8 * NVB;                         // chunks per position of the B tile
+        constexpr int PPB = 256 / CPB;                       // positions per pass over the 256 producer threads (NVB <= 8: >= 4)
+        const int chB = tid % CPB, pB = tid / CPB;
+        const int cpa = p.cpa;                               // chunks per position of the A tile (8, 16 or 32)
+        const int chA = tid & (cpa - 1), pA = tid / cpa, ppa = 256 / cpa, nA = cpa >> 3;    // nA = items per thread
+        // KSMALL: A is K-major, warp w owns rows [16 w, +16), lane = position (2 per lane-pair as before)
+        const int psub = lane >> 1, cq = lane & 1;
+        const bool a_on = KSMALL ? 16 * warp < p.ksmall : true;
+
+        // MN-major destination of (position k in 0..31, 16-byte channel chunk ch) inside a tile of `atoms` channel atoms
+        auto mn_off = [](int atoms, int k, int ch) -> uint32_t {
+            const uint32_t r = (uint32_t)k & 3u;
+            return (uint32_t)(k >> 2) * (uint32_t)(atoms * 512) + (uint32_t)(ch >> 3) * 512u + r * 128u + (((((uint32_t)ch >> 1) & 3u) ^ r) << 5) +
+                   ((uint32_t)ch & 1u) * 16u;
+        };
+        // asynchronous producers: cp.async straight into the tiles (FP32 bit patterns; the tensor core truncates to tf32), the
+        // copies' completion arrives on the stage's full barrier; threads only wait for a free stage
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % nst;
             const int pos0 = (kb_lo + i) * 32;
-            long long xo[2], yo[2];
-            locate(pos0 + psub, xo[0], yo[0]);
-            locate(pos0 + 16 + psub, xo[1], yo[1]);
-            if (a_on) {
-                if (!p.ksmall) {
+            if (i >= nst) mbar_wait(&empty_bar[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
+            const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            if (!KSMALL) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                for (int j = 0; j < 4; ++j)
+                    if (j < nA) {
+                        long long xo, yo;
+                        locate(pos0 + pA + ppa * j, xo, yo);
+                        cp_async16(sa + mn_off(4, pA + ppa * j, chA), xo >= 0 ? p.x + xo + 4 * chA : p.x, xo >= 0 ? 16u : 0u);
+                    }
+            } else if (a_on) {
+                long long xo[2], yo[2];
+                locate(pos0 + psub, xo[0], yo[0]);
+                locate(pos0 + 16 + psub, xo[1], yo[1]);
 #pragma unroll
-                        for (int g = 0; g < 2; ++g)
-                            va[2 * h + g] = xo[h] >= 0 ? ldg4(p.x + xo[h] + 16 * warp + 8 * g + 4 * cq) : make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int g = 0; g < 2; ++g)
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            float e[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int m = 16 * warp + 8 * g + 4 * cq + u;      // row = tap * Ci + channel
-                                e[u] = 0.f;
-                                if (m < p.ksmall && xo[h] >= 0 && yo[h] >= 0) {
-                                    const int tap = m / p.Ci, c = m - tap * p.Ci;
-                                    const TcgFTap tq = p.taps[tap];
-                                    const int xt = (int)((xo[h] >> 20) & 1023) + tq.xt, xh = (int)((xo[h] >> 10) & 1023) + tq.xh, xw = (int)(xo[h] & 1023) + tq.xw;
-                                    if ((unsigned)xt < (unsigned)p.Tx && (unsigned)xh < (unsigned)p.Hx && (unsigned)xw < (unsigned)p.Wx)
-                                        e[u] = __ldg(p.x + (xo[h] >> 30) + ((long long)(tq.xt * p.Hx + tq.xh) * p.Wx + tq.xw) * p.Ci + c);
+                        for (int u = 0; u < 4; ++u) {
+                            const int m = 16 * warp + 8 * g + 4 * cq + u;      // row = tap * Ci + channel
+                            const float* src = p.x;
+                            uint32_t nbytes = 0;
+                            if (m < p.ksmall && xo[h] >= 0 && yo[h] >= 0) {
+                                const int tap = m / p.Ci, c = m - tap * p.Ci;
+                                const TcgFTap tq = p.taps[tap];
+                                const int xt = (int)((xo[h] >> 20) & 1023) + tq.xt, xh = (int)((xo[h] >> 10) & 1023) + tq.xh, xw = (int)(xo[h] & 1023) + tq.xw;
+                                if ((unsigned)xt < (unsigned)p.Tx && (unsigned)xh < (unsigned)p.Hx && (unsigned)xw < (unsigned)p.Wx) {
+                                    src = p.x + (xo[h] >> 30) + ((long long)(tq.xt * p.Hx + tq.xh) * p.Wx + tq.xw) * p.Ci + c;
+                                    nbytes = 4;
                                 }
                             }
-                            va[2 * h + g] = make_float4(e[0], e[1], e[2], e[3]);
+                            const uint32_t row = (uint32_t)m, k = (uint32_t)(16 * h + psub);
+                            cp_async4(sa + (row >> 3) * 1024u + (row & 7u) * 128u + (((k >> 2) ^ (row & 7u)) << 4) + (k & 3u) * 4u, src, nbytes);
                         }
-                }
             }
-            if (B_PAIR) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int g = 0; g < CPW / 8; ++g)
-                        vb[(CPW / 8) * h + g] = yo[h] >= 0 ? ldg4(p.dy + yo[h] + CPW * warp + 8 * g + 4 * cq) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                long long x1, y1;
-                locate(pos0 + lane, x1, y1);
-                vb[0] = y1 >= 0 ? ldg4(p.dy + y1 + CPW * warp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < NVB; ++j) {
+                long long xo, yo;
+                locate(pos0 + pB + PPB * j, xo, yo);
+                const bool ok = yo >= 0 && (KSMALL || xo >= 0);
+                cp_async16(sa + 16384 + mn_off(NVB, pB + PPB * j, chB), ok ? p.dy + yo + 4 * chB : p.dy, ok ? 16u : 0u);
             }
-        };
-        auto sts_t = [&](uint8_t* tile, int row0, int k, float4 v) {       // 4 consecutive rows (channels), column k
-            const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t row = (uint32_t)(row0 + u);
-                *reinterpret_cast<float*>(tile + (row >> 3) * 1024u + (row & 7u) * 128u + ((((uint32_t)k >> 2) ^ (row & 7u)) << 4) + ((uint32_t)k & 3u) * 4u) =
-                    to_tf32(e[u]);
-            }
-        };
-        auto store = [&](int i, const float4 (&va)[4], const float4 (&vb)[NVB]) {
-            const int s = i % nst;
-            if (i >= nst) mbar_wait(&empty_bar[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
-            uint8_t* sa = smem + (size_t)s * stage_bytes;
-            if (a_on) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) sts_t(sa, 16 * warp + 8 * g + 4 * cq, 16 * h + psub, va[2 * h + g]);
-            }
-            if (B_PAIR) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int g = 0; g < CPW / 8; ++g) sts_t(sa + 16384, CPW * warp + 8 * g + 4 * cq, 16 * h + psub, vb[(CPW / 8) * h + g]);
-            } else {
-                sts_t(sa + 16384, CPW * warp, lane, vb[0]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[s]);
-        };
-        float4 a0[4], b0[NVB], a1[4], b1[NVB];
-        if (nkb > 0) load(0, a0, b0);
-        for (int i = 0; i < nkb; i += 2) {
-            if (i + 1 < nkb) load(i + 1, a1, b1);
-            store(i, a0, b0);
-            if (i + 1 < nkb) {
-                if (i + 2 < nkb) load(i + 2, a0, b0);
-                store(i + 1, a1, b1);
-            }
+            cp_async_mbar_arrive_noinc(&full_bar[s]);
         }
         // ---- epilogue: accumulator row = input channel (or (tap, channel)), columns = output channels -> dw += D
         mbar_wait(&acc_bar, 0);
@@ -488,7 +550,7 @@ __global__ void __launch_bounds__(TCG_THREADS, NVB <= 4 ? 2 : 1) tcg_filtergrad_
         constexpr int cph = N >= 64 ? N / 2 : 32;
         const int c_lo = half * cph, c_hi = min(N, c_lo + cph);
         const int row = m0 + q * 32 + lane;
-        const int row_lim = p.ksmall ? p.ksmall : p.Ci;
+        const int row_lim = KSMALL ? p.ksmall : p.Ci;
         float* dst = p.dw + (long long)tp.widx * p.wblk + (long long)row * p.Co + n0;
         for (int c = c_lo; c < c_hi; c += 32) {
             uint32_t v[32];
@@ -769,19 +831,24 @@ int tcg_folded_bwd_data(const float* dy, const float* wf, float* dx, const ConvG
 }
 
 namespace {
-template <int NVB>
+template <int NVB, bool KSMALL>
 int launch_filtergrad_t(const TcgFilterArgs& a, dim3 grid, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        RDG_CUDA(cudaFuncSetAttribute(tcg_filtergrad_kernel<NVB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+        RDG_CUDA(cudaFuncSetAttribute(tcg_filtergrad_kernel<NVB, KSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
         attr_done = true;
     }
-    tcg_filtergrad_kernel<NVB><<<grid, TCG_THREADS, smem_bytes(NVB * 32, a.nstages, false), st>>>(a);
+    tcg_filtergrad_kernel<NVB, KSMALL><<<grid, TCG_THREADS, smem_bytes(NVB * 32, a.nstages, false), st>>>(a);
     RDG_LAUNCH_CHECK();
     return 0;
 }
+unsigned long long fast_div_mul(int d) { return ((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d; }
 int launch_filtergrad(TcgFilterArgs& a, int ntap, cudaStream_t st) {
     a.Mt = a.ksmall ? 1 : ceil_div(a.Ci, 128);
+    if (a.rows >= (1 << 24) || a.Wc >= 256 || a.Hc >= 256 || a.Tc >= 256) { rdg_set_error("tcg filter gradient: more than 2^24 positions"); return RDG_TCG_E_SHAPE; }
+    a.mW = fast_div_mul(a.Wc); a.mH = fast_div_mul(a.Hc); a.mT = fast_div_mul(a.Tc);
+    a.cpa = std::min(a.Ci, 128) / 4;
+    if (!a.ksmall && ((a.Ci & 31) || (a.cpa & (a.cpa - 1)) || (a.Ci > 128 && a.Ci % 128))) { rdg_set_error("tcg filter gradient: Ci must be 32, 64 or a multiple of 128"); return RDG_TCG_E_SHAPE; }
     int N = 0;
     for (int n : {256, 128, 64, 32})
         if (a.Co % n == 0 && (n <= 64 || (long long)ntap * a.Mt * (a.Co / n) >= 96)) { N = n; break; }
@@ -794,11 +861,19 @@ int launch_filtergrad(TcgFilterArgs& a, int ntap, cudaStream_t st) {
     ks = std::max(1, std::min(ks, nkb / 4));
     a.ksplit = ks;
     dim3 grid(ntap, a.Mt * (a.Co / N), ks);
+    if (a.ksmall) {
+        switch (N) {
+            case 32:  return launch_filtergrad_t<1, true>(a, grid, st);
+            case 64:  return launch_filtergrad_t<2, true>(a, grid, st);
+            case 128: return launch_filtergrad_t<4, true>(a, grid, st);
+            default:  return launch_filtergrad_t<8, true>(a, grid, st);
+        }
+    }
     switch (N) {
-        case 32:  return launch_filtergrad_t<1>(a, grid, st);
-        case 64:  return launch_filtergrad_t<2>(a, grid, st);
-        case 128: return launch_filtergrad_t<4>(a, grid, st);
-        default:  return launch_filtergrad_t<8>(a, grid, st);
+        case 32:  return launch_filtergrad_t<1, false>(a, grid, st);
+        case 64:  return launch_filtergrad_t<2, false>(a, grid, st);
+        case 128: return launch_filtergrad_t<4, false>(a, grid, st);
+        default:  return launch_filtergrad_t<8, false>(a, grid, st);
     }
 }
 }  // namespace
