@@ -251,6 +251,21 @@ __global__ void interp_kernel(const float* __restrict__ xr, const float* __restr
     const float a = alpha[i / per];
     xh[i] = a * xr[i] + (1.f - a) * xf[i];          // RandomWeightedAverage, gan_train_cwgangp_pixelnorm.py:221-224
 }
+// Flatten + Dense(1) (gan_train_cwgangp_pixelnorm.py:303-304): one warp per sample, score[b] = x[b,:] . w + bias
+__global__ void dense_score_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                   float* __restrict__ score, int B, int K) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)b * K);
+    const float4* wr = reinterpret_cast<const float4*>(w);
+    float s = 0.f;
+    for (int i = lane; i < K / 4; i += 32) {
+        const float4 a = xr[i], c = __ldg(wr + i);
+        s = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, s))));
+    }
+    s = warp_sum(s);
+    if (lane == 0) score[b] = s + bias[0];
+}
 // ---- output conv Conv3D(64->1,'same') through per-tap products (training, tensor-core mode): P[pos][tap] = y[pos] . w4[tap]
 // logits[b,t,h,w] = b4 + sum_tap P[(t+kt-1, h+kh-1, w+kw-1)][tap]       (gan_train_cwgangp_pixelnorm.py:345)
 __global__ void tap_gather_logits_kernel(const float* __restrict__ P, const float* __restrict__ b4, float* __restrict__ logits,
@@ -489,6 +504,14 @@ int ew_pad_w4(const float* w4, float* w4p, cudaStream_t st) {
 int ew_fill3(float* dst, int n, float a, float b, float c, cudaStream_t st) {
     if (!n) return 0;
     fill3_kernel<<<EW_GRID(3 * n)>>>(dst, n, a, b, c);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int ew_dense_score(const float* x, const float* w, const float* bias, float* score, int B, int K, cudaStream_t st) {
+    if (!B) return 0;
+    if (K & 3) { rdg_set_error("ew_dense_score: K must be a multiple of 4"); return -1; }
+    dense_score_kernel<<<ceil_div(B, 8), 256, 0, st>>>(x, w, bias, score, B, K);
     RDG_LAUNCH_CHECK();
     return 0;
 }

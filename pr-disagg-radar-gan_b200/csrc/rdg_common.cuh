@@ -107,6 +107,7 @@ int ew_tap_gather_logits(const float* P, const float* b4, float* logits, int B, 
 int ew_tap_scatter_dlogits(const float* dl, float* Gd, int B, int nd, cudaStream_t st);                      // Gd [B,24,nd,nd,32]
 int ew_pad_w4(const float* w4, float* w4p, cudaStream_t st);     // -> [32][64] then [64][32]
 int ew_fill3(float* dst, int n, float a, float b, float c, cudaStream_t st);
+int ew_dense_score(const float* x, const float* w, const float* bias, float* score, int B, int K, cudaStream_t st);   // Flatten + Dense(1)
 int ew_interp(const float* xr, const float* xf, const float* alpha, float* xhat, int B, long long per, cudaStream_t st);
 int ew_fill(float* dst, long long n, float v, cudaStream_t st);
 int ew_mean_scaled(const float* x, long long n, float scale, float* out, cudaStream_t st);   // out = scale * mean(x)

@@ -593,9 +593,11 @@ int pick_stages(int N, bool split) {
 size_t smem_bytes(int N, int nst, bool split) { return (size_t)nst * (16384 + N * 128) * (split ? 2 : 1) + 1024; }
 
 int tile_n_for(int Nt, int mtiles) {
-    // widest accumulator that still leaves enough CTAs; Nt is a multiple of 32
+    // The kernels are bound by the L2 -> shared-memory operand stream: bytes per CTA and k-block = 16 KB (A) + 128 N (B), so the
+    // widest accumulator minimises the traffic (A is gathered once per N tile); split-K supplies the parallelism instead.
+    (void)mtiles;
     for (int N : {256, 128, 64, 32})
-        if (Nt % N == 0 && (N <= 64 || (long long)mtiles * (Nt / N) >= 96)) return N;
+        if (Nt % N == 0) return N;
     return 0;
 }
 
@@ -626,9 +628,10 @@ int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const
     if (split && a.N > 128) a.N = 128;           // the 3xTF32 stage is twice as large
     a.nstages = pick_stages(a.N, split);
     const int ctas = mtiles * (a.Nt / a.N);
+    const int want = (a.N / 32) * (split ? 2 : 1) <= 4 ? 296 : 148;      // resident CTAs: two per SM where the kernel allows it
     int nslice = 1;
-    if (ctas < 148 && max_kb >= 8) {
-        nslice = (296 + ctas - 1) / ctas;
+    if (ctas < want / 2 + want / 4 && max_kb >= 8) {
+        nslice = (want + ctas - 1) / ctas;
         nslice = std::min(nslice, max_kb / 4);
         nslice = std::max(nslice, 1);
     }
@@ -851,13 +854,14 @@ int launch_filtergrad(TcgFilterArgs& a, int ntap, cudaStream_t st) {
     if (!a.ksmall && ((a.Ci & 31) || (a.cpa & (a.cpa - 1)) || (a.Ci > 128 && a.Ci % 128))) { rdg_set_error("tcg filter gradient: Ci must be 32, 64 or a multiple of 128"); return RDG_TCG_E_SHAPE; }
     int N = 0;
     for (int n : {256, 128, 64, 32})
-        if (a.Co % n == 0 && (n <= 64 || (long long)ntap * a.Mt * (a.Co / n) >= 96)) { N = n; break; }
+        if (a.Co % n == 0) { N = n; break; }     // widest B tile: the A tile is fetched once per N tile (operand-stream bound)
     if (!N) { rdg_set_error("tcg filter gradient: Co must be a multiple of 32"); return RDG_TCG_E_SHAPE; }
     a.N = N;
     a.nstages = pick_stages(N, false);
     const int ctas = ntap * a.Mt * (a.Co / N);
     const int nkb = (a.rows + 31) / 32;
-    int ks = (592 + ctas - 1) / ctas;
+    const int want = N <= 128 ? 592 : 296;
+    int ks = (want + ctas - 1) / ctas;
     ks = std::max(1, std::min(ks, nkb / 4));
     a.ksplit = ks;
     dim3 grid(ntap, a.Mt * (a.Co / N), ks);

@@ -523,8 +523,7 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
         TRY(critic_conv_fwd_tc(c, l, A3.h[l], c->c_params + c->c_off[2 * l + 1], A3.h[l + 1], g, ACT_LRELU, masks3 ? masks3[l] : nullptr, st,
                                A3.a[l + 1], 1));
     }
-    TRY(simt_conv_fwd(A3.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A3.score, rdg_critic_dense_geom(c, 3 * B), ACT_NONE,
-                      nullptr, 1.f, st));
+    TRY(ew_dense_score(A3.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A3.score, 3 * B, (int)critic_act_elems(c, 4), st));
     TRY(ew_mean_scaled(A3.score + B, B, -1.f, lsc + 0, st));      // l_valid = mean(-D(real))  (:215-216, targets :452-454)
     TRY(ew_mean_scaled(A3.score, B, 1.f, lsc + 1, st));           // l_fake  = mean(+D(fake))
 
@@ -608,7 +607,7 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     ConvGeom gp{};       // the output conv's tap products as a 1x1x1 "conv" 64 -> 32 over the 24 x nd x nd grid
     gp.B = B; gp.Ti = gp.To = RDG_NHOURS; gp.Hi = gp.Ho = c->nd; gp.Wi = gp.Wo = c->nd; gp.Ci = 64; gp.Co = 32;
     gp.KT = gp.KH = gp.KW = 1; gp.stride = 1;
-    TRY(tcg_conv_fwd(G.y[3], c->g_w4p, nullptr, ptap, gp, ACT_NONE, nullptr, 1.f, st, nullptr, 1));
+    TRY(tcg_conv_fwd(G.y[3], c->g_w4p, nullptr, ptap, gp, ACT_NONE, nullptr, 1.f, st, nullptr, 1));     // the image feeds the critic's LeakyReLUs: 3xTF32 too
     TRY(ew_tap_gather_logits(ptap, c->g_params + c->g_off[9], G.logits, B, c->nd, st));
     TRY(ew_softmax_hours(G.logits, G.img, B, c->nd * c->nd, nullptr, 1, 1, 1.f, 0, nullptr, st));
 
@@ -618,7 +617,7 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
         ConvGeom g = rdg_critic_conv_geom(c, l, B);
         TRY(critic_conv_fwd_tc(c, l, A.h[l], c->c_params + c->c_off[2 * l + 1], A.h[l + 1], g, ACT_LRELU, masks ? masks[l] : nullptr, st, A.a[l + 1], 1));
     }
-    TRY(simt_conv_fwd(A.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A.score, rdg_critic_dense_geom(c, B), ACT_NONE, nullptr, 1.f, st));
+    TRY(ew_dense_score(A.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A.score, B, (int)critic_act_elems(c, 4), st));
     TRY(ew_mean_scaled(A.score, B, -1.f, loss_dev, st));                   // wasserstein_loss with target -1 (:408, :452)
     TRY(ew_fill(dscore, B, -1.f / (float)B, st));
     TRY(simt_conv_bwd_data(dscore, c->c_params + c->c_off[8], t0, rdg_critic_dense_geom(c, B), st));
