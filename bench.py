@@ -412,8 +412,8 @@ def main():
         ms_graph = timed(ig.replay, 20)
         losses, gl = ig.d_losses.cpu().numpy(), float(ig.g_loss.item())
         dl, gls = torch.zeros((5, 4), device=dev), torch.zeros(1, device=dev)
-        ms_crit = timed(lambda: tr.critic_step_device(x_real[0], tcond[0], dl[0]), 20)
-        ms_gen = timed(lambda: tr.generator_step_device(tcond[0], gls), 20)
+        ms_crit = timed(lambda: (tr.critic_step_device(x_real[0], tcond[0], dl[0]), tr.finish()), 20)
+        ms_gen = timed(lambda: (tr.generator_step_device(tcond[0], gls), tr.finish()), 20)
         tg = torch.Generator(device=dev); tg.manual_seed(5 + rank)
         tr32 = GanTrainer(tgen, tcrit, gen_mode="fp16", seed=100, train_mode="fp32")
 
@@ -458,7 +458,7 @@ def main():
                 barrier()
             tr.profile_comm = True
             tr.comm_ms()
-            ms_eager = timed(lambda: [tr.critic_step_device(x_real[k], tcond[k], dl[k]) for k in range(5)] + [tr.generator_step_device(tcond[0], gls)], 10)
+            ms_eager = timed(lambda: [tr.critic_step_device(x_real[k], tcond[k], dl[k]) for k in range(5)] + [tr.generator_step_device(tcond[0], gls), tr.finish()], 10)
             comm = tr.comm_ms() / 13.0
             tr.profile_comm = False
             dp = {"ranks": world, "grad_parity_rel_l2": errs, "allreduce_ms_per_iteration": comm,

@@ -154,11 +154,14 @@ int  rdg_set_train_mode(rdg_ctx* ctx, int mode);
 /* The same evaluations with the step's random inputs drawn on the device (Philox: key = seed, counter = element / stream / a step
  * counter that lives in device memory): latent ~ N(0,1) (:470, :177-193), alpha ~ U[0,1) (:223), Dropout(0.25) keep masks
  * (:289-301; dropout = 0 disables them).  No host value enters the launch arguments, so the calls of a whole 5 + 1 iteration
- * (plus rdg_adam_apply_dev and the gradient all-reduce) can be captured in one CUDA graph and replayed.  Need train mode 1. */
+ * (plus rdg_adam_apply_dev and the gradient all-reduce) can be captured in one CUDA graph and replayed.  Need train mode 1.
+ * phases: 3 = the whole evaluation; 1 = only the part that does not read the critic's weights (random draws, generator forward,
+ * interpolation, critic inputs), 2 = the rest.  Issuing 1 and 2 separately lets the head of a step run while another stream
+ * still exchanges / applies the previous step's critic gradients. */
 int  rdg_critic_step_dev(rdg_ctx* ctx, const float* x_real_dev, const float* cond_dev, int B, int gen_mode,
-                         unsigned long long seed, int dropout, float* losses4_dev, void* stream);
+                         unsigned long long seed, int dropout, float* losses4_dev, int phases, void* stream);
 int  rdg_generator_step_dev(rdg_ctx* ctx, const float* cond_dev, int B, unsigned long long seed, int dropout,
-                            float* loss_dev, void* stream);
+                            float* loss_dev, int phases, void* stream);
 /* rdg_adam_apply with the shared step counter kept (and incremented) in device memory, followed by the refresh of the derived
  * weight images the next step reads; gen_mode = the mode of the frozen generator forward in the critic step. */
 int  rdg_adam_apply_dev(rdg_ctx* ctx, int which, float lr, float beta1, float beta2, float eps, float grad_scale,

@@ -281,8 +281,9 @@ extern "C" int rdg_generator_set_weights(rdg_ctx* c, const float* const* tensors
     c->fold32_stale = true; c->g_tcw_stale = true; c->gen_stale_kinds = 3;
     r = rdg_repack_generator(c, nullptr, 3);
     if (r) return r;
-    RDG_CUDA(cudaDeviceSynchronize());
     c->gen_ready = true;
+    if (c->train_mode == 1 && (r = rdg_refresh_train_weights(c, 0, nullptr))) return r;
+    RDG_CUDA(cudaDeviceSynchronize());
     return 0;
 }
 
@@ -307,6 +308,8 @@ extern "C" int rdg_critic_set_weights(rdg_ctx* c, const float* const* tensors, c
     if (r) return r;
     c->critic_ready = true;
     c->critic_packed_stale = true; c->c_wT_stale = true;
+    if (c->train_mode == 1 && (r = rdg_refresh_train_weights(c, 1, nullptr))) return r;
+    RDG_CUDA(cudaDeviceSynchronize());
     return 0;
 }
 extern "C" int rdg_critic_get_weights(rdg_ctx* c, float* const* tensors, const size_t* sizes, int n) {

@@ -66,4 +66,5 @@ ConvGeom rdg_critic_conv_geom(const rdg_ctx* c, int layer, int B);
 ConvGeom rdg_critic_dense_geom(const rdg_ctx* c, int B);
 int rdg_repack_generator(rdg_ctx* c, cudaStream_t st, int kinds);   // kinds: bit 0 = bf16, bit 1 = fp16
 static inline int rdg_kind_bit(int mode) { return mode == 1 /* RDG_MODE_BF16 */ ? 1 : 2; }
-int rdg_refold32(rdg_ctx* c, cudaStream_t st);      // refresh g_wfold32 if the generator weights changed
+int rdg_refold32(rdg_ctx* c, cudaStream_t st);
+int rdg_refresh_train_weights(rdg_ctx* c, int which, cudaStream_t st);   // train.cu: derived images of train mode 1 (which: 0 gen, 1 critic)      // refresh g_wfold32 if the generator weights changed

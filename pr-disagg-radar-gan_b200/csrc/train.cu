@@ -235,7 +235,8 @@ namespace {
 int critic_step_tc_masks(rdg_ctx* c, const float* x_real, const float* cond, const float* latent, const float* alpha,
                          const float* const* mf, const float* const* mr, const float* const* mh, int B, int gen_mode, float* losses4,
                          cudaStream_t st);
-int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const float* const* masks, int B, float* loss_dev, cudaStream_t st);
+int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const float* const* masks, int B, float* loss_dev, cudaStream_t st,
+                      int phases = 3);
 }
 
 // critic_model.train_on_batch evaluation without the optimizer update
@@ -482,8 +483,10 @@ int critic_conv_fwd_tc(rdg_ctx* c, int l, const float* x, const float* bias, flo
 }
 
 // masks3: per layer ONE buffer of 3B samples [fake | real | interpolated] (or all null)
+// phases: bit 0 = the part that does not read the critic's weights (frozen generator forward, interpolation, critic inputs), bit 1 =
+// the rest.  Issued separately, phase 1 of a step overlaps the gradient exchange + Adam update of the previous step (other stream).
 int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const float* latent, const float* alpha, const float* const* masks3,
-                   int B, int gen_mode, float* losses4, cudaStream_t st) {
+                   int B, int gen_mode, float* losses4, cudaStream_t st, int phases = 3) {
     const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
     size_t max_act = 0, sum_act = 0;
     for (int l = 0; l < 5; ++l) { max_act = std::max(max_act, critic_act_elems(c, l)); sum_act += critic_act_elems(c, l); }
@@ -507,16 +510,19 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     float* vbuf = ws.f((size_t)B * max_act);
     float* dscore3 = ws.f(3 * B); float* norm = ws.f(B); float* lsc = ws.f(8);
     if (!lsc || !vbuf || !da[4]) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
-    TRY(refresh_critic_wT(c, st));
     const float ms = 1.f / 0.75f;
 
-    // frozen generator forward (:370, generator.trainable = False :363)
-    TRY(rdg_generator_forward(c, latent, cond, 1, fake_img, B, gen_mode, RDG_OUT_FRACTION, 1.f, nullptr, st));
+    if (phases & 1) {
+        // frozen generator forward (:370, generator.trainable = False :363)
+        TRY(rdg_generator_forward(c, latent, cond, 1, fake_img, B, gen_mode, RDG_OUT_FRACTION, 1.f, nullptr, st));
+        TRY(ew_interp(x_real, fake_img, alpha, xhat, B, (long long)px, st));                    // RandomWeightedAverage :221-224
+        TRY(ew_critic_input(fake_img, cond, A3.h[0], B, c->nd, c->ncond, st));
+        TRY(ew_critic_input(x_real, cond, A3.h[0] + (size_t)B * critic_act_elems(c, 0), B, c->nd, c->ncond, st));
+        TRY(ew_critic_input(xhat, cond, hat_h[0], B, c->nd, c->ncond, st));
+    }
+    if (!(phases & 2)) return 0;
+    TRY(refresh_critic_wT(c, st));
     RDG_CUDA(cudaMemsetAsync(c->c_grads, 0, c->c_total * 4, st));
-    TRY(ew_interp(x_real, fake_img, alpha, xhat, B, (long long)px, st));                    // RandomWeightedAverage :221-224
-    TRY(ew_critic_input(fake_img, cond, A3.h[0], B, c->nd, c->ncond, st));
-    TRY(ew_critic_input(x_real, cond, A3.h[0] + (size_t)B * critic_act_elems(c, 0), B, c->nd, c->ncond, st));
-    TRY(ew_critic_input(xhat, cond, hat_h[0], B, c->nd, c->ncond, st));
     // critic forward on [fake | real | interpolated] (:372, :373, :379)
     for (int l = 0; l < 4; ++l) {
         ConvGeom g = rdg_critic_conv_geom(c, l, 3 * B);
@@ -570,7 +576,8 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     return 0;
 }
 
-int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const float* const* masks, int B, float* loss_dev, cudaStream_t st) {
+int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const float* const* masks, int B, float* loss_dev, cudaStream_t st,
+                      int phases) {
     const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
     size_t cmax = 0, csum = 0, gsum = 0, gmax = 0;
     for (int l = 0; l < 5; ++l) { cmax = std::max(cmax, critic_act_elems(c, l)); csum += critic_act_elems(c, l); }
@@ -591,12 +598,15 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     float* dw4 = ws.f(2048);
     float* dscore = ws.f(B);
     if (!dscore || !dwf || !ptap) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
-    TRY(refresh_gen_tcw(c, st));
-    TRY(refresh_critic_wT(c, st));
     const float ms = 1.f / 0.75f;
-
-    // ---- generator forward keeping what the backward needs (:319-350)
     ConvGeom dg = rdg_gen_dense_geom(c, B);
+    ConvGeom gp{};       // the output conv's tap products as a 1x1x1 "conv" 64 -> 32 over the 24 x nd x nd grid
+    gp.B = B; gp.Ti = gp.To = RDG_NHOURS; gp.Hi = gp.Ho = c->nd; gp.Wi = gp.Wo = c->nd; gp.Ci = 64; gp.Co = 32;
+    gp.KT = gp.KH = gp.KW = 1; gp.stride = 1;
+
+    if (phases & 1) {
+    TRY(refresh_gen_tcw(c, st));
+    // ---- generator forward keeping what the backward needs (:319-350); does not read the critic's weights
     TRY(ew_assemble_gen_input(latent, cond, 1, 0, G.x0, B, c->nd * c->nd * c->ncond, st));
     TRY(tcg_conv_fwd(G.x0, c->g_denseT, c->g_params + c->g_off[1], G.y[0], dg, ACT_LRELU, nullptr, 1.f, st, G.d0_pre, 1));
     for (int l = 0; l < 3; ++l) {
@@ -604,15 +614,15 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
         TRY(tcg_folded_fwd(G.y[l], c->g_wfoldT[l], c->g_params + c->g_off[3 + 2 * l], G.cpre[l + 1], g, st, 1));
         TRY(ew_pixelnorm(G.cpre[l + 1], G.y[l + 1], (long long)B * g.To * g.Ho * g.Wo, g.Co, 1, st));
     }
-    ConvGeom gp{};       // the output conv's tap products as a 1x1x1 "conv" 64 -> 32 over the 24 x nd x nd grid
-    gp.B = B; gp.Ti = gp.To = RDG_NHOURS; gp.Hi = gp.Ho = c->nd; gp.Wi = gp.Wo = c->nd; gp.Ci = 64; gp.Co = 32;
-    gp.KT = gp.KH = gp.KW = 1; gp.stride = 1;
     TRY(tcg_conv_fwd(G.y[3], c->g_w4p, nullptr, ptap, gp, ACT_NONE, nullptr, 1.f, st, nullptr, 1));     // the image feeds the critic's LeakyReLUs: 3xTF32 too
     TRY(ew_tap_gather_logits(ptap, c->g_params + c->g_off[9], G.logits, B, c->nd, st));
     TRY(ew_softmax_hours(G.logits, G.img, B, c->nd * c->nd, nullptr, 1, 1, 1.f, 0, nullptr, st));
+    TRY(ew_critic_input(G.img, cond, A.h[0], B, c->nd, c->ncond, st));
+    }
+    if (!(phases & 2)) return 0;
+    TRY(refresh_critic_wT(c, st));
 
     // ---- critic on the generated sample (critic frozen :395, dropout active) and its backward to the image
-    TRY(ew_critic_input(G.img, cond, A.h[0], B, c->nd, c->ncond, st));
     for (int l = 0; l < 4; ++l) {
         ConvGeom g = rdg_critic_conv_geom(c, l, B);
         TRY(critic_conv_fwd_tc(c, l, A.h[l], c->c_params + c->c_off[2 * l + 1], A.h[l + 1], g, ACT_LRELU, masks ? masks[l] : nullptr, st, A.a[l + 1], 1));
@@ -721,9 +731,22 @@ int critic_step_tc_masks(rdg_ctx* c, const float* x_real, const float* cond, con
 }
 }  // namespace
 
+// Derived weight images of the tensor-core training mode (transposed / folded / padded copies): rebuilt whenever the master
+// weights change OUTSIDE a training step too (set_weights, checkpoint load), so that a captured iteration can be replayed on
+// them without any host-side staleness check.
+int rdg_refresh_train_weights(rdg_ctx* c, int which, cudaStream_t st) {
+    if (which == 0) return c->gen_ready ? refresh_gen_tcw(c, st) : 0;
+    return c->critic_ready ? refresh_critic_wT(c, st) : 0;
+}
+
 extern "C" int rdg_set_train_mode(rdg_ctx* c, int mode) {
     if (!c || (mode != 0 && mode != 1)) return RDG_E_BADARG;
+    RDG_CUDA(cudaSetDevice(c->device));
     c->train_mode = mode;
+    if (mode == 1) {
+        TRY(rdg_refresh_train_weights(c, 0, nullptr));
+        TRY(rdg_refresh_train_weights(c, 1, nullptr));
+    }
     return 0;
 }
 
@@ -731,29 +754,32 @@ extern "C" int rdg_set_train_mode(rdg_ctx* c, int mode) {
 // Philox state (key = seed, counter = (element, stream, step counter in device memory)): no host work between the calls, so a
 // whole 5 + 1 iteration can be captured in one CUDA graph and replayed (the step counter advances inside the graph).
 extern "C" int rdg_critic_step_dev(rdg_ctx* c, const float* x_real_dev, const float* cond_dev, int B, int gen_mode,
-                                   unsigned long long seed, int dropout, float* losses4_dev, void* stream) {
+                                   unsigned long long seed, int dropout, float* losses4_dev, int phases, void* stream) {
     if (!c || B < 1 || !x_real_dev || !cond_dev || !losses4_dev) { rdg_set_error("rdg_critic_step_dev: bad arguments"); return RDG_E_BADARG; }
     if (!c->gen_ready || !c->critic_ready) { rdg_set_error("weights not set"); return RDG_E_NOWEIGHT; }
     if (c->train_mode != 1) { rdg_set_error("rdg_critic_step_dev needs the tensor-core training mode (rdg_set_train_mode(ctx, 1))"); return RDG_E_BADARG; }
     RDG_CUDA(cudaSetDevice(c->device));
     TRY(ensure_train_state(c)); TRY(ensure_tstate(c));
     cudaStream_t st = (cudaStream_t)stream;
+    if (phases < 1 || phases > 3) { rdg_set_error("rdg_critic_step_dev: phases must be 1, 2 or 3"); return RDG_E_BADARG; }
     const RndLayout L = rnd_layout(c, B, 3);
     TRY(ensure_rnd(c, L.total));
-    TRY(ew_train_tick(c->tstate, st));
-    TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 0, 0.f, st));   // np.random.normal :470
-    TRY(ew_fill_random_dev(c->rnd_buf + L.alpha, B, seed, c->tstate, 2, 1, 0.f, st));                              // tf.random.uniform :223
     const float* masks3[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (dropout) {        // Dropout(0.25) of the three critic invocations (:289-301): one draw over the four 3B mask tensors
-        TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 3, 2, 0.75f, st));
+    if (dropout)
         for (int l = 0; l < 4; ++l) masks3[l] = c->rnd_buf + L.mask[l];
+    if (phases & 1) {
+        TRY(ew_train_tick(c->tstate, st));
+        TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 0, 0.f, st));   // np.random.normal :470
+        TRY(ew_fill_random_dev(c->rnd_buf + L.alpha, B, seed, c->tstate, 2, 1, 0.f, st));                              // tf.random.uniform :223
+        if (dropout)      // Dropout(0.25) of the three critic invocations (:289-301): one draw over the four 3B mask tensors
+            TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 3, 2, 0.75f, st));
     }
     return critic_step_tc(c, x_real_dev, cond_dev, c->rnd_buf + L.latent, c->rnd_buf + L.alpha, dropout ? masks3 : nullptr, B, gen_mode,
-                          losses4_dev, st);
+                          losses4_dev, st, phases);
 }
 
 extern "C" int rdg_generator_step_dev(rdg_ctx* c, const float* cond_dev, int B, unsigned long long seed, int dropout, float* loss_dev,
-                                      void* stream) {
+                                      int phases, void* stream) {
     if (!c || B < 1 || !cond_dev || !loss_dev) { rdg_set_error("rdg_generator_step_dev: bad arguments"); return RDG_E_BADARG; }
     if (!c->gen_ready || !c->critic_ready) { rdg_set_error("weights not set"); return RDG_E_NOWEIGHT; }
     if (c->train_mode != 1) { rdg_set_error("rdg_generator_step_dev needs the tensor-core training mode (rdg_set_train_mode(ctx, 1))"); return RDG_E_BADARG; }
@@ -761,15 +787,17 @@ extern "C" int rdg_generator_step_dev(rdg_ctx* c, const float* cond_dev, int B, 
     TRY(ensure_train_state(c)); TRY(ensure_tstate(c));
     cudaStream_t st = (cudaStream_t)stream;
     const RndLayout L = rnd_layout(c, B, 1);
+    if (phases < 1 || phases > 3) { rdg_set_error("rdg_generator_step_dev: phases must be 1, 2 or 3"); return RDG_E_BADARG; }
     TRY(ensure_rnd(c, rnd_layout(c, B, 3).total));      // same buffer as the critic step: size it once
-    TRY(ew_train_tick(c->tstate, st));
-    TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 0, 0.f, st));   // generate_latent_points :177-193
     const float* masks[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (dropout) {
-        TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 3, 2, 0.75f, st));
+    if (dropout)
         for (int l = 0; l < 4; ++l) masks[l] = c->rnd_buf + L.mask[l];
+    if (phases & 1) {
+        TRY(ew_train_tick(c->tstate, st));
+        TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 0, 0.f, st));   // generate_latent_points :177-193
+        if (dropout) TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 3, 2, 0.75f, st));
     }
-    return generator_step_tc(c, c->rnd_buf + L.latent, cond_dev, dropout ? masks : nullptr, B, loss_dev, st);
+    return generator_step_tc(c, c->rnd_buf + L.latent, cond_dev, dropout ? masks : nullptr, B, loss_dev, st, phases);
 }
 
 // Keras-Adam with the shared step counter in device memory (incremented by the call), followed by the refresh of every derived

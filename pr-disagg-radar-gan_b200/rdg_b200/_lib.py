@@ -60,8 +60,9 @@ SIGNATURES = {
     "rdg_adam_reset": (C.c_int, [C.c_void_p, C.c_int]),
     "rdg_set_train_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "rdg_critic_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_ulonglong, C.c_int,
-                                      C.c_void_p, C.c_void_p]),
-    "rdg_generator_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "rdg_generator_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_ulonglong, C.c_int, C.c_void_p, C.c_int,
+                                         C.c_void_p]),
     "rdg_adam_apply_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                      C.c_void_p]),
     "rdg_train_state": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_ulonglong)]),

@@ -376,6 +376,7 @@ class GanTrainer:
     # -- checkpoint / resume.  The reference writes weights only (:520-521) and has no resume path
     # (`start_epoch` just labels plots, :526-529); this adds the optimizer state so training continues bit-identically.
     def state_dict(self):
+        self.finish()
         torch.cuda.synchronize(self.ctx.device)
         adam_t, rng_ctr = self._pull_counters()
         assert adam_t == self.optimizer.iterations, "host / device Adam step counters diverged"
@@ -446,29 +447,69 @@ class GanTrainer:
         _lib.check(self.ctx.lib.rdg_adam_apply_dev(self.ctx.handle, which, opt.lr, opt.beta_1, opt.beta_2, opt.epsilon,
                                                    1.0 / world, _lib.MODES[self.gen_mode], self.ctx._stream()))
 
-    # -- device-resident steps (tensor-core mode): noise / alpha / dropout masks drawn on the GPU, nothing read back
+    # -- device-resident steps (tensor-core mode): noise / alpha / dropout masks drawn on the GPU, nothing read back.
+    # Each step is issued in two phases: phase 1 does not read the critic's weights (random draws, generator forward,
+    # interpolation, critic inputs) and runs on the caller's stream WHILE a second stream still all-reduces and applies the previous
+    # step's critic gradients; phase 2 waits for that update.  A generator update is awaited before anything else runs.
+    def _update_stream(self):
+        if getattr(self, "_upd_stream", None) is None:
+            self._upd_stream = torch.cuda.Stream(device=self.ctx.device)
+            self._pending, self._pending_which = None, None
+        return self._upd_stream
+
+    def finish(self):
+        """Make the caller's stream wait for the last overlapped update (call before reading weights / losses on another path)."""
+        if getattr(self, "_pending", None) is not None:
+            torch.cuda.current_stream(self.ctx.device).wait_event(self._pending)
+            self._pending, self._pending_which = None, None
+
+    def _launch_update(self, which):
+        main, upd = torch.cuda.current_stream(self.ctx.device), self._update_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        upd.wait_event(ev)
+        with torch.cuda.stream(upd):
+            self._apply(which)
+            self._pending = torch.cuda.Event()
+            self._pending.record(upd)
+        self._pending_which = which
+
+    def _critic_calls(self, x_real, cond, losses_out):
+        ctx = self.ctx
+        args = (ctx.handle, C.c_void_p(x_real.data_ptr()), C.c_void_p(cond.data_ptr()), int(x_real.shape[0]),
+                _lib.MODES[self.gen_mode], self.seed + self.rank, int(self.dropout), C.c_void_p(losses_out.data_ptr()))
+        return [lambda ph=ph: _lib.check(ctx.lib.rdg_critic_step_dev(*args, ph, ctx._stream())) for ph in (1, 2)]
+
+    def _generator_calls(self, cond, loss_out):
+        ctx = self.ctx
+        args = (ctx.handle, C.c_void_p(cond.data_ptr()), int(cond.shape[0]), self.seed + self.rank, int(self.dropout),
+                C.c_void_p(loss_out.data_ptr()))
+        return [lambda ph=ph: _lib.check(ctx.lib.rdg_generator_step_dev(*args, ph, ctx._stream())) for ph in (1, 2)]
+
+    def _run_step(self, which, phase1, phase2):
+        """phase1 / phase2: callables that enqueue the two phases on the current stream (C calls or graph replays)."""
+        self._set_mode()
+        self._update_stream()
+        if self._pending_which == self.WHICH_GEN:
+            self.finish()                   # everything reads the generator: wait for its update first
+        phase1()
+        self.finish()                       # phase 2 reads the critic's weights and overwrites its gradient buffer
+        phase2()
+        self._launch_update(which)
+
     def critic_step_device(self, x_real, cond, losses_out):
         """One critic step (gradients + exchange + update) on device tensors; losses_out: cuda float32 [4]."""
-        ctx = self.ctx
-        self._set_mode()
-        _lib.check(ctx.lib.rdg_critic_step_dev(ctx.handle, C.c_void_p(x_real.data_ptr()), C.c_void_p(cond.data_ptr()),
-                                               int(x_real.shape[0]), _lib.MODES[self.gen_mode], self.seed + self.rank,
-                                               int(self.dropout), C.c_void_p(losses_out.data_ptr()), ctx._stream()))
-        self._apply(self.WHICH_CRITIC)
+        self._run_step(self.WHICH_CRITIC, *self._critic_calls(x_real, cond, losses_out))
 
     def generator_step_device(self, cond, loss_out):
-        ctx = self.ctx
-        self._set_mode()
-        _lib.check(ctx.lib.rdg_generator_step_dev(ctx.handle, C.c_void_p(cond.data_ptr()), int(cond.shape[0]),
-                                                  self.seed + self.rank, int(self.dropout), C.c_void_p(loss_out.data_ptr()),
-                                                  ctx._stream()))
-        self._apply(self.WHICH_GEN)
+        self._run_step(self.WHICH_GEN, *self._generator_calls(cond, loss_out))
 
-    def capture_iteration(self, batch, n_critic=5):
+    def capture_iteration(self, batch, n_critic=5, segmented=None):
         """Capture one training iteration (n_critic critic steps + 1 generator step, reference :468-482, with the gradient
         exchange and the Adam updates) in a CUDA graph.  Returns an IterationGraph: fill `x_real` [n_critic,B,24,nd,nd,1],
         `cond` [n_critic,B,nd,nd,ncond] and `cond_gen` [B,nd,nd,ncond] (static device tensors) and call replay();
-        `d_losses` [n_critic,4] and `g_loss` [1] are device tensors read whenever the caller wants (no sync per step)."""
+        `d_losses` [n_critic,4] and `g_loss` [1] are device tensors read whenever the caller wants (no sync per step).
+        segmented (default: world size > 1): one graph per step phase with the gradient exchange issued between them."""
         if self.train_mode != "tf32":
             raise RuntimeError("capture_iteration needs train_mode='tf32' (device-resident step inputs)")
         dev = f"cuda:{self.ctx.device}"
@@ -486,7 +527,9 @@ class GanTrainer:
             for k in range(n_critic):
                 self.critic_step_device(ig.x_real[k], ig.cond[k], ig.d_losses[k])
             self.generator_step_device(ig.cond_gen, ig.g_loss)
+            self.finish()               # the iteration ends with the generator update joined back
 
+        self.finish()
         it0 = self.optimizer.iterations
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(self.ctx.device))
@@ -494,18 +537,37 @@ class GanTrainer:
             body()                      # eager pass: allocations, attribute calls and weight images happen outside the capture
         torch.cuda.current_stream(self.ctx.device).wait_stream(s)
         torch.cuda.synchronize(self.ctx.device)
-        ig.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ig.graph):
-            body()
+        if segmented is None:
+            segmented = self._world() > 1
+        if not segmented:
+            ig.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ig.graph):
+                body()
+            # the eager pass was a real iteration; the capture itself launches nothing, only the host mirror moved
+            self.optimizer.iterations = it0 + n_critic + 1
+        else:
+            # data-parallel: the NCCL exchange stays outside the graphs (one graph per step phase; the all-reduce + Adam of a
+            # step are issued eagerly on the update stream between them and overlap the next step's first phase)
+            ig.graph = None
+            ig.segments = []
+            calls = [(self.WHICH_CRITIC, self._critic_calls(ig.x_real[k], ig.cond[k], ig.d_losses[k])) for k in range(n_critic)]
+            calls.append((self.WHICH_GEN, self._generator_calls(ig.cond_gen, ig.g_loss)))
+            for which, (p1, p2) in calls:
+                gs = []
+                for fn in (p1, p2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fn()
+                    gs.append(g)
+                ig.segments.append((which, gs[0], gs[1]))
         torch.cuda.synchronize(self.ctx.device)
-        # the eager pass was a real iteration; the capture itself launches nothing, only the host mirror moved
-        self.optimizer.iterations = it0 + n_critic + 1
         return ig
 
     # -- the two train_on_batch calls
     def critic_grads(self, x_real, cond, latent, alpha=None, masks3="draw"):
         """Losses + gradients of one critic step, no update.  masks3: "draw" | None | (mf, mr, mh)."""
         ctx = self.ctx
+        self.finish()
         xr, c, z = ctx.dev(x_real), ctx.dev(cond), ctx.dev(latent)
         B = int(xr.shape[0])
         if alpha is None:
@@ -534,6 +596,7 @@ class GanTrainer:
 
     def generator_grads(self, latent, cond, masks="draw"):
         ctx = self.ctx
+        self.finish()
         z, c = ctx.dev(latent), ctx.dev(cond)
         B = int(z.shape[0])
         if isinstance(masks, str):
@@ -565,5 +628,11 @@ class IterationGraph:
     """A captured training iteration (GanTrainer.capture_iteration)."""
 
     def replay(self):
-        self.graph.replay()
-        self.trainer.optimizer.iterations += self.n_critic + 1
+        t = self.trainer
+        if self.graph is not None:
+            self.graph.replay()
+            t.optimizer.iterations += self.n_critic + 1
+            return
+        for which, g1, g2 in self.segments:
+            t._run_step(which, g1.replay, g2.replay)      # _apply (all-reduce + Adam) advances the host step mirror itself
+        t.finish()

@@ -106,7 +106,8 @@ def test_tc_mode_close_to_fp32_mode(nets):
         assert _rel_l2(a, b) <= GRAD_TOL
 
 
-def test_device_steps_and_graph_replay(ctx16):
+@pytest.mark.parametrize("segmented", [False, True])
+def test_device_steps_and_graph_replay(ctx16, segmented):
     """rdg_critic_step_dev / rdg_generator_step_dev / rdg_adam_apply_dev: noise, alpha and dropout masks from the device Philox
     state; a captured iteration replays to the same trajectory as the same calls issued eagerly (identical seeds and counters;
     the only difference allowed is the summation order of the filter-gradient atomics)."""
@@ -131,16 +132,18 @@ def test_device_steps_and_graph_replay(ctx16):
         for k in range(5):
             tr.critic_step_device(xr[k], cd[k], dl[k])
         tr.generator_step_device(cd[0], gl)
+        tr.finish()
         eager_losses.append((dl.cpu().numpy().copy(), float(gl.item())))
+        if len(eager_losses) == 1:
+            w_eager = [w.copy() for w in tr.generator.get_weights()] + [w.copy() for w in tr.critic.get_weights()]
     assert tr.optimizer.iterations == 6 * n_iter == tr._pull_counters()[0]
-    w_eager = [w.copy() for w in tr.generator.get_weights()] + [w.copy() for w in tr.critic.get_weights()]
     assert all(np.isfinite(l[0]).all() and np.isfinite(l[1]) for l in eager_losses)
     # the steps really used fresh randomness each time: same data, different losses
     assert abs(eager_losses[0][0][0, 0] - eager_losses[0][0][1, 0]) > 0
 
     # captured (capture_iteration runs one eager pass on its own constant buffers before capturing)
     tr3 = fresh()
-    ig3 = tr3.capture_iteration(B)
+    ig3 = tr3.capture_iteration(B, segmented=segmented)     # segmented: the data-parallel form (NCCL between per-phase graphs)
     # rewind: fresh weights / moments / counters, then replay n_iter times on the real data
     tr3.generator.set_weights(W.init_generator_weights(7)); tr3.critic.set_weights(W.init_critic_weights(8))
     ctx16.lib.rdg_adam_reset(ctx16.handle, 0); ctx16.lib.rdg_adam_reset(ctx16.handle, 1)
@@ -152,11 +155,15 @@ def test_device_steps_and_graph_replay(ctx16):
         torch.cuda.synchronize()
         np.testing.assert_allclose(ig3.d_losses.cpu().numpy(), eager_losses[it][0], rtol=2e-3, atol=2e-4)
         assert abs(float(ig3.g_loss.item()) - eager_losses[it][1]) <= 2e-3 * max(1.0, abs(eager_losses[it][1]))
+        if it == 0:
+            w_graph = tr3.generator.get_weights() + tr3.critic.get_weights()
     assert tr3.optimizer.iterations == 6 * n_iter == tr3._pull_counters()[0]
-    w_graph = tr3.generator.get_weights() + tr3.critic.get_weights()
-    for a, b in zip(w_graph, w_eager):
+    # Weights after the FIRST iteration.  The filter gradients accumulate with FP32 atomics (summation order varies from run to
+    # run, ~1e-7 relative) and beta_1 = 0 Adam steps by lr * sign(g) at first, so elements whose gradient is rounding noise step
+    # the other way: two eager runs of the same iteration already differ in ~2 % of the generator's weights (tools/diag_replay.py);
+    # the trajectories then separate like any chaotic training run.  Hence: one iteration, and a distribution bound.
+    for i, (a, b) in enumerate(zip(w_graph, w_eager)):
         d = np.abs(a - b)
-        # beta_1 = 0 Adam is sign-SGD-like in its first steps: elements whose gradient is summation-order noise may step the
-        # other way; everything else agrees closely
-        assert np.mean(d <= 1e-4 * np.abs(b) + 5e-6) >= 0.97 or a.size < 100
-        assert d.max() <= 2e-3
+        frac = float(np.mean(d <= 1e-4 * np.abs(b) + 5e-6))
+        assert frac >= 0.9 or a.size < 100, f"tensor {i} {a.shape}: only {frac:.4f} of the elements agree, max diff {d.max():.3e}"
+        assert d.max() <= 1e-3, f"tensor {i} {a.shape}: max diff {d.max():.3e}"

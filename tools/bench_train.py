@@ -26,7 +26,12 @@ def main():
                     help="precision of the FROZEN generator forward inside the critic step")
     ap.add_argument("--paths", default="keras_fp32,keras_tf32,device,graph")
     ap.add_argument("--profile-steps", action="store_true", help="CUDA-event time of one critic step and one generator step (device path)")
+    ap.add_argument("--segmented", action="store_true", help="graph path: per-phase graphs (the data-parallel form) on one GPU too")
+    ap.add_argument("--dump-after", type=float, default=0, help="debug: dump all Python stacks after this many seconds")
     args = ap.parse_args()
+    if args.dump_after > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.dump_after, exit=True)
     from rdg_b200 import weights as W
     from rdg_b200.engine import Context, Generator, Critic, GanTrainer
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -70,6 +75,7 @@ def main():
     res = {}
     paths = args.paths.split(",")
     for name in paths:
+        print(f"[rank {rank}] path {name}", file=sys.stderr, flush=True)
         if name.startswith("keras"):
             tr = GanTrainer(gen, crit, gen_mode=args.gen_mode, seed=100, train_mode=name.split("_")[1])
 
@@ -88,15 +94,16 @@ def main():
                 for k in range(5):
                     tr.critic_step_device(x_real[k], cond[k], dl[k])
                 tr.generator_step_device(cond[0], gl)
+                tr.finish()
             res[name] = timed(iteration, args.iters)
             if args.profile_steps:
-                res["critic_step_ms"] = timed(lambda: tr.critic_step_device(x_real[0], cond[0], dl[0]), args.iters * 5)[0]
-                res["generator_step_ms"] = timed(lambda: tr.generator_step_device(cond[0], gl), args.iters * 5)[0]
+                res["critic_step_ms"] = timed(lambda: (tr.critic_step_device(x_real[0], cond[0], dl[0]), tr.finish()), args.iters * 5)[0]
+                res["generator_step_ms"] = timed(lambda: (tr.generator_step_device(cond[0], gl), tr.finish()), args.iters * 5)[0]
             res["losses_last"] = {"critic": dl[-1].cpu().tolist(), "generator": float(gl.item())}
         elif name == "graph":
             tr = GanTrainer(gen, crit, gen_mode=args.gen_mode, seed=100, train_mode="tf32")
             tr.profile_comm = False
-            ig = tr.capture_iteration(B)
+            ig = tr.capture_iteration(B, segmented=True if args.segmented else None)
             ig.x_real.copy_(x_real); ig.cond.copy_(cond); ig.cond_gen.copy_(cond[0])
             res[name] = timed(ig.replay, args.iters)
             res["graph_losses_last"] = {"critic": ig.d_losses[-1].cpu().tolist(), "generator": float(ig.g_loss.item())}
