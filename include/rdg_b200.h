@@ -132,6 +132,10 @@ int  rdg_critic_step_grads(rdg_ctx* ctx, const float* x_real_dev, const float* c
                            float* losses4_dev, void* stream);
 int  rdg_generator_step_grads(rdg_ctx* ctx, const float* latent_dev, const float* cond_dev,
                               const float* const* masks, int B, float* loss_dev, void* stream);
+/* critic_model.predict's third output (gan_train_cwgangp_pixelnorm.py:461, :238-241): grad[b] = d D(sample_b, cond_b) / d sample_b
+ * [B,24,nd,nd] (FP32, no dropout), optionally the scores [B] as well; GradientPenalty = sqrt(sum(grad^2)) - 1 per sample. */
+int  rdg_critic_input_grad(rdg_ctx* ctx, const float* sample_dev, const float* cond_dev, float* score_dev,
+                           float* grad_dev, int B, void* stream);
 /* which: 0 = generator, 1 = critic.  Returns device pointer + element count of the flat
  * FP32 gradient / parameter buffers (Keras tensor order, concatenated). */
 int  rdg_grad_buffer(rdg_ctx* ctx, int which, float** grads_dev, size_t* n);

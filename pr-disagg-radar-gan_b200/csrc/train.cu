@@ -360,6 +360,31 @@ extern "C" int rdg_critic_step_grads(rdg_ctx* c, const float* x_real_dev, const 
     return 0;
 }
 
+// score[b] = D(sample_b, cond_b) (optional) and grad[b] = d D(sample_b, cond_b) / d sample_b, inference mode (no dropout), FP32:
+// the quantity GradientPenalty takes the norm of (gan_train_cwgangp_pixelnorm.py:238-241); critic_model.predict's third output.
+extern "C" int rdg_critic_input_grad(rdg_ctx* c, const float* sample_dev, const float* cond_dev, float* score_dev, float* grad_dev, int B,
+                                     void* stream) {
+    if (!c || B < 1 || !sample_dev || !cond_dev || !grad_dev) { rdg_set_error("rdg_critic_input_grad: bad arguments"); return RDG_E_BADARG; }
+    if (!c->critic_ready) { rdg_set_error("weights not set"); return RDG_E_NOWEIGHT; }
+    RDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
+    size_t cmax = 0, csum = 0;
+    for (int l = 0; l < 5; ++l) { cmax = std::max(cmax, critic_act_elems(c, l)); csum += critic_act_elems(c, l); }
+    TRY(ensure_train_ws(c, ((size_t)B * (2 * csum + 3 * cmax + 64) + 4096) * 4 + 32 * 256));
+    Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
+    CriticActs A;
+    TRY(critic_alloc(c, ws, B, A));
+    float* t0 = ws.f((size_t)B * cmax); float* t1 = ws.f((size_t)B * cmax); float* dx0 = ws.f((size_t)B * cmax);
+    float* dscore = ws.f(B);
+    if (!dscore) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
+    TRY(critic_fwd_train(c, sample_dev, cond_dev, nullptr, B, A, st));
+    if (score_dev) RDG_CUDA(cudaMemcpyAsync(score_dev, A.score, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    TRY(ew_fill(dscore, B, 1.f, st));
+    TRY(critic_bwd(c, A, nullptr, dscore, B, nullptr, dx0, t0, t1, st));
+    return ew_extract_channel0(dx0, grad_dev, (long long)B * px, 1 + c->ncond, st);
+}
+
 // generator_model.train_on_batch evaluation without the optimizer update (:395-408, :482):
 // loss = mean(-D(G(z, c), c)); gradients w.r.t. the generator weights are left in the generator gradient buffer.
 extern "C" int rdg_generator_step_grads(rdg_ctx* c, const float* latent_dev, const float* cond_dev, const float* const* masks,

@@ -117,11 +117,24 @@ class _CriticModel:
     def train_on_batch(self, inputs, targets=None, alpha=None, masks3="draw"):
         return self._t.critic_train_on_batch(inputs, targets, alpha, masks3)
 
-    def predict(self, inputs):
-        """[valid, fake, gp] without updating (reference :461 uses it to build the graph)."""
+    def predict(self, inputs, alpha=None):
+        """[valid, fake, disc_gp] without updating (reference :461 calls it once before training): critic scores of the real
+        and the generated samples and the GradientPenalty output sqrt(sum(grad^2)) - 1 per sample (:238-241) at the
+        RandomWeightedAverage of both (:221-224; alpha ~ U[0,1) per sample unless given).  predict() runs without dropout."""
+        import torch
         x_real, cond, latent = inputs
+        x_real = np.asarray(x_real, np.float32); cond = np.asarray(cond, np.float32)
         fake_img = generator.predict([latent, cond])
-        return [critic.predict([x_real, cond]), critic.predict([fake_img, cond]), None]
+        n = x_real.shape[0]
+        if alpha is None:
+            alpha = np.random.uniform(size=(n, 1, 1, 1, 1))
+        alpha = np.asarray(alpha, np.float32).reshape(n, 1, 1, 1, 1)
+        xhat = alpha * x_real + (1 - alpha) * fake_img
+        t = self._t
+        # gradient of sum_b D(xhat_b) w.r.t. xhat: the generator-step backward of the critic with cotangent 1 per sample
+        g = t.critic_input_gradient(xhat, cond)
+        gp = np.sqrt(np.sum(g.reshape(n, -1) ** 2, axis=1, keepdims=True)) - 1
+        return [critic.predict([x_real, cond]), critic.predict([fake_img, cond]), gp.astype(np.float32)]
 
 
 class _GeneratorModel:
@@ -191,6 +204,8 @@ def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None, device_sam
     n_channel = {None: 1, 'doy': 3, 'lon': 2}[extra]
     if domain is not None:
         ndomain = int(domain)
+    global params
+    params = f'{startdate}-{enddate}-tp_thresh_daily{tp_thresh_daily}_n_thresh{n_thresh}_ndomain{ndomain}_stride{stride}'
     np.random.seed(seed)
     data = synthetic_radar(seed=seed) if data_array is None else np.asarray(data_array, np.float32)
     assert data.ndim == 4 and data.shape[1] == nhours
@@ -208,8 +223,13 @@ def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None, device_sam
     generator = create_generator()        # generator first, like the reference (:361-362)
     critic = create_discriminator()
     optimizer = Adam(lr=0.0001, beta_1=0, beta_2=0.9)     # reference :385
+    # Under torch.distributed (data-parallel replicas) GanTrainer broadcasts rank 0's weights / Adam state and gives every rank its
+    # own device random stream; the host-side draws (batch indices, latent noise: np.random below) get a per-rank seed as well,
+    # AFTER the weight initialisation above, which therefore is the same on every rank.
     trainer = GanTrainer(generator, critic, optimizer, gen_mode=gen_mode or os.environ.get('RDG_TRAIN_GEN_MODE', 'fp32'),
                          seed=seed)
+    if trainer.rank:
+        np.random.seed(seed + trainer.rank)
     critic_model = _CriticModel(trainer)
     generator_model = _GeneratorModel(trainer)
     if device_sampler is None:
@@ -312,6 +332,10 @@ def train(n_epochs, _batch_size, start_epoch=0, bat_per_epo=None, save=True):
             for k, (d, g) in enumerate(zip(hist['d_loss'], hist['g_loss'])):
                 f.write(f'{k},{d},{g}\n')
         if save:
+            # Weight files in the Keras HDF5 layout (model_weights tree + layer_names / weight_names attributes), WITHOUT the
+            # model_config attribute tf.keras.models.load_model needs (it holds the marshalled Lambda of :349-350, which only
+            # TensorFlow can write): load them with create_generator().load_weights(path) on the reference side, or with
+            # rdg_b200.hdf5.load_keras_weights here.
             os.makedirs(outdir, exist_ok=True)
             _hdf5.save_keras_weights(f'{outdir}/gen_{params}_{epoch:04d}.h5', generator.get_weights(), 'generator')
             _hdf5.save_keras_weights(f'{outdir}/disc_{params}_{epoch:04d}.h5', critic.get_weights(), 'critic')

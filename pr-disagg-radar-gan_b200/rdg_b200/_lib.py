@@ -53,6 +53,7 @@ SIGNATURES = {
                                         C.c_int, C.c_void_p, C.c_void_p]),
     "rdg_generator_step_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int,
                                            C.c_void_p, C.c_void_p]),
+    "rdg_critic_input_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "rdg_grad_buffer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _c_size_p]),
     "rdg_param_buffer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _c_size_p]),
     "rdg_adam_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_longlong,

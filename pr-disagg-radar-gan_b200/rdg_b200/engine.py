@@ -609,6 +609,19 @@ class GanTrainer:
                                                     self._maskptrs(m), B, C.c_void_p(loss.data_ptr()), ctx._stream()))
         return loss
 
+    def critic_input_gradient(self, sample, cond):
+        """d sum_b D(sample_b, cond_b) / d sample without dropout -> (B,24,nd,nd,1) numpy: the gradient GradientPenalty takes the
+        norm of (gan_train_cwgangp_pixelnorm.py:238-241), from rdg_critic_input_grad (critic forward + transposed-conv chain)."""
+        ctx = self.ctx
+        self.finish()
+        x, c = ctx.dev(sample), ctx.dev(cond)
+        B = int(x.shape[0])
+        g = torch.empty((B, W.NHOURS, ctx.nd, ctx.nd), device=x.device, dtype=torch.float32)
+        _lib.check(ctx.lib.rdg_critic_input_grad(ctx.handle, C.c_void_p(x.data_ptr()), C.c_void_p(c.data_ptr()), None,
+                                                 C.c_void_p(g.data_ptr()), B, ctx._stream()))
+        torch.cuda.synchronize(ctx.device)
+        return g.cpu().numpy().reshape(B, W.NHOURS, ctx.nd, ctx.nd, 1)
+
     def generator_train_on_batch(self, inputs, target=None, masks="draw"):
         """generator_model.train_on_batch([latent, cond], valid) -> g_loss (:482)."""
         latent, cond = inputs

@@ -101,3 +101,28 @@ def test_training_script_surface(tmp_path, monkeypatch):
     assert os.path.exists("hist.csv")
     out = m.generate(np.full((16, 16, 1), 0.1, np.float32))
     assert out.shape == (1, 24, 16, 16, 1) and abs(out.sum() - 256.0) < 1e-2
+
+
+def test_critic_model_predict_returns_three_outputs(tmp_path, monkeypatch):
+    """critic_model.predict([X_real, cond, latent]) -> [valid, fake, disc_gp] like the reference's compiled model (:387-392, :461):
+    the third output is GradientPenalty = sqrt(sum(grad^2)) - 1 at the RandomWeightedAverage, checked against the independent
+    numpy restatement's hand-written backward (oracle/rdg_oracle_np.py)."""
+    import rdg_oracle_np as ON
+    monkeypatch.chdir(tmp_path)
+    sys.modules.pop("gan_train_cwgangp_pixelnorm", None)
+    m = importlib.import_module("gan_train_cwgangp_pixelnorm")
+    m.setup(seed=4)
+    rng = np.random.default_rng(8)
+    X, c = next(m.generate_real_samples(3))
+    z = rng.standard_normal((3, 100)).astype(np.float32)
+    alpha = rng.random((3, 1, 1, 1, 1)).astype(np.float32)
+    valid, fake, gp = m.critic_model.predict([X, c, z], alpha=alpha)
+    assert valid.shape == fake.shape == gp.shape == (3, 1)
+    cw = [w.astype(np.float64) for w in m.critic.get_weights()]
+    fake_img = m.generator.predict([z, c]).astype(np.float64)
+    for b in range(3):
+        xhat = alpha[b].astype(np.float64) * X[b] + (1 - alpha[b].astype(np.float64)) * fake_img[b]
+        s, g = ON.critic_one(cw, xhat, c[b].astype(np.float64), want_input_grad=True)
+        want = np.sqrt((g * g).sum()) - 1
+        assert abs(float(gp[b, 0]) - want) <= 1e-4 * max(1.0, abs(want))
+        assert abs(float(valid[b, 0]) - ON.critic_one(cw, X[b].astype(np.float64), c[b].astype(np.float64))) <= 1e-4
