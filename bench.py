@@ -334,6 +334,22 @@ def main():
                "h2d_bytes_per_step": int(lat_h.numel() * 4 + cond_p.numel() * 4),
                "d2h_bytes_per_step": int(B * 24 * 16 * 16 * 4), "steps": n_e2e,
                "api": f"rdg_generate_host, pinned buffers, {grp_cond} conditions per call"}
+        # the same call with a PAGEABLE result buffer (what gen.predict hands over): internal pinned staging ring + host callbacks
+        n_pg = min(n_cond, 2 * grp_cond)
+        out_pg = np.empty((grp, 24, 16, 16), np.float32)
+        gen.generate_ensemble_host(lat_h[:grp], cond_p[:grp_cond], spc, out=out_pg, mode=args.mode, out_mm=True)
+        barrier()
+        t0 = time.perf_counter()
+        for c0 in range(0, n_pg, grp_cond):
+            gen.generate_ensemble_host(lat_h[c0 * spc:(c0 + grp_cond) * spc], cond_p[c0:c0 + grp_cond], spc, out=out_pg, mode=args.mode, out_mm=True)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e["pageable_out_value"] = world * n_pg * spc / float(t.item())
+        c_last = max(0, n_pg - grp_cond)
+        assert np.array_equal(out_pg[:1000], out[c_last * spc:c_last * spc + 1000].cpu().numpy()), "pageable e2e output differs"
+        del out_pg
         # the last group's e2e result equals the device-resident result
         last0 = ((n_cond - 1) // grp_cond) * grp_cond * spc
         assert torch.equal(out_h[:1000], out[last0:last0 + 1000].cpu()), "e2e output differs from device-resident output"

@@ -71,9 +71,12 @@ int  rdg_generator_forward(rdg_ctx* ctx, const float* latent_dev, const float* c
                            int scen_per_cond, float* out_dev, int B, int mode, int out_kind,
                            float norm_scale, int* nonfinite_flag_dev, void* stream);
 
-/* Host-buffer end-to-end variant of the same call: chunks the batch, overlaps H2D of the
- * next chunk / compute / D2H of the previous one on three streams with pinned staging.
- * Blocking.  Returns RDG_E_NONFINITE like check_numerics would raise. */
+/* Host-buffer end-to-end variant of the same call: chunks the batch and overlaps H2D of the next chunk / compute / D2H of the
+ * previous one on three streams of the context.  Pinned (cudaHostAlloc / cudaHostRegister) buffers are copied from / to
+ * directly; a PAGEABLE result buffer (a plain numpy array) larger than one chunk goes through an internal ring of three pinned
+ * staging slots that host callbacks on a fourth stream drain into the caller's buffer, so the copies still overlap.
+ * Blocking.  Runs on the context's own streams: if generator weights were changed on a caller stream the call first waits for
+ * the device.  Returns RDG_E_NONFINITE like check_numerics would raise. */
 int  rdg_generate_host(rdg_ctx* ctx, const float* latent_host, const float* cond_host,
                        int scen_per_cond, float* out_host, long long B, int mode, int out_kind,
                        float norm_scale);

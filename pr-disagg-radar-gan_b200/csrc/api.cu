@@ -186,8 +186,14 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     cudaFree(c->e2e_cond);
+    for (int i = 0; i < 3; ++i) {
+        if (c->stage_out[i]) cudaFreeHost(c->stage_out[i]);
+        if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+        if (c->ev_host[i]) cudaEventDestroy(c->ev_host[i]);
+    }
+    if (c->s_host) cudaStreamDestroy(c->s_host);
     cudaFree(c->train_ws);
-    cudaFree(c->c_wT); cudaFree(c->c_w1p); cudaFree(c->g_denseT); cudaFree(c->g_w4p); cudaFree(c->tstate); cudaFree(c->rnd_buf);
+    cudaFree(c->c_wT); cudaFree(c->c_w1p); cudaFree(c->c_w1p_score); cudaFree(c->g_denseT); cudaFree(c->g_w4p); cudaFree(c->tstate); cudaFree(c->rnd_buf);
     for (int i = 0; i < 3; ++i) cudaFree(c->g_wfoldT[i]);
     for (int i = 0; i < 3; ++i) {
         if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
@@ -465,12 +471,34 @@ extern "C" int rdg_generator_forward(rdg_ctx* c, const float* latent_dev, const 
     return 0;
 }
 
+namespace {
+struct HostCopyJob { void* dst; const void* src; size_t bytes; };
+void CUDART_CB host_copy_cb(void* p) {
+    HostCopyJob* j = static_cast<HostCopyJob*>(p);
+    memcpy(j->dst, j->src, j->bytes);
+    delete j;
+}
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+void drain_host_pipeline(rdg_ctx* c) {
+    cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_d2h);
+    if (c->s_host) cudaStreamSynchronize(c->s_host);
+}
+}  // namespace
+
+// Stream contract of the *_host calls: they run on the context's own three (four) streams and block until the result is in the
+// caller's buffer.  Weight-mutating calls (set_weights, rdg_adam_apply*) run on the CALLER's stream, so a *_host call that finds
+// the packed generator weights stale first waits for the whole device (the only ordering available without the caller's stream).
 extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const float* cond_host, int spc, float* out_host,
                                  long long B, int mode, int out_kind, float norm_scale) {
     if (!c || B < 0 || spc < 1 || mode < 0 || mode > 2) { rdg_set_error("rdg_generate_host: bad arguments"); return RDG_E_BADARG; }
     if (!c->gen_ready) { rdg_set_error("generator weights not set"); return RDG_E_NOWEIGHT; }
     if (B == 0) return 0;
     RDG_CUDA(cudaSetDevice(c->device));
+    if (c->gen_stale_kinds || c->fold32_stale) RDG_CUDA(cudaDeviceSynchronize());
     if (mode != RDG_MODE_FP32 && (c->gen_stale_kinds & rdg_kind_bit(mode))) { int r = rdg_repack_generator(c, c->s_comp, rdg_kind_bit(mode)); if (r) return r; }
     const int chunk = chunk_for_mode(c, mode);
     const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
@@ -485,6 +513,17 @@ extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const flo
         c->e2e_cond = nullptr;
         RDG_CUDA(cudaMalloc(&c->e2e_cond, (size_t)n_cond * ncf * 4));
         c->e2e_cond_cap = (size_t)n_cond * ncf;
+    }
+    // Pageable result buffer (e.g. the numpy array of gen.predict): a cudaMemcpyAsync into it would be staged by the driver
+    // synchronously, chunk by chunk, with no overlap.  Instead the D2H copies land in a ring of three pinned staging slots and a
+    // host callback on a fourth stream moves each slot into the caller's buffer while the next chunk is already on the wire.
+    const bool staged = B > chunk && !is_pinned_host(out_host);
+    if (staged) {
+        if (!c->s_host) RDG_CUDA(cudaStreamCreateWithFlags(&c->s_host, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) {
+            if (!c->stage_out[i]) RDG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->stage_out[i]), (size_t)c->max_chunk * plane * 4, cudaHostAllocDefault));
+            if (!c->ev_stage[i]) { RDG_CUDA(cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming)); RDG_CUDA(cudaEventCreateWithFlags(&c->ev_host[i], cudaEventDisableTiming)); }
+        }
     }
     RDG_CUDA(cudaMemsetAsync(c->flag_dev, 0, sizeof(int), c->s_comp));
     RDG_CUDA(cudaMemcpyAsync(c->e2e_cond, cond_host, (size_t)n_cond * ncf * 4, cudaMemcpyHostToDevice, c->s_comp));
@@ -501,14 +540,28 @@ extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const flo
         if (it >= 2) RDG_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_out[k], 0));
         int r = gen_forward_chunk(c, c->e2e_lat[k], c->e2e_cond, spc, (int)b0, c->e2e_out[k], n, mode, out_kind, norm_scale,
                                   c->flag_dev, c->s_comp);
-        if (r) return r;
+        if (r) { drain_host_pipeline(c); return r; }
         RDG_CUDA(cudaEventRecord(c->ev_comp[k], c->s_comp));
         RDG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[k], 0));
-        RDG_CUDA(cudaMemcpyAsync(out_host + b0 * plane, c->e2e_out[k], (size_t)n * plane * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-        RDG_CUDA(cudaEventRecord(c->ev_out[k], c->s_d2h));
+        if (!staged) {
+            RDG_CUDA(cudaMemcpyAsync(out_host + b0 * plane, c->e2e_out[k], (size_t)n * plane * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            RDG_CUDA(cudaEventRecord(c->ev_out[k], c->s_d2h));
+        } else {
+            const int slot = (int)(it % 3);
+            if (it >= 3) RDG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_host[slot], 0));      // slot drained by its host copy
+            RDG_CUDA(cudaMemcpyAsync(c->stage_out[slot], c->e2e_out[k], (size_t)n * plane * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            RDG_CUDA(cudaEventRecord(c->ev_out[k], c->s_d2h));
+            RDG_CUDA(cudaEventRecord(c->ev_stage[slot], c->s_d2h));
+            RDG_CUDA(cudaStreamWaitEvent(c->s_host, c->ev_stage[slot], 0));
+            HostCopyJob* job = new HostCopyJob{out_host + b0 * plane, c->stage_out[slot], (size_t)n * plane * 4};
+            cudaError_t e = cudaLaunchHostFunc(c->s_host, host_copy_cb, job);
+            if (e != cudaSuccess) { delete job; drain_host_pipeline(c); rdg_set_error("cudaLaunchHostFunc -> %s", cudaGetErrorString(e)); return (int)e; }
+            RDG_CUDA(cudaEventRecord(c->ev_host[slot], c->s_host));
+        }
     }
     int flag = 0;
     RDG_CUDA(cudaStreamSynchronize(c->s_d2h));
+    if (staged) RDG_CUDA(cudaStreamSynchronize(c->s_host));
     RDG_CUDA(cudaMemcpyAsync(&flag, c->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, c->s_comp));
     RDG_CUDA(cudaStreamSynchronize(c->s_comp));
     RDG_CUDA(cudaStreamSynchronize(c->s_h2d));
@@ -645,7 +698,12 @@ extern "C" int rdg_critic_forward_tc(rdg_ctx* c, const float* sample_dev, const 
                 if (!c->c_wpack[k][l - 1]) RDG_CUDA(cudaMalloc(&c->c_wpack[k][l - 1], (size_t)27 * g.Ci * g.Co * 2));
                 if ((r = pack_critic_weights(k == 0 ? RDG_HALF_BF16 : RDG_HALF_FP16, c->c_params + c->c_off[2 * l], c->c_wpack[k][l - 1], g.Ci, g.Co, st))) return r;
             }
-        c->launches += 6;
+        {   // first conv as a [Co][Kpad] tf32 operand image (k = tap * Ci + channel), tcg_gemm.cu
+            ConvGeom g = rdg_critic_conv_geom(c, 0, 1);
+            if (!c->c_w1p_score) RDG_CUDA(cudaMalloc(&c->c_w1p_score, (size_t)g.Co * tcg_smallci_kpad(27, g.Ci) * 4));
+            if ((r = tcg_pack_smallci_weights(c->c_params + c->c_off[0], c->c_w1p_score, 27, g.Ci, g.Co, st))) return r;
+        }
+        c->launches += 7;
         c->critic_packed_stale = false;
     }
     const int hk = mode == RDG_MODE_BF16 ? RDG_HALF_BF16 : RDG_HALF_FP16, wk = hk == RDG_HALF_BF16 ? 0 : 1;
@@ -659,8 +717,11 @@ extern "C" int rdg_critic_forward_tc(rdg_ctx* c, const float* sample_dev, const 
         auto take = [&](size_t bytes) { void* q = p; p += (bytes + 255) / 256 * 256; return q; };
         ConvGeom g0 = rdg_critic_conv_geom(c, 0, n);
         void* cur = take((size_t)n * g0.To * g0.Ho * g0.Wo * g0.Co * 2);
-        if ((r = critic_first_conv(hk, sample_dev + (size_t)b0 * px, cond_dev + (size_t)b0 * c->nd * c->nd * c->ncond, c->c_params + c->c_off[0],
-                                   c->c_params + c->c_off[1], cur, n, c->nd, c->ncond, g0, st))) return r;
+        if (g0.Ci <= 4 && getenv("RDG_CRITIC_D1") == nullptr) {     // tensor cores (RDG_CRITIC_D1=simt: the CUDA-core kernel)
+            if ((r = tcg_critic_first_conv16(hk, sample_dev + (size_t)b0 * px, cond_dev + (size_t)b0 * c->nd * c->nd * c->ncond, c->c_w1p_score,
+                                             c->c_params + c->c_off[1], cur, g0, st))) return r;
+        } else if ((r = critic_first_conv(hk, sample_dev + (size_t)b0 * px, cond_dev + (size_t)b0 * c->nd * c->nd * c->ncond, c->c_params + c->c_off[0],
+                                          c->c_params + c->c_off[1], cur, n, c->nd, c->ncond, g0, st))) return r;
         for (int l = 1; l < 4; ++l) {
             ConvGeom g = rdg_critic_conv_geom(c, l, n);
             void* y = take((size_t)n * g.To * g.Ho * g.Wo * g.Co * 2);

@@ -32,6 +32,7 @@ struct rdg_ctx {
     void* train_ws = nullptr; size_t train_ws_bytes = 0;
     // tensor-core training mode (tcg_gemm.cu, train_tc.cu): 0 = FP32 SIMT (<= 1e-5 parity mode), 1 = tcgen05 kind::tf32
     int train_mode = 0;
+    float* c_w1p_score = nullptr;                    // the same image kept fresh for the scoring mode (critic_packed_stale)
     float* c_w1p = nullptr;                          // critic first conv packed [Co][Kpad] (k = tap * Ci + channel), tcg_pack_smallci_weights
     float* c_wT = nullptr; bool c_wT_stale = true;   // critic conv kernels D2..D4 with (Ci, Co) swapped, at the offsets of c_params
     float* g_wfoldT[3] = {};                         // folded generator kernels transposed: [8 phases][8 taps][Co][Ci]
@@ -49,6 +50,8 @@ struct rdg_ctx {
     // [0] filter gradients of the main chain, [1] the gradient-penalty chain of the critic step, [2] its filter gradients
     cudaStream_t s_aux[3] = {}; cudaEvent_t ev_fork[3] = {}, ev_join[3] = {};
     cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
+    // pageable result buffers: ring of pinned staging slots drained by host callbacks on a fourth stream (rdg_generate_host)
+    float* stage_out[3] = {}; cudaStream_t s_host = nullptr; cudaEvent_t ev_stage[3] = {}, ev_host[3] = {};
     float* e2e_lat[2] = {}; float* e2e_out[2] = {}; float* e2e_cond = nullptr; size_t e2e_cond_cap = 0;
     // rdg_generate_stats_host staging (grow-only): observations, area means, CRPS area means, per-chunk CRPS field
     float* st_buf[4] = {}; size_t st_cap[4] = {};

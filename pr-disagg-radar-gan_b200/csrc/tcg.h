@@ -25,6 +25,10 @@ int tcg_pack_smallci_weights(const float* w, float* wTp, int taps, int Ci, int C
 int tcg_conv_fwd_smallci(const float* x, const float* wTp, const float* bias, float* y, const ConvGeom& g, int act, const float* mask,
                          float mask_scale, cudaStream_t st, float* pre = nullptr, int precise = 0);
 int tcg_conv_bwd_filter_smallci(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st);
+// scoring mode: first critic conv with the sample / condition concat fused into the gather, LeakyReLU, 16-bit output (half_kind:
+// RDG_HALF_BF16 / RDG_HALF_FP16 of gen_tc.h)
+int tcg_critic_first_conv16(int half_kind, const float* sample, const float* cond, const float* wTp, const float* bias, void* out16,
+                            const ConvGeom& g, cudaStream_t st);
 // dx = conv_transpose(dy, w); w in the Keras layout (KT,KH,KW,Ci,Co).  stride 1 or 2, g.up == 0.
 int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);
 // dw += sum_{b,pos} x (x) dy (accumulates with atomics; caller zeroes).  No bias gradient (use simt_colsum).

@@ -20,6 +20,7 @@
 // vector red.global.add (filter gradients, which accumulate into the shared gradient buffer anyway).
 #include "tc_ptx.cuh"
 #include "tcg.h"
+#include "gen_tc.h"
 #include <algorithm>
 
 namespace {
@@ -45,6 +46,9 @@ struct TcgRowArgs {
     long long out_elems;      // elements of the output tensor (stride between split-K slices)
     int nclass, nslice, nstages;
     int ksmall;               // > 0: few-channel input, k = tap * Cs + channel runs over ksmall = taps * Cs valid elements (Kc = padded)
+    const float* src2;        // ksmall only, != null: channel 0 comes from `src` [B,Ts,Hs,Ws] (1 channel) and channels 1.. from src2
+                              // [B,Hs,Ws,Cs-1] broadcast over t: the critic's sample / condition concat (:275-282) fused into the gather
+    void* out16; int half_kind;   // != null: the result is stored as 16-bit (RDG_HALF_BF16 / RDG_HALF_FP16) instead of FP32 `out`
     TcgClass cls[8];
     TcgTap taps[64];
 };
@@ -162,11 +166,11 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
     } else {
         // ---- producers: thread = (row sub-index rsub, 16-byte chunk) of every 32-row slab of the A and B tiles
         const int chunk = tid & 7, rsub = tid >> 3;
-        int rbase[4], rcoord[4];
+        int rbase[4], rcoord[4], rb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = row0 + rsub + 32 * j;
-            rbase[j] = -1; rcoord[j] = 0;
+            rbase[j] = -1; rcoord[j] = 0; rb[j] = 0;
             if (r < cl.rows) {
                 int q = r;
                 const int w2 = q % cl.Wc; q /= cl.Wc;
@@ -175,10 +179,10 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
                 const int ts = p.a * t2, hs = p.a * h2, ws = p.a * w2;
                 rbase[j] = (((b * p.Ts + ts) * p.Hs + hs) * p.Ws + ws) * p.Cs;
                 rcoord[j] = ts | (hs << 10) | (ws << 20);
+                rb[j] = b;
             }
         }
         const uint32_t sw_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)(rsub & 7) * 128u + (uint32_t)((chunk ^ (rsub & 7)) << 4);
-
         auto load = [&](int i, float4 (&va)[4], float4 (&vb)[NB]) {
             const int kb = kb_lo + i;
             int te = 0, kc = kb;
@@ -281,11 +285,11 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int k = k0 + u;
-                        int eo = -1, ect = 0, ech = 0, ecw = 0;
+                        int eo = -1, ect = 0, ech = 0, ecw = 0, ec = 0;
                         if (k < p.ksmall) {
                             const int tap = k / p.Cs, c = k - tap * p.Cs;
                             const TcgTap tq = p.taps[cl.tap_begin + tap];
-                            ect = tq.ct; ech = tq.ch; ecw = tq.cw;
+                            ect = tq.ct; ech = tq.ch; ecw = tq.cw; ec = c;
                             eo = ((tq.ct * p.Hs + tq.ch) * p.Ws + tq.cw) * p.Cs + c;
                         }
 #pragma unroll
@@ -293,7 +297,13 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
                             const int ts = (rcoord[j] & 1023) + ect, hs = ((rcoord[j] >> 10) & 1023) + ech, ws = (rcoord[j] >> 20) + ecw;
                             const bool ok = eo != -1 && rbase[j] >= 0 && (unsigned)ts < (unsigned)p.Ts && (unsigned)hs < (unsigned)p.Hs &&
                                             (unsigned)ws < (unsigned)p.Ws;
-                            cp_async4(sa + j * 4096 + 4 * u, ok ? p.src + rbase[j] + eo : p.src, ok ? 4u : 0u);
+                            const float* g = p.src;
+                            if (ok) {
+                                if (!p.src2) g = p.src + rbase[j] + eo;
+                                else if (ec == 0) g = p.src + ((rb[j] * p.Ts + ts) * p.Hs + hs) * p.Ws + ws;
+                                else g = p.src2 + ((rb[j] * p.Hs + hs) * p.Ws + ws) * (p.Cs - 1) + (ec - 1);
+                            }
+                            cp_async4(sa + j * 4096 + 4 * u, g, ok ? 4u : 0u);
                         }
                     }
                 }
@@ -349,7 +359,14 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
                         const float4 m = ldg4(p.mask + off + c + j);
                         x[0] *= m.x * p.mask_scale; x[1] *= m.y * p.mask_scale; x[2] *= m.z * p.mask_scale; x[3] *= m.w * p.mask_scale;
                     }
-                    *reinterpret_cast<float4*>(p.out + off + c + j) = make_float4(x[0], x[1], x[2], x[3]);
+                    if (p.out16) {
+                        uint2 h;
+                        if (p.half_kind == RDG_HALF_BF16) { h.x = HalfOps<__nv_bfloat16>::pack(x[0], x[1]); h.y = HalfOps<__nv_bfloat16>::pack(x[2], x[3]); }
+                        else { h.x = HalfOps<__half>::pack(x[0], x[1]); h.y = HalfOps<__half>::pack(x[2], x[3]); }
+                        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out16) + off + c + j) = h;
+                    } else {
+                        *reinterpret_cast<float4*>(p.out + off + c + j) = make_float4(x[0], x[1], x[2], x[3]);
+                    }
                 }
             }
         }
@@ -731,6 +748,37 @@ int tcg_conv_fwd_smallci(const float* x, const float* wTp, const float* bias, fl
         for (int kh = 0; kh < g.KH; ++kh)
             for (int kw = 0; kw < g.KW; ++kw, ++n) a.taps[n] = TcgTap{(int8_t)(kt - g.pt), (int8_t)(kh - g.ph), (int8_t)(kw - g.pw), 0, 0};
     return launch_rowgemm(a, mtiles, a.kchunks, st, bias, y, act, mask, mask_scale, pre, precise != 0);
+}
+
+// The critic's first conv in the 16-bit scoring mode (critic_tc.cu consumes 16-bit activations): sample [B,24,nd,nd] and cond
+// [B,nd,nd,ncond] are concatenated inside the gather (:275-282), single-pass tf32, LeakyReLU, 16-bit channels-last output.
+int tcg_critic_first_conv16(int half_kind, const float* sample, const float* cond, const float* wTp, const float* bias, void* out16,
+                            const ConvGeom& g, cudaStream_t st) {
+    const int taps = g.KT * g.KH * g.KW;
+    if (g.up || g.Ci > 4 || g.Ci < 2 || (g.Co & 31) || taps > 64 || taps * g.Ci > 128) { rdg_set_error("tcg_critic_first_conv16: unsupported geometry"); return RDG_TCG_E_SHAPE; }
+    const long long rows = (long long)g.B * g.To * g.Ho * g.Wo;
+    if (rows == 0) return 0;
+    if (!fits_i32((long long)g.B * g.Ti * g.Hi * g.Wi * g.Ci) || !fits_i32(rows * g.Co)) { rdg_set_error("tcg_critic_first_conv16: tensor too large"); return RDG_TCG_E_SHAPE; }
+    TcgRowArgs a{};
+    a.src = sample; a.src2 = cond; a.w = wTp; a.out = nullptr; a.out16 = out16; a.half_kind = half_kind;
+    a.a = g.stride; a.os = 1;
+    a.Ts = g.Ti; a.Hs = g.Hi; a.Ws = g.Wi; a.Cs = g.Ci;
+    a.To = g.To; a.Ho = g.Ho; a.Wo = g.Wo; a.Nt = g.Co;
+    a.ksmall = taps * g.Ci;
+    a.Kc = tcg_smallci_kpad(taps, g.Ci); a.kchunks = a.Kc / 32; a.wrow = a.Kc; a.wtap = 0;
+    a.out_elems = rows * g.Co;
+    const int mtiles = ceil_div(rows, 128);
+    a.N = tile_n_for(g.Co, mtiles);
+    a.nclass = 1;
+    a.cls[0] = TcgClass{g.To, g.Ho, g.Wo, (int)rows, 0, 0, 0, 0, 0, taps};
+    int n = 0;
+    for (int kt = 0; kt < g.KT; ++kt)
+        for (int kh = 0; kh < g.KH; ++kh)
+            for (int kw = 0; kw < g.KW; ++kw, ++n) a.taps[n] = TcgTap{(int8_t)(kt - g.pt), (int8_t)(kh - g.ph), (int8_t)(kw - g.pw), 0, 0};
+    a.nstages = pick_stages(a.N, false);
+    a.nslice = 1;
+    a.bias = bias; a.act = ACT_LRELU; a.mask_scale = 1.f;
+    return launch_rowgemm_n(a, dim3(mtiles, a.Nt / a.N, 1), false, st);
 }
 
 int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st) {
