@@ -148,6 +148,27 @@ __global__ void critic_input_kernel(const float* __restrict__ sample, const floa
     x[i] = c == 0 ? sample[i / C] : cond[(b * nd * nd + p) * ncond + (c - 1)];
 }
 
+// The three critic inputs of a critic step in one pass (gan_train_cwgangp_pixelnorm.py:221-224, :275-282, :372-379):
+// x3 = [fake | real | alpha*real + (1-alpha)*fake], each [B,24,nd,nd,1+ncond] with the condition tiled over the hours
+__global__ void critic_inputs3_kernel(const float* __restrict__ fake, const float* __restrict__ real, const float* __restrict__ alpha,
+                                      const float* __restrict__ cond, float* __restrict__ x3, int B, int nd, int ncond) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, t, p)
+    const int P = nd * nd;
+    const long long n = (long long)B * RDG_NHOURS * P;
+    if (i >= n) return;
+    const int p = (int)(i % P);
+    const long long b = i / ((long long)RDG_NHOURS * P);
+    const int C = 1 + ncond;
+    const float f = fake[i], r = real[i], a = alpha[b];
+    const float v[3] = {f, r, a * r + (1.f - a) * f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float* d = x3 + ((long long)k * n + i) * C;
+        d[0] = v[k];
+        for (int c = 0; c < ncond; ++c) d[1 + c] = cond[(b * P + p) * ncond + c];
+    }
+}
+
 // Philox4x32-10 counter-based generator + Box-Muller; element i uses counter (offset+i)/4.
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
@@ -444,6 +465,15 @@ int ew_critic_input(const float* sample, const float* cond, float* x, int B, int
     RDG_LAUNCH_CHECK();
     return 0;
 }
+int ew_critic_inputs3(const float* fake, const float* real, const float* alpha, const float* cond, float* x3, int B, int nd, int ncond,
+                      cudaStream_t st) {
+    const long long n = (long long)B * RDG_NHOURS * nd * nd;
+    if (!n) return 0;
+    critic_inputs3_kernel<<<EW_GRID(n)>>>(fake, real, alpha, cond, x3, B, nd, ncond);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
 int ew_fill_normal(float* dst, long long n, uint64_t seed, uint64_t offset, cudaStream_t st) {
     if (!n) return 0;
     fill_normal_kernel<<<EW_GRID((n + 3) / 4)>>>(dst, n, seed, offset);

@@ -846,15 +846,17 @@ __global__ void pack_w4_kernel(const float* __restrict__ k4, HT* __restrict__ ds
 // Fixed-point scale of the on-chip output-conv sum (gen_tc_planes.cu): |sum_k P_k| <= sum_k |y|_2 |w_k|_2 and
 // PixelNorm bounds |y|_2 <= sqrt(64) = 8, so 2 * 8 * sum_k |w_k|_2 (2x margin for the 16-bit roundings) bounds every
 // partial sum; scale = largest power of two keeping that below 2^31.
-__global__ void w4_scale_kernel(const float* __restrict__ k4, float* __restrict__ dst) {
-    float s = 0.f;
-    for (int tap = 0; tap < 27; ++tap) {
-        float q = 0.f;
-        for (int c = threadIdx.x; c < 64; c += 32) q += k4[tap * 64 + c] * k4[tap * 64 + c];
-        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        s += sqrtf(q);
-    }
+__global__ void __launch_bounds__(27 * 32) w4_scale_kernel(const float* __restrict__ k4, float* __restrict__ dst) {
+    __shared__ float nrm[27];
+    const int tap = threadIdx.x >> 5, lane = threadIdx.x & 31;       // one warp per tap
+    const float a = k4[tap * 64 + lane], b = k4[tap * 64 + 32 + lane];
+    float q = a * a + b * b;
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) nrm[tap] = sqrtf(q);
+    __syncthreads();
     if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int t = 0; t < 27; ++t) s += nrm[t];
         const float bound = 16.f * s;
         int e = 20;
         if (bound > 0.f && bound < INFINITY) {
@@ -919,7 +921,7 @@ int pack_w4_tile(int half_kind, const float* k4, void* dst, cudaStream_t st) {
     if (half_kind == RDG_HALF_BF16) pack_w4_kernel<__nv_bfloat16><<<8, 256, 0, st>>>(k4, (__nv_bfloat16*)dst);
     else pack_w4_kernel<__half><<<8, 256, 0, st>>>(k4, (__half*)dst);
     RDG_LAUNCH_CHECK();
-    w4_scale_kernel<<<1, 32, 0, st>>>(k4, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dst) + 32 * 64 * 2));
+    w4_scale_kernel<<<1, 27 * 32, 0, st>>>(k4, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dst) + 32 * 64 * 2));
     RDG_LAUNCH_CHECK();
     return 0;
 }

@@ -22,7 +22,8 @@ struct ConvGeom {
     int up;
 };
 
-enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ACCUM = 2 /* backward-data only: dst += result */ };
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ACCUM = 2 /* backward-data only: dst += result */,
+       ACT_LRELU_BWD = 3 /* tcg kernels: result *= LeakyReLU'(pre) (pre is READ: the pre-activation the gradient flows into) [* mask] */ };
 
 void rdg_set_error(const char* fmt, ...);
 
@@ -54,6 +55,7 @@ int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, c
 int simt_colsum(const float* x, float* out, long long rows, int C, cudaStream_t st);
 // dx = conv_transpose(dy, w): gradient w.r.t. the (logical, i.e. upsampled if g.up) input.
 int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st, int accumulate = 0);
+int simt_conv_bwd_data_ch0(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);   // input channel 0 only
 
 // ---- upsample-folded FP32 forms of UpSampling3D(2) + Conv3D(3^3,'same') (simt_folded.cu) ----
 // wf: [8 phases][2,2,2,Ci,Co] folded kernels (f32 sums of the 3^3 kernel's taps); g = the layer's geometry (g.up == 1).
@@ -107,6 +109,9 @@ int ew_tap_gather_logits(const float* P, const float* b4, float* logits, int B, 
 int ew_tap_scatter_dlogits(const float* dl, float* Gd, int B, int nd, cudaStream_t st);                      // Gd [B,24,nd,nd,32]
 int ew_pad_w4(const float* w4, float* w4p, cudaStream_t st);     // -> [32][64] then [64][32]
 int ew_fill3(float* dst, int n, float a, float b, float c, cudaStream_t st);
+// x3 [3B,24,nd,nd,1+ncond] = critic inputs [fake | real | alpha*real + (1-alpha)*fake] with the condition tiled over the hours
+int ew_critic_inputs3(const float* fake, const float* real, const float* alpha, const float* cond, float* x3, int B, int nd, int ncond,
+                      cudaStream_t st);
 int ew_dense_score(const float* x, const float* w, const float* bias, float* score, int B, int K, cudaStream_t st);   // Flatten + Dense(1)
 int ew_interp(const float* xr, const float* xf, const float* alpha, float* xhat, int B, long long per, cudaStream_t st);
 int ew_fill(float* dst, long long n, float v, cudaStream_t st);

@@ -258,16 +258,16 @@ __global__ void __launch_bounds__(NT) conv_bwd_filter_kernel(const float* __rest
 // The 64x64-tile kernels waste 62/64 of a tile on them.  dx[m][ci] = sum_{valid taps} sum_co dy[n(m,tap)][co] * w[tap][ci][co]:
 // one thread per (input position, ci), weights in shared memory, dy rows read as float4.
 __global__ void __launch_bounds__(256) conv_bwd_data_smallci_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                                    float* __restrict__ dx, ConvGeom g) {
+                                                                    float* __restrict__ dx, ConvGeom g, int ci_n) {
     extern __shared__ __align__(16) float ws[];              // [tap][ci][co]
     const int ntaps = g.KT * g.KH * g.KW;
     for (int i = threadIdx.x; i < ntaps * g.Ci * g.Co; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
     const long long M = (long long)g.B * g.Ti * g.Hi * g.Wi;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * g.Ci) return;
-    const int ci = (int)(idx % g.Ci);
-    const PosDec p = decode_pos(idx / g.Ci, g.Ti, g.Hi, g.Wi);
+    if (idx >= M * ci_n) return;          // ci_n < Ci: only the first ci_n input channels are wanted (the others are left untouched)
+    const int ci = (int)(idx % ci_n);
+    const PosDec p = decode_pos(idx / ci_n, g.Ti, g.Hi, g.Wi);
     float acc = 0.f;
     for (int kt = 0; kt < g.KT; ++kt) {
         int nt = p.t + g.pt - kt;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) conv_bwd_data_smallci_kernel(const float*
             }
         }
     }
-    dx[idx] = acc;
+    dx[(idx / ci_n) * g.Ci + ci] = acc;
 }
 
 // dW[tap][ci][co] += sum_m x[gather(m,tap)][ci] * dy[m][co] when Ci * Co <= 256 (few input OR few output channels: the
@@ -547,7 +547,7 @@ int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeo
     const int act_mode = accumulate ? ACT_ACCUM : ACT_NONE;
     if (accumulate && (g.stride == 2 || g.Ci <= 4)) { rdg_set_error("simt_conv_bwd_data: accumulate is only supported by the generic path"); return -1; }
     if (!g.up && g.Ci <= 4 && (g.Co & 3) == 0 && (size_t)ntaps_ * g.Ci * g.Co * 4 <= 48 * 1024) {
-        conv_bwd_data_smallci_kernel<<<ceil_div(M * g.Ci, 256), 256, (size_t)ntaps_ * g.Ci * g.Co * 4, st>>>(dy, w, dx, g);
+        conv_bwd_data_smallci_kernel<<<ceil_div(M * g.Ci, 256), 256, (size_t)ntaps_ * g.Ci * g.Co * 4, st>>>(dy, w, dx, g, g.Ci);
         RDG_LAUNCH_CHECK();
         return 0;
     }
@@ -597,6 +597,18 @@ int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeo
         return 0;
     }
     conv_gemm_kernel<1><<<grid, NT, 0, st>>>(dy, w, nullptr, dx, g, act_mode, nullptr, 1.f, nullptr, nullptr);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+// gradient w.r.t. input channel 0 only (dx keeps its Ci-channel layout; channels >= 1 are not written): the critic's first conv in
+// the training steps, where only the sample channel's gradient is used (gradient-penalty norm :238-241, generator step)
+int simt_conv_bwd_data_ch0(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st) {
+    const long long M = (long long)g.B * g.Ti * g.Hi * g.Wi;
+    const int ntaps_ = g.KT * g.KH * g.KW;
+    if (M == 0) return 0;
+    if (g.up || g.Ci > 4 || (g.Co & 3) || (size_t)ntaps_ * g.Ci * g.Co * 4 > 48 * 1024) return simt_conv_bwd_data(dy, w, dx, g, st, 0);
+    conv_bwd_data_smallci_kernel<<<ceil_div(M, 256), 256, (size_t)ntaps_ * g.Ci * g.Co * 4, st>>>(dy, w, dx, g, 1);
     RDG_LAUNCH_CHECK();
     return 0;
 }

@@ -11,6 +11,8 @@
 // [nblk][R][C] -> [nblk][C][R]
 int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, cudaStream_t st);
 
+// act: ACT_NONE / ACT_LRELU, or ACT_LRELU_BWD with `pre` READ as the pre-activation whose LeakyReLU derivative multiplies the
+// result (the linear second-order pass of the gradient penalty: u_l = conv_l(u_{l-1}) * LeakyReLU'(a_l) * mask).
 // y = act(conv(x, w) + bias) [* mask * mask_scale]; wT = the kernel with its last two axes swapped: (KT,KH,KW,Co,Ci).
 // g.up must be 0 (the generator's upsampled convs go through the folded entry points below).
 // precise: 3xTF32 (operands split into tf32 high + low parts, three MMAs per k step: FP32-grade products).  Forward passes use it:
@@ -30,7 +32,10 @@ int tcg_conv_bwd_filter_smallci(const float* x, const float* dy, float* dw, cons
 int tcg_critic_first_conv16(int half_kind, const float* sample, const float* cond, const float* wTp, const float* bias, void* out16,
                             const ConvGeom& g, cudaStream_t st);
 // dx = conv_transpose(dy, w); w in the Keras layout (KT,KH,KW,Ci,Co).  stride 1 or 2, g.up == 0.
-int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);
+// pre_in != null: the LeakyReLU (+ dropout) backward of the layer below is fused into the epilogue: dx = conv_transpose(dy, w) *
+// LeakyReLU'(pre_in) [* mask * mask_scale], i.e. the cotangent of that layer's PRE-activation (pre_in, mask: shaped like dx).
+int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st, const float* pre_in = nullptr,
+                      const float* mask = nullptr, float mask_scale = 1.f);
 // dw += sum_{b,pos} x (x) dy (accumulates with atomics; caller zeroes).  No bias gradient (use simt_colsum).
 int tcg_conv_bwd_filter(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st);
 

@@ -350,7 +350,13 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
                         x[e] = __uint_as_float(v[j + e]);
                         if (p.bias) x[e] += __ldg(p.bias + n0 + c + j + e);
                     }
-                    if (p.pre) *reinterpret_cast<float4*>(p.pre + off + c + j) = make_float4(x[0], x[1], x[2], x[3]);
+                    if (p.act == ACT_LRELU_BWD) {          // fused LeakyReLU backward: the cotangent of the pre-activation
+                        const float4 a = ldg4(p.pre + off + c + j);
+                        x[0] *= a.x > 0.f ? 1.f : 0.2f; x[1] *= a.y > 0.f ? 1.f : 0.2f;
+                        x[2] *= a.z > 0.f ? 1.f : 0.2f; x[3] *= a.w > 0.f ? 1.f : 0.2f;
+                    } else if (p.pre) {
+                        *reinterpret_cast<float4*>(p.pre + off + c + j) = make_float4(x[0], x[1], x[2], x[3]);
+                    }
                     if (p.act == ACT_LRELU) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) x[e] = x[e] > 0.f ? x[e] : 0.2f * x[e];
@@ -391,7 +397,10 @@ __global__ void tcg_splitk_epilogue_kernel(const float* __restrict__ part, int n
         const float4 b = ldg4(bias + (int)((i * 4) % N));
         s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
     }
-    if (pre) reinterpret_cast<float4*>(pre)[i] = s;
+    if (act == ACT_LRELU_BWD) {
+        const float4 a = reinterpret_cast<const float4*>(pre)[i];
+        s.x *= a.x > 0.f ? 1.f : 0.2f; s.y *= a.y > 0.f ? 1.f : 0.2f; s.z *= a.z > 0.f ? 1.f : 0.2f; s.w *= a.w > 0.f ? 1.f : 0.2f;
+    } else if (pre) reinterpret_cast<float4*>(pre)[i] = s;
     if (act == ACT_LRELU) {
         s.x = s.x > 0.f ? s.x : 0.2f * s.x; s.y = s.y > 0.f ? s.y : 0.2f * s.y;
         s.z = s.z > 0.f ? s.z : 0.2f * s.z; s.w = s.w > 0.f ? s.w : 0.2f * s.w;
@@ -781,7 +790,8 @@ int tcg_critic_first_conv16(int half_kind, const float* sample, const float* con
     return launch_rowgemm_n(a, dim3(mtiles, a.Nt / a.N, 1), false, st);
 }
 
-int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st) {
+int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st, const float* pre_in, const float* mask,
+                      float mask_scale) {
     if (g.up || (g.Co & 3) || (g.Ci & 31) || (g.stride != 1 && g.stride != 2) || g.KT * g.KH * g.KW > 64) {
         rdg_set_error("tcg_conv_bwd_data: unsupported geometry"); return RDG_TCG_E_SHAPE;
     }
@@ -825,7 +835,8 @@ int tcg_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom
             }
     a.nclass = ncls;
     a.N = tile_n_for(g.Ci, tiles);
-    return launch_rowgemm(a, tiles, max_taps * a.kchunks, st, nullptr, dx, ACT_NONE, nullptr, 1.f, nullptr);
+    return launch_rowgemm(a, tiles, max_taps * a.kchunks, st, nullptr, dx, pre_in ? ACT_LRELU_BWD : ACT_NONE, pre_in ? mask : nullptr, mask_scale,
+                          const_cast<float*>(pre_in));
 }
 
 int tcg_folded_fwd(const float* x, const float* wfT, const float* bias, float* y, const ConvGeom& g, cudaStream_t st, int precise) {

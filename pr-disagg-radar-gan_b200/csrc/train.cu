@@ -527,7 +527,6 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
         hat_a[l] = l ? A3.a[l] + 2 * e : nullptr;
     }
     float* fake_img = ws.f((size_t)B * px);
-    float* xhat = ws.f((size_t)B * px);
     float* dh = ws.f((size_t)3 * B * max_act);
     float* da[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int l = 1; l <= 4; ++l) da[l] = ws.f((size_t)3 * B * critic_act_elems(c, l));
@@ -540,10 +539,8 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     if (phases & 1) {
         // frozen generator forward (:370, generator.trainable = False :363)
         TRY(rdg_generator_forward(c, latent, cond, 1, fake_img, B, gen_mode, RDG_OUT_FRACTION, 1.f, nullptr, st));
-        TRY(ew_interp(x_real, fake_img, alpha, xhat, B, (long long)px, st));                    // RandomWeightedAverage :221-224
-        TRY(ew_critic_input(fake_img, cond, A3.h[0], B, c->nd, c->ncond, st));
-        TRY(ew_critic_input(x_real, cond, A3.h[0] + (size_t)B * critic_act_elems(c, 0), B, c->nd, c->ncond, st));
-        TRY(ew_critic_input(xhat, cond, hat_h[0], B, c->nd, c->ncond, st));
+        // RandomWeightedAverage (:221-224) + the three [sample, condition] concatenations (:275-282) in one pass
+        TRY(ew_critic_inputs3(fake_img, x_real, alpha, cond, A3.h[0], B, c->nd, c->ncond, st));
     }
     if (!(phases & 2)) return 0;
     TRY(refresh_critic_wT(c, st));
@@ -565,17 +562,23 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     TRY(ss.fork());
     TRY(simt_conv_bwd_filter(A3.h[4], dscore3, c->c_grads + c->c_off[8], c->c_grads + c->c_off[9], rdg_critic_dense_geom(c, 2 * B), ss.aux()));
     TRY(simt_conv_bwd_data(dscore3, c->c_params + c->c_off[8], dh, rdg_critic_dense_geom(c, 3 * B), st));
+    // da_l = cotangent of the pre-activation a_l.  The LeakyReLU (+ dropout) backward of layer l-1 is fused into the epilogue of
+    // layer l's transposed conv: da_{l-1} = convT_l(da_l) * LeakyReLU'(a_{l-1}) * mask_{l-1}
+    TRY(ew_lrelu_bwd(A3.a[4], dh, da[4], (long long)3 * B * critic_act_elems(c, 4), masks3 ? masks3[3] : nullptr, ms, st));
     for (int l = 4; l >= 1; --l) {
         ConvGeom g = rdg_critic_conv_geom(c, l - 1, 3 * B);
-        TRY(ew_lrelu_bwd(A3.a[l], dh, da[l], (long long)3 * B * critic_act_elems(c, l), masks3 ? masks3[l - 1] : nullptr, ms, st));
         TRY(ss.fork());       // bias gradients of the Wasserstein terms: the first 2B samples
         TRY(simt_colsum(da[l], c->c_grads + c->c_off[2 * (l - 1) + 1], (long long)2 * B * (critic_act_elems(c, l) / g.Co), g.Co, ss.aux()));
         if (l > 1) {
-            if (tc_layer_ok(g)) TRY(tcg_conv_bwd_data(da[l], c->c_params + c->c_off[2 * (l - 1)], dh, g, st));
-            else TRY(simt_conv_bwd_data(da[l], c->c_params + c->c_off[2 * (l - 1)], dh, g, st));
+            if (tc_layer_ok(g)) {
+                TRY(tcg_conv_bwd_data(da[l], c->c_params + c->c_off[2 * (l - 1)], da[l - 1], g, st, A3.a[l - 1], masks3 ? masks3[l - 2] : nullptr, ms));
+            } else {
+                TRY(simt_conv_bwd_data(da[l], c->c_params + c->c_off[2 * (l - 1)], dh, g, st));
+                TRY(ew_lrelu_bwd(A3.a[l - 1], dh, da[l - 1], (long long)3 * B * critic_act_elems(c, l - 1), masks3 ? masks3[l - 2] : nullptr, ms, st));
+            }
         } else {              // only the penalty needs the gradient w.r.t. the critic input: interpolated third
             ConvGeom g1 = rdg_critic_conv_geom(c, 0, B);
-            TRY(simt_conv_bwd_data(da[1] + (size_t)2 * B * critic_act_elems(c, 1), c->c_params + c->c_off[0], g0, g1, st));
+            TRY(simt_conv_bwd_data_ch0(da[1] + (size_t)2 * B * critic_act_elems(c, 1), c->c_params + c->c_off[0], g0, g1, st));
         }
     }
     // gradient penalty (:230-244): norm of the input gradient, 'mse' against zeros, cotangent of 10 * mean((n-1)^2)
@@ -591,9 +594,13 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
         if (l > 1 && tc_layer_ok(g3)) TRY(tcg_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], g3, ss.aux()));
         else if (l == 1 && g3.Ci <= 4) TRY(tcg_conv_bwd_filter_smallci(A3.h[0], da[1], c->c_grads + c->c_off[0], g3, ss.aux()));
         else TRY(simt_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], nullptr, g3, ss.aux()));
-        TRY(critic_conv_fwd_tc(c, l - 1, hat_h[l - 1], nullptr, vbuf, g, ACT_NONE, nullptr, st, nullptr, 0));
-        TRY(ew_lrelu_bwd(hat_a[l], vbuf, hat_h[l], (long long)B * critic_act_elems(c, l),
-                         masks3 ? masks3[l - 1] + (size_t)2 * B * critic_act_elems(c, l) : nullptr, ms, st));
+        const float* mh = masks3 ? masks3[l - 1] + (size_t)2 * B * critic_act_elems(c, l) : nullptr;
+        if ((l == 1 && g.Ci <= 4) || (l > 1 && tc_layer_ok(g))) {     // u_l = conv_l(u_{l-1}) * LeakyReLU'(a_l) * mask_l in one epilogue
+            TRY(critic_conv_fwd_tc(c, l - 1, hat_h[l - 1], nullptr, hat_h[l], g, ACT_LRELU_BWD, mh, st, hat_a[l], 0));
+        } else {
+            TRY(simt_conv_fwd(hat_h[l - 1], c->c_params + c->c_off[2 * (l - 1)], nullptr, vbuf, g, ACT_NONE, nullptr, 1.f, st));
+            TRY(ew_lrelu_bwd(hat_a[l], vbuf, hat_h[l], (long long)B * critic_act_elems(c, l), mh, ms, st));
+        }
     }
     TRY(simt_colsum(hat_h[4], c->c_grads + c->c_off[8], B, (int)critic_act_elems(c, 4), st));      // d/dW5 of the penalty
     TRY(ss.join());
@@ -656,11 +663,21 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     TRY(ew_mean_scaled(A.score, B, -1.f, loss_dev, st));                   // wasserstein_loss with target -1 (:408, :452)
     TRY(ew_fill(dscore, B, -1.f / (float)B, st));
     TRY(simt_conv_bwd_data(dscore, c->c_params + c->c_off[8], t0, rdg_critic_dense_geom(c, B), st));
-    for (int l = 4; l >= 1; --l) {
-        ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
-        TRY(ew_lrelu_bwd(A.a[l], t0, t1, (long long)B * critic_act_elems(c, l), masks ? masks[l - 1] : nullptr, ms, st));
-        if (l > 1 && tc_layer_ok(g)) TRY(tcg_conv_bwd_data(t1, c->c_params + c->c_off[2 * (l - 1)], t0, g, st));
-        else TRY(simt_conv_bwd_data(t1, c->c_params + c->c_off[2 * (l - 1)], l > 1 ? t0 : dx0, g, st));
+    {   // t1 / t0 alternate as the cotangents of the pre-activations a_4 .. a_1 (LeakyReLU backward fused into the transposed convs)
+        float* cur = t1; float* nxt = t0;
+        TRY(ew_lrelu_bwd(A.a[4], t0, cur, (long long)B * critic_act_elems(c, 4), masks ? masks[3] : nullptr, ms, st));
+        for (int l = 4; l >= 1; --l) {
+            ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
+            if (l > 1 && tc_layer_ok(g)) {
+                TRY(tcg_conv_bwd_data(cur, c->c_params + c->c_off[2 * (l - 1)], nxt, g, st, A.a[l - 1], masks ? masks[l - 2] : nullptr, ms));
+                std::swap(cur, nxt);
+            } else if (l > 1) {
+                TRY(simt_conv_bwd_data(cur, c->c_params + c->c_off[2 * (l - 1)], nxt, g, st));
+                TRY(ew_lrelu_bwd(A.a[l - 1], nxt, cur, (long long)B * critic_act_elems(c, l - 1), masks ? masks[l - 2] : nullptr, ms, st));
+            } else {
+                TRY(simt_conv_bwd_data_ch0(cur, c->c_params + c->c_off[0], dx0, g, st));
+            }
+        }
     }
     TRY(ew_extract_channel0(dx0, dimg, (long long)B * px, 1 + c->ncond, st));
     RDG_CUDA(cudaMemsetAsync(c->g_grads, 0, c->g_total * 4, st));

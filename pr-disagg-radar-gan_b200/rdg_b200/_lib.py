@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librdg_b200.so")
+LIB_PATH = os.environ.get("RDG_LIB") or os.path.join(_HERE, "librdg_b200.so")     # RDG_LIB: another build of the same library (A/B timing)
 
 MODE_FP32, MODE_BF16, MODE_FP16 = 0, 1, 2
 OUT_FRACTION, OUT_MM = 0, 1
