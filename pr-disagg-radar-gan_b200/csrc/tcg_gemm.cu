@@ -627,6 +627,21 @@ int tile_n_for(int Nt, int mtiles) {
     return 0;
 }
 
+// K slices per output tile: minimise (waves of CTAs) x (k-blocks per slice): the launches are a few waves long, so a slice count
+// that spills two CTAs into an extra wave costs a third of the kernel.  `slots` = CTAs resident on the whole GPU; every slice
+// costs a fixed prologue / epilogue (about two k-blocks) and one more partial tile to reduce.
+int pick_slices(int ctas, int nkb, int slots, int min_kb = 4) {
+    int best = 1;
+    double best_cost = 1e30;
+    const int nmax = std::max(1, nkb / min_kb);
+    for (int n = 1; n <= nmax; ++n) {
+        const long long waves = ((long long)ctas * n + slots - 1) / slots;
+        const double cost = (double)waves * ((nkb + n - 1) / n + 2.0) + 0.05 * n;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = n; }
+    }
+    return best;
+}
+
 template <int NB, bool SPLIT>
 int launch_rowgemm_t(const TcgRowArgs& a, dim3 grid, cudaStream_t st) {
     static bool attr_done = false;
@@ -654,13 +669,8 @@ int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const
     if (split && a.N > 128) a.N = 128;           // the 3xTF32 stage is twice as large
     a.nstages = pick_stages(a.N, split);
     const int ctas = mtiles * (a.Nt / a.N);
-    const int want = (a.N / 32) * (split ? 2 : 1) <= 4 ? 296 : 148;      // resident CTAs: two per SM where the kernel allows it
-    int nslice = 1;
-    if (ctas < want / 2 + want / 4 && max_kb >= 8) {
-        nslice = (want + ctas - 1) / ctas;
-        nslice = std::min(nslice, max_kb / 4);
-        nslice = std::max(nslice, 1);
-    }
+    const int slots = (a.N / 32) * (split ? 2 : 1) <= 4 ? 296 : 148;      // resident CTAs: two per SM where the kernel allows it
+    const int nslice = max_kb >= 8 ? pick_slices(ctas, max_kb, slots) : 1;
     a.nslice = nslice;
     dim3 grid(mtiles, a.Nt / a.N, nslice);
     if (nslice > 1) {
@@ -919,9 +929,7 @@ int launch_filtergrad(TcgFilterArgs& a, int ntap, cudaStream_t st) {
     a.nstages = pick_stages(N, false);
     const int ctas = ntap * a.Mt * (a.Co / N);
     const int nkb = (a.rows + 31) / 32;
-    const int want = N <= 128 ? 592 : 296;
-    int ks = (want + ctas - 1) / ctas;
-    ks = std::max(1, std::min(ks, nkb / 4));
+    const int ks = pick_slices(ctas, nkb, N <= 128 ? 296 : 148);
     a.ksplit = ks;
     dim3 grid(ntap, a.Mt * (a.Co / N), ks);
     if (a.ksmall) {
