@@ -629,14 +629,14 @@ int tile_n_for(int Nt, int mtiles) {
 
 // K slices per output tile: minimise (waves of CTAs) x (k-blocks per slice): the launches are a few waves long, so a slice count
 // that spills two CTAs into an extra wave costs a third of the kernel.  `slots` = CTAs resident on the whole GPU; every slice
-// costs a fixed prologue / epilogue (about two k-blocks) and one more partial tile to reduce.
+// costs a fixed prologue / epilogue (about four k-blocks, tuned on the training iteration) and one more partial tile to reduce.
 int pick_slices(int ctas, int nkb, int slots, int min_kb = 4) {
     int best = 1;
     double best_cost = 1e30;
     const int nmax = std::max(1, nkb / min_kb);
     for (int n = 1; n <= nmax; ++n) {
         const long long waves = ((long long)ctas * n + slots - 1) / slots;
-        const double cost = (double)waves * ((nkb + n - 1) / n + 2.0) + 0.05 * n;
+        const double cost = (double)waves * ((nkb + n - 1) / n + 4.0) + 0.05 * n;
         if (cost < best_cost - 1e-9) { best_cost = cost; best = n; }
     }
     return best;
