@@ -193,7 +193,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     }
     if (c->s_host) cudaStreamDestroy(c->s_host);
     cudaFree(c->train_ws);
-    cudaFree(c->c_wT); cudaFree(c->c_w1p); cudaFree(c->c_w1p_score); cudaFree(c->g_denseT); cudaFree(c->g_w4p); cudaFree(c->tstate); cudaFree(c->rnd_buf);
+    cudaFree(c->c_wT); cudaFree(c->c_w1p); cudaFree(c->c_w1p_score); cudaFree(c->c_w1q_score); cudaFree(c->g_denseT); cudaFree(c->g_w4p); cudaFree(c->tstate); cudaFree(c->rnd_buf);
     for (int i = 0; i < 3; ++i) cudaFree(c->g_wfoldT[i]);
     for (int i = 0; i < 3; ++i) {
         if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
@@ -702,6 +702,8 @@ extern "C" int rdg_critic_forward_tc(rdg_ctx* c, const float* sample_dev, const 
             ConvGeom g = rdg_critic_conv_geom(c, 0, 1);
             if (!c->c_w1p_score) RDG_CUDA(cudaMalloc(&c->c_w1p_score, (size_t)g.Co * tcg_smallci_kpad(27, g.Ci) * 4));
             if ((r = tcg_pack_smallci_weights(c->c_params + c->c_off[0], c->c_w1p_score, 27, g.Ci, g.Co, st))) return r;
+            if (!c->c_w1q_score) RDG_CUDA(cudaMalloc(&c->c_w1q_score, (size_t)g.Co * g.Ci * 32 * 4));
+            if ((r = tcg_pack_smallci_weights_chmajor(c->c_params + c->c_off[0], c->c_w1q_score, 27, g.Ci, g.Co, st))) return r;
         }
         c->launches += 7;
         c->critic_packed_stale = false;
@@ -719,7 +721,7 @@ extern "C" int rdg_critic_forward_tc(rdg_ctx* c, const float* sample_dev, const 
         void* cur = take((size_t)n * g0.To * g0.Ho * g0.Wo * g0.Co * 2);
         if (g0.Ci <= 4 && getenv("RDG_CRITIC_D1") == nullptr) {     // tensor cores (RDG_CRITIC_D1=simt: the CUDA-core kernel)
             if ((r = tcg_critic_first_conv16(hk, sample_dev + (size_t)b0 * px, cond_dev + (size_t)b0 * c->nd * c->nd * c->ncond, c->c_w1p_score,
-                                             c->c_params + c->c_off[1], cur, g0, st))) return r;
+                                             c->c_w1q_score, c->c_params + c->c_off[1], cur, g0, st))) return r;
         } else if ((r = critic_first_conv(hk, sample_dev + (size_t)b0 * px, cond_dev + (size_t)b0 * c->nd * c->nd * c->ncond, c->c_params + c->c_off[0],
                                           c->c_params + c->c_off[1], cur, n, c->nd, c->ncond, g0, st))) return r;
         for (int l = 1; l < 4; ++l) {

@@ -32,6 +32,7 @@ struct rdg_ctx {
     void* train_ws = nullptr; size_t train_ws_bytes = 0;
     // tensor-core training mode (tcg_gemm.cu, train_tc.cu): 0 = FP32 SIMT (<= 1e-5 parity mode), 1 = tcgen05 kind::tf32
     int train_mode = 0;
+    float* c_w1q_score = nullptr;                    // channel-major image [Co][Ci * 32] for the sample-resident first-conv kernel (nd = 16)
     float* c_w1p_score = nullptr;                    // the same image kept fresh for the scoring mode (critic_packed_stale)
     float* c_w1p = nullptr;                          // critic first conv packed [Co][Kpad] (k = tap * Ci + channel), tcg_pack_smallci_weights
     float* c_wT = nullptr; bool c_wT_stale = true;   // critic conv kernels D2..D4 with (Ci, Co) swapped, at the offsets of c_params

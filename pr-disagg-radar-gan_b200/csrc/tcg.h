@@ -29,8 +29,10 @@ int tcg_conv_fwd_smallci(const float* x, const float* wTp, const float* bias, fl
 int tcg_conv_bwd_filter_smallci(const float* x, const float* dy, float* dw, const ConvGeom& g, cudaStream_t st);
 // scoring mode: first critic conv with the sample / condition concat fused into the gather, LeakyReLU, 16-bit output (half_kind:
 // RDG_HALF_BF16 / RDG_HALF_FP16 of gen_tc.h)
-int tcg_critic_first_conv16(int half_kind, const float* sample, const float* cond, const float* wTp, const float* bias, void* out16,
-                            const ConvGeom& g, cudaStream_t st);
+// wTq (optional): tcg_pack_smallci_weights_chmajor image [Co][Ci * 32] for the sample-resident kernel used at nd = 16
+int tcg_pack_smallci_weights_chmajor(const float* w, float* wTq, int taps, int Ci, int Co, cudaStream_t st);
+int tcg_critic_first_conv16(int half_kind, const float* sample, const float* cond, const float* wTp, const float* wTq, const float* bias,
+                            void* out16, const ConvGeom& g, cudaStream_t st);
 // dx = conv_transpose(dy, w); w in the Keras layout (KT,KH,KW,Ci,Co).  stride 1 or 2, g.up == 0.
 // pre_in != null: the LeakyReLU (+ dropout) backward of the layer below is fused into the epilogue: dx = conv_transpose(dy, w) *
 // LeakyReLU'(pre_in) [* mask * mask_scale], i.e. the cotangent of that layer's PRE-activation (pre_in, mask: shaped like dx).

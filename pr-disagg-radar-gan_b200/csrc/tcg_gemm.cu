@@ -22,6 +22,8 @@
 #include "tcg.h"
 #include "gen_tc.h"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 using namespace rdg_tc;
@@ -592,6 +594,163 @@ __global__ void __launch_bounds__(TCG_THREADS, NVB <= 4 ? 2 : 1) tcg_filtergrad_
     if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols_for(N)); }
 }
 
+// ------------------------------------------------------------------------------------------------ critic first conv, sample-resident
+// Scoring mode at nd = 16 (B = tens of thousands): Conv3D(64, 3^3, strides 2, 'valid') on [sample | cond] (Ci = 1 + ncond <= 4).
+// A persistent CTA takes one sample at a time: its 24x16x16 field (24 KB) and condition land in shared memory with 16-byte cp.async,
+// the im2col A tiles (128 output positions x Kpad, k = tap * Ci + channel) are built from shared memory (no global gathers), the
+// packed kernel [64][Kpad] stays resident as the B operand, 5 M tiles per sample (539 positions) with double-buffered A tiles and
+// accumulators: workers build tile m + 1 while the tensor core runs tile m, then drain tile m (bias, LeakyReLU, 16-bit store).
+struct CriticD1Args {
+    const float* sample; const float* cond; const float* wTp; const float* bias; void* out16;
+    int B, ncond, kchunks, half_kind;
+};
+constexpr int D1_ND = 16, D1_T = 24, D1_TO = 11, D1_HO = 7, D1_ROWS = D1_TO * D1_HO * D1_HO;   // 539 output positions
+constexpr int D1_MT = (D1_ROWS + 127) / 128;                                                    // 5 M tiles
+
+__global__ void __launch_bounds__(TCG_THREADS, 2) critic_d1_resident_kernel(const __grid_constant__ CriticD1Args p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t a_full[2], a_empty[2], acc_full[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kch = p.kchunks;                                      // = input channels (one k-block per channel)
+    const uint32_t a_bytes = (uint32_t)kch * 16384u;                // one A buffer: kch k-blocks of [128 rows x 128 B]
+    uint8_t* sB = smem;                                             // [kch][64 rows x 128 B]
+    uint8_t* sA = sB + (size_t)kch * 8192;                          // two A buffers
+    float* s_in = reinterpret_cast<float*>(sA + 2 * (size_t)a_bytes);   // [24][16][16]
+    float* s_cd = s_in + D1_T * D1_ND * D1_ND;                      // [16][16][ncond]
+    float* s_bias = s_cd + D1_ND * D1_ND * 3;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(&tmem_slot, 128);
+    if (tid < 64) s_bias[tid] = p.bias[tid];
+    // resident B operand: packed kernel rows (co) x Kpad, K-major swizzled
+    for (int i = tid; i < kch * 64 * 8 && tid < 256; i += 256) {
+        const int kc = i / 512, r = (i >> 3) & 63, ch = i & 7;
+        cp_async16(smem_u32(sB + (size_t)kc * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4)), p.wTp + (size_t)r * (kch * 32) + kc * 32 + ch * 4, 16u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = idesc_tf32(64);
+    const int n_mine = ((int)p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // samples of this CTA
+
+    if (warp == 8) {
+        // tile sequence number g = local sample * 5 + m; buffer = g & 1
+        for (int g = 0; g < n_mine * D1_MT; ++g) {
+            const int bsel = g & 1;
+            mbar_wait(&a_full[bsel], (uint32_t)(g >> 1) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                for (int kc = 0; kc < kch; ++kc) {
+                    const uint64_t ad = make_sdesc(smem_u32(sA + (size_t)bsel * a_bytes + (size_t)kc * 16384));
+                    const uint64_t bd = make_sdesc(smem_u32(sB + (size_t)kc * 8192));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem + bsel * 64, ad + 2 * k, bd + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                }
+                tc_commit(&a_empty[bsel]);
+                tc_commit(&acc_full[bsel]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // K is channel-major here: k-block c holds the 27 taps of input channel c (k = c * 32 + tap, taps 27..31 zero), so a thread
+        // owns ONE output row and one channel: 27 (sample) or 9 (condition, constant over kt) shared-memory reads at stride-2
+        // positions (2-way conflicts at most), then eight conflict-free 16-byte stores of its 128-byte tile row
+        const int brow = tid & 127, bgrp = tid >> 7;
+        auto build = [&](int g, int m) {          // A tile of M tile m into buffer g & 1
+            const int bsel = g & 1;
+            if (g >= 2) mbar_wait(&a_empty[bsel], ((uint32_t)(g >> 1) & 1u) ^ 1u);
+            const int row = m * 128 + brow;
+            const bool rv = row < D1_ROWS;
+            const int to = row / 49, rem = row - to * 49, ho = rem / 7, wo = rem - ho * 7;
+            const float* base = s_in + ((2 * to) * D1_ND + 2 * ho) * D1_ND + 2 * wo;
+            const float* cbase = s_cd + ((2 * ho) * D1_ND + 2 * wo) * p.ncond;
+            for (int kc = bgrp; kc < kch; kc += 2) {
+                float v[32];
+#pragma unroll
+                for (int t = 0; t < 32; ++t) v[t] = 0.f;
+                if (rv) {
+                    if (kc == 0) {
+#pragma unroll
+                        for (int t = 0; t < 27; ++t) v[t] = base[((t / 9) * D1_ND + (t / 3) % 3) * D1_ND + t % 3];
+                    } else {
+                        float cv[9];
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) cv[t] = cbase[((t / 3) * D1_ND + t % 3) * p.ncond + (kc - 1)];
+#pragma unroll
+                        for (int t = 0; t < 27; ++t) v[t] = cv[t % 9];
+                    }
+                }
+                uint8_t* d = sA + (size_t)bsel * a_bytes + (size_t)kc * 16384 + (brow >> 3) * 1024 + (brow & 7) * 128;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    *reinterpret_cast<float4*>(d + ((ch ^ (brow & 7)) << 4)) = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[bsel]);
+        };
+        auto drain = [&](int g, int m, long long s) {     // accumulator of tile g -> bias, LeakyReLU, 16-bit store
+            const int bsel = g & 1;
+            mbar_wait(&acc_full[bsel], (uint32_t)(g >> 1) & 1u);
+            tc_fence_after();
+            const int q = warp & 3, half = warp >> 2;
+            const int row = m * 128 + q * 32 + lane;
+            uint32_t v[32];
+            tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bsel * 64 + half * 32), v);
+            tc_fence_before();
+            if (row < D1_ROWS) {
+                uint16_t* o = reinterpret_cast<uint16_t*>(p.out16) + ((size_t)s * D1_ROWS + row) * 64 + half * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float x[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { x[e] = __uint_as_float(v[j + e]) + s_bias[half * 32 + j + e]; x[e] = x[e] > 0.f ? x[e] : 0.2f * x[e]; }
+                    uint4 h;
+                    if (p.half_kind == RDG_HALF_BF16) {
+                        h.x = HalfOps<__nv_bfloat16>::pack(x[0], x[1]); h.y = HalfOps<__nv_bfloat16>::pack(x[2], x[3]);
+                        h.z = HalfOps<__nv_bfloat16>::pack(x[4], x[5]); h.w = HalfOps<__nv_bfloat16>::pack(x[6], x[7]);
+                    } else {
+                        h.x = HalfOps<__half>::pack(x[0], x[1]); h.y = HalfOps<__half>::pack(x[2], x[3]);
+                        h.z = HalfOps<__half>::pack(x[4], x[5]); h.w = HalfOps<__half>::pack(x[6], x[7]);
+                    }
+                    *reinterpret_cast<uint4*>(o + j) = h;
+                }
+            }
+        };
+        int g = 0;
+        for (long long s = blockIdx.x; s < p.B; s += gridDim.x) {
+            // the previous sample's tiles have all been BUILT (not necessarily drained): the input buffer is free
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float* src = p.sample + (size_t)s * D1_T * D1_ND * D1_ND;
+            for (int i = tid; i < D1_T * D1_ND * D1_ND / 4; i += 256) cp_async16(smem_u32(s_in + 4 * i), src + 4 * i, 16u);
+            for (int i = tid; i < D1_ND * D1_ND * p.ncond; i += 256) cp_async4(smem_u32(s_cd + i), p.cond + (size_t)s * D1_ND * D1_ND * p.ncond + i, 4u);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int g0 = g;
+            build(g0, 0);
+            for (int m = 1; m < D1_MT; ++m) {
+                build(g0 + m, m);
+                drain(g0 + m - 1, m - 1, s);
+            }
+            drain(g0 + D1_MT - 1, D1_MT - 1, s);
+            g += D1_MT;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
 __global__ void transpose_blocks_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
     __shared__ float tile[32][33];
     const float* s = src + (size_t)blockIdx.z * R * C;
@@ -736,6 +895,22 @@ __global__ void pack_smallci_kernel(const float* __restrict__ w, float* __restri
 }
 }  // namespace
 
+namespace {
+__global__ void pack_smallci_chmajor_kernel(const float* __restrict__ w, float* __restrict__ wTq, int taps, int Ci, int Co) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Co * Ci * 32) return;
+    const int n = i / (Ci * 32), k = i - n * (Ci * 32), c = k >> 5, tap = k & 31;
+    wTq[i] = tap < taps ? w[((size_t)tap * Ci + c) * Co + n] : 0.f;
+}
+}  // namespace
+
+// channel-major variant for the sample-resident kernel: [Co][Ci * 32], k = channel * 32 + tap (taps <= 32)
+int tcg_pack_smallci_weights_chmajor(const float* w, float* wTq, int taps, int Ci, int Co, cudaStream_t st) {
+    pack_smallci_chmajor_kernel<<<ceil_div((long long)Co * Ci * 32, 256), 256, 0, st>>>(w, wTq, taps, Ci, Co);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
 int tcg_pack_smallci_weights(const float* w, float* wTp, int taps, int Ci, int Co, cudaStream_t st) {
     const int Kpad = tcg_smallci_kpad(taps, Ci);
     pack_smallci_kernel<<<ceil_div((long long)Co * Kpad, 256), 256, 0, st>>>(w, wTp, taps * Ci, Kpad, Co);
@@ -771,13 +946,33 @@ int tcg_conv_fwd_smallci(const float* x, const float* wTp, const float* bias, fl
 
 // The critic's first conv in the 16-bit scoring mode (critic_tc.cu consumes 16-bit activations): sample [B,24,nd,nd] and cond
 // [B,nd,nd,ncond] are concatenated inside the gather (:275-282), single-pass tf32, LeakyReLU, 16-bit channels-last output.
-int tcg_critic_first_conv16(int half_kind, const float* sample, const float* cond, const float* wTp, const float* bias, void* out16,
-                            const ConvGeom& g, cudaStream_t st) {
+int tcg_critic_first_conv16(int half_kind, const float* sample, const float* cond, const float* wTp, const float* wTq, const float* bias,
+                            void* out16, const ConvGeom& g, cudaStream_t st) {
     const int taps = g.KT * g.KH * g.KW;
     if (g.up || g.Ci > 4 || g.Ci < 2 || (g.Co & 31) || taps > 64 || taps * g.Ci > 128) { rdg_set_error("tcg_critic_first_conv16: unsupported geometry"); return RDG_TCG_E_SHAPE; }
     const long long rows = (long long)g.B * g.To * g.Ho * g.Wo;
     if (rows == 0) return 0;
     if (!fits_i32((long long)g.B * g.Ti * g.Hi * g.Wi * g.Ci) || !fits_i32(rows * g.Co)) { rdg_set_error("tcg_critic_first_conv16: tensor too large"); return RDG_TCG_E_SHAPE; }
+
+    // nd = 16: sample-resident kernel (shared-memory im2col, resident weights); other domains: the general gather kernel below
+    if (wTq && taps == 27 && g.Ti == D1_T && g.Hi == D1_ND && g.Wi == D1_ND && g.Co == 64 && g.stride == 2 && g.pt == 0 && g.ph == 0 && g.pw == 0 && g.To == D1_TO &&
+        !(getenv("RDG_CRITIC_D1") && strcmp(getenv("RDG_CRITIC_D1"), "gather") == 0)) {
+        CriticD1Args a{};
+        a.sample = sample; a.cond = cond; a.wTp = wTq; a.bias = bias; a.out16 = out16;
+        a.B = g.B; a.ncond = g.Ci - 1; a.kchunks = g.Ci; a.half_kind = half_kind;
+        const size_t smem = 1024 + (size_t)a.kchunks * 8192 + 2 * (size_t)a.kchunks * 16384 + (D1_T * D1_ND * D1_ND + D1_ND * D1_ND * 3 + 64) * 4;
+        static bool attr_done = false;
+        if (!attr_done) {
+            RDG_CUDA(cudaFuncSetAttribute(critic_d1_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+            attr_done = true;
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int ctas = std::min(g.B, sms * (smem <= 110 * 1024 ? 2 : 1));
+        critic_d1_resident_kernel<<<ctas, TCG_THREADS, smem, st>>>(a);
+        RDG_LAUNCH_CHECK();
+        return 0;
+    }
     TcgRowArgs a{};
     a.src = sample; a.src2 = cond; a.w = wTp; a.out = nullptr; a.out16 = out16; a.half_kind = half_kind;
     a.a = g.stride; a.os = 1;
