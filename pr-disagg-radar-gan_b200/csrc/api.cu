@@ -186,6 +186,8 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     cudaFree(c->e2e_cond);
+    if (c->small_pin) cudaFreeHost(c->small_pin);
+    cudaFree(c->small_dev);
     for (int i = 0; i < 3; ++i) {
         if (c->stage_out[i]) cudaFreeHost(c->stage_out[i]);
         if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
@@ -504,6 +506,32 @@ extern "C" int rdg_generate_host(rdg_ctx* c, const float* latent_host, const flo
     const size_t plane = (size_t)RDG_NHOURS * c->nd * c->nd;
     const size_t ncf = (size_t)c->nd * c->nd * c->ncond;
     const long long n_cond = (B + spc - 1) / spc;
+    // Small calls (example.py: 10 scenarios): one stream, inputs and result through small pinned buffers owned by the context
+    // (a cudaMemcpyAsync from / to pageable memory is staged synchronously by the driver, ~10 us each, and the three-stream
+    // hand-offs of the pipeline below cost more than they hide for a single chunk).
+    constexpr long long kSmall = 64;
+    if (B <= kSmall && B <= chunk) {
+        const size_t in_f = (size_t)kSmall * RDG_LATENT + (size_t)kSmall * ncf, out_f = (size_t)kSmall * plane;
+        if (!c->small_pin) {
+            RDG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->small_pin), (in_f + out_f + 16) * 4, cudaHostAllocDefault));
+            RDG_CUDA(cudaMalloc(&c->small_dev, (in_f + out_f) * 4));
+        }
+        float* h_lat = c->small_pin; float* h_cond = h_lat + kSmall * RDG_LATENT; float* h_out = c->small_pin + in_f;
+        float* d_lat = c->small_dev; float* d_cond = d_lat + kSmall * RDG_LATENT; float* d_out = c->small_dev + in_f;
+        memcpy(h_lat, latent_host, (size_t)B * RDG_LATENT * 4);
+        memcpy(h_cond, cond_host, (size_t)n_cond * ncf * 4);
+        RDG_CUDA(cudaMemsetAsync(c->flag_dev, 0, sizeof(int), c->s_comp));
+        RDG_CUDA(cudaMemcpyAsync(d_lat, h_lat, ((size_t)kSmall * RDG_LATENT + (size_t)n_cond * ncf) * 4, cudaMemcpyHostToDevice, c->s_comp));
+        int r = gen_forward_chunk(c, d_lat, d_cond, spc, 0, d_out, (int)B, mode, out_kind, norm_scale, c->flag_dev, c->s_comp);
+        if (r) { cudaStreamSynchronize(c->s_comp); return r; }
+        RDG_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)B * plane * 4, cudaMemcpyDeviceToHost, c->s_comp));
+        int* h_flag = reinterpret_cast<int*>(h_out + (size_t)B * plane);
+        RDG_CUDA(cudaMemcpyAsync(h_flag, c->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, c->s_comp));
+        RDG_CUDA(cudaStreamSynchronize(c->s_comp));
+        memcpy(out_host, h_out, (size_t)B * plane * 4);
+        if (*h_flag) { rdg_set_error("found nan in output of per_gridpoint_softmax"); return RDG_E_NONFINITE; }
+        return 0;
+    }
     for (int i = 0; i < 2; ++i) {
         if (!c->e2e_lat[i]) RDG_CUDA(cudaMalloc(&c->e2e_lat[i], (size_t)c->max_chunk * RDG_LATENT * 4));
         if (!c->e2e_out[i]) RDG_CUDA(cudaMalloc(&c->e2e_out[i], (size_t)c->max_chunk * plane * 4));

@@ -53,6 +53,7 @@ struct rdg_ctx {
     cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
     // pageable result buffers: ring of pinned staging slots drained by host callbacks on a fourth stream (rdg_generate_host)
     float* stage_out[3] = {}; cudaStream_t s_host = nullptr; cudaEvent_t ev_stage[3] = {}, ev_host[3] = {};
+    float* small_pin = nullptr; float* small_dev = nullptr;   // single-stream path of rdg_generate_host for calls of <= 64 scenarios
     float* e2e_lat[2] = {}; float* e2e_out[2] = {}; float* e2e_cond = nullptr; size_t e2e_cond_cap = 0;
     // rdg_generate_stats_host staging (grow-only): observations, area means, CRPS area means, per-chunk CRPS field
     float* st_buf[4] = {}; size_t st_cap[4] = {};
