@@ -475,7 +475,7 @@ def main():
                 barrier()
             tr.profile_comm = True
             tr.comm_ms()
-            ms_eager = timed(lambda: [tr.critic_step_device(x_real[k], tcond[k], dl[k]) for k in range(5)] + [tr.generator_step_device(tcond[0], gls), tr.finish()], 10)
+            ms_eager = timed(lambda: (tr.iteration_device(x_real, tcond, tcond[0], dl, gls), tr.finish()), 10)
             comm = tr.comm_ms() / 13.0
             tr.profile_comm = False
             dp = {"ranks": world, "grad_parity_rel_l2": errs, "allreduce_ms_per_iteration": comm,

@@ -173,8 +173,10 @@ int  rdg_generator_step_dev(rdg_ctx* ctx, const float* cond_dev, int B, unsigned
  * weight images the next step reads; gen_mode = the mode of the frozen generator forward in the critic step. */
 int  rdg_adam_apply_dev(rdg_ctx* ctx, int which, float lr, float beta1, float beta2, float eps, float grad_scale,
                         int gen_mode, void* stream);
-/* set = 0: read, set = 1: write the device-resident counters (Adam step, Philox step); synchronises the device. */
-int  rdg_train_state(rdg_ctx* ctx, int set, long long* adam_t, unsigned long long* rng_ctr);
+/* set = 0: read, set = 1: write the device-resident counters: the shared Adam step and the two Philox step counters rng_ctr2[0]
+ * (critic steps) / rng_ctr2[1] (generator steps: phase 1 of a generator step may run next to the critic steps of its iteration, so
+ * the two kinds of step count separately); synchronises the device. */
+int  rdg_train_state(rdg_ctx* ctx, int set, long long* adam_t, unsigned long long* rng_ctr2);
 
 /* ---- building blocks exposed for tests (same kernels the calls above use) ---- */
 /* y = x / sqrt(mean_c(x^2) + 1e-8), optional LeakyReLU(0.2) (gan_train...py:255-266, :333) */

@@ -30,6 +30,10 @@ struct rdg_ctx {
     float* g_grads = nullptr; float* g_m = nullptr; float* g_v = nullptr;
     float* c_grads = nullptr; float* c_m = nullptr; float* c_v = nullptr;
     void* train_ws = nullptr; size_t train_ws_bytes = 0;
+    // the generator step of the tensor-core mode has its own workspace and random-input buffer: its first phase (generator forward)
+    // reads no critic state and runs on another stream next to the critic steps of the same iteration
+    void* train_ws_gen = nullptr; size_t train_ws_gen_bytes = 0;
+    float* rnd_buf_gen = nullptr; size_t rnd_gen_cap = 0;
     // tensor-core training mode (tcg_gemm.cu, train_tc.cu): 0 = FP32 SIMT (<= 1e-5 parity mode), 1 = tcgen05 kind::tf32
     int train_mode = 0;
     float* c_w1q_score = nullptr;                    // channel-major image [Co][Ci * 32] for the sample-resident first-conv kernel (nd = 16)

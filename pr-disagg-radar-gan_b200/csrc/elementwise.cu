@@ -201,7 +201,7 @@ __global__ void fill_normal_kernel(float* __restrict__ dst, long long n, uint64_
 
 // ---- device-resident training state: lets a captured CUDA graph of a training step be replayed (the Philox counter and the
 // Adam step live in device memory and are advanced by kernels inside the graph instead of being baked into kernel arguments)
-__global__ void train_tick_kernel(RdgTrainState* s) { s->rng_ctr += 1ull; }
+__global__ void train_tick_kernel(RdgTrainState* s, int which) { s->rng_ctr[which] += 1ull; }
 __global__ void adam_prepare_kernel(RdgTrainState* s, float lr, float b1, float b2) {
     const long long t = ++s->adam_t;      // shared step counter of the one optimizer object (gan_train_cwgangp_pixelnorm.py:385)
     s->lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
@@ -225,10 +225,10 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 }
 // kind 0: N(0,1) (Box-Muller), 1: U[0,1), 2: Bernoulli(keep) as 0/1 floats.  Philox counter = (quad index, stream id, step counter)
 __global__ void fill_random_dev_kernel(float* __restrict__ dst, long long n, uint64_t seed, const RdgTrainState* __restrict__ s,
-                                       uint32_t stream_id, int kind, float keep) {
+                                       int which, uint32_t stream_id, int kind, float keep) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q * 4 >= n) return;
-    uint32_t c[4] = {(uint32_t)q, (uint32_t)((uint64_t)q >> 32), stream_id, (uint32_t)s->rng_ctr};
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)((uint64_t)q >> 32), stream_id + 16u * (uint32_t)which, (uint32_t)s->rng_ctr[which]};
     uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
 #pragma unroll
     for (int r = 0; r < 10; ++r) philox_round(c, k);
@@ -488,8 +488,8 @@ int ew_adam(float* p, const float* g, float* m, float* v, long long n, float lr_
     return 0;
 }
 
-int ew_train_tick(RdgTrainState* s, cudaStream_t st) {
-    train_tick_kernel<<<1, 1, 0, st>>>(s);
+int ew_train_tick(RdgTrainState* s, int which, cudaStream_t st) {
+    train_tick_kernel<<<1, 1, 0, st>>>(s, which);
     RDG_LAUNCH_CHECK();
     return 0;
 }
@@ -503,11 +503,11 @@ int ew_adam_dev(float* p, const float* g, float* m, float* v, long long n, RdgTr
     RDG_LAUNCH_CHECK();
     return 0;
 }
-int ew_fill_random_dev(float* dst, long long n, uint64_t seed, const RdgTrainState* s, uint32_t stream_id, int kind, float keep,
+int ew_fill_random_dev(float* dst, long long n, uint64_t seed, const RdgTrainState* s, int which, uint32_t stream_id, int kind, float keep,
                        cudaStream_t st) {
     if (!n) return 0;
     if ((reinterpret_cast<uintptr_t>(dst) & 15) != 0) { rdg_set_error("ew_fill_random_dev: destination must be 16-byte aligned"); return -1; }
-    fill_random_dev_kernel<<<EW_GRID((n + 3) / 4)>>>(dst, n, seed, s, stream_id, kind, keep);
+    fill_random_dev_kernel<<<EW_GRID((n + 3) / 4)>>>(dst, n, seed, s, which, stream_id, kind, keep);
     RDG_LAUNCH_CHECK();
     return 0;
 }

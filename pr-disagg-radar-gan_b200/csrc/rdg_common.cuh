@@ -95,13 +95,13 @@ int ew_adam(float* p, const float* g, float* m, float* v, long long n, float lr_
             float beta2, float eps, float grad_scale, cudaStream_t st);
 
 // device-resident training state (replayable CUDA graphs): Philox step counter, shared Adam step counter, bias-corrected rate
-struct RdgTrainState { unsigned long long rng_ctr; long long adam_t; float lr_t; float pad_; };
-int ew_train_tick(RdgTrainState* s, cudaStream_t st);
+struct RdgTrainState { unsigned long long rng_ctr[2]; long long adam_t; float lr_t; float pad_; };   // rng_ctr: [0] critic steps, [1] generator steps
+int ew_train_tick(RdgTrainState* s, int which, cudaStream_t st);     // which: 0 critic-step counter, 1 generator-step counter
 // Keras-Adam with the step counter in *s (incremented here) instead of a host argument
 int ew_adam_dev(float* p, const float* g, float* m, float* v, long long n, RdgTrainState* s, float lr, float beta1, float beta2,
                 float eps, float grad_scale, cudaStream_t st);
-// kind 0 N(0,1), 1 U[0,1), 2 Bernoulli(keep) 0/1; Philox key = seed, counter = (index, stream_id, s->rng_ctr)
-int ew_fill_random_dev(float* dst, long long n, uint64_t seed, const RdgTrainState* s, uint32_t stream_id, int kind, float keep,
+// kind 0 N(0,1), 1 U[0,1), 2 Bernoulli(keep) 0/1; Philox key = seed, counter = (index, stream_id, s->rng_ctr[which])
+int ew_fill_random_dev(float* dst, long long n, uint64_t seed, const RdgTrainState* s, int which, uint32_t stream_id, int kind, float keep,
                        cudaStream_t st);
 
 // training-step helpers

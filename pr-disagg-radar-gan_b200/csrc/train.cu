@@ -89,11 +89,13 @@ struct Bump {
     }
 };
 
-int ensure_train_ws(rdg_ctx* c, size_t bytes) {
-    if (c->train_ws_bytes >= bytes) return 0;
-    if (c->train_ws) { RDG_CUDA(cudaDeviceSynchronize()); RDG_CUDA(cudaFree(c->train_ws)); c->train_ws = nullptr; c->train_ws_bytes = 0; }
-    RDG_CUDA(cudaMalloc(&c->train_ws, bytes));
-    c->train_ws_bytes = bytes;
+int ensure_train_ws(rdg_ctx* c, size_t bytes, bool gen = false) {
+    void*& p = gen ? c->train_ws_gen : c->train_ws;
+    size_t& have = gen ? c->train_ws_gen_bytes : c->train_ws_bytes;
+    if (have >= bytes) return 0;
+    if (p) { RDG_CUDA(cudaDeviceSynchronize()); RDG_CUDA(cudaFree(p)); p = nullptr; have = 0; }
+    RDG_CUDA(cudaMalloc(&p, bytes));
+    have = bytes;
     return 0;
 }
 
@@ -617,8 +619,8 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     ConvGeom dg1 = rdg_gen_dense_geom(c, 1);
     const size_t need = ((size_t)B * (2 * csum + 3 * cmax + 2 * gsum + dg1.Ci + dg1.Co + 4 * px + 2 * gmax + 32 * px + 64) +
                          folded_weight_elems(256, 256) + 8192) * 4 + 64 * 256;
-    TRY(ensure_train_ws(c, need));
-    Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
+    TRY(ensure_train_ws(c, need, true));
+    Bump ws{reinterpret_cast<uint8_t*>(c->train_ws_gen), reinterpret_cast<uint8_t*>(c->train_ws_gen) + c->train_ws_gen_bytes};
     GenActs G; CriticActs A;
     TRY(gen_alloc(c, ws, B, G)); TRY(critic_alloc(c, ws, B, A));
     float* t0 = ws.f((size_t)B * cmax); float* t1 = ws.f((size_t)B * cmax);
@@ -723,11 +725,13 @@ namespace {
 
 size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
 
-int ensure_rnd(rdg_ctx* c, size_t floats) {
-    if (c->rnd_cap >= floats) return 0;
-    if (c->rnd_buf) { RDG_CUDA(cudaDeviceSynchronize()); RDG_CUDA(cudaFree(c->rnd_buf)); c->rnd_buf = nullptr; c->rnd_cap = 0; }
-    RDG_CUDA(cudaMalloc(&c->rnd_buf, floats * 4));
-    c->rnd_cap = floats;
+int ensure_rnd(rdg_ctx* c, size_t floats, bool gen = false) {
+    float*& p = gen ? c->rnd_buf_gen : c->rnd_buf;
+    size_t& have = gen ? c->rnd_gen_cap : c->rnd_cap;
+    if (have >= floats) return 0;
+    if (p) { RDG_CUDA(cudaDeviceSynchronize()); RDG_CUDA(cudaFree(p)); p = nullptr; have = 0; }
+    RDG_CUDA(cudaMalloc(&p, floats * 4));
+    have = floats;
     return 0;
 }
 int ensure_tstate(rdg_ctx* c) {
@@ -810,11 +814,11 @@ extern "C" int rdg_critic_step_dev(rdg_ctx* c, const float* x_real_dev, const fl
     if (dropout)
         for (int l = 0; l < 4; ++l) masks3[l] = c->rnd_buf + L.mask[l];
     if (phases & 1) {
-        TRY(ew_train_tick(c->tstate, st));
-        TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 0, 0.f, st));   // np.random.normal :470
-        TRY(ew_fill_random_dev(c->rnd_buf + L.alpha, B, seed, c->tstate, 2, 1, 0.f, st));                              // tf.random.uniform :223
+        TRY(ew_train_tick(c->tstate, 0, st));
+        TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 0, 1, 0, 0.f, st));   // np.random.normal :470
+        TRY(ew_fill_random_dev(c->rnd_buf + L.alpha, B, seed, c->tstate, 0, 2, 1, 0.f, st));                              // tf.random.uniform :223
         if (dropout)      // Dropout(0.25) of the three critic invocations (:289-301): one draw over the four 3B mask tensors
-            TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 3, 2, 0.75f, st));
+            TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 0, 3, 2, 0.75f, st));
     }
     return critic_step_tc(c, x_real_dev, cond_dev, c->rnd_buf + L.latent, c->rnd_buf + L.alpha, dropout ? masks3 : nullptr, B, gen_mode,
                           losses4_dev, st, phases);
@@ -830,16 +834,16 @@ extern "C" int rdg_generator_step_dev(rdg_ctx* c, const float* cond_dev, int B, 
     cudaStream_t st = (cudaStream_t)stream;
     const RndLayout L = rnd_layout(c, B, 1);
     if (phases < 1 || phases > 3) { rdg_set_error("rdg_generator_step_dev: phases must be 1, 2 or 3"); return RDG_E_BADARG; }
-    TRY(ensure_rnd(c, rnd_layout(c, B, 3).total));      // same buffer as the critic step: size it once
+    TRY(ensure_rnd(c, L.total, true));                  // own buffer: phase 1 may run next to a critic step
     const float* masks[4] = {nullptr, nullptr, nullptr, nullptr};
     if (dropout)
-        for (int l = 0; l < 4; ++l) masks[l] = c->rnd_buf + L.mask[l];
+        for (int l = 0; l < 4; ++l) masks[l] = c->rnd_buf_gen + L.mask[l];
     if (phases & 1) {
-        TRY(ew_train_tick(c->tstate, st));
-        TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 0, 0.f, st));   // generate_latent_points :177-193
-        if (dropout) TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 3, 2, 0.75f, st));
+        TRY(ew_train_tick(c->tstate, 1, st));
+        TRY(ew_fill_random_dev(c->rnd_buf_gen + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 1, 0, 0.f, st));   // generate_latent_points :177-193
+        if (dropout) TRY(ew_fill_random_dev(c->rnd_buf_gen + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 1, 3, 2, 0.75f, st));
     }
-    return generator_step_tc(c, c->rnd_buf + L.latent, cond_dev, dropout ? masks : nullptr, B, loss_dev, st, phases);
+    return generator_step_tc(c, c->rnd_buf_gen + L.latent, cond_dev, dropout ? masks : nullptr, B, loss_dev, st, phases);
 }
 
 // Keras-Adam with the shared step counter in device memory (incremented by the call), followed by the refresh of every derived
@@ -868,7 +872,8 @@ extern "C" int rdg_adam_apply_dev(rdg_ctx* c, int which, float lr, float beta1, 
     return 0;
 }
 
-// host <-> device copy of the training counters (checkpoints; keeping `optimizer.iterations` in step with replayed graphs)
+// host <-> device copy of the training counters (checkpoints; keeping `optimizer.iterations` in step with replayed graphs);
+// rng_ctr: two values, the Philox step counters of the critic steps and of the generator steps
 extern "C" int rdg_train_state(rdg_ctx* c, int set, long long* adam_t, unsigned long long* rng_ctr) {
     if (!c || !adam_t || !rng_ctr) return RDG_E_BADARG;
     RDG_CUDA(cudaSetDevice(c->device));
@@ -877,8 +882,8 @@ extern "C" int rdg_train_state(rdg_ctx* c, int set, long long* adam_t, unsigned 
     RDG_CUDA(cudaDeviceSynchronize());
     RDG_CUDA(cudaMemcpy(&s, c->tstate, sizeof(s), cudaMemcpyDeviceToHost));
     if (set) {
-        s.adam_t = *adam_t; s.rng_ctr = *rng_ctr;
+        s.adam_t = *adam_t; s.rng_ctr[0] = rng_ctr[0]; s.rng_ctr[1] = rng_ctr[1];
         RDG_CUDA(cudaMemcpy(c->tstate, &s, sizeof(s), cudaMemcpyHostToDevice));
-    } else { *adam_t = s.adam_t; *rng_ctr = s.rng_ctr; }
+    } else { *adam_t = s.adam_t; rng_ctr[0] = s.rng_ctr[0]; rng_ctr[1] = s.rng_ctr[1]; }
     return 0;
 }

@@ -318,13 +318,16 @@ class GanTrainer:
         return dist.get_rank(self.pg) if dist.is_available() and dist.is_initialized() else 0
 
     def _push_counters(self, adam_t, rng_ctr):
-        a, r = C.c_longlong(int(adam_t)), C.c_ulonglong(int(rng_ctr))
-        _lib.check(self.ctx.lib.rdg_train_state(self.ctx.handle, 1, C.byref(a), C.byref(r)))
+        """rng_ctr: (critic-step counter, generator-step counter) of the device Philox state, or one int for both."""
+        rc = tuple(int(x) for x in np.atleast_1d(rng_ctr))
+        rc = rc * 2 if len(rc) == 1 else rc
+        a, r = C.c_longlong(int(adam_t)), (C.c_ulonglong * 2)(rc[0], rc[1])
+        _lib.check(self.ctx.lib.rdg_train_state(self.ctx.handle, 1, C.byref(a), r))
 
     def _pull_counters(self):
-        a, r = C.c_longlong(0), C.c_ulonglong(0)
-        _lib.check(self.ctx.lib.rdg_train_state(self.ctx.handle, 0, C.byref(a), C.byref(r)))
-        return int(a.value), int(r.value)
+        a, r = C.c_longlong(0), (C.c_ulonglong * 2)(0, 0)
+        _lib.check(self.ctx.lib.rdg_train_state(self.ctx.handle, 0, C.byref(a), r))
+        return int(a.value), (int(r[0]), int(r[1]))
 
     def sync_replicas(self, src=0):
         """Make every rank's weights and optimizer state those of `src` (data-parallel replicas must start identical: the
@@ -380,7 +383,7 @@ class GanTrainer:
         torch.cuda.synchronize(self.ctx.device)
         adam_t, rng_ctr = self._pull_counters()
         assert adam_t == self.optimizer.iterations, "host / device Adam step counters diverged"
-        sd = {"iterations": np.int64(self.optimizer.iterations), "rng_ctr": np.uint64(rng_ctr),
+        sd = {"iterations": np.int64(self.optimizer.iterations), "rng_ctr": np.array(rng_ctr, np.uint64),
               "adam": np.array([self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon], np.float64),
               "rng_state": self._gen.get_state().cpu().numpy()}
         for which, name, net in ((0, "gen", self.generator), (1, "critic", self.critic)):
@@ -400,7 +403,7 @@ class GanTrainer:
         self.optimizer.iterations = int(sd["iterations"])
         self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon = (float(x) for x in sd["adam"])
         self._gen.set_state(torch.as_tensor(np.asarray(sd["rng_state"], np.uint8)))
-        self._push_counters(self.optimizer.iterations, int(sd.get("rng_ctr", 0)))
+        self._push_counters(self.optimizer.iterations, sd.get("rng_ctr", 0))
         torch.cuda.synchronize(self.ctx.device)
 
     def save_checkpoint(self, path):
@@ -504,6 +507,43 @@ class GanTrainer:
     def generator_step_device(self, cond, loss_out):
         self._run_step(self.WHICH_GEN, *self._generator_calls(cond, loss_out))
 
+    def _run_iteration(self, critic_calls, gen_calls):
+        """One iteration = the critic steps, then the generator step (reference :468-482).  Phase 1 of the generator step (noise,
+        generator forward with saved activations) reads neither the critic nor anything the critic steps write, so it is issued
+        on a third stream at the START of the iteration and runs next to the critic steps, whose launches are too small to fill the
+        GPU; the generator step's second phase (critic pass + backward) follows the last critic update as before."""
+        dev = self.ctx.device
+        main = torch.cuda.current_stream(dev)
+        self._set_mode()
+        self._update_stream()
+        if getattr(self, "_gen_stream", None) is None:
+            self._gen_stream = torch.cuda.Stream(device=dev)
+        if self._pending_which == self.WHICH_GEN:
+            self.finish()                   # the previous iteration's generator update
+        if os.environ.get("RDG_GEN_OVERLAP", "1") == "0":          # A/B switch: everything in stream order
+            for p1, p2 in critic_calls:
+                self._run_step(self.WHICH_CRITIC, p1, p2)
+            self._run_step(self.WHICH_GEN, gen_calls[0], gen_calls[1])
+            return
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        self._gen_stream.wait_event(ev0)
+        with torch.cuda.stream(self._gen_stream):
+            gen_calls[0]()
+            ev_g = torch.cuda.Event()
+            ev_g.record(self._gen_stream)
+        for p1, p2 in critic_calls:
+            self._run_step(self.WHICH_CRITIC, p1, p2)
+        main.wait_event(ev_g)
+        self._run_step(self.WHICH_GEN, lambda: None, gen_calls[1])
+
+    def iteration_device(self, x_real, cond, cond_gen, d_losses, g_loss):
+        """x_real [n_critic,B,24,nd,nd,1], cond [n_critic,B,nd,nd,ncond], cond_gen [B,nd,nd,ncond], d_losses [n_critic,4], g_loss [1]:
+        device tensors.  Issues one whole iteration (see _run_iteration); call finish() before reading weights."""
+        n = int(x_real.shape[0])
+        self._run_iteration([self._critic_calls(x_real[k], cond[k], d_losses[k]) for k in range(n)],
+                            self._generator_calls(cond_gen, g_loss))
+
     def capture_iteration(self, batch, n_critic=5, segmented=None):
         """Capture one training iteration (n_critic critic steps + 1 generator step, reference :468-482, with the gradient
         exchange and the Adam updates) in a CUDA graph.  Returns an IterationGraph: fill `x_real` [n_critic,B,24,nd,nd,1],
@@ -524,9 +564,7 @@ class GanTrainer:
         ig.x_real[:] = 1.0 / W.NHOURS
 
         def body():
-            for k in range(n_critic):
-                self.critic_step_device(ig.x_real[k], ig.cond[k], ig.d_losses[k])
-            self.generator_step_device(ig.cond_gen, ig.g_loss)
+            self.iteration_device(ig.x_real, ig.cond, ig.cond_gen, ig.d_losses, ig.g_loss)
             self.finish()               # the iteration ends with the generator update joined back
 
         self.finish()
@@ -646,6 +684,7 @@ class IterationGraph:
             self.graph.replay()
             t.optimizer.iterations += self.n_critic + 1
             return
-        for which, g1, g2 in self.segments:
-            t._run_step(which, g1.replay, g2.replay)      # _apply (all-reduce + Adam) advances the host step mirror itself
+        # _apply (all-reduce + Adam) advances the host step mirror itself
+        t._run_iteration([(g1.replay, g2.replay) for w, g1, g2 in self.segments if w == t.WHICH_CRITIC],
+                         [(g1.replay, g2.replay) for w, g1, g2 in self.segments if w == t.WHICH_GEN][0])
         t.finish()

@@ -129,14 +129,12 @@ def test_device_steps_and_graph_replay(ctx16, segmented):
     dl = torch.zeros((5, 4), device="cuda"); gl = torch.zeros(1, device="cuda")
     eager_losses = []
     for _ in range(n_iter):
-        for k in range(5):
-            tr.critic_step_device(xr[k], cd[k], dl[k])
-        tr.generator_step_device(cd[0], gl)
+        tr.iteration_device(xr, cd, cd[0], dl, gl)
         tr.finish()
         eager_losses.append((dl.cpu().numpy().copy(), float(gl.item())))
         if len(eager_losses) == 1:
             w_eager = [w.copy() for w in tr.generator.get_weights()] + [w.copy() for w in tr.critic.get_weights()]
-    assert tr.optimizer.iterations == 6 * n_iter == tr._pull_counters()[0]
+    assert tr.optimizer.iterations == 6 * n_iter == tr._pull_counters()[0] and tr._pull_counters()[1] == (5 * n_iter, n_iter)
     assert all(np.isfinite(l[0]).all() and np.isfinite(l[1]) for l in eager_losses)
     # the steps really used fresh randomness each time: same data, different losses
     assert abs(eager_losses[0][0][0, 0] - eager_losses[0][0][1, 0]) > 0
@@ -148,7 +146,7 @@ def test_device_steps_and_graph_replay(ctx16, segmented):
     tr3.generator.set_weights(W.init_generator_weights(7)); tr3.critic.set_weights(W.init_critic_weights(8))
     ctx16.lib.rdg_adam_reset(ctx16.handle, 0); ctx16.lib.rdg_adam_reset(ctx16.handle, 1)
     tr3.optimizer.iterations = 0
-    tr3._push_counters(0, 0)
+    tr3._push_counters(0, (0, 0))
     ig3.x_real.copy_(xr); ig3.cond.copy_(cd); ig3.cond_gen.copy_(cd[0])
     for it in range(n_iter):
         ig3.replay()

@@ -91,9 +91,7 @@ def main():
             dl = torch.zeros((5, 4), device=dev); gl = torch.zeros(1, device=dev)
 
             def iteration():
-                for k in range(5):
-                    tr.critic_step_device(x_real[k], cond[k], dl[k])
-                tr.generator_step_device(cond[0], gl)
+                tr.iteration_device(x_real, cond, cond[0], dl, gl)
                 tr.finish()
             res[name] = timed(iteration, args.iters)
             if args.profile_steps:
