@@ -550,7 +550,22 @@ def main():
             b1.record(); torch.cuda.synchronize()
             ms = b0.elapsed_time(b1) / nrep
             ld[f"B{LB}"] = {"scenarios_per_s": round(LB / ms * 1e3, 1), "executed_tflops": round(LB * 2 * 10.845e9 / ms / 1e9, 1)}
+        # one cWGAN-GP iteration at nd = 64, batch 32, tensor-core training mode, replayed from a CUDA graph
+        from rdg_b200.engine import Critic, GanTrainer
+        lcrit = Critic(W.init_critic_weights(1, 64), ctx=lctx)
+        ltr = GanTrainer(lgen, lcrit, gen_mode="fp16", seed=3, train_mode="tf32")
+        lig = ltr.capture_iteration(32)
+        lx = torch.rand((5, 32, 24, 64, 64, 1), device=dev); lx /= lx.sum(dim=2, keepdim=True)
+        lig.x_real.copy_(lx); lig.cond.copy_(lctx.dev(synth_conditions(160, 64, 5).reshape(5, 32, 64, 64, 1))); lig.cond_gen.copy_(lig.cond[0])
+        lig.replay(); torch.cuda.synchronize()
+        b0.record()
+        for _ in range(3):
+            lig.replay()
+        b1.record(); torch.cuda.synchronize()
+        ld["train_ms_per_iteration_batch32"] = round(b0.elapsed_time(b1) / 3, 2)
+        ld["train_finite"] = bool(torch.isfinite(lig.d_losses).all().item() and torch.isfinite(lig.g_loss).all().item())
         extras["largedomain_nd64"] = ld
+        del lig, ltr
         lctx.close()
 
     burst, sustained, hbm, src = load_peaks()

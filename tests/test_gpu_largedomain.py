@@ -80,3 +80,39 @@ def test_dropin_training_module_large_domain(tmp_path, monkeypatch):
     finally:
         m.ndomain = 16
         m.setup(seed=0, extra=None, device_sampler=False)
+
+
+def test_tensor_core_training_mode_large_domain(big):
+    """train_mode="tf32" at ndomain = 64 (Dense 4196 -> 49152, convs on 16^2 / 32^2 / 64^2 grids, critic Flatten 8192): losses and every
+    gradient tensor of a critic step and a generator step against the library's own FP32 SIMT mode on the same inputs (the FP32
+    mode is pinned against the oracle above and in test_gpu_critic_train.py); bound 1e-2 relative L2 per tensor."""
+    from rdg_b200.engine import GanTrainer
+    gen, crit, gw, cw = big
+    gen.set_weights(gw); crit.set_weights(cw)
+    B = 2
+    z, cond, rng = _inputs(B, seed=71)
+    x = rng.random((B, 24, ND, ND, 1)).astype(np.float32); x /= x.sum(axis=1, keepdims=True)
+    alpha = rng.random(B).astype(np.float32)
+    masks3 = [[(rng.random(s) < 0.75).astype(np.float32) for s in O.critic_mask_shapes(ND, B)] for _ in range(3)]
+
+    def split(flat, shapes):
+        out, off = [], 0
+        for shp in shapes:
+            n = int(np.prod(shp)); out.append(flat[off:off + n].reshape(shp)); off += (n + 3) // 4 * 4
+        return out
+
+    res = {}
+    for mode in ("fp32", "tf32"):
+        tr = GanTrainer(gen, crit, gen_mode="fp32", train_mode=mode)
+        lc = tr.critic_grads(x, cond, z, alpha, masks3).cpu().numpy()
+        gc = split(tr.grad_tensor(1).cpu().numpy().copy(), W.critic_shapes(ND, 1))
+        lg = float(tr.generator_grads(z, cond, masks3[0]).item())
+        gg = split(tr.grad_tensor(0).cpu().numpy().copy(), W.generator_shapes(ND, 1))
+        res[mode] = (lc, gc, lg, gg)
+    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / (np.linalg.norm(b) + 1e-30))
+    np.testing.assert_allclose(res["tf32"][0], res["fp32"][0], rtol=2e-3, atol=1e-4)
+    assert abs(res["tf32"][2] - res["fp32"][2]) <= 2e-3 * max(1.0, abs(res["fp32"][2]))
+    for i, (a, b) in enumerate(zip(res["tf32"][1], res["fp32"][1])):
+        assert rel(a, b) <= 1e-2, f"critic tensor {i}: {rel(a, b):.2e}"
+    for i, (a, b) in enumerate(zip(res["tf32"][3][:9], res["fp32"][3][:9])):
+        assert rel(a, b) <= 1e-2, f"generator tensor {i}: {rel(a, b):.2e}"
