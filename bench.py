@@ -472,13 +472,27 @@ def main():
                         tr32.generator_grads(gathered[2], gathered[1], None)
                     ref = tr32.grad_tensor(which)
                     errs[name] = float(((g - ref).norm() / ref.norm()).item())
+                    # the same sum taken rank batch by rank batch on ONE GPU (identical kernel configuration per batch, so no
+                    # LeakyReLU unit sits on the other side of its kink): isolates the exchange itself
+                    acc = torch.zeros_like(g)
+                    for r_ in range(world):
+                        sl = slice(r_ * TB, (r_ + 1) * TB)
+                        if which == 1:
+                            tr32.critic_grads(gathered[0][sl], gathered[1][sl], gathered[2][sl], gathered[3][sl], None)
+                        else:
+                            tr32.generator_grads(gathered[2][sl], gathered[1][sl], None)
+                        acc += tr32.grad_tensor(which)
+                    acc /= world
+                    errs[name + "_rankwise"] = float(((g - acc).norm() / acc.norm()).item())
                 barrier()
             tr.profile_comm = True
             tr.comm_ms()
             ms_eager = timed(lambda: (tr.iteration_device(x_real, tcond, tcond[0], dl, gls), tr.finish()), 10)
             comm = tr.comm_ms() / 13.0
             tr.profile_comm = False
-            dp = {"ranks": world, "grad_parity_rel_l2": errs, "allreduce_ms_per_iteration": comm,
+            dp = {"ranks": world, "grad_parity_rel_l2": errs,
+                  "grad_parity_note": "N-rank averaged gradients vs rank 0 on the gathered N*32 batch (FP32 mode); *_rankwise: vs rank 0 summing the same "
+                                      "rank batches one by one (same split-K configuration, no LeakyReLU kink crossings)", "allreduce_ms_per_iteration": comm,
                   "allreduce_share_of_eager_iteration": comm / ms_eager, "exchange": "NCCL all-reduce of the flat FP32 gradient buffer + Adam on an update stream between per-phase graphs, overlapping the next step's generator forward"}
         # critic scoring (config #3, forward only): synthetic hourly fraction fields, tensor-core scoring mode vs the FP32 path
         CB = 20000
