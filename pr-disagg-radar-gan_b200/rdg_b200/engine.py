@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import threading
 
 import numpy as np
 import torch
@@ -43,8 +42,7 @@ class Context:
         self.handle = h
         mc, sm = C.c_int(), C.c_int()
         self.lib.rdg_ctx_info(self.handle, None, None, C.byref(mc), C.byref(sm))
-        self.max_chunk, self.sm_count = mc.value, sm.value
-        self._lock = threading.Lock()
+        self.max_chunk, self.sm_count = mc.value, sm.value       # one context = one caller at a time (not thread-safe, like a Keras model)
 
     def close(self):
         if getattr(self, "handle", None):
