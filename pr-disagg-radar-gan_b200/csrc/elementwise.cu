@@ -253,6 +253,54 @@ __global__ void fill_random_dev_kernel(float* __restrict__ dst, long long n, uin
     else for (int j = 0; q * 4 + j < n; ++j) dst[q * 4 + j] = z[j];
 }
 
+__device__ __forceinline__ void philox_draw(uint32_t (&c)[4], uint64_t seed) {
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+}
+__global__ void step_random_dev_kernel(float* __restrict__ buf, long long qa, long long n_normal, long long off_u, long long qb, long long n_u,
+                                       long long off_m, long long n_m, float keep, uint64_t seed, RdgTrainState* s, int which) {
+    const uint32_t ctr = (uint32_t)(*reinterpret_cast<volatile unsigned long long*>(&s->rng_ctr[which]) + 1ull);
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float* dst; long long n; uint32_t sid; int kind;
+    if (q < qa) { dst = buf; n = n_normal; sid = 1; kind = 0; }
+    else if (q < qa + qb) { q -= qa; dst = buf + off_u; n = n_u; sid = 2; kind = 1; }
+    else { q -= qa + qb; dst = buf + off_m; n = n_m; sid = 3; kind = 2; }
+    if (q * 4 < n) {
+        uint32_t c[4] = {(uint32_t)q, (uint32_t)((uint64_t)q >> 32), sid + 16u * (uint32_t)which, ctr};
+        philox_draw(c, seed);
+        float z[4];
+        if (kind == 0) {
+            float u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = ((float)c[j] + 0.5f) * 2.3283064365386963e-10f;
+            const float r0 = sqrtf(-2.f * logf(u[0])), r1 = sqrtf(-2.f * logf(u[2]));
+            float s0, c0, s1, c1;
+            sincospif(2.f * u[1], &s0, &c0);
+            sincospif(2.f * u[3], &s1, &c1);
+            z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float u = (float)(c[j] >> 8) * 5.9604644775390625e-08f;
+                z[j] = kind == 1 ? u : (u < keep ? 1.f : 0.f);
+            }
+        }
+        if (q * 4 + 3 < n) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(z[0], z[1], z[2], z[3]);
+        else for (int j = 0; q * 4 + j < n; ++j) dst[q * 4 + j] = z[j];
+    }
+    // the last block to finish advances the step counter (every thread above read the old value)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&s->done[which], 1u) == gridDim.x - 1) {
+            s->done[which] = 0u;
+            s->rng_ctr[which] += 1ull;
+            __threadfence();
+        }
+    }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
                             float gs) {
@@ -287,6 +335,43 @@ __global__ void dense_score_kernel(const float* __restrict__ x, const float* __r
     s = warp_sum(s);
     if (lane == 0) score[b] = s + bias[0];
 }
+// Tail of the critic forward / head of its backward in one launch (tensor-core training mode): the per-sample cotangents of the
+// scores dscore[b] = cot[b / B] (segments of B samples: e.g. [+1/B | -1/B | 1] for fake | real | interpolated, :452-454, :238-241),
+// the Wasserstein loss terms loss_k = sign_k * mean(score of segment k) (k < nloss), and the cotangent of the last conv's
+// pre-activation da4[b][k] = dscore[b] * W5[k] * LeakyReLU'(a4[b][k]) * mask (the Dense(1) backward + LeakyReLU/dropout backward).
+__global__ void critic_tail_kernel(const float* __restrict__ score, const float* __restrict__ w5, const float* __restrict__ a4,
+                                   const float* __restrict__ mask, float mask_scale, int B, int nseg, int K, float c0, float c1, float c2,
+                                   float s0, float s1, int nloss, float* __restrict__ loss, float* __restrict__ dscore,
+                                   float* __restrict__ da4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // float4 index into [nseg*B][K]
+    const long long n4 = (long long)nseg * B * K / 4;
+    if (i < n4) {
+        const long long e = i * 4;
+        const int b = (int)(e / K), k = (int)(e - (long long)b * K);
+        const int seg = b / B;
+        const float ct = seg == 0 ? c0 : (seg == 1 ? c1 : c2);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w5 + k));
+        const float4 a = reinterpret_cast<const float4*>(a4)[i];
+        float4 r = make_float4(ct * w.x * (a.x > 0.f ? 1.f : 0.2f), ct * w.y * (a.y > 0.f ? 1.f : 0.2f),
+                               ct * w.z * (a.z > 0.f ? 1.f : 0.2f), ct * w.w * (a.w > 0.f ? 1.f : 0.2f));
+        if (mask) {
+            const float4 m = reinterpret_cast<const float4*>(mask)[i];
+            r.x *= m.x * mask_scale; r.y *= m.y * mask_scale; r.z *= m.z * mask_scale; r.w *= m.w * mask_scale;
+        }
+        reinterpret_cast<float4*>(da4)[i] = r;
+        if (k == 0 && dscore) dscore[b] = ct;
+    }
+    if (blockIdx.x == 0) {                       // the loss terms: one warp per term, fixed summation order
+        const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (wp < nloss) {
+            float s = 0.f;
+            for (int j = lane; j < B; j += 32) s += score[wp * B + j];
+            s = warp_sum(s);
+            if (lane == 0) loss[wp] = (wp == 0 ? s0 : s1) * s / (float)B;
+        }
+    }
+}
+
 // ---- output conv Conv3D(64->1,'same') through per-tap products (training, tensor-core mode): P[pos][tap] = y[pos] . w4[tap]
 // logits[b,t,h,w] = b4 + sum_tap P[(t+kt-1, h+kh-1, w+kw-1)][tap]       (gan_train_cwgangp_pixelnorm.py:345)
 __global__ void tap_gather_logits_kernel(const float* __restrict__ P, const float* __restrict__ b4, float* __restrict__ logits,
@@ -384,8 +469,14 @@ __global__ void gp_norm_kernel(const float* __restrict__ g0, int C, long long pe
     if (threadIdx.x == 0) norm[blockIdx.x] = sqrtf(s);      // no epsilon, like the reference
 }
 __global__ void gp_cotangent_kernel(const float* __restrict__ g0, const float* __restrict__ norm, float coef,
-                                    float* __restrict__ u0, int C, long long n, long long per) {
+                                    float* __restrict__ u0, int C, long long n, long long per, int B, float* __restrict__ loss_out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loss_out && blockIdx.x == 0 && threadIdx.x < 32) {       // 'mse' against zeros of the penalty output: mean((norm - 1)^2)
+        float s = 0.f;
+        for (int b = threadIdx.x; b < B; b += 32) { const float d = norm[b] - 1.f; s = fmaf(d, d, s); }
+        s = warp_sum(s);
+        if (threadIdx.x == 0) loss_out[0] = s / (float)B;
+    }
     if (i >= n) return;
     const int c = (int)(i % C);
     const long long b = i / (per * C);
@@ -546,6 +637,25 @@ int ew_dense_score(const float* x, const float* w, const float* bias, float* sco
     return 0;
 }
 
+int ew_critic_tail(const float* score, const float* w5, const float* a4, const float* mask, float mask_scale, int B, int nseg, int K,
+                   const float* cot3, const float* sign2, int nloss, float* loss, float* dscore, float* da4, cudaStream_t st) {
+    if (K & 3) { rdg_set_error("ew_critic_tail: K must be a multiple of 4"); return -1; }
+    const long long n4 = (long long)nseg * B * K / 4;
+    critic_tail_kernel<<<EW_GRID(n4)>>>(score, w5, a4, mask, mask_scale, B, nseg, K, cot3[0], cot3[1], cot3[2], sign2[0], sign2[1], nloss,
+                                          loss, dscore, da4);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int ew_step_random_dev(float* buf, long long n_normal, long long off_u, long long n_u, long long off_m, long long n_m, float keep, uint64_t seed,
+                       RdgTrainState* s, int which, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(buf) & 15) || (off_u & 3) || (off_m & 3)) { rdg_set_error("ew_step_random_dev: regions must be 16-byte aligned"); return -1; }
+    const long long qa = (n_normal + 3) / 4, qb = (n_u + 3) / 4, qc = (n_m + 3) / 4;
+    step_random_dev_kernel<<<EW_GRID(qa + qb + qc)>>>(buf, qa, n_normal, off_u, qb, n_u, off_m, n_m, keep, seed, s, which);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
 int ew_interp(const float* xr, const float* xf, const float* alpha, float* xhat, int B, long long per, cudaStream_t st) {
     long long n = (long long)B * per;
     if (!n) return 0;
@@ -570,10 +680,10 @@ int ew_gp_norm(const float* g0, int C, int B, long long per, float* norm, cudaSt
     RDG_LAUNCH_CHECK();
     return 0;
 }
-int ew_gp_cotangent(const float* g0, const float* norm, float coef, float* u0, int C, int B, long long per, cudaStream_t st) {
+int ew_gp_cotangent(const float* g0, const float* norm, float coef, float* u0, int C, int B, long long per, cudaStream_t st, float* loss_out) {
     long long n = (long long)B * per * C;
     if (!n) return 0;
-    gp_cotangent_kernel<<<EW_GRID(n)>>>(g0, norm, coef, u0, C, n, per);
+    gp_cotangent_kernel<<<EW_GRID(n)>>>(g0, norm, coef, u0, C, n, per, B, loss_out);
     RDG_LAUNCH_CHECK();
     return 0;
 }

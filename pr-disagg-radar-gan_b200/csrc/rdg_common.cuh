@@ -95,8 +95,13 @@ int ew_adam(float* p, const float* g, float* m, float* v, long long n, float lr_
             float beta2, float eps, float grad_scale, cudaStream_t st);
 
 // device-resident training state (replayable CUDA graphs): Philox step counter, shared Adam step counter, bias-corrected rate
-struct RdgTrainState { unsigned long long rng_ctr[2]; long long adam_t; float lr_t; float pad_; };   // rng_ctr: [0] critic steps, [1] generator steps
-int ew_train_tick(RdgTrainState* s, int which, cudaStream_t st);     // which: 0 critic-step counter, 1 generator-step counter
+struct RdgTrainState { unsigned long long rng_ctr[2]; long long adam_t; float lr_t; float pad_; unsigned int done[2]; unsigned int pad2_[2]; };   // rng_ctr: [0] critic steps, [1] generator steps
+int ew_train_tick(RdgTrainState* s, int which, cudaStream_t st);
+// All random inputs of one step in ONE launch, counter advanced by the launch itself (the last block to finish increments it; every
+// thread uses the old value + 1): buf[0 .. n_normal) ~ N(0,1) (stream 1), buf[off_u .. +n_u) ~ U[0,1) (stream 2), buf[off_m .. +n_m)
+// Bernoulli(keep) (stream 3).  Same values as ew_train_tick + three ew_fill_random_dev calls.
+int ew_step_random_dev(float* buf, long long n_normal, long long off_u, long long n_u, long long off_m, long long n_m, float keep, uint64_t seed,
+                       RdgTrainState* s, int which, cudaStream_t st);     // which: 0 critic-step counter, 1 generator-step counter
 // Keras-Adam with the step counter in *s (incremented here) instead of a host argument
 int ew_adam_dev(float* p, const float* g, float* m, float* v, long long n, RdgTrainState* s, float lr, float beta1, float beta2,
                 float eps, float grad_scale, cudaStream_t st);
@@ -112,12 +117,17 @@ int ew_fill3(float* dst, int n, float a, float b, float c, cudaStream_t st);
 // x3 [3B,24,nd,nd,1+ncond] = critic inputs [fake | real | alpha*real + (1-alpha)*fake] with the condition tiled over the hours
 int ew_critic_inputs3(const float* fake, const float* real, const float* alpha, const float* cond, float* x3, int B, int nd, int ncond,
                       cudaStream_t st);
+// critic forward tail + backward head: dscore[b] = cot3[b / B], loss[k] = sign2[k] * mean(score[kB .. kB+B)) for k < nloss,
+// da4 = dscore x w5 * LeakyReLU'(a4) [* mask * mask_scale]   (nseg segments of B samples, K = flattened features)
+int ew_critic_tail(const float* score, const float* w5, const float* a4, const float* mask, float mask_scale, int B, int nseg, int K,
+                   const float* cot3, const float* sign2, int nloss, float* loss, float* dscore, float* da4, cudaStream_t st);
 int ew_dense_score(const float* x, const float* w, const float* bias, float* score, int B, int K, cudaStream_t st);   // Flatten + Dense(1)
 int ew_interp(const float* xr, const float* xf, const float* alpha, float* xhat, int B, long long per, cudaStream_t st);
 int ew_fill(float* dst, long long n, float v, cudaStream_t st);
 int ew_mean_scaled(const float* x, long long n, float scale, float* out, cudaStream_t st);   // out = scale * mean(x)
 int ew_gp_norm(const float* g0, int C, int B, long long per, float* norm, cudaStream_t st);   // ||g0[b,...,0]||_2
-int ew_gp_cotangent(const float* g0, const float* norm, float coef, float* u0, int C, int B, long long per, cudaStream_t st);
+int ew_gp_cotangent(const float* g0, const float* norm, float coef, float* u0, int C, int B, long long per, cudaStream_t st,
+                    float* loss_out = nullptr);      // loss_out != null: also mean((norm - 1)^2) (saves the ew_gp_loss launch)
 int ew_gp_loss(const float* norm, int B, float* out, cudaStream_t st);                       // mean((norm-1)^2)
 int ew_extract_channel0(const float* x, float* out, long long n, int C, cudaStream_t st);
 int ew_combine_losses(const float* lv, const float* lf, const float* lgp, float gp_weight, float* out4, cudaStream_t st);

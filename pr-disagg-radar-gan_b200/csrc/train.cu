@@ -554,19 +554,20 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
                                A3.a[l + 1], 1));
     }
     TRY(ew_dense_score(A3.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A3.score, 3 * B, (int)critic_act_elems(c, 4), st));
-    TRY(ew_mean_scaled(A3.score + B, B, -1.f, lsc + 0, st));      // l_valid = mean(-D(real))  (:215-216, targets :452-454)
-    TRY(ew_mean_scaled(A3.score, B, 1.f, lsc + 1, st));           // l_fake  = mean(+D(fake))
-
-    // one backward-data chain for the three thirds: cotangents of the scores [+1/B | -1/B | 1]
+    // one backward-data chain for the three thirds: cotangents of the scores [+1/B | -1/B | 1].  One launch forms them, the two
+    // Wasserstein terms l_fake = mean(+D(fake)) -> lsc[1], l_valid = mean(-D(real)) -> lsc[0] (:215-216, targets :452-454) and
+    // da_4 = Dense(1)^T backward * LeakyReLU'(a_4) * mask_4
     SideStream ss{c, st, 0};
     TRY(ss.init());
-    TRY(ew_fill3(dscore3, B, 1.f / (float)B, -1.f / (float)B, 1.f, st));
+    {
+        const float cot3[3] = {1.f / (float)B, -1.f / (float)B, 1.f}, sign2[2] = {1.f, -1.f};
+        TRY(ew_critic_tail(A3.score, c->c_params + c->c_off[8], A3.a[4], masks3 ? masks3[3] : nullptr, ms, B, 3, (int)critic_act_elems(c, 4), cot3,
+                           sign2, 2, lsc + 4, dscore3, da[4], st));      // lsc[4] = l_fake, lsc[5] = l_valid
+    }
     TRY(ss.fork());
     TRY(simt_conv_bwd_filter(A3.h[4], dscore3, c->c_grads + c->c_off[8], c->c_grads + c->c_off[9], rdg_critic_dense_geom(c, 2 * B), ss.aux()));
-    TRY(simt_conv_bwd_data(dscore3, c->c_params + c->c_off[8], dh, rdg_critic_dense_geom(c, 3 * B), st));
     // da_l = cotangent of the pre-activation a_l.  The LeakyReLU (+ dropout) backward of layer l-1 is fused into the epilogue of
     // layer l's transposed conv: da_{l-1} = convT_l(da_l) * LeakyReLU'(a_{l-1}) * mask_{l-1}
-    TRY(ew_lrelu_bwd(A3.a[4], dh, da[4], (long long)3 * B * critic_act_elems(c, 4), masks3 ? masks3[3] : nullptr, ms, st));
     for (int l = 4; l >= 1; --l) {
         ConvGeom g = rdg_critic_conv_geom(c, l - 1, 3 * B);
         TRY(ss.fork());       // bias gradients of the Wasserstein terms: the first 2B samples
@@ -586,8 +587,7 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     // gradient penalty (:230-244): norm of the input gradient, 'mse' against zeros, cotangent of 10 * mean((n-1)^2)
     const int C0 = 1 + c->ncond;
     TRY(ew_gp_norm(g0, C0, B, (long long)px, norm, st));
-    TRY(ew_gp_loss(norm, B, lsc + 2, st));
-    TRY(ew_gp_cotangent(g0, norm, 10.f * 2.f / (float)B, hat_h[0], C0, B, (long long)px, st));     // u_0 replaces h_0 of the third
+    TRY(ew_gp_cotangent(g0, norm, 10.f * 2.f / (float)B, hat_h[0], C0, B, (long long)px, st, lsc + 2));   // u_0 replaces h_0 of the third; l_gp
     // second-order pass (LeakyReLU'' = 0): u_l = S_l (.) conv_l(u_{l-1}); filter gradients of BOTH loss parts in one contraction
     for (int l = 1; l <= 4; ++l) {
         ConvGeom g3 = rdg_critic_conv_geom(c, l - 1, 3 * B);
@@ -606,7 +606,7 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     }
     TRY(simt_colsum(hat_h[4], c->c_grads + c->c_off[8], B, (int)critic_act_elems(c, 4), st));      // d/dW5 of the penalty
     TRY(ss.join());
-    TRY(ew_combine_losses(lsc + 0, lsc + 1, lsc + 2, 10.f, losses4, st));
+    TRY(ew_combine_losses(lsc + 5, lsc + 4, lsc + 2, 10.f, losses4, st));      // [l_valid, l_fake, l_gp]
     return 0;
 }
 
@@ -662,12 +662,12 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
         TRY(critic_conv_fwd_tc(c, l, A.h[l], c->c_params + c->c_off[2 * l + 1], A.h[l + 1], g, ACT_LRELU, masks ? masks[l] : nullptr, st, A.a[l + 1], 1));
     }
     TRY(ew_dense_score(A.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A.score, B, (int)critic_act_elems(c, 4), st));
-    TRY(ew_mean_scaled(A.score, B, -1.f, loss_dev, st));                   // wasserstein_loss with target -1 (:408, :452)
-    TRY(ew_fill(dscore, B, -1.f / (float)B, st));
-    TRY(simt_conv_bwd_data(dscore, c->c_params + c->c_off[8], t0, rdg_critic_dense_geom(c, B), st));
-    {   // t1 / t0 alternate as the cotangents of the pre-activations a_4 .. a_1 (LeakyReLU backward fused into the transposed convs)
+    {   // t1 / t0 alternate as the cotangents of the pre-activations a_4 .. a_1 (LeakyReLU backward fused into the transposed convs);
+        // the first launch also forms the loss mean(-D(G(z))) (wasserstein_loss with target -1, :408, :452) and its cotangent -1/B
         float* cur = t1; float* nxt = t0;
-        TRY(ew_lrelu_bwd(A.a[4], t0, cur, (long long)B * critic_act_elems(c, 4), masks ? masks[3] : nullptr, ms, st));
+        const float cot3[3] = {-1.f / (float)B, 0.f, 0.f}, sign2[2] = {-1.f, 0.f};
+        TRY(ew_critic_tail(A.score, c->c_params + c->c_off[8], A.a[4], masks ? masks[3] : nullptr, ms, B, 1, (int)critic_act_elems(c, 4), cot3, sign2,
+                           1, loss_dev, dscore, cur, st));
         for (int l = 4; l >= 1; --l) {
             ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
             if (l > 1 && tc_layer_ok(g)) {
@@ -814,11 +814,10 @@ extern "C" int rdg_critic_step_dev(rdg_ctx* c, const float* x_real_dev, const fl
     if (dropout)
         for (int l = 0; l < 4; ++l) masks3[l] = c->rnd_buf + L.mask[l];
     if (phases & 1) {
-        TRY(ew_train_tick(c->tstate, 0, st));
-        TRY(ew_fill_random_dev(c->rnd_buf + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 0, 1, 0, 0.f, st));   // np.random.normal :470
-        TRY(ew_fill_random_dev(c->rnd_buf + L.alpha, B, seed, c->tstate, 0, 2, 1, 0.f, st));                              // tf.random.uniform :223
-        if (dropout)      // Dropout(0.25) of the three critic invocations (:289-301): one draw over the four 3B mask tensors
-            TRY(ew_fill_random_dev(c->rnd_buf + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 0, 3, 2, 0.75f, st));
+        // latent ~ N(0,1) (np.random.normal :470), alpha ~ U[0,1) (tf.random.uniform :223) and the Dropout(0.25) keep masks of the
+        // three critic invocations (:289-301: one draw over the four 3B mask tensors) in one launch that also advances the counter
+        TRY(ew_step_random_dev(c->rnd_buf, (long long)B * RDG_LATENT, (long long)L.alpha, B, (long long)L.mask[0],
+                               dropout ? (long long)(L.total - L.mask[0]) : 0, 0.75f, seed, c->tstate, 0, st));
     }
     return critic_step_tc(c, x_real_dev, cond_dev, c->rnd_buf + L.latent, c->rnd_buf + L.alpha, dropout ? masks3 : nullptr, B, gen_mode,
                           losses4_dev, st, phases);
@@ -839,9 +838,9 @@ extern "C" int rdg_generator_step_dev(rdg_ctx* c, const float* cond_dev, int B, 
     if (dropout)
         for (int l = 0; l < 4; ++l) masks[l] = c->rnd_buf_gen + L.mask[l];
     if (phases & 1) {
-        TRY(ew_train_tick(c->tstate, 1, st));
-        TRY(ew_fill_random_dev(c->rnd_buf_gen + L.latent, (long long)B * RDG_LATENT, seed, c->tstate, 1, 1, 0, 0.f, st));   // generate_latent_points :177-193
-        if (dropout) TRY(ew_fill_random_dev(c->rnd_buf_gen + L.mask[0], (long long)(L.total - L.mask[0]), seed, c->tstate, 1, 3, 2, 0.75f, st));
+        // latent (generate_latent_points :177-193) and the dropout masks of the critic pass, one launch
+        TRY(ew_step_random_dev(c->rnd_buf_gen, (long long)B * RDG_LATENT, (long long)L.alpha, 0, (long long)L.mask[0],
+                               dropout ? (long long)(L.total - L.mask[0]) : 0, 0.75f, seed, c->tstate, 1, st));
     }
     return generator_step_tc(c, c->rnd_buf_gen + L.latent, cond_dev, dropout ? masks : nullptr, B, loss_dev, st, phases);
 }
