@@ -164,7 +164,10 @@ int  rdg_set_train_mode(rdg_ctx* ctx, int mode);
  * (plus rdg_adam_apply_dev and the gradient all-reduce) can be captured in one CUDA graph and replayed.  Need train mode 1.
  * phases: 3 = the whole evaluation; 1 = only the part that does not read the critic's weights (random draws, generator forward,
  * interpolation, critic inputs), 2 = the rest.  Issuing 1 and 2 separately lets the head of a step run while another stream
- * still exchanges / applies the previous step's critic gradients. */
+ * still exchanges / applies the previous step's critic gradients.  rdg_critic_step_dev: phases | RDG_STEP_SLOT1 runs the call
+ * on the context's SECOND set of step buffers (workspace + random inputs), both phases of one step with the same choice: with
+ * alternating sets, phase 1 of step k+1 (frozen generator forward, draws) can run on another stream next to phase 2 of step k. */
+#define RDG_STEP_SLOT1 16
 int  rdg_critic_step_dev(rdg_ctx* ctx, const float* x_real_dev, const float* cond_dev, int B, int gen_mode,
                          unsigned long long seed, int dropout, float* losses4_dev, int phases, void* stream);
 int  rdg_generator_step_dev(rdg_ctx* ctx, const float* cond_dev, int B, unsigned long long seed, int dropout,

@@ -30,6 +30,8 @@ struct rdg_ctx {
     float* g_grads = nullptr; float* g_m = nullptr; float* g_v = nullptr;
     float* c_grads = nullptr; float* c_m = nullptr; float* c_v = nullptr;
     void* train_ws = nullptr; size_t train_ws_bytes = 0;
+    void* train_ws1 = nullptr; size_t train_ws1_bytes = 0;     // second critic-step workspace + random inputs (RDG_STEP_SLOT1):
+    float* rnd_buf1 = nullptr; size_t rnd1_cap = 0;            // lets phase 1 of step k+1 run next to phase 2 of step k
     // the generator step of the tensor-core mode has its own workspace and random-input buffer: its first phase (generator forward)
     // reads no critic state and runs on another stream next to the critic steps of the same iteration
     void* train_ws_gen = nullptr; size_t train_ws_gen_bytes = 0;

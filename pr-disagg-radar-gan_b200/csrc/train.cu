@@ -89,9 +89,10 @@ struct Bump {
     }
 };
 
-int ensure_train_ws(rdg_ctx* c, size_t bytes, bool gen = false) {
-    void*& p = gen ? c->train_ws_gen : c->train_ws;
-    size_t& have = gen ? c->train_ws_gen_bytes : c->train_ws_bytes;
+// kind: 0 = critic step (slot 0), 1 = generator step, 2 = critic step slot 1
+int ensure_train_ws(rdg_ctx* c, size_t bytes, int kind = 0) {
+    void*& p = kind == 1 ? c->train_ws_gen : kind == 2 ? c->train_ws1 : c->train_ws;
+    size_t& have = kind == 1 ? c->train_ws_gen_bytes : kind == 2 ? c->train_ws1_bytes : c->train_ws_bytes;
     if (have >= bytes) return 0;
     if (p) { RDG_CUDA(cudaDeviceSynchronize()); RDG_CUDA(cudaFree(p)); p = nullptr; have = 0; }
     RDG_CUDA(cudaMalloc(&p, bytes));
@@ -513,13 +514,14 @@ int critic_conv_fwd_tc(rdg_ctx* c, int l, const float* x, const float* bias, flo
 // phases: bit 0 = the part that does not read the critic's weights (frozen generator forward, interpolation, critic inputs), bit 1 =
 // the rest.  Issued separately, phase 1 of a step overlaps the gradient exchange + Adam update of the previous step (other stream).
 int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const float* latent, const float* alpha, const float* const* masks3,
-                   int B, int gen_mode, float* losses4, cudaStream_t st, int phases = 3) {
+                   int B, int gen_mode, float* losses4, cudaStream_t st, int phases = 3, int slot = 0) {
     const size_t px = (size_t)RDG_NHOURS * c->nd * c->nd;
     size_t max_act = 0, sum_act = 0;
     for (int l = 0; l < 5; ++l) { max_act = std::max(max_act, critic_act_elems(c, l)); sum_act += critic_act_elems(c, l); }
     const size_t need = ((size_t)B * (3 * (3 * sum_act + 64) + 6 * max_act + 3 * px) + 8192) * 4 + 128 * 256;
-    TRY(ensure_train_ws(c, need));
-    Bump ws{reinterpret_cast<uint8_t*>(c->train_ws), reinterpret_cast<uint8_t*>(c->train_ws) + c->train_ws_bytes};
+    TRY(ensure_train_ws(c, need, slot ? 2 : 0));
+    uint8_t* wsb = reinterpret_cast<uint8_t*>(slot ? c->train_ws1 : c->train_ws);
+    Bump ws{wsb, wsb + (slot ? c->train_ws1_bytes : c->train_ws_bytes)};
     CriticActs A3;
     TRY(critic_alloc(c, ws, 3 * B, A3));
     float* hat_h[5]; float* hat_a[5];
@@ -619,7 +621,7 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     ConvGeom dg1 = rdg_gen_dense_geom(c, 1);
     const size_t need = ((size_t)B * (2 * csum + 3 * cmax + 2 * gsum + dg1.Ci + dg1.Co + 4 * px + 2 * gmax + 32 * px + 64) +
                          folded_weight_elems(256, 256) + 8192) * 4 + 64 * 256;
-    TRY(ensure_train_ws(c, need, true));
+    TRY(ensure_train_ws(c, need, 1));
     Bump ws{reinterpret_cast<uint8_t*>(c->train_ws_gen), reinterpret_cast<uint8_t*>(c->train_ws_gen) + c->train_ws_gen_bytes};
     GenActs G; CriticActs A;
     TRY(gen_alloc(c, ws, B, G)); TRY(critic_alloc(c, ws, B, A));
@@ -725,9 +727,9 @@ namespace {
 
 size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
 
-int ensure_rnd(rdg_ctx* c, size_t floats, bool gen = false) {
-    float*& p = gen ? c->rnd_buf_gen : c->rnd_buf;
-    size_t& have = gen ? c->rnd_gen_cap : c->rnd_cap;
+int ensure_rnd(rdg_ctx* c, size_t floats, int kind = 0) {     // kind as in ensure_train_ws
+    float*& p = kind == 1 ? c->rnd_buf_gen : kind == 2 ? c->rnd_buf1 : c->rnd_buf;
+    size_t& have = kind == 1 ? c->rnd_gen_cap : kind == 2 ? c->rnd1_cap : c->rnd_cap;
     if (have >= floats) return 0;
     if (p) { RDG_CUDA(cudaDeviceSynchronize()); RDG_CUDA(cudaFree(p)); p = nullptr; have = 0; }
     RDG_CUDA(cudaMalloc(&p, floats * 4));
@@ -807,20 +809,23 @@ extern "C" int rdg_critic_step_dev(rdg_ctx* c, const float* x_real_dev, const fl
     RDG_CUDA(cudaSetDevice(c->device));
     TRY(ensure_train_state(c)); TRY(ensure_tstate(c));
     cudaStream_t st = (cudaStream_t)stream;
-    if (phases < 1 || phases > 3) { rdg_set_error("rdg_critic_step_dev: phases must be 1, 2 or 3"); return RDG_E_BADARG; }
+    const int slot = (phases & RDG_STEP_SLOT1) ? 1 : 0;
+    phases &= ~RDG_STEP_SLOT1;
+    if (phases < 1 || phases > 3) { rdg_set_error("rdg_critic_step_dev: phases must be 1, 2 or 3 (| RDG_STEP_SLOT1)"); return RDG_E_BADARG; }
     const RndLayout L = rnd_layout(c, B, 3);
-    TRY(ensure_rnd(c, L.total));
+    TRY(ensure_rnd(c, L.total, slot ? 2 : 0));
+    float* rnd = slot ? c->rnd_buf1 : c->rnd_buf;
     const float* masks3[4] = {nullptr, nullptr, nullptr, nullptr};
     if (dropout)
-        for (int l = 0; l < 4; ++l) masks3[l] = c->rnd_buf + L.mask[l];
+        for (int l = 0; l < 4; ++l) masks3[l] = rnd + L.mask[l];
     if (phases & 1) {
         // latent ~ N(0,1) (np.random.normal :470), alpha ~ U[0,1) (tf.random.uniform :223) and the Dropout(0.25) keep masks of the
         // three critic invocations (:289-301: one draw over the four 3B mask tensors) in one launch that also advances the counter
-        TRY(ew_step_random_dev(c->rnd_buf, (long long)B * RDG_LATENT, (long long)L.alpha, B, (long long)L.mask[0],
+        TRY(ew_step_random_dev(rnd, (long long)B * RDG_LATENT, (long long)L.alpha, B, (long long)L.mask[0],
                                dropout ? (long long)(L.total - L.mask[0]) : 0, 0.75f, seed, c->tstate, 0, st));
     }
-    return critic_step_tc(c, x_real_dev, cond_dev, c->rnd_buf + L.latent, c->rnd_buf + L.alpha, dropout ? masks3 : nullptr, B, gen_mode,
-                          losses4_dev, st, phases);
+    return critic_step_tc(c, x_real_dev, cond_dev, rnd + L.latent, rnd + L.alpha, dropout ? masks3 : nullptr, B, gen_mode,
+                          losses4_dev, st, phases, slot);
 }
 
 extern "C" int rdg_generator_step_dev(rdg_ctx* c, const float* cond_dev, int B, unsigned long long seed, int dropout, float* loss_dev,
@@ -833,7 +838,7 @@ extern "C" int rdg_generator_step_dev(rdg_ctx* c, const float* cond_dev, int B, 
     cudaStream_t st = (cudaStream_t)stream;
     const RndLayout L = rnd_layout(c, B, 1);
     if (phases < 1 || phases > 3) { rdg_set_error("rdg_generator_step_dev: phases must be 1, 2 or 3"); return RDG_E_BADARG; }
-    TRY(ensure_rnd(c, L.total, true));                  // own buffer: phase 1 may run next to a critic step
+    TRY(ensure_rnd(c, L.total, 1));                  // own buffer: phase 1 may run next to a critic step
     const float* masks[4] = {nullptr, nullptr, nullptr, nullptr};
     if (dropout)
         for (int l = 0; l < 4; ++l) masks[l] = c->rnd_buf_gen + L.mask[l];

@@ -475,11 +475,12 @@ class GanTrainer:
             self._pending.record(upd)
         self._pending_which = which
 
-    def _critic_calls(self, x_real, cond, losses_out):
+    def _critic_calls(self, x_real, cond, losses_out, slot=0):
+        """slot: which of the context's two sets of step buffers the step uses (RDG_STEP_SLOT1 = 16 in `phases`)."""
         ctx = self.ctx
         args = (ctx.handle, C.c_void_p(x_real.data_ptr()), C.c_void_p(cond.data_ptr()), int(x_real.shape[0]),
                 _lib.MODES[self.gen_mode], self.seed + self.rank, int(self.dropout), C.c_void_p(losses_out.data_ptr()))
-        return [lambda ph=ph: _lib.check(ctx.lib.rdg_critic_step_dev(*args, ph, ctx._stream())) for ph in (1, 2)]
+        return [lambda ph=ph: _lib.check(ctx.lib.rdg_critic_step_dev(*args, ph | (16 if slot else 0), ctx._stream())) for ph in (1, 2)]
 
     def _generator_calls(self, cond, loss_out):
         ctx = self.ctx
@@ -509,7 +510,10 @@ class GanTrainer:
         """One iteration = the critic steps, then the generator step (reference :468-482).  Phase 1 of the generator step (noise,
         generator forward with saved activations) reads neither the critic nor anything the critic steps write, so it is issued
         on a third stream at the START of the iteration and runs next to the critic steps, whose launches are too small to fill the
-        GPU; the generator step's second phase (critic pass + backward) follows the last critic update as before."""
+        GPU; the generator step's second phase (critic pass + backward) follows the last critic update as before.
+        The critic steps' own first phases (draws, frozen generator forward, interpolation: they read only the generator, which
+        the critic steps do not change) run on a prefetch stream one step ahead: the steps alternate between the context's two
+        buffer sets, so phase 1 of step k+1 overlaps phase 2 of step k and only phase 2 stays on the critical path."""
         dev = self.ctx.device
         main = torch.cuda.current_stream(dev)
         self._set_mode()
@@ -530,8 +534,32 @@ class GanTrainer:
             gen_calls[0]()
             ev_g = torch.cuda.Event()
             ev_g.record(self._gen_stream)
-        for p1, p2 in critic_calls:
-            self._run_step(self.WHICH_CRITIC, p1, p2)
+        if os.environ.get("RDG_PREFETCH", "1") == "0":             # A/B switch: critic phases in stream order
+            for p1, p2 in critic_calls:
+                self._run_step(self.WHICH_CRITIC, p1, p2)
+        else:
+            if getattr(self, "_pre_stream", None) is None:
+                self._pre_stream = torch.cuda.Stream(device=dev)
+            pre = self._pre_stream
+            pre.wait_event(ev0)
+            slot_free, ready = {}, {}
+
+            def prefetch(k):
+                with torch.cuda.stream(pre):
+                    if k % 2 in slot_free:
+                        pre.wait_event(slot_free[k % 2])       # phase 2 of step k-2 has finished with this buffer set
+                    critic_calls[k][0]()
+                    ready[k] = torch.cuda.Event()
+                    ready[k].record(pre)
+
+            prefetch(0)
+            for k, (_, p2) in enumerate(critic_calls):
+                if k + 1 < len(critic_calls):
+                    prefetch(k + 1)
+                main.wait_event(ready[k])
+                self._run_step(self.WHICH_CRITIC, lambda: None, p2)
+                slot_free[k % 2] = torch.cuda.Event()
+                slot_free[k % 2].record(main)
         main.wait_event(ev_g)
         self._run_step(self.WHICH_GEN, lambda: None, gen_calls[1])
 
@@ -539,7 +567,7 @@ class GanTrainer:
         """x_real [n_critic,B,24,nd,nd,1], cond [n_critic,B,nd,nd,ncond], cond_gen [B,nd,nd,ncond], d_losses [n_critic,4], g_loss [1]:
         device tensors.  Issues one whole iteration (see _run_iteration); call finish() before reading weights."""
         n = int(x_real.shape[0])
-        self._run_iteration([self._critic_calls(x_real[k], cond[k], d_losses[k]) for k in range(n)],
+        self._run_iteration([self._critic_calls(x_real[k], cond[k], d_losses[k], slot=k % 2) for k in range(n)],
                             self._generator_calls(cond_gen, g_loss))
 
     def capture_iteration(self, batch, n_critic=5, segmented=None):
@@ -586,7 +614,7 @@ class GanTrainer:
             # step are issued eagerly on the update stream between them and overlap the next step's first phase)
             ig.graph = None
             ig.segments = []
-            calls = [(self.WHICH_CRITIC, self._critic_calls(ig.x_real[k], ig.cond[k], ig.d_losses[k])) for k in range(n_critic)]
+            calls = [(self.WHICH_CRITIC, self._critic_calls(ig.x_real[k], ig.cond[k], ig.d_losses[k], slot=k % 2)) for k in range(n_critic)]
             calls.append((self.WHICH_GEN, self._generator_calls(ig.cond_gen, ig.g_loss)))
             for which, (p1, p2) in calls:
                 gs = []
