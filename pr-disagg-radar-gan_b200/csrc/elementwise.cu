@@ -68,6 +68,81 @@ __global__ void pixelnorm_lrelu_bwd_kernel(const float* __restrict__ x, const fl
     }
 }
 
+// The same two functions for C = 64 / 128 / 256 (every PixelNorm of the generator) with the row held in registers: 16-byte
+// loads, C/4 (at most 32) lanes per row, so a 64-channel row takes half a warp and nothing is read twice.  The scalar kernels
+// above ran at a third of the HBM/L2 rate on the 50 MB activations of a batch-32 training step.
+template <int L>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) pixelnorm_vec_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int lrelu) {
+    constexpr int L = C / 4 < 32 ? C / 4 : 32, V = C / (4 * L), RPW = 32 / L;
+    const int lane = threadIdx.x & 31, l = lane % L;
+    const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / L;
+    const bool ok = row < rows;
+    const float4* xr = reinterpret_cast<const float4*>(x) + (ok ? row : 0) * (C / 4);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        v[j] = xr[j * L + l];
+        s = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, s))));
+    }
+    s = group_sum<L>(s);
+    if (!ok) return;
+    const float l2 = sqrtf(s / (float)C + 1.0e-8f);
+    float4* yr = reinterpret_cast<float4*>(y) + row * (C / 4);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        float4 o = make_float4(v[j].x / l2, v[j].y / l2, v[j].z / l2, v[j].w / l2);
+        if (lrelu) {
+            o.x = o.x > 0.f ? o.x : 0.2f * o.x; o.y = o.y > 0.f ? o.y : 0.2f * o.y;
+            o.z = o.z > 0.f ? o.z : 0.2f * o.z; o.w = o.w > 0.f ? o.w : 0.2f * o.w;
+        }
+        yr[j * L + l] = o;
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) pixelnorm_lrelu_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                      float* __restrict__ dx, long long rows) {
+    constexpr int L = C / 4 < 32 ? C / 4 : 32, V = C / (4 * L), RPW = 32 / L;
+    const int lane = threadIdx.x & 31, l = lane % L;
+    const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / L;
+    const bool ok = row < rows;
+    const float4* xr = reinterpret_cast<const float4*>(x) + (ok ? row : 0) * (C / 4);
+    const float4* gr = reinterpret_cast<const float4*>(dy) + (ok ? row : 0) * (C / 4);
+    float4 v[V], g[V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        v[j] = xr[j * L + l];
+        g[j] = gr[j * L + l];
+        s = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, s))));
+    }
+    s = group_sum<L>(s);
+    const float l2 = sqrtf(s / (float)C + 1.0e-8f);
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        v[j].x /= l2; v[j].y /= l2; v[j].z /= l2; v[j].w /= l2;              // yn
+        g[j].x *= v[j].x > 0.f ? 1.f : 0.2f; g[j].y *= v[j].y > 0.f ? 1.f : 0.2f;
+        g[j].z *= v[j].z > 0.f ? 1.f : 0.2f; g[j].w *= v[j].w > 0.f ? 1.f : 0.2f;
+        dot = fmaf(g[j].x, v[j].x, fmaf(g[j].y, v[j].y, fmaf(g[j].z, v[j].z, fmaf(g[j].w, v[j].w, dot))));
+    }
+    dot = group_sum<L>(dot) / (float)C;
+    if (!ok) return;
+    float4* dr = reinterpret_cast<float4*>(dx) + row * (C / 4);
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+        dr[j * L + l] = make_float4((g[j].x - v[j].x * dot) / l2, (g[j].y - v[j].y * dot) / l2, (g[j].z - v[j].z * dot) / l2,
+                                    (g[j].w - v[j].w * dot) / l2);
+}
+
 // logits [B,24,P] -> fractions (or mm) [B,24,P]; thread per (b,p)
 __global__ void softmax_hours_kernel(const float* __restrict__ logits, float* __restrict__ out, long long B, int P,
                                      const float* __restrict__ cond, int spc, int ncond, float scale, int out_mm,
@@ -512,13 +587,21 @@ int ew_assemble_gen_input(const float* latent, const float* cond, int spc, int b
 }
 int ew_pixelnorm(const float* x, float* y, long long rows, int C, int lrelu, cudaStream_t st) {
     if (!rows) return 0;
-    pixelnorm_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, y, rows, C, lrelu);
+    const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (al && C == 64) pixelnorm_vec_kernel<64><<<ceil_div(rows, 16), 256, 0, st>>>(x, y, rows, lrelu);
+    else if (al && C == 128) pixelnorm_vec_kernel<128><<<ceil_div(rows, 8), 256, 0, st>>>(x, y, rows, lrelu);
+    else if (al && C == 256) pixelnorm_vec_kernel<256><<<ceil_div(rows, 8), 256, 0, st>>>(x, y, rows, lrelu);
+    else pixelnorm_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, y, rows, C, lrelu);
     RDG_LAUNCH_CHECK();
     return 0;
 }
 int ew_pixelnorm_lrelu_bwd(const float* x_pre, const float* dy, float* dx, long long rows, int C, cudaStream_t st) {
     if (!rows) return 0;
-    pixelnorm_lrelu_bwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x_pre, dy, dx, rows, C);
+    const bool al = ((reinterpret_cast<uintptr_t>(x_pre) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+    if (al && C == 64) pixelnorm_lrelu_bwd_vec_kernel<64><<<ceil_div(rows, 16), 256, 0, st>>>(x_pre, dy, dx, rows);
+    else if (al && C == 128) pixelnorm_lrelu_bwd_vec_kernel<128><<<ceil_div(rows, 8), 256, 0, st>>>(x_pre, dy, dx, rows);
+    else if (al && C == 256) pixelnorm_lrelu_bwd_vec_kernel<256><<<ceil_div(rows, 8), 256, 0, st>>>(x_pre, dy, dx, rows);
+    else pixelnorm_lrelu_bwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x_pre, dy, dx, rows, C);
     RDG_LAUNCH_CHECK();
     return 0;
 }

@@ -55,7 +55,8 @@ int simt_conv_fwd(const float* x, const float* w, const float* bias, float* y, c
 int simt_colsum(const float* x, float* out, long long rows, int C, cudaStream_t st);
 // dx = conv_transpose(dy, w): gradient w.r.t. the (logical, i.e. upsampled if g.up) input.
 int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st, int accumulate = 0);
-int simt_conv_bwd_data_ch0(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st);   // input channel 0 only
+int simt_conv_bwd_data_ch0(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st,
+                           float* scratch = nullptr);   // input channel 0 only; scratch: ntaps * B*To*Ho*Wo floats (tap-product form)
 
 // ---- upsample-folded FP32 forms of UpSampling3D(2) + Conv3D(3^3,'same') (simt_folded.cu) ----
 // wf: [8 phases][2,2,2,Ci,Co] folded kernels (f32 sums of the 3^3 kernel's taps); g = the layer's geometry (g.up == 1).

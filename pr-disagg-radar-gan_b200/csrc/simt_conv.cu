@@ -603,10 +603,86 @@ int simt_conv_bwd_data(const float* dy, const float* w, float* dx, const ConvGeo
 
 // gradient w.r.t. input channel 0 only (dx keeps its Ci-channel layout; channels >= 1 are not written): the critic's first conv in
 // the training steps, where only the sample channel's gradient is used (gradient-penalty norm :238-241, generator step)
-int simt_conv_bwd_data_ch0(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st) {
+//
+// With a scratch buffer and Co = 64 the work is done as tap products: P[tap][pos] = <dy[pos][:], w[tap][0][:]> for every output
+// position and tap (one small dense pass, dy read once, coalesced), then every input pixel sums the <= 8 products that reach it.
+// The direct form below walks 8 taps x 64 channels of strided global loads per thread and took 55 us at batch 32, on the
+// critical path of every step; this form takes two short launches.
+__global__ void __launch_bounds__(256) ch0_tap_products_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                               float* __restrict__ P, long long M1, int Ci, int ntaps) {
+    __shared__ float sa[64][65];
+    __shared__ __align__(16) float sw[32][64];
+    const long long pos0 = (long long)blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+        const int r = i >> 4, c4 = i & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pos0 + r < M1) v = __ldg(reinterpret_cast<const float4*>(dy + (pos0 + r) * 64) + c4);
+        sa[r][c4 * 4 + 0] = v.x; sa[r][c4 * 4 + 1] = v.y; sa[r][c4 * 4 + 2] = v.z; sa[r][c4 * 4 + 3] = v.w;
+    }
+    for (int i = threadIdx.x; i < ntaps * 64; i += 256) sw[i >> 6][i & 63] = w[(size_t)(i >> 6) * Ci * 64 + (i & 63)];
+    __syncthreads();
+    const int pos = threadIdx.x & 63, grp = threadIdx.x >> 6;        // a warp shares its taps: weight reads are broadcasts
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int c4 = 0; c4 < 16; ++c4) {
+        const float a0 = sa[pos][c4 * 4], a1 = sa[pos][c4 * 4 + 1], a2 = sa[pos][c4 * 4 + 2], a3 = sa[pos][c4 * 4 + 3];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int tap = grp + 4 * j;
+            if (tap < ntaps) {
+                const float4 b = *reinterpret_cast<const float4*>(&sw[tap][c4 * 4]);
+                acc[j] = fmaf(a0, b.x, fmaf(a1, b.y, fmaf(a2, b.z, fmaf(a3, b.w, acc[j]))));
+            }
+        }
+    }
+    if (pos0 + pos < M1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (grp + 4 * j < ntaps) P[(long long)(grp + 4 * j) * M1 + pos0 + pos] = acc[j];
+    }
+}
+
+__global__ void __launch_bounds__(256) ch0_gather_kernel(const float* __restrict__ P, float* __restrict__ dx, ConvGeom g, long long M1) {
+    const long long M = (long long)g.B * g.Ti * g.Hi * g.Wi;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M) return;
+    const PosDec p = decode_pos(idx, g.Ti, g.Hi, g.Wi);
+    float acc = 0.f;
+    for (int kt = 0; kt < g.KT; ++kt) {
+        int nt = p.t + g.pt - kt;
+        if (nt < 0 || nt % g.stride) continue;
+        nt /= g.stride;
+        if (nt >= g.To) continue;
+        for (int kh = 0; kh < g.KH; ++kh) {
+            int nh = p.h + g.ph - kh;
+            if (nh < 0 || nh % g.stride) continue;
+            nh /= g.stride;
+            if (nh >= g.Ho) continue;
+            for (int kw = 0; kw < g.KW; ++kw) {
+                int nw = p.w + g.pw - kw;
+                if (nw < 0 || nw % g.stride) continue;
+                nw /= g.stride;
+                if (nw >= g.Wo) continue;
+                acc += P[(long long)((kt * g.KH + kh) * g.KW + kw) * M1 + (((long long)p.b * g.To + nt) * g.Ho + nh) * g.Wo + nw];
+            }
+        }
+    }
+    dx[idx * g.Ci] = acc;
+}
+
+int simt_conv_bwd_data_ch0(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st, float* scratch) {
     const long long M = (long long)g.B * g.Ti * g.Hi * g.Wi;
     const int ntaps_ = g.KT * g.KH * g.KW;
     if (M == 0) return 0;
+    if (scratch && !g.up && g.Co == 64 && ntaps_ <= 32) {
+        const long long M1 = (long long)g.B * g.To * g.Ho * g.Wo;
+        ch0_tap_products_kernel<<<ceil_div(M1, 64), 256, 0, st>>>(dy, w, scratch, M1, g.Ci, ntaps_);
+        RDG_LAUNCH_CHECK();
+        ch0_gather_kernel<<<ceil_div(M, 256), 256, 0, st>>>(scratch, dx, g, M1);
+        RDG_LAUNCH_CHECK();
+        return 0;
+    }
     if (g.up || g.Ci > 4 || (g.Co & 3) || (size_t)ntaps_ * g.Ci * g.Co * 4 > 48 * 1024) return simt_conv_bwd_data(dy, w, dx, g, st, 0);
     conv_bwd_data_smallci_kernel<<<ceil_div(M, 256), 256, (size_t)ntaps_ * g.Ci * g.Co * 4, st>>>(dy, w, dx, g, 1);
     RDG_LAUNCH_CHECK();

@@ -384,17 +384,36 @@ __global__ void __launch_bounds__(TCG_THREADS, (NB * (SPLIT ? 2 : 1) <= 4) ? 2 :
     if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols_for(N)); }
 }
 
-// out = act(sum of slices + bias) [* mask]; same contract as the SIMT split-K epilogue
-__global__ void tcg_splitk_epilogue_kernel(const float* __restrict__ part, int nslice, long long MN4, int N, const float* __restrict__ bias,
-                                           float* __restrict__ y, int act, const float* __restrict__ mask, float mask_scale,
-                                           float* __restrict__ pre) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= MN4) return;
-    float4 s = reinterpret_cast<const float4*>(part)[i];
-    for (int z = 1; z < nslice; ++z) {
-        const float4 t = reinterpret_cast<const float4*>(part)[(long long)z * MN4 + i];
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+// out = act(sum of slices + bias) [* mask]; same contract as the SIMT split-K epilogue.  G thread groups of a block share the
+// slices of 256 / G outputs (small outputs with many slices: the deep layers at batch 32 have 16-96 blocks' worth of outputs and
+// 27-54 slices, one thread walking them all is a 10-15 us latency chain); the sum order is fixed, so results are reproducible.
+template <int G>
+__global__ void __launch_bounds__(256) tcg_splitk_epilogue_kernel(const float* __restrict__ part, int nslice, long long MN4, int N,
+                                                                  const float* __restrict__ bias, float* __restrict__ y, int act,
+                                                                  const float* __restrict__ mask, float mask_scale, float* __restrict__ pre) {
+    constexpr int W = 256 / G;
+    const int tx = threadIdx.x % W, ty = threadIdx.x / W;
+    const long long i = (long long)blockIdx.x * W + tx;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < MN4) {
+#pragma unroll 4
+        for (int z = ty; z < nslice; z += G) {
+            const float4 t = reinterpret_cast<const float4*>(part)[(long long)z * MN4 + i];
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
     }
+    if (G > 1) {
+        __shared__ float4 red[256];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        if (ty) return;
+#pragma unroll
+        for (int g = 1; g < G; ++g) {
+            const float4 t = red[g * W + tx];
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+    }
+    if (i >= MN4) return;
     if (bias) {
         const float4 b = ldg4(bias + (int)((i * 4) % N));
         s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
@@ -839,7 +858,12 @@ int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const
         int r = launch_rowgemm_n(a, grid, split, st);
         if (r) return r;
         const long long mn4 = a.out_elems / 4;
-        tcg_splitk_epilogue_kernel<<<ceil_div(mn4, 256), 256, 0, st>>>(part, nslice, mn4, a.Nt, bias, y, act, mask, mask_scale, pre);
+        if (ceil_div(mn4, 256) >= 592 || nslice < 4)
+            tcg_splitk_epilogue_kernel<1><<<ceil_div(mn4, 256), 256, 0, st>>>(part, nslice, mn4, a.Nt, bias, y, act, mask, mask_scale, pre);
+        else if (nslice < 16)
+            tcg_splitk_epilogue_kernel<4><<<ceil_div(mn4, 64), 256, 0, st>>>(part, nslice, mn4, a.Nt, bias, y, act, mask, mask_scale, pre);
+        else
+            tcg_splitk_epilogue_kernel<8><<<ceil_div(mn4, 32), 256, 0, st>>>(part, nslice, mn4, a.Nt, bias, y, act, mask, mask_scale, pre);
         RDG_LAUNCH_CHECK();
         RDG_CUDA(cudaFreeAsync(part, st));
         return 0;

@@ -559,8 +559,10 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     // one backward-data chain for the three thirds: cotangents of the scores [+1/B | -1/B | 1].  One launch forms them, the two
     // Wasserstein terms l_fake = mean(+D(fake)) -> lsc[1], l_valid = mean(-D(real)) -> lsc[0] (:215-216, targets :452-454) and
     // da_4 = Dense(1)^T backward * LeakyReLU'(a_4) * mask_4
-    SideStream ss{c, st, 0};
-    TRY(ss.init());
+    // side streams: bias / Dense gradients on the first; the four filter gradients round-robin over all three, so that they run
+    // next to each other and next to the second-order chain (each is a sub-wave grid) instead of queueing behind one another
+    SideStream ss{c, st, 0}, ssk[3] = {{c, st, 0}, {c, st, 1}, {c, st, 2}};
+    for (auto& s : ssk) TRY(s.init());
     {
         const float cot3[3] = {1.f / (float)B, -1.f / (float)B, 1.f}, sign2[2] = {1.f, -1.f};
         TRY(ew_critic_tail(A3.score, c->c_params + c->c_off[8], A3.a[4], masks3 ? masks3[3] : nullptr, ms, B, 3, (int)critic_act_elems(c, 4), cot3,
@@ -583,7 +585,7 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
             }
         } else {              // only the penalty needs the gradient w.r.t. the critic input: interpolated third
             ConvGeom g1 = rdg_critic_conv_geom(c, 0, B);
-            TRY(simt_conv_bwd_data_ch0(da[1] + (size_t)2 * B * critic_act_elems(c, 1), c->c_params + c->c_off[0], g0, g1, st));
+            TRY(simt_conv_bwd_data_ch0(da[1] + (size_t)2 * B * critic_act_elems(c, 1), c->c_params + c->c_off[0], g0, g1, st, vbuf));
         }
     }
     // gradient penalty (:230-244): norm of the input gradient, 'mse' against zeros, cotangent of 10 * mean((n-1)^2)
@@ -594,10 +596,11 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     for (int l = 1; l <= 4; ++l) {
         ConvGeom g3 = rdg_critic_conv_geom(c, l - 1, 3 * B);
         ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
-        TRY(ss.fork());
-        if (l > 1 && tc_layer_ok(g3)) TRY(tcg_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], g3, ss.aux()));
-        else if (l == 1 && g3.Ci <= 4) TRY(tcg_conv_bwd_filter_smallci(A3.h[0], da[1], c->c_grads + c->c_off[0], g3, ss.aux()));
-        else TRY(simt_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], nullptr, g3, ss.aux()));
+        SideStream& sf = ssk[(l - 1) % 3];
+        TRY(sf.fork());
+        if (l > 1 && tc_layer_ok(g3)) TRY(tcg_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], g3, sf.aux()));
+        else if (l == 1 && g3.Ci <= 4) TRY(tcg_conv_bwd_filter_smallci(A3.h[0], da[1], c->c_grads + c->c_off[0], g3, sf.aux()));
+        else TRY(simt_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], nullptr, g3, sf.aux()));
         const float* mh = masks3 ? masks3[l - 1] + (size_t)2 * B * critic_act_elems(c, l) : nullptr;
         if ((l == 1 && g.Ci <= 4) || (l > 1 && tc_layer_ok(g))) {     // u_l = conv_l(u_{l-1}) * LeakyReLU'(a_l) * mask_l in one epilogue
             TRY(critic_conv_fwd_tc(c, l - 1, hat_h[l - 1], nullptr, hat_h[l], g, ACT_LRELU_BWD, mh, st, hat_a[l], 0));
@@ -607,7 +610,7 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
         }
     }
     TRY(simt_colsum(hat_h[4], c->c_grads + c->c_off[8], B, (int)critic_act_elems(c, 4), st));      // d/dW5 of the penalty
-    TRY(ss.join());
+    for (auto& s : ssk) TRY(s.join());
     TRY(ew_combine_losses(lsc + 5, lsc + 4, lsc + 2, 10.f, losses4, st));      // [l_valid, l_fake, l_gp]
     return 0;
 }
@@ -619,8 +622,8 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     for (int l = 0; l < 5; ++l) { cmax = std::max(cmax, critic_act_elems(c, l)); csum += critic_act_elems(c, l); }
     for (int l = 0; l < 4; ++l) { gsum += gen_act(c, l); gmax = std::max(gmax, gen_act(c, l)); }
     ConvGeom dg1 = rdg_gen_dense_geom(c, 1);
-    const size_t need = ((size_t)B * (2 * csum + 3 * cmax + 2 * gsum + dg1.Ci + dg1.Co + 4 * px + 2 * gmax + 32 * px + 64) +
-                         folded_weight_elems(256, 256) + 8192) * 4 + 64 * 256;
+    const size_t need = ((size_t)B * (2 * csum + 3 * cmax + 3 * gsum + dg1.Ci + dg1.Co + 4 * px + 2 * gmax + 32 * px + 64) +
+                         3 * folded_weight_elems(256, 256) + 8192) * 4 + 64 * 256;
     TRY(ensure_train_ws(c, need, 1));
     Bump ws{reinterpret_cast<uint8_t*>(c->train_ws_gen), reinterpret_cast<uint8_t*>(c->train_ws_gen) + c->train_ws_gen_bytes};
     GenActs G; CriticActs A;
@@ -628,12 +631,17 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     float* t0 = ws.f((size_t)B * cmax); float* t1 = ws.f((size_t)B * cmax);
     float* dx0 = ws.f((size_t)B * cmax);
     float* dimg = ws.f((size_t)B * px); float* dlog = ws.f((size_t)B * px);
-    float* dy = ws.f((size_t)B * gmax); float* dc = ws.f((size_t)B * gmax);
+    float* dy = ws.f((size_t)B * gmax);
+    float* dcl[3]; float* dwfl[3];                    // per block: cotangent of the conv output, folded filter gradient (read by the
+    for (int l = 0; l < 3; ++l) {                     // block's own side stream while the chain moves on to the next block)
+        ConvGeom g = rdg_gen_conv_geom(c, l, B);
+        dcl[l] = ws.f((size_t)B * g.To * g.Ho * g.Wo * g.Co);
+        dwfl[l] = ws.f(folded_weight_elems(g.Ci, g.Co));
+    }
     float* ptap = ws.f((size_t)B * px * 32);          // per-tap products P (forward), gathered cotangents Gd (backward)
-    float* dwf = ws.f(folded_weight_elems(256, 256));
     float* dw4 = ws.f(2048);
     float* dscore = ws.f(B);
-    if (!dscore || !dwf || !ptap) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
+    if (!dscore || !dwfl[2] || !ptap) { rdg_set_error("training workspace too small"); return RDG_E_NOMEM; }
     const float ms = 1.f / 0.75f;
     ConvGeom dg = rdg_gen_dense_geom(c, B);
     ConvGeom gp{};       // the output conv's tap products as a 1x1x1 "conv" 64 -> 32 over the 24 x nd x nd grid
@@ -679,7 +687,7 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
                 TRY(simt_conv_bwd_data(cur, c->c_params + c->c_off[2 * (l - 1)], nxt, g, st));
                 TRY(ew_lrelu_bwd(A.a[l - 1], nxt, cur, (long long)B * critic_act_elems(c, l - 1), masks ? masks[l - 2] : nullptr, ms, st));
             } else {
-                TRY(simt_conv_bwd_data_ch0(cur, c->c_params + c->c_off[0], dx0, g, st));
+                TRY(simt_conv_bwd_data_ch0(cur, c->c_params + c->c_off[0], dx0, g, st, nxt));
             }
         }
     }
@@ -688,8 +696,10 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     TRY(ew_softmax_hours_bwd(G.img, dimg, dlog, B, c->nd * c->nd, st));
 
     // ---- generator backward
-    SideStream ss{c, st, 0};
-    TRY(ss.init());
+    // filter / bias gradients: the output conv's on side stream 0, block l's on side stream (3 - l) % 3 -- they only accumulate
+    // into the gradient buffer and overlap each other and the backward-data chain; everything joins before the Dense layer
+    SideStream ss{c, st, 0}, ssk[3] = {{c, st, 0}, {c, st, 1}, {c, st, 2}};
+    for (auto& s : ssk) TRY(s.init());
     {   // output conv: Gd[pos][tap] = dlogits[pos - offset(tap)]; dy3 = Gd . w4, dw4 = Gd^T . y3, db4 = sum dlogits
         TRY(ew_tap_scatter_dlogits(dlog, ptap, B, c->nd, st));
         ConvGeom gb = gp; gb.Ci = 32; gb.Co = 64;
@@ -703,17 +713,19 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     for (int l = 2; l >= 0; --l) {   // upsample + conv + pixelnorm + lrelu blocks
         ConvGeom g = rdg_gen_conv_geom(c, l, B);
         const long long rows = (long long)B * g.To * g.Ho * g.Wo;
-        TRY(ss.join());                               // the previous block's filter gradient still reads dc
+        float* dc = dcl[l]; float* dwf = dwfl[l];
+        SideStream& sf = ssk[(3 - l) % 3];
         TRY(ew_pixelnorm_lrelu_bwd(G.cpre[l + 1], dy, dc, rows, g.Co, st));
-        TRY(ss.fork());
-        RDG_CUDA(cudaMemsetAsync(dwf, 0, folded_weight_elems(g.Ci, g.Co) * 4, ss.aux()));
-        TRY(tcg_folded_bwd_filter(G.y[l], dc, dwf, g, ss.aux()));
-        TRY(folded_unfold_grad(dwf, c->g_grads + c->g_off[2 + 2 * l], g.Ci, g.Co, ss.aux()));
-        TRY(simt_colsum(dc, c->g_grads + c->g_off[3 + 2 * l], rows, g.Co, ss.aux()));
+        TRY(sf.fork());
+        RDG_CUDA(cudaMemsetAsync(dwf, 0, folded_weight_elems(g.Ci, g.Co) * 4, sf.aux()));
+        TRY(tcg_folded_bwd_filter(G.y[l], dc, dwf, g, sf.aux()));
+        TRY(folded_unfold_grad(dwf, c->g_grads + c->g_off[2 + 2 * l], g.Ci, g.Co, sf.aux()));
+        TRY(simt_colsum(dc, c->g_grads + c->g_off[3 + 2 * l], rows, g.Co, sf.aux()));
         TRY(tcg_folded_bwd_data(dc, c->g_wfold32[l], dy, g, st));
     }
-    TRY(ss.join());
+    for (auto& s : ssk) TRY(s.join());
     {   // dense + lrelu
+        float* dc = dcl[0];
         TRY(ew_lrelu_bwd(G.d0_pre, dy, dc, (long long)B * dg.Co, nullptr, 1.f, st));
         TRY(simt_conv_bwd_filter(G.x0, dc, c->g_grads + c->g_off[0], c->g_grads + c->g_off[1], dg, st));
     }
