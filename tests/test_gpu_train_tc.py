@@ -155,7 +155,7 @@ def test_device_steps_and_graph_replay(ctx16, segmented):
         # the weights already differ where Adam stepped by lr * sign(rounding noise) (see below), so the losses drift apart
         rt, at = (2e-3, 2e-4) if it == 0 else (2e-2, 2e-3)
         np.testing.assert_allclose(ig3.d_losses.cpu().numpy(), eager_losses[it][0], rtol=rt, atol=at, err_msg=f"iteration {it}")
-        assert abs(float(ig3.g_loss.item()) - eager_losses[it][1]) <= 5 * rt * max(1.0, abs(eager_losses[it][1])), f"iteration {it}"
+        assert abs(float(ig3.g_loss.item()) - eager_losses[it][1]) <= rt * max(1.0, abs(eager_losses[it][1])), f"iteration {it}"
         if it == 0:
             w_graph = tr3.generator.get_weights() + tr3.critic.get_weights()
     assert tr3.optimizer.iterations == 6 * n_iter == tr3._pull_counters()[0]
