@@ -172,6 +172,21 @@ int  rdg_critic_step_dev(rdg_ctx* ctx, const float* x_real_dev, const float* con
                          unsigned long long seed, int dropout, float* losses4_dev, int phases, void* stream);
 int  rdg_generator_step_dev(rdg_ctx* ctx, const float* cond_dev, int B, unsigned long long seed, int dropout,
                             float* loss_dev, int phases, void* stream);
+/* ---- data-parallel gradient exchange over NVLink peer memory (one node, one process per GPU; csrc/dp_peer.cu) ----
+ * Replaces the NCCL all-reduce a data-parallel run of the reference's train() (:463-491) would issue before each optimizer
+ * update (:385, :412) by the library's own kernels, so that the exchange can be captured in the CUDA graph of an iteration.
+ * rdg_peer_export: CUDA IPC handles (rdg_peer_handle_bytes() bytes) of this context's two gradient buffers and its flag array;
+ * gather them from all ranks (any host-side transport) and pass the concatenation, in rank order, to rdg_peer_connect on every
+ * rank.  rdg_peer_allreduce(ctx, which, stream): in-place SUM over the ranks of the gradient buffer (`which` as in
+ * rdg_grad_buffer), stream-ordered: barrier, two-shot reduce (rank r sums the r-th slice in rank order and stores it to every
+ * rank), barrier.  Every rank must make the same sequence of calls.  The 1/world scale belongs in rdg_adam_apply*'s grad_scale.
+ * rdg_peer_status: world size (0 = not connected) and whether a barrier ever timed out (10 s) waiting for a peer. */
+int  rdg_peer_handle_bytes(void);
+int  rdg_peer_export(rdg_ctx* ctx, unsigned char* handles);
+int  rdg_peer_connect(rdg_ctx* ctx, int world, int rank, const unsigned char* all_handles);
+int  rdg_peer_disconnect(rdg_ctx* ctx);
+int  rdg_peer_allreduce(rdg_ctx* ctx, int which, void* stream);
+int  rdg_peer_status(rdg_ctx* ctx, int* world, int* timeouts);
 /* rdg_adam_apply with the shared step counter kept (and incremented) in device memory, followed by the refresh of the derived
  * weight images the next step reads; gen_mode = the mode of the frozen generator forward in the critic step. */
 int  rdg_adam_apply_dev(rdg_ctx* ctx, int which, float lr, float beta1, float beta2, float eps, float grad_scale,

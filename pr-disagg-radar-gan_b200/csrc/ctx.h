@@ -46,6 +46,15 @@ struct rdg_ctx {
     float* g_denseT = nullptr;                       // Dense kernel transposed [N][K]
     float* g_w4p = nullptr;                          // output conv: [32 taps (27 + zeros)][64] followed by its transpose [64][32]
     bool g_tcw_stale = true;
+    // data-parallel exchange over NVLink peer memory (dp_peer.cu): the peers' gradient buffers / flag arrays mapped through CUDA IPC
+    struct RdgPeer {
+        int world = 0, rank = 0;
+        void* mapped[8][3] = {};                     // what cudaIpcOpenMemHandle returned, per rank: generator grads, critic grads, flags
+        float** d_grads[2] = {};                     // device arrays [world] of gradient buffer pointers (own buffer at index rank)
+        unsigned** d_flags = nullptr;                // device array [world] of flag-array pointers
+        unsigned* flags = nullptr;                   // this rank's flag array (exported)
+        unsigned* epoch = nullptr;                   // barrier count, device-resident (graph replay)
+    } peer;
     RdgTrainState* tstate = nullptr;                 // device-resident Philox / Adam step counters (replayable CUDA graphs)
     float* rnd_buf = nullptr; size_t rnd_cap = 0;    // latent / alpha / dropout masks drawn on the device (rdg_*_step_dev)
     // forward workspace
@@ -71,6 +80,8 @@ struct rdg_ctx {
     std::vector<cudaEvent_t> prof_pool;
 };
 
+using RdgPeer = rdg_ctx::RdgPeer;
+void rdg_peer_destroy(rdg_ctx* c);
 ConvGeom rdg_gen_conv_geom(const rdg_ctx* c, int layer, int B);
 ConvGeom rdg_gen_dense_geom(const rdg_ctx* c, int B);
 ConvGeom rdg_critic_conv_geom(const rdg_ctx* c, int layer, int B);

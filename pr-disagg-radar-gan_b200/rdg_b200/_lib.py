@@ -68,6 +68,12 @@ SIGNATURES = {
                                      C.c_void_p]),
     "rdg_train_state": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_ulonglong)]),
     "rdg_adam_buffers": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _c_size_p]),
+    "rdg_peer_handle_bytes": (C.c_int, []),
+    "rdg_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rdg_peer_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rdg_peer_disconnect": (C.c_int, [C.c_void_p]),
+    "rdg_peer_allreduce": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "rdg_peer_status": (C.c_int, [C.c_void_p, _c_int_p, _c_int_p]),
     "rdg_pixelnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "rdg_softmax_hours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "rdg_conv3d": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

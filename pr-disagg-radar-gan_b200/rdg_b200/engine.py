@@ -305,8 +305,45 @@ class GanTrainer:
         self._graph = None
         self._set_mode()
         self._push_counters(self.optimizer.iterations, 0)
+        self.peer_exchange = False
         if self._world() > 1:
             self.sync_replicas()
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """Map the other ranks' gradient buffers through CUDA IPC (csrc/dp_peer.cu) so that the gradient exchange is the library's
+        own NVLink kernel (graph-capturable) instead of an NCCL call.  Used when every rank of the group sits on this node and the
+        mapping works on all of them (agreed collectively); otherwise, or with RDG_PEER_ALLREDUCE=0, the exchange stays on NCCL."""
+        import socket
+        import zlib
+        import torch.distributed as dist
+        world, ctx = self._world(), self.ctx
+        if world > 8 or os.environ.get("RDG_PEER_ALLREDUCE", "1") == "0" or dist.get_backend(self.pg) != "nccl":
+            return
+        if getattr(ctx, "_peer_world", 0) == world:
+            self.peer_exchange = True
+            return
+        dev = f"cuda:{ctx.device}"
+        nb = int(ctx.lib.rdg_peer_handle_bytes())
+        buf = (C.c_ubyte * nb)()
+        ok = int(ctx.lib.rdg_peer_export(ctx.handle, buf) == 0)
+        info = torch.tensor([zlib.crc32(socket.gethostname().encode()), ok], dtype=torch.int64, device=dev)
+        infos = [torch.empty_like(info) for _ in range(world)]
+        dist.all_gather(infos, info, group=self.pg)
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=self.pg)
+        good = all(int(i[1]) == 1 and int(i[0]) == int(infos[0][0]) for i in infos)
+        if good:
+            blob = torch.cat(handles).cpu().numpy().tobytes()
+            good = ctx.lib.rdg_peer_connect(ctx.handle, world, self.rank, (C.c_ubyte * len(blob)).from_buffer_copy(blob)) == 0
+        agreed = torch.tensor([int(good)], dtype=torch.int64, device=dev)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.pg)
+        if int(agreed.item()) == 1:
+            ctx._peer_world = world
+            self.peer_exchange = True
+        elif good:
+            ctx.lib.rdg_peer_disconnect(ctx.handle)
 
     def _set_mode(self):
         _lib.check(self.ctx.lib.rdg_set_train_mode(self.ctx.handle, 1 if self.train_mode == "tf32" else 0))
@@ -439,7 +476,10 @@ class GanTrainer:
             if self.profile_comm:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            allreduce_sum_(g, self.pg)           # 1/world is folded into the fused Adam kernel (grad_scale)
+            if self.peer_exchange:               # own two-shot all-reduce over NVLink peer memory, stream-ordered, capturable
+                _lib.check(self.ctx.lib.rdg_peer_allreduce(self.ctx.handle, which, self.ctx._stream()))
+            else:
+                allreduce_sum_(g, self.pg)       # 1/world is folded into the fused Adam kernel (grad_scale)
             if self.profile_comm:
                 e1.record()
                 self._comm_events.append((e0, e1))
@@ -575,7 +615,8 @@ class GanTrainer:
         exchange and the Adam updates) in a CUDA graph.  Returns an IterationGraph: fill `x_real` [n_critic,B,24,nd,nd,1],
         `cond` [n_critic,B,nd,nd,ncond] and `cond_gen` [B,nd,nd,ncond] (static device tensors) and call replay();
         `d_losses` [n_critic,4] and `g_loss` [1] are device tensors read whenever the caller wants (no sync per step).
-        segmented (default: world size > 1): one graph per step phase with the gradient exchange issued between them."""
+        segmented (default: data-parallel over NCCL): one graph per step phase with the gradient exchange issued between them;
+        with the peer-memory exchange (`peer_exchange`) a data-parallel iteration is one graph like the single-GPU one."""
         if self.train_mode != "tf32":
             raise RuntimeError("capture_iteration needs train_mode='tf32' (device-resident step inputs)")
         dev = f"cuda:{self.ctx.device}"
@@ -602,7 +643,7 @@ class GanTrainer:
         torch.cuda.current_stream(self.ctx.device).wait_stream(s)
         torch.cuda.synchronize(self.ctx.device)
         if segmented is None:
-            segmented = self._world() > 1
+            segmented = self._world() > 1 and not self.peer_exchange      # NCCL calls stay outside the graphs
         if not segmented:
             ig.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ig.graph):
