@@ -490,10 +490,27 @@ def main():
             ms_eager = timed(lambda: (tr.iteration_device(x_real, tcond, tcond[0], dl, gls), tr.finish()), 10)
             comm = tr.comm_ms() / 13.0
             tr.profile_comm = False
+            ms_nccl = None
+            if tr.peer_exchange:             # the same iteration with the exchange on NCCL (one graph per step phase), for comparison
+                os.environ["RDG_PEER_ALLREDUCE"] = "0"
+                tr_n = GanTrainer(tgen, tcrit, gen_mode="fp16", seed=100, train_mode="tf32")
+                os.environ.pop("RDG_PEER_ALLREDUCE")
+                ig_n = tr_n.capture_iteration(TB)
+                ig_n.x_real.copy_(x_real); ig_n.cond.copy_(tcond); ig_n.cond_gen.copy_(tcond[0])
+                ms_nccl = timed(ig_n.replay, 20)
+                tr_n.finish()
+                w_, t_ = C.c_int(0), C.c_int(0)
+                _lib.check(tctx.lib.rdg_peer_status(tctx.handle, C.byref(w_), C.byref(t_)))
             dp = {"ranks": world, "grad_parity_rel_l2": errs,
                   "grad_parity_note": "N-rank averaged gradients vs rank 0 on the gathered N*32 batch (FP32 mode); *_rankwise: vs rank 0 summing the same "
                                       "rank batches one by one (same split-K configuration, no LeakyReLU kink crossings)", "allreduce_ms_per_iteration": comm,
-                  "allreduce_share_of_eager_iteration": comm / ms_eager, "exchange": "NCCL all-reduce of the flat FP32 gradient buffer + Adam on an update stream between per-phase graphs, overlapping the next step's generator forward"}
+                  "allreduce_share_of_eager_iteration": comm / ms_eager,
+                  "exchange": ("own two-shot all-reduce over NVLink peer memory (CUDA IPC, csrc/dp_peer.cu) + Adam on an update stream, captured "
+                               "inside the ONE iteration graph") if tr.peer_exchange else
+                              ("NCCL all-reduce of the flat FP32 gradient buffer + Adam on an update stream between per-phase graphs, "
+                               "overlapping the next step's generator forward"),
+                  "peer_exchange": bool(tr.peer_exchange), "ms_per_iteration_nccl_between_phase_graphs": ms_nccl,
+                  "peer_barrier_timeouts": int(t_.value) if tr.peer_exchange else None}
         # critic scoring (config #3, forward only): synthetic hourly fraction fields, tensor-core scoring mode vs the FP32 path
         CB = 20000
         cx = torch.rand((CB, 24, 16, 16), device=dev); cx = cx / cx.sum(dim=1, keepdim=True)
