@@ -195,6 +195,7 @@ extern "C" void rdg_ctx_destroy(rdg_ctx* c) {
     }
     if (c->s_host) cudaStreamDestroy(c->s_host);
     rdg_peer_destroy(c);
+    cudaFree(c->splitk_arena[0].buf); cudaFree(c->splitk_arena[1].buf);
     cudaFree(c->train_ws); cudaFree(c->train_ws_gen); cudaFree(c->rnd_buf_gen); cudaFree(c->train_ws1); cudaFree(c->rnd_buf1);
     cudaFree(c->c_wT); cudaFree(c->c_w1p); cudaFree(c->c_w1p_score); cudaFree(c->c_w1q_score); cudaFree(c->g_denseT); cudaFree(c->g_w4p); cudaFree(c->tstate); cudaFree(c->rnd_buf);
     for (int i = 0; i < 3; ++i) cudaFree(c->g_wfoldT[i]);

@@ -5,6 +5,8 @@
 #include <vector>
 #include "rdg_common.cuh"
 
+#include "tcg.h"
+
 struct rdg_ctx {
     int device = 0, nd = 16, ncond = 1, max_chunk = 0, sm_count = 0;
     // FP32 master parameters, Keras tensor order, concatenated (each tensor 16-byte aligned)
@@ -55,6 +57,7 @@ struct rdg_ctx {
         unsigned* flags = nullptr;                   // this rank's flag array (exported)
         unsigned* epoch = nullptr;                   // barrier count, device-resident (graph replay)
     } peer;
+    TcgArena splitk_arena[2];                        // split-K partial slices: [0] critic passes + generator backward (one stream), [1] generator-step forward
     RdgTrainState* tstate = nullptr;                 // device-resident Philox / Adam step counters (replayable CUDA graphs)
     float* rnd_buf = nullptr; size_t rnd_cap = 0;    // latent / alpha / dropout masks drawn on the device (rdg_*_step_dev)
     // forward workspace

@@ -9,6 +9,16 @@
 #define RDG_TCG_E_SHAPE (-12)   // geometry the tensor-core training kernels do not cover (callers fall back to nothing: it is an error)
 
 // [nblk][R][C] -> [nblk][C][R]
+// Split-K partial slices.  A step phase lends the row GEMMs one grow-only buffer for the duration of a TcgArenaScope: all split
+// launches of a phase run on one stream and each use of the buffer ends with that launch's reduction kernel, so the next launch
+// may overwrite it.  Without a scope (or on another stream than the phase's first split launch) a launch brackets itself with a
+// stream-ordered allocation + free -- two extra nodes per launch on the dependency chain of a captured step.
+struct TcgArena { float* buf = nullptr; size_t bytes = 0; cudaStream_t stream = nullptr; bool bound = false; };
+struct TcgArenaScope {
+    explicit TcgArenaScope(TcgArena* a);
+    ~TcgArenaScope();
+    TcgArena* prev;
+};
 int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, cudaStream_t st);
 
 // act: ACT_NONE / ACT_LRELU, or ACT_LRELU_BWD with `pre` READ as the pre-activation whose LeakyReLU derivative multiplies the

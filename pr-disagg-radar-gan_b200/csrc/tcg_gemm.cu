@@ -842,6 +842,24 @@ int launch_rowgemm_n(const TcgRowArgs& a, dim3 grid, bool split, cudaStream_t st
     return RDG_TCG_E_SHAPE;
 }
 
+thread_local TcgArena* t_arena = nullptr;
+
+// partial-slice buffer of `bytes` for a split launch on `st`: the phase's arena when it can serve it, else null (caller allocates)
+float* arena_take(size_t bytes, cudaStream_t st) {
+    TcgArena* ar = t_arena;
+    if (!ar || (ar->bound && ar->stream != st)) return nullptr;
+    if (ar->bytes < bytes) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;   // no growth while capturing
+        if (ar->buf) { if (cudaDeviceSynchronize() != cudaSuccess) return nullptr; cudaFree(ar->buf); ar->buf = nullptr; ar->bytes = 0; }
+        const size_t want = bytes + bytes / 4;
+        if (cudaMalloc(&ar->buf, want) != cudaSuccess) { cudaGetLastError(); ar->buf = nullptr; return nullptr; }
+        ar->bytes = want;
+    }
+    ar->bound = true; ar->stream = st;
+    return ar->buf;
+}
+
 int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const float* bias, float* y, int act, const float* mask,
                    float mask_scale, float* pre, bool split = false) {
     if (split && a.N > 128) a.N = 128;           // the 3xTF32 stage is twice as large
@@ -852,8 +870,10 @@ int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const
     a.nslice = nslice;
     dim3 grid(mtiles, a.Nt / a.N, nslice);
     if (nslice > 1) {
-        float* part = nullptr;
-        RDG_CUDA(cudaMallocAsync(&part, (size_t)nslice * a.out_elems * sizeof(float), st));
+        const size_t part_bytes = (size_t)nslice * a.out_elems * sizeof(float);
+        float* part = arena_take(part_bytes, st);
+        const bool own = part == nullptr;
+        if (own) RDG_CUDA(cudaMallocAsync(&part, part_bytes, st));
         a.part = part; a.bias = nullptr; a.pre = nullptr; a.mask = nullptr; a.act = ACT_NONE;
         int r = launch_rowgemm_n(a, grid, split, st);
         if (r) return r;
@@ -865,7 +885,7 @@ int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const
         else
             tcg_splitk_epilogue_kernel<8><<<ceil_div(mn4, 32), 256, 0, st>>>(part, nslice, mn4, a.Nt, bias, y, act, mask, mask_scale, pre);
         RDG_LAUNCH_CHECK();
-        RDG_CUDA(cudaFreeAsync(part, st));
+        if (own) RDG_CUDA(cudaFreeAsync(part, st));
         return 0;
     }
     a.part = nullptr; a.bias = bias; a.pre = pre; a.mask = mask; a.mask_scale = mask_scale; a.act = act;
@@ -875,6 +895,12 @@ int launch_rowgemm(TcgRowArgs& a, int mtiles, int max_kb, cudaStream_t st, const
 bool fits_i32(long long v) { return v < (1ll << 31); }
 
 }  // namespace
+
+TcgArenaScope::TcgArenaScope(TcgArena* a) : prev(t_arena) {
+    if (a) a->bound = false;
+    t_arena = a;
+}
+TcgArenaScope::~TcgArenaScope() { t_arena = prev; }
 
 int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, cudaStream_t st) {
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32), nblk);

@@ -547,6 +547,7 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
         TRY(ew_critic_inputs3(fake_img, x_real, alpha, cond, A3.h[0], B, c->nd, c->ncond, st));
     }
     if (!(phases & 2)) return 0;
+    TcgArenaScope arena(&c->splitk_arena[0]);
     TRY(refresh_critic_wT(c, st));
     RDG_CUDA(cudaMemsetAsync(c->c_grads, 0, c->c_total * 4, st));
     // critic forward on [fake | real | interpolated] (:372, :373, :379)
@@ -649,6 +650,7 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     gp.KT = gp.KH = gp.KW = 1; gp.stride = 1;
 
     if (phases & 1) {
+    TcgArenaScope arena(&c->splitk_arena[1]);
     TRY(refresh_gen_tcw(c, st));
     // ---- generator forward keeping what the backward needs (:319-350); does not read the critic's weights
     TRY(ew_assemble_gen_input(latent, cond, 1, 0, G.x0, B, c->nd * c->nd * c->ncond, st));
@@ -664,6 +666,7 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
     TRY(ew_critic_input(G.img, cond, A.h[0], B, c->nd, c->ncond, st));
     }
     if (!(phases & 2)) return 0;
+    TcgArenaScope arena(&c->splitk_arena[0]);
     TRY(refresh_critic_wT(c, st));
 
     // ---- critic on the generated sample (critic frozen :395, dropout active) and its backward to the image
