@@ -304,9 +304,17 @@ def generate(cond):
 def train(n_epochs, _batch_size, start_epoch=0, bat_per_epo=None, save=True):
     """reference :431-521.  Same schedule (n_disc critic steps, then one generator step), same NaN guard
     (:487-488), same per-epoch checkpoints (:520-521) written as Keras-layout HDF5; the matplotlib sample /
-    loss figures (:494-518) are outside the accelerated path and omitted, hist.csv is kept."""
+    loss figures (:494-518) are outside the accelerated path and omitted, hist.csv is kept.
+    In the tensor-core training mode (RDG_TRAIN_MODE=tf32; RDG_TRAIN_GRAPH=0 to opt out) an iteration is not issued as six
+    train_on_batch calls but replayed from one CUDA graph (GanTrainer.capture_iteration): the n_disc real batches and the
+    generator step's conditions are copied into the graph's input buffers, the latent noise / interpolation weights / dropout
+    masks come from the device random streams (same distributions as :470, :223, :289-301), and the losses of the LAST critic
+    step and of the generator step are read once per iteration for the reference's log line and NaN guard."""
     global batch_size
     batch_size = _batch_size
+    graph = None
+    if trainer.train_mode == 'tf32' and os.environ.get('RDG_TRAIN_GRAPH', '1') == '1':
+        graph = trainer.capture_iteration(batch_size, n_critic=n_disc, preserve_state=True)
     sample_gen = generate_real_samples(batch_size)                 # GeneratorEnqueuer worker processes in the reference
     gan_sample_gen = generate_latent_points_as_generator(batch_size)
     valid = -np.ones((batch_size, 1)); fake = np.ones((batch_size, 1)); dummy = np.zeros((batch_size, 1))
@@ -315,13 +323,25 @@ def train(n_epochs, _batch_size, start_epoch=0, bat_per_epo=None, save=True):
     for i in range(n_epochs):
         epoch = 1 + i + start_epoch
         for j in range(bat_per_epo):
-            for _ in range(n_disc):
-                X_real, cond_real = next(sample_gen)
-                latent = np.random.normal(size=(batch_size, latent_dim))
-                d_loss = critic_model.train_on_batch([X_real, cond_real, latent], [valid, fake, dummy])
-                d_loss = np.mean([d_loss[1], d_loss[2]])
-            latent, cond = next(gan_sample_gen)
-            g_loss = generator_model.train_on_batch([latent, cond], valid)
+            if graph is not None:
+                for k in range(n_disc):
+                    X_real, cond_real = next(sample_gen)
+                    graph.x_real[k].copy_(_ctx().dev(X_real).reshape(graph.x_real[k].shape), non_blocking=True)
+                    graph.cond[k].copy_(_ctx().dev(cond_real).reshape(graph.cond[k].shape), non_blocking=True)
+                _, cond = next(gan_sample_gen)
+                graph.cond_gen.copy_(_ctx().dev(cond).reshape(graph.cond_gen.shape), non_blocking=True)
+                graph.replay()
+                d_last = graph.d_losses[-1].cpu().numpy()              # [total, l_valid, l_fake, l_gp] of the last critic step
+                d_loss = np.mean([d_last[1], d_last[2]])
+                g_loss = float(graph.g_loss.item())
+            else:
+                for _ in range(n_disc):
+                    X_real, cond_real = next(sample_gen)
+                    latent = np.random.normal(size=(batch_size, latent_dim))
+                    d_loss = critic_model.train_on_batch([X_real, cond_real, latent], [valid, fake, dummy])
+                    d_loss = np.mean([d_loss[1], d_loss[2]])
+                latent, cond = next(gan_sample_gen)
+                g_loss = generator_model.train_on_batch([latent, cond], valid)
             print(f'{epoch}, {j + 1}/{bat_per_epo}, d_loss {d_loss} g:{g_loss} ')
             if np.isnan(g_loss) or np.isnan(d_loss):
                 raise ValueError('encountered nan in g_loss and/or d_loss')

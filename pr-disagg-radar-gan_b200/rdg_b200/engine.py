@@ -610,13 +610,16 @@ class GanTrainer:
         self._run_iteration([self._critic_calls(x_real[k], cond[k], d_losses[k], slot=k % 2) for k in range(n)],
                             self._generator_calls(cond_gen, g_loss))
 
-    def capture_iteration(self, batch, n_critic=5, segmented=None):
+    def capture_iteration(self, batch, n_critic=5, segmented=None, preserve_state=False):
         """Capture one training iteration (n_critic critic steps + 1 generator step, reference :468-482, with the gradient
         exchange and the Adam updates) in a CUDA graph.  Returns an IterationGraph: fill `x_real` [n_critic,B,24,nd,nd,1],
         `cond` [n_critic,B,nd,nd,ncond] and `cond_gen` [B,nd,nd,ncond] (static device tensors) and call replay();
         `d_losses` [n_critic,4] and `g_loss` [1] are device tensors read whenever the caller wants (no sync per step).
         segmented (default: data-parallel over NCCL): one graph per step phase with the gradient exchange issued between them;
-        with the peer-memory exchange (`peer_exchange`) a data-parallel iteration is one graph like the single-GPU one."""
+        with the peer-memory exchange (`peer_exchange`) a data-parallel iteration is one graph like the single-GPU one.
+        The capture is preceded by one REAL iteration on constant placeholder data (it sizes every workspace outside the capture);
+        preserve_state=True puts weights, Adam moments, step and random counters back afterwards, so that a training run can
+        capture at its start without taking a step on the placeholders."""
         if self.train_mode != "tf32":
             raise RuntimeError("capture_iteration needs train_mode='tf32' (device-resident step inputs)")
         dev = f"cuda:{self.ctx.device}"
@@ -635,6 +638,7 @@ class GanTrainer:
             self.finish()               # the iteration ends with the generator update joined back
 
         self.finish()
+        saved = self.state_dict() if preserve_state else None
         it0 = self.optimizer.iterations
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(self.ctx.device))
@@ -666,6 +670,8 @@ class GanTrainer:
                     gs.append(g)
                 ig.segments.append((which, gs[0], gs[1]))
         torch.cuda.synchronize(self.ctx.device)
+        if saved is not None:
+            self.load_state_dict(saved)
         return ig
 
     # -- the two train_on_batch calls
