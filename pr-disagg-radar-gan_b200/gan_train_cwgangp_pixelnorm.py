@@ -159,6 +159,7 @@ def synthetic_radar(days=64, ny=64, nx=64, seed=0):
     return (base * prof).astype(np.float32)
 
 
+_GRAPHS = {}         # captured training iterations of train() (tensor-core mode)
 sampler = None       # rdg_b200.sampler.DeviceSampler when the batches are drawn on the GPU (setup(device_sampler=True))
 extra_inputs = None  # None | 'doy' | 'lon': the additional-input variants of revision1/additional_inputs/
 timelist_all = None  # 'doy': day of year of every day of `data` (..._doy.py:128)
@@ -201,6 +202,7 @@ def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None, device_sam
     if extra not in (None, 'doy', 'lon'):
         raise ValueError("extra must be None, 'doy' or 'lon'")
     extra_inputs = extra
+    _GRAPHS.clear()
     n_channel = {None: 1, 'doy': 3, 'lon': 2}[extra]
     if domain is not None:
         ndomain = int(domain)
@@ -226,7 +228,10 @@ def setup(data_array=None, valid_indices=None, seed=0, gen_mode=None, device_sam
     # Under torch.distributed (data-parallel replicas) GanTrainer broadcasts rank 0's weights / Adam state and gives every rank its
     # own device random stream; the host-side draws (batch indices, latent noise: np.random below) get a per-rank seed as well,
     # AFTER the weight initialisation above, which therefore is the same on every rank.
-    trainer = GanTrainer(generator, critic, optimizer, gen_mode=gen_mode or os.environ.get('RDG_TRAIN_GEN_MODE', 'fp32'),
+    # precision of the FROZEN generator forward inside the critic step: FP32 in the FP32 parity mode, the fp16 tensor-core forward
+    # (<= 1e-2 of the oracle) in the tensor-core training mode unless RDG_TRAIN_GEN_MODE says otherwise
+    default_gen_mode = 'fp16' if os.environ.get('RDG_TRAIN_MODE', 'fp32') == 'tf32' else 'fp32'
+    trainer = GanTrainer(generator, critic, optimizer, gen_mode=gen_mode or os.environ.get('RDG_TRAIN_GEN_MODE', default_gen_mode),
                          seed=seed)
     if trainer.rank:
         np.random.seed(seed + trainer.rank)
@@ -314,23 +319,35 @@ def train(n_epochs, _batch_size, start_epoch=0, bat_per_epo=None, save=True):
     batch_size = _batch_size
     graph = None
     if trainer.train_mode == 'tf32' and os.environ.get('RDG_TRAIN_GRAPH', '1') == '1':
-        graph = trainer.capture_iteration(batch_size, n_critic=n_disc, preserve_state=True)
+        key = (id(trainer), batch_size, n_disc)          # captured once per trainer and batch size (a capture costs ~0.4 s)
+        if key not in _GRAPHS:
+            _GRAPHS.clear()
+            _GRAPHS[key] = trainer.capture_iteration(batch_size, n_critic=n_disc, preserve_state=True)
+        graph = _GRAPHS[key]
     sample_gen = generate_real_samples(batch_size)                 # GeneratorEnqueuer worker processes in the reference
     gan_sample_gen = generate_latent_points_as_generator(batch_size)
     valid = -np.ones((batch_size, 1)); fake = np.ones((batch_size, 1)); dummy = np.zeros((batch_size, 1))
     if bat_per_epo is None:
         bat_per_epo = int(n_samples / batch_size)
+    staged = None
+
+    def _draw_iteration():
+        return [next(sample_gen) for _ in range(n_disc)], next(gan_sample_gen)[1]
+
     for i in range(n_epochs):
         epoch = 1 + i + start_epoch
         for j in range(bat_per_epo):
             if graph is not None:
-                for k in range(n_disc):
-                    X_real, cond_real = next(sample_gen)
+                if staged is None:
+                    staged = _draw_iteration()
+                reals, cond = staged
+                for k, (X_real, cond_real) in enumerate(reals):
                     graph.x_real[k].copy_(_ctx().dev(X_real).reshape(graph.x_real[k].shape), non_blocking=True)
                     graph.cond[k].copy_(_ctx().dev(cond_real).reshape(graph.cond[k].shape), non_blocking=True)
-                _, cond = next(gan_sample_gen)
                 graph.cond_gen.copy_(_ctx().dev(cond).reshape(graph.cond_gen.shape), non_blocking=True)
                 graph.replay()
+                # the next iteration's batches are drawn on the host while the GPU runs this one (same np.random order)
+                staged = _draw_iteration() if (j + 1 < bat_per_epo or i + 1 < n_epochs) else None
                 d_last = graph.d_losses[-1].cpu().numpy()              # [total, l_valid, l_fake, l_gp] of the last critic step
                 d_loss = np.mean([d_last[1], d_last[2]])
                 g_loss = float(graph.g_loss.item())
