@@ -644,38 +644,38 @@ __global__ void __launch_bounds__(256) ch0_tap_products_kernel(const float* __re
 }
 
 __global__ void __launch_bounds__(256) ch0_gather_kernel(const float* __restrict__ P, float* __restrict__ dx, ConvGeom g, long long M1) {
-    const long long M = (long long)g.B * g.Ti * g.Hi * g.Wi;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // 32-bit index arithmetic (the host checks the sizes); per axis only the taps k = (p + pad) mod stride, + stride, ... reach p
+    const int M = g.B * g.Ti * g.Hi * g.Wi;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M) return;
-    const PosDec p = decode_pos(idx, g.Ti, g.Hi, g.Wi);
+    int r = idx;
+    const int w = r % g.Wi; r /= g.Wi;
+    const int h = r % g.Hi; r /= g.Hi;
+    const int t = r % g.Ti; const int b = r / g.Ti;
+    const int s = g.stride;
     float acc = 0.f;
-    for (int kt = 0; kt < g.KT; ++kt) {
-        int nt = p.t + g.pt - kt;
-        if (nt < 0 || nt % g.stride) continue;
-        nt /= g.stride;
-        if (nt >= g.To) continue;
-        for (int kh = 0; kh < g.KH; ++kh) {
-            int nh = p.h + g.ph - kh;
-            if (nh < 0 || nh % g.stride) continue;
-            nh /= g.stride;
-            if (nh >= g.Ho) continue;
-            for (int kw = 0; kw < g.KW; ++kw) {
-                int nw = p.w + g.pw - kw;
-                if (nw < 0 || nw % g.stride) continue;
-                nw /= g.stride;
-                if (nw >= g.Wo) continue;
-                acc += P[(long long)((kt * g.KH + kh) * g.KW + kw) * M1 + (((long long)p.b * g.To + nt) * g.Ho + nh) * g.Wo + nw];
+    for (int kt = (t + g.pt) % s; kt < g.KT; kt += s) {
+        const int nt = (t + g.pt - kt) / s;
+        if (t + g.pt - kt < 0 || nt >= g.To) continue;
+        for (int kh = (h + g.ph) % s; kh < g.KH; kh += s) {
+            const int nh = (h + g.ph - kh) / s;
+            if (h + g.ph - kh < 0 || nh >= g.Ho) continue;
+            const int rowbase = ((b * g.To + nt) * g.Ho + nh) * g.Wo;
+            for (int kw = (w + g.pw) % s; kw < g.KW; kw += s) {
+                const int nw = (w + g.pw - kw) / s;
+                if (w + g.pw - kw < 0 || nw >= g.Wo) continue;
+                acc += __ldg(P + (long long)((kt * g.KH + kh) * g.KW + kw) * M1 + rowbase + nw);
             }
         }
     }
-    dx[idx * g.Ci] = acc;
+    dx[(long long)idx * g.Ci] = acc;
 }
 
 int simt_conv_bwd_data_ch0(const float* dy, const float* w, float* dx, const ConvGeom& g, cudaStream_t st, float* scratch) {
     const long long M = (long long)g.B * g.Ti * g.Hi * g.Wi;
     const int ntaps_ = g.KT * g.KH * g.KW;
     if (M == 0) return 0;
-    if (scratch && !g.up && g.Co == 64 && ntaps_ <= 32) {
+    if (scratch && !g.up && g.Co == 64 && ntaps_ <= 32 && M * g.Ci < (1ll << 31)) {
         const long long M1 = (long long)g.B * g.To * g.Ho * g.Wo;
         ch0_tap_products_kernel<<<ceil_div(M1, 64), 256, 0, st>>>(dy, w, scratch, M1, g.Ci, ntaps_);
         RDG_LAUNCH_CHECK();
