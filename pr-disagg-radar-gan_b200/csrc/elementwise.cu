@@ -335,8 +335,13 @@ __device__ __forceinline__ void philox_draw(uint32_t (&c)[4], uint64_t seed) {
 }
 __global__ void step_random_dev_kernel(float* __restrict__ buf, long long qa, long long n_normal, long long off_u, long long qb, long long n_u,
                                        long long off_m, long long n_m, float keep, uint64_t seed, RdgTrainState* s, int which) {
-    const uint32_t ctr = (uint32_t)(*reinterpret_cast<volatile unsigned long long*>(&s->rng_ctr[which]) + 1ull);
-    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // a bounded grid walks the quads (one same-address atomic per BLOCK below: 4700 one-quad blocks made that the bottleneck, 33 us)
+    __shared__ uint32_t s_ctr;
+    if (threadIdx.x == 0) s_ctr = (uint32_t)(*reinterpret_cast<volatile unsigned long long*>(&s->rng_ctr[which]) + 1ull);
+    __syncthreads();
+    const uint32_t ctr = s_ctr;
+    for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < qa + qb + (n_m + 3) / 4; q0 += (long long)gridDim.x * blockDim.x) {
+    long long q = q0;
     float* dst; long long n; uint32_t sid; int kind;
     if (q < qa) { dst = buf; n = n_normal; sid = 1; kind = 0; }
     else if (q < qa + qb) { q -= qa; dst = buf + off_u; n = n_u; sid = 2; kind = 1; }
@@ -364,7 +369,8 @@ __global__ void step_random_dev_kernel(float* __restrict__ buf, long long qa, lo
         if (q * 4 + 3 < n) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(z[0], z[1], z[2], z[3]);
         else for (int j = 0; q * 4 + j < n; ++j) dst[q * 4 + j] = z[j];
     }
-    // the last block to finish advances the step counter (every thread above read the old value)
+    }
+    // the last block to finish advances the step counter (every block read the old value before it arrived here)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -734,7 +740,8 @@ int ew_step_random_dev(float* buf, long long n_normal, long long off_u, long lon
                        RdgTrainState* s, int which, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(buf) & 15) || (off_u & 3) || (off_m & 3)) { rdg_set_error("ew_step_random_dev: regions must be 16-byte aligned"); return -1; }
     const long long qa = (n_normal + 3) / 4, qb = (n_u + 3) / 4, qc = (n_m + 3) / 4;
-    step_random_dev_kernel<<<EW_GRID(qa + qb + qc)>>>(buf, qa, n_normal, off_u, qb, n_u, off_m, n_m, keep, seed, s, which);
+    const long long nblk = (qa + qb + qc + 255) / 256;
+    step_random_dev_kernel<<<(unsigned)(nblk < 1184 ? nblk : 1184), 256, 0, st>>>(buf, qa, n_normal, off_u, qb, n_u, off_m, n_m, keep, seed, s, which);
     RDG_LAUNCH_CHECK();
     return 0;
 }
