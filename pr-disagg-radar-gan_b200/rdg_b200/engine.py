@@ -494,9 +494,17 @@ class GanTrainer:
     # step's critic gradients; phase 2 waits for that update.  A generator update is awaited before anything else runs.
     def _update_stream(self):
         if getattr(self, "_upd_stream", None) is None:
-            self._upd_stream = torch.cuda.Stream(device=self.ctx.device)
+            # the update sits on the critical path between two steps: high priority, like the capture stream of an iteration
+            self._upd_stream = torch.cuda.Stream(device=self.ctx.device, priority=self._critical_priority())
             self._pending, self._pending_which = None, None
         return self._upd_stream
+
+    @staticmethod
+    def _critical_priority():
+        """Stream priority of the critical chain (critic passes, updates).  The prefetch / generator-forward / filter-gradient
+        streams keep the default (lowest) priority, so that when both have thread blocks pending the SMs go to the chain every
+        later launch waits for.  RDG_STREAM_PRIORITY=0 puts everything on the default priority (A/B timing)."""
+        return -1 if os.environ.get("RDG_STREAM_PRIORITY", "1") == "1" else 0
 
     def finish(self):
         """Make the caller's stream wait for the last overlapped update (call before reading weights / losses on another path)."""
@@ -640,7 +648,7 @@ class GanTrainer:
         self.finish()
         saved = self.state_dict() if preserve_state else None
         it0 = self.optimizer.iterations
-        s = torch.cuda.Stream(device=dev)
+        s = torch.cuda.Stream(device=dev, priority=self._critical_priority())       # kernel nodes inherit the capturing stream's priority
         s.wait_stream(torch.cuda.current_stream(self.ctx.device))
         with torch.cuda.stream(s):
             body()                      # eager pass: allocations, attribute calls and weight images happen outside the capture
@@ -650,7 +658,7 @@ class GanTrainer:
             segmented = self._world() > 1 and not self.peer_exchange      # NCCL calls stay outside the graphs
         if not segmented:
             ig.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ig.graph):
+            with torch.cuda.graph(ig.graph, stream=s):
                 body()
             # the eager pass was a real iteration; the capture itself launches nothing, only the host mirror moved
             self.optimizer.iterations = it0 + n_critic + 1
@@ -665,7 +673,7 @@ class GanTrainer:
                 gs = []
                 for fn in (p1, p2):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=s if fn is p2 else None):       # first phases run off the critical chain
                         fn()
                     gs.append(g)
                 ig.segments.append((which, gs[0], gs[1]))
