@@ -811,28 +811,40 @@ namespace {
 // per axis, phase 0: tap0 <- {k0}, tap1 <- {k1,k2}; phase 1: tap0 <- {k0,k1}, tap1 <- {k2}; sums in f32,
 // rounded once to 16 bit, stored as [phase][tap][chunk][Cout rows x 64 k] with the 16-byte chunks of
 // row n XOR-swizzled by (n & 7) -- the SWIZZLE_128B K-major image tcgen05.mma reads.
+// A block packs one (phase, tap, 64-channel chunk, 64 output channels) sub-tile through shared memory: the source is read along
+// Cout (its fast index), the image written along the 64 k positions of a row (its fast index).  The training loop re-packs after
+// every generator update; one thread per packed element read the source with a stride of Cout floats (56 us for the 256 -> 256
+// layer, now a few).  Same sums in the same order as before (kt, kh, kw ascending), rounded once.
 template <typename HT>
-__global__ void pack_folded_kernel(const float* __restrict__ k, HT* __restrict__ dst, int Cin, int Cout) {
-    const long long total = (long long)64 * Cin * Cout;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int nchunk = Cin / 64;
-    const int within = (int)(idx % ((long long)Cout * 64));
-    long long tile = idx / ((long long)Cout * 64);
-    const int chunk = (int)(tile % nchunk); tile /= nchunk;
-    const int a = (int)(tile % 8), p = (int)(tile / 8);
-    const int n = within / 64, pos = within % 64;
-    const int j = (pos >> 3) ^ (n & 7), e = pos & 7;
-    const int ci = chunk * 64 + j * 8 + e;
+__global__ void __launch_bounds__(256) pack_folded_kernel(const float* __restrict__ k, HT* __restrict__ dst, int Cin, int Cout) {
+    __shared__ float tile[64][65];
+    const int nchunk = Cin / 64, nblk_n = Cout / 64;
+    int b = blockIdx.x;
+    const int nb = b % nblk_n; b /= nblk_n;
+    const int chunk = b % nchunk; b /= nchunk;
+    const int a = b % 8, p = b / 8;
     const int pt = p >> 2, ph = (p >> 1) & 1, pw = p & 1, at = a >> 2, ah = (a >> 1) & 1, aw = a & 1;
     auto lo = [](int phs, int tp) { return phs == 0 ? (tp == 0 ? 0 : 1) : (tp == 0 ? 0 : 2); };
     auto hi = [](int phs, int tp) { return phs == 0 ? (tp == 0 ? 0 : 2) : (tp == 0 ? 1 : 2); };
-    float sum = 0.f;
-    for (int kt = lo(pt, at); kt <= hi(pt, at); ++kt)
-        for (int kh = lo(ph, ah); kh <= hi(ph, ah); ++kh)
-            for (int kw = lo(pw, aw); kw <= hi(pw, aw); ++kw)
-                sum += k[((long long)((kt * 3 + kh) * 3 + kw) * Cin + ci) * Cout + n];
-    dst[idx] = HalfOps<HT>::from_float(sum);
+    const int nl = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+    for (int cl = r0; cl < 64; cl += 4) {
+        const int ci = chunk * 64 + cl;
+        float sum = 0.f;
+        for (int kt = lo(pt, at); kt <= hi(pt, at); ++kt)
+            for (int kh = lo(ph, ah); kh <= hi(ph, ah); ++kh)
+                for (int kw = lo(pw, aw); kw <= hi(pw, aw); ++kw)
+                    sum += k[((long long)((kt * 3 + kh) * 3 + kw) * Cin + ci) * Cout + nb * 64 + nl];
+        tile[cl][nl] = sum;
+    }
+    __syncthreads();
+    // image: [phase][tap][chunk][Cout rows x 64 k], 16-byte chunks of row n XOR-swizzled by (n & 7)
+    HT* out = dst + ((long long)((p * 8 + a) * nchunk + chunk) * Cout + nb * 64) * 64;
+    const int pos = threadIdx.x & 63;
+    for (int n_l = r0; n_l < 64; n_l += 4) {
+        const int n = nb * 64 + n_l;
+        const int j = (pos >> 3) ^ (n & 7), e = pos & 7;
+        out[n_l * 64 + pos] = HalfOps<HT>::from_float(tile[j * 8 + e][n_l]);
+    }
 }
 // output conv (3,3,3,64,1) as a [32 taps x 64 ch] swizzled B tile (taps 27..31 zero)
 template <typename HT>
@@ -909,11 +921,12 @@ int softmax_fixed_inplace(float* out, const void* w4tile, const float* b4, const
 }
 
 int pack_folded_weights(int half_kind, const float* k, void* dst, int Cin, int Cout, cudaStream_t st) {
-    const long long total = (long long)64 * Cin * Cout;
+    if ((Cin & 63) || (Cout & 63)) { rdg_set_error("pack_folded_weights: Cin and Cout must be multiples of 64"); return RDG_TC_E_SHAPE; }
+    const int blocks = 64 * (Cin / 64) * (Cout / 64);
     if (half_kind == RDG_HALF_BF16)
-        pack_folded_kernel<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, st>>>(k, (__nv_bfloat16*)dst, Cin, Cout);
+        pack_folded_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(k, (__nv_bfloat16*)dst, Cin, Cout);
     else
-        pack_folded_kernel<__half><<<ceil_div(total, 256), 256, 0, st>>>(k, (__half*)dst, Cin, Cout);
+        pack_folded_kernel<__half><<<blocks, 256, 0, st>>>(k, (__half*)dst, Cin, Cout);
     RDG_LAUNCH_CHECK();
     return 0;
 }

@@ -122,7 +122,13 @@ struct SideStream {
     rdg_ctx* c; cudaStream_t main; int k;       // k: which of the context's side streams (see ctx.h)
     int init() {
         if (!c->s_aux[k]) {
-            RDG_CUDA(cudaStreamCreateWithFlags(&c->s_aux[k], cudaStreamNonBlocking));
+            // between the critical chain (captured from a higher-priority stream, engine.py) and the prefetch streams (default,
+            // lowest): the step's own join waits for these filter gradients
+            int lo = 0, hi = 0;
+            RDG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            int pr = -2;                                  // engine.py: chain -3, prefetch -1, generator-step forward 0
+            pr = pr < hi ? hi : (pr > lo ? lo : pr);
+            RDG_CUDA(cudaStreamCreateWithPriority(&c->s_aux[k], cudaStreamNonBlocking, pr));
             RDG_CUDA(cudaEventCreateWithFlags(&c->ev_fork[k], cudaEventDisableTiming));
             RDG_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
         }

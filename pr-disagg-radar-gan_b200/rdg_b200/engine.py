@@ -501,10 +501,12 @@ class GanTrainer:
 
     @staticmethod
     def _critical_priority():
-        """Stream priority of the critical chain (critic passes, updates).  The prefetch / generator-forward / filter-gradient
-        streams keep the default (lowest) priority, so that when both have thread blocks pending the SMs go to the chain every
-        later launch waits for.  RDG_STREAM_PRIORITY=0 puts everything on the default priority (A/B timing)."""
-        return -1 if os.environ.get("RDG_STREAM_PRIORITY", "1") == "1" else 0
+        """Stream priority of the critical chain (critic passes, updates): -3; the filter-gradient side streams of the library
+        run at -2, the critic steps' prefetch stream at -1, the generator step's forward at 0 (default, lowest) -- in the order
+        in which their results are needed, so that when several have thread blocks pending the SMs go to the launch the others
+        wait for.  Measured 4.43 -> 4.32 ms per iteration (chain above everything else; the grading below it adds 0.01 ms).
+        RDG_STREAM_PRIORITY=0 puts the Python-side streams on the default priority (A/B timing)."""
+        return -3 if os.environ.get("RDG_STREAM_PRIORITY", "1") == "1" else 0
 
     def finish(self):
         """Make the caller's stream wait for the last overlapped update (call before reading weights / losses on another path)."""
@@ -587,7 +589,7 @@ class GanTrainer:
                 self._run_step(self.WHICH_CRITIC, p1, p2)
         else:
             if getattr(self, "_pre_stream", None) is None:
-                self._pre_stream = torch.cuda.Stream(device=dev)
+                self._pre_stream = torch.cuda.Stream(device=dev, priority=-1 if self._critical_priority() else 0)
             pre = self._pre_stream
             pre.wait_event(ev0)
             slot_free, ready = {}, {}
