@@ -579,10 +579,25 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     TRY(simt_conv_bwd_filter(A3.h[4], dscore3, c->c_grads + c->c_off[8], c->c_grads + c->c_off[9], rdg_critic_dense_geom(c, 2 * B), ss.aux()));
     // da_l = cotangent of the pre-activation a_l.  The LeakyReLU (+ dropout) backward of layer l-1 is fused into the epilogue of
     // layer l's transposed conv: da_{l-1} = convT_l(da_l) * LeakyReLU'(a_{l-1}) * mask_{l-1}
+    // filter gradients: the Wasserstein part (fake | real, the first 2B samples: h_{l-1} and da_l are final here) starts right
+    // away on a side stream and runs next to the rest of the backward chain; only the penalty part (u_{l-1}, interpolated third)
+    // has to wait for the second-order pass below.  Both accumulate into the same gradient buffer.
+    auto filter_grad = [&](int l, const float* x, const float* dy, int nb, cudaStream_t s) -> int {
+        ConvGeom gf = rdg_critic_conv_geom(c, l - 1, nb);
+        float* dw = c->c_grads + c->c_off[2 * (l - 1)];
+        if (l > 1 && tc_layer_ok(gf)) return tcg_conv_bwd_filter(x, dy, dw, gf, s);
+        if (l == 1 && gf.Ci <= 4) return tcg_conv_bwd_filter_smallci(x, dy, dw, gf, s);
+        return simt_conv_bwd_filter(x, dy, dw, nullptr, gf, s);
+    };
     for (int l = 4; l >= 1; --l) {
         ConvGeom g = rdg_critic_conv_geom(c, l - 1, 3 * B);
         TRY(ss.fork());       // bias gradients of the Wasserstein terms: the first 2B samples
         TRY(simt_colsum(da[l], c->c_grads + c->c_off[2 * (l - 1) + 1], (long long)2 * B * (critic_act_elems(c, l) / g.Co), g.Co, ss.aux()));
+        {
+            SideStream& sf = ssk[l % 3];
+            TRY(sf.fork());
+            TRY(filter_grad(l, A3.h[l - 1], da[l], 2 * B, sf.aux()));
+        }
         if (l > 1) {
             if (tc_layer_ok(g)) {
                 TRY(tcg_conv_bwd_data(da[l], c->c_params + c->c_off[2 * (l - 1)], da[l - 1], g, st, A3.a[l - 1], masks3 ? masks3[l - 2] : nullptr, ms));
@@ -605,9 +620,8 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
         ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
         SideStream& sf = ssk[(l - 1) % 3];
         TRY(sf.fork());
-        if (l > 1 && tc_layer_ok(g3)) TRY(tcg_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], g3, sf.aux()));
-        else if (l == 1 && g3.Ci <= 4) TRY(tcg_conv_bwd_filter_smallci(A3.h[0], da[1], c->c_grads + c->c_off[0], g3, sf.aux()));
-        else TRY(simt_conv_bwd_filter(A3.h[l - 1], da[l], c->c_grads + c->c_off[2 * (l - 1)], nullptr, g3, sf.aux()));
+        TRY(filter_grad(l, hat_h[l - 1], da[l] + (size_t)2 * B * critic_act_elems(c, l), B, sf.aux()));
+        (void)g3;
         const float* mh = masks3 ? masks3[l - 1] + (size_t)2 * B * critic_act_elems(c, l) : nullptr;
         if ((l == 1 && g.Ci <= 4) || (l > 1 && tc_layer_ok(g))) {     // u_l = conv_l(u_{l-1}) * LeakyReLU'(a_l) * mask_l in one epilogue
             TRY(critic_conv_fwd_tc(c, l - 1, hat_h[l - 1], nullptr, hat_h[l], g, ACT_LRELU_BWD, mh, st, hat_a[l], 0));
