@@ -20,6 +20,8 @@ struct TcgArenaScope {
     TcgArena* prev;
 };
 int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, cudaStream_t st);
+// up to four of those in one launch
+int tcg_transpose_blocks_batch(int n, const float* const* src, float* const* dst, const int* nblk, const int* R, const int* C, cudaStream_t st);
 
 // act: ACT_NONE / ACT_LRELU, or ACT_LRELU_BWD with `pre` READ as the pre-activation whose LeakyReLU derivative multiplies the
 // result (the linear second-order pass of the gradient penalty: u_l = conv_l(u_{l-1}) * LeakyReLU'(a_l) * mask).

@@ -786,6 +786,36 @@ __global__ void transpose_blocks_kernel(const float* __restrict__ src, float* __
     }
 }
 
+// several transposes in one launch (the derived weight images of one network are rebuilt after every optimizer step, on the
+// critical path between two steps: one launch instead of one per layer)
+struct TransposeBatch {
+    const float* src[4]; float* dst[4];
+    int R[4], C[4], bx[4], by[4];        // rows, columns, 32x32 tiles per matrix along C / R
+    int begin[5];                        // first linear block of segment i (begin[n] = total); each segment = nblk matrices
+    int n;
+};
+__global__ void transpose_batch_kernel(const __grid_constant__ TransposeBatch tb) {
+    __shared__ float tile[32][33];
+    int seg = 0;
+    while (seg + 1 < tb.n && (int)blockIdx.x >= tb.begin[seg + 1]) ++seg;
+    const int R = tb.R[seg], C = tb.C[seg];
+    int b = blockIdx.x - tb.begin[seg];
+    const int tx = b % tb.bx[seg]; b /= tb.bx[seg];
+    const int ty = b % tb.by[seg]; const int z = b / tb.by[seg];
+    const float* s = tb.src[seg] + (size_t)z * R * C;
+    float* d = tb.dst[seg] + (size_t)z * R * C;
+    const int c0 = tx * 32, r0 = ty * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[j][threadIdx.x] = s[(size_t)r * C + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < R && c < C) d[(size_t)c * R + r] = tile[threadIdx.x][j];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 // shared-memory ring depth: two CTAs per SM (about 100 KB each) where the kernel's launch bounds allow it, else one
 int pick_stages(int N, bool split) {
@@ -905,6 +935,23 @@ TcgArenaScope::~TcgArenaScope() { t_arena = prev; }
 int tcg_transpose_blocks(const float* src, float* dst, int nblk, int R, int C, cudaStream_t st) {
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32), nblk);
     transpose_blocks_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, R, C);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+
+int tcg_transpose_blocks_batch(int n, const float* const* src, float* const* dst, const int* nblk, const int* R, const int* C, cudaStream_t st) {
+    if (n < 1 || n > 4) { rdg_set_error("tcg_transpose_blocks_batch: 1..4 segments"); return RDG_TCG_E_SHAPE; }
+    TransposeBatch tb{};
+    tb.n = n;
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        tb.src[i] = src[i]; tb.dst[i] = dst[i]; tb.R[i] = R[i]; tb.C[i] = C[i];
+        tb.bx[i] = ceil_div(C[i], 32); tb.by[i] = ceil_div(R[i], 32);
+        tb.begin[i] = total;
+        total += tb.bx[i] * tb.by[i] * nblk[i];
+    }
+    tb.begin[n] = total;
+    transpose_batch_kernel<<<total, dim3(32, 8), 0, st>>>(tb);
     RDG_LAUNCH_CHECK();
     return 0;
 }

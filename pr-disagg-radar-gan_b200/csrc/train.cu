@@ -482,9 +482,14 @@ int refresh_critic_wT(rdg_ctx* c, cudaStream_t st) {
     if (!c->c_w1p) RDG_CUDA(cudaMalloc(&c->c_w1p, (size_t)g0.Co * tcg_smallci_kpad(27, g0.Ci) * 4));
     if (!c->c_wT_stale) return 0;
     TRY(tcg_pack_smallci_weights(c->c_params + c->c_off[0], c->c_w1p, 27, g0.Ci, g0.Co, st));
-    for (int l = 1; l < 4; ++l) {
-        ConvGeom g = rdg_critic_conv_geom(c, l, 1);
-        TRY(tcg_transpose_blocks(c->c_params + c->c_off[2 * l], c->c_wT + c->c_off[2 * l], 27, g.Ci, g.Co, st));
+    {
+        const float* src[3]; float* dst[3]; int nblk[3], R[3], C[3];
+        for (int l = 1; l < 4; ++l) {
+            ConvGeom g = rdg_critic_conv_geom(c, l, 1);
+            src[l - 1] = c->c_params + c->c_off[2 * l]; dst[l - 1] = c->c_wT + c->c_off[2 * l];
+            nblk[l - 1] = 27; R[l - 1] = g.Ci; C[l - 1] = g.Co;
+        }
+        TRY(tcg_transpose_blocks_batch(3, src, dst, nblk, R, C, st));
     }
     c->c_wT_stale = false;
     return 0;
@@ -499,8 +504,12 @@ int refresh_gen_tcw(rdg_ctx* c, cudaStream_t st) {
     if (!c->g_denseT) RDG_CUDA(cudaMalloc(&c->g_denseT, (size_t)dg.Ci * dg.Co * 4));
     if (!c->g_w4p) RDG_CUDA(cudaMalloc(&c->g_w4p, 2 * 2048 * 4));
     if (!c->g_tcw_stale) return 0;
-    for (int l = 0; l < 3; ++l) TRY(tcg_transpose_blocks(c->g_wfold32[l], c->g_wfoldT[l], 64, cin[l], cout[l], st));
-    TRY(tcg_transpose_blocks(c->g_params + c->g_off[0], c->g_denseT, 1, dg.Ci, dg.Co, st));
+    {
+        const float* src[4] = {c->g_wfold32[0], c->g_wfold32[1], c->g_wfold32[2], c->g_params + c->g_off[0]};
+        float* dst[4] = {c->g_wfoldT[0], c->g_wfoldT[1], c->g_wfoldT[2], c->g_denseT};
+        const int nblk[4] = {64, 64, 64, 1}, R[4] = {cin[0], cin[1], cin[2], dg.Ci}, C[4] = {cout[0], cout[1], cout[2], dg.Co};
+        TRY(tcg_transpose_blocks_batch(4, src, dst, nblk, R, C, st));
+    }
     TRY(ew_pad_w4(c->g_params + c->g_off[8], c->g_w4p, st));
     c->g_tcw_stale = false;
     return 0;
