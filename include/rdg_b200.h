@@ -180,7 +180,8 @@ int  rdg_generator_step_dev(rdg_ctx* ctx, const float* cond_dev, int B, unsigned
  * rank.  rdg_peer_allreduce(ctx, which, stream): in-place SUM over the ranks of the gradient buffer (`which` as in
  * rdg_grad_buffer), stream-ordered: barrier, two-shot reduce (rank r sums the r-th slice in rank order and stores it to every
  * rank), barrier.  Every rank must make the same sequence of calls.  The 1/world scale belongs in rdg_adam_apply*'s grad_scale.
- * rdg_peer_status: world size (0 = not connected) and whether a barrier ever timed out (10 s) waiting for a peer. */
+ * rdg_peer_status: world size (0 = not connected) and whether a barrier ever timed out (60 s) waiting for a peer
+ * (the sums of that exchange are then not the global sums: treat it as a failed run). */
 int  rdg_peer_handle_bytes(void);
 int  rdg_peer_export(rdg_ctx* ctx, unsigned char* handles);
 int  rdg_peer_connect(rdg_ctx* ctx, int world, int rank, const unsigned char* all_handles);

@@ -15,7 +15,7 @@
 //   * the barriers are flag words in peer-visible memory: rank r stores the (monotonic, device-resident) epoch into slot r of every
 //     rank's flag array with a system-scope release and spins on its own array with system-scope acquires.  The first barrier
 //     publishes the gradients (they were written by earlier kernels of the same stream), the second keeps a rank from zeroing
-//     its buffer for the next step while a peer still reads it.  A spin that lasts 10 s sets an error word and gives up
+//     its buffer for the next step while a peer still reads it.  A spin that lasts 60 s sets an error word and gives up
 //     (a rank that died must not hang the others' GPUs); rdg_peer_status reports it.
 // The 1/N scale stays fused in the Adam kernel (grad_scale), exactly as with NCCL.
 #include <cstdint>
@@ -30,6 +30,7 @@ namespace {
 constexpr int kMaxRanks = 8;
 constexpr int kErrSlot = 16;                 // flags[16]: set when a barrier timed out
 constexpr int kFlagWords = 32;
+constexpr unsigned long long kBarrierTimeoutNs = 60ull * 1000000000ull;   // ranks may be seconds apart in their first iteration (allocations)
 constexpr int kHandleBytes = 3 * 64;         // generator gradients, critic gradients, flags
 
 #define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
@@ -59,7 +60,7 @@ __global__ void peer_barrier_kernel(unsigned* const* __restrict__ peer_flags, un
         st_release_sys(peer_flags[r] + rank, k);
         const unsigned long long t0 = globaltimer_ns();
         while ((int)(ld_acquire_sys(my_flags + r) - k) < 0) {
-            if (globaltimer_ns() - t0 > 10000000000ull) { my_flags[kErrSlot] = 1u; break; }
+            if (globaltimer_ns() - t0 > kBarrierTimeoutNs) { my_flags[kErrSlot] = 1u; break; }
             __nanosleep(64);
         }
     }

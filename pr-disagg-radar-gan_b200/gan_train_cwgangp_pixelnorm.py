@@ -364,6 +364,7 @@ def train(n_epochs, _batch_size, start_epoch=0, bat_per_epo=None, save=True):
                 raise ValueError('encountered nan in g_loss and/or d_loss')
             hist['d_loss'].append(d_loss)
             hist['g_loss'].append(g_loss)
+        trainer.check_exchange()          # data-parallel runs: no barrier of the gradient exchange timed out during the epoch
         with open('hist.csv', 'w') as f:
             f.write(',d_loss,g_loss\n')
             for k, (d, g) in enumerate(zip(hist['d_loss'], hist['g_loss'])):

@@ -345,6 +345,16 @@ class GanTrainer:
         elif good:
             ctx.lib.rdg_peer_disconnect(ctx.handle)
 
+    def check_exchange(self):
+        """Raise if a barrier of the peer-memory gradient exchange ever gave up waiting for another rank (a rank died or fell more
+        than a minute behind): the replicas are then no longer identical.  Synchronises the device; call it at epoch boundaries."""
+        if not self.peer_exchange:
+            return
+        w, t = C.c_int(0), C.c_int(0)
+        _lib.check(self.ctx.lib.rdg_peer_status(self.ctx.handle, C.byref(w), C.byref(t)))
+        if t.value:
+            raise RuntimeError("data-parallel gradient exchange: a barrier timed out waiting for a peer rank")
+
     def _set_mode(self):
         _lib.check(self.ctx.lib.rdg_set_train_mode(self.ctx.handle, 1 if self.train_mode == "tf32" else 0))
 
@@ -416,6 +426,7 @@ class GanTrainer:
     def state_dict(self):
         self.finish()
         torch.cuda.synchronize(self.ctx.device)
+        self.check_exchange()
         adam_t, rng_ctr = self._pull_counters()
         assert adam_t == self.optimizer.iterations, "host / device Adam step counters diverged"
         sd = {"iterations": np.int64(self.optimizer.iterations), "rng_ctr": np.array(rng_ctr, np.uint64),
