@@ -640,7 +640,8 @@ class GanTrainer:
         with the peer-memory exchange (`peer_exchange`) a data-parallel iteration is one graph like the single-GPU one.
         The capture is preceded by one REAL iteration on constant placeholder data (it sizes every workspace outside the capture);
         preserve_state=True puts weights, Adam moments, step and random counters back afterwards, so that a training run can
-        capture at its start without taking a step on the placeholders."""
+        capture at its start without taking a step on the placeholders.  Under data parallelism the call is collective (the
+        placeholder iteration exchanges gradients): every rank must make it, with the same arguments."""
         if self.train_mode != "tf32":
             raise RuntimeError("capture_iteration needs train_mode='tf32' (device-resident step inputs)")
         dev = f"cuda:{self.ctx.device}"
