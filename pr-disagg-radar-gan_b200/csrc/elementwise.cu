@@ -564,6 +564,40 @@ __global__ void gp_cotangent_kernel(const float* __restrict__ g0, const float* _
     const float nb = norm[b];
     u0[i] = c == 0 ? coef * (nb - 1.f) / nb * g0[i] : 0.f;
 }
+// norm + cotangent of one sample per block (tensor-core training mode: one launch on the critical chain instead of two); the
+// penalty loss itself is formed from norm[] by combine_losses_norm_kernel
+__global__ void __launch_bounds__(1024) gp_fused_kernel(const float* __restrict__ g0, float coef, float* __restrict__ u0, int C, long long per,
+                                                        float* __restrict__ norm) {
+    __shared__ float s_norm;
+    const float* g = g0 + (long long)blockIdx.x * per * C;
+    float* u = u0 + (long long)blockIdx.x * per * C;
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < per; i += blockDim.x) { const float v = g[i * C]; s = fmaf(v, v, s); }
+    s = block_sum(s);
+    if (threadIdx.x == 0) { s_norm = sqrtf(s); norm[blockIdx.x] = s_norm; }      // no epsilon, like the reference
+    __syncthreads();
+    const float nb = s_norm, f = coef * (nb - 1.f) / nb;
+    for (long long i = threadIdx.x; i < per * C; i += blockDim.x) u[i] = (i % C) == 0 ? f * g[i] : 0.f;
+}
+__global__ void combine_losses_norm_kernel(const float* lv, const float* lf, const float* __restrict__ norm, int B, float w, float* out4) {
+    float s = 0.f;
+    for (int b = threadIdx.x; b < B; b += 32) { const float d = norm[b] - 1.f; s = fmaf(d, d, s); }
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+        const float lgp = s / (float)B;            // 'mse' against zeros of the penalty output: mean((norm - 1)^2)
+        out4[1] = lv[0]; out4[2] = lf[0]; out4[3] = lgp;
+        out4[0] = lv[0] + lf[0] + w * lgp;         // loss_weights [1, 1, 10], gan_train_cwgangp_pixelnorm.py:388-392
+    }
+}
+// loss_k = sign_k * mean(score of segment k): one warp per term, fixed summation order
+__global__ void score_losses_kernel(const float* __restrict__ score, int B, int nloss, float s0, float s1, float* __restrict__ loss) {
+    const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wp >= nloss) return;
+    float s = 0.f;
+    for (int j = lane; j < B; j += 32) s += score[wp * B + j];
+    s = warp_sum(s);
+    if (lane == 0) loss[wp] = (wp == 0 ? s0 : s1) * s / (float)B;
+}
 __global__ void gp_loss_kernel(const float* __restrict__ norm, int B, float* __restrict__ out) {
     float s = 0.f;
     for (int i = threadIdx.x; i < B; i += blockDim.x) { float d = norm[i] - 1.f; s = fmaf(d, d, s); }
@@ -774,6 +808,22 @@ int ew_gp_cotangent(const float* g0, const float* norm, float coef, float* u0, i
     long long n = (long long)B * per * C;
     if (!n) return 0;
     gp_cotangent_kernel<<<EW_GRID(n)>>>(g0, norm, coef, u0, C, n, per, B, loss_out);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_gp_fused(const float* g0, float coef, float* u0, int C, int B, long long per, float* norm, cudaStream_t st) {
+    if (!B) return 0;
+    gp_fused_kernel<<<B, 1024, 0, st>>>(g0, coef, u0, C, per, norm);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_combine_losses_norm(const float* lv, const float* lf, const float* norm, int B, float gp_weight, float* out4, cudaStream_t st) {
+    combine_losses_norm_kernel<<<1, 32, 0, st>>>(lv, lf, norm, B, gp_weight, out4);
+    RDG_LAUNCH_CHECK();
+    return 0;
+}
+int ew_score_losses(const float* score, int B, int nloss, float s0, float s1, float* loss, cudaStream_t st) {
+    score_losses_kernel<<<1, 64, 0, st>>>(score, B, nloss, s0, s1, loss);
     RDG_LAUNCH_CHECK();
     return 0;
 }

@@ -132,3 +132,8 @@ int ew_gp_cotangent(const float* g0, const float* norm, float coef, float* u0, i
 int ew_gp_loss(const float* norm, int B, float* out, cudaStream_t st);                       // mean((norm-1)^2)
 int ew_extract_channel0(const float* x, float* out, long long n, int C, cudaStream_t st);
 int ew_combine_losses(const float* lv, const float* lf, const float* lgp, float gp_weight, float* out4, cudaStream_t st);
+// tensor-core training mode: norm + cotangent of the penalty in one launch (one block per sample), the penalty loss formed from
+// norm[] when the losses are combined, and the Wasserstein loss terms as their own (off-chain) launch
+int ew_gp_fused(const float* g0, float coef, float* u0, int C, int B, long long per, float* norm, cudaStream_t st);
+int ew_combine_losses_norm(const float* lv, const float* lf, const float* norm, int B, float gp_weight, float* out4, cudaStream_t st);
+int ew_score_losses(const float* score, int B, int nloss, float s0, float s1, float* loss, cudaStream_t st);

@@ -571,7 +571,6 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
         TRY(critic_conv_fwd_tc(c, l, A3.h[l], c->c_params + c->c_off[2 * l + 1], A3.h[l + 1], g, ACT_LRELU, masks3 ? masks3[l] : nullptr, st,
                                A3.a[l + 1], 1));
     }
-    TRY(ew_dense_score(A3.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A3.score, 3 * B, (int)critic_act_elems(c, 4), st));
     // one backward-data chain for the three thirds: cotangents of the scores [+1/B | -1/B | 1].  One launch forms them, the two
     // Wasserstein terms l_fake = mean(+D(fake)) -> lsc[1], l_valid = mean(-D(real)) -> lsc[0] (:215-216, targets :452-454) and
     // da_4 = Dense(1)^T backward * LeakyReLU'(a_4) * mask_4
@@ -580,9 +579,14 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     SideStream ss{c, st, 0}, ssk[3] = {{c, st, 0}, {c, st, 1}, {c, st, 2}};
     for (auto& s : ssk) TRY(s.init());
     {
+        // the scores only feed the reported losses (the cotangents of the scores are constants): Dense(1) forward and the two
+        // Wasserstein terms run on a side stream, the backward chain starts right away
+        TRY(ss.fork());
+        TRY(ew_dense_score(A3.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A3.score, 3 * B, (int)critic_act_elems(c, 4), ss.aux()));
+        TRY(ew_score_losses(A3.score, B, 2, 1.f, -1.f, lsc + 4, ss.aux()));       // lsc[4] = l_fake, lsc[5] = l_valid
         const float cot3[3] = {1.f / (float)B, -1.f / (float)B, 1.f}, sign2[2] = {1.f, -1.f};
-        TRY(ew_critic_tail(A3.score, c->c_params + c->c_off[8], A3.a[4], masks3 ? masks3[3] : nullptr, ms, B, 3, (int)critic_act_elems(c, 4), cot3,
-                           sign2, 2, lsc + 4, dscore3, da[4], st));      // lsc[4] = l_fake, lsc[5] = l_valid
+        TRY(ew_critic_tail(nullptr, c->c_params + c->c_off[8], A3.a[4], masks3 ? masks3[3] : nullptr, ms, B, 3, (int)critic_act_elems(c, 4), cot3,
+                           sign2, 0, nullptr, dscore3, da[4], st));
     }
     TRY(ss.fork());
     TRY(simt_conv_bwd_filter(A3.h[4], dscore3, c->c_grads + c->c_off[8], c->c_grads + c->c_off[9], rdg_critic_dense_geom(c, 2 * B), ss.aux()));
@@ -621,8 +625,7 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     }
     // gradient penalty (:230-244): norm of the input gradient, 'mse' against zeros, cotangent of 10 * mean((n-1)^2)
     const int C0 = 1 + c->ncond;
-    TRY(ew_gp_norm(g0, C0, B, (long long)px, norm, st));
-    TRY(ew_gp_cotangent(g0, norm, 10.f * 2.f / (float)B, hat_h[0], C0, B, (long long)px, st, lsc + 2));   // u_0 replaces h_0 of the third; l_gp
+    TRY(ew_gp_fused(g0, 10.f * 2.f / (float)B, hat_h[0], C0, B, (long long)px, norm, st));      // u_0 replaces h_0 of the third
     // second-order pass (LeakyReLU'' = 0): u_l = S_l (.) conv_l(u_{l-1}); filter gradients of BOTH loss parts in one contraction
     for (int l = 1; l <= 4; ++l) {
         ConvGeom g3 = rdg_critic_conv_geom(c, l - 1, 3 * B);
@@ -641,7 +644,7 @@ int critic_step_tc(rdg_ctx* c, const float* x_real, const float* cond, const flo
     }
     TRY(simt_colsum(hat_h[4], c->c_grads + c->c_off[8], B, (int)critic_act_elems(c, 4), st));      // d/dW5 of the penalty
     for (auto& s : ssk) TRY(s.join());
-    TRY(ew_combine_losses(lsc + 5, lsc + 4, lsc + 2, 10.f, losses4, st));      // [l_valid, l_fake, l_gp]
+    TRY(ew_combine_losses_norm(lsc + 5, lsc + 4, norm, B, 10.f, losses4, st));      // [l_valid, l_fake, l_gp = mean((norm - 1)^2)]
     return 0;
 }
 
@@ -703,13 +706,18 @@ int generator_step_tc(rdg_ctx* c, const float* latent, const float* cond, const 
         ConvGeom g = rdg_critic_conv_geom(c, l, B);
         TRY(critic_conv_fwd_tc(c, l, A.h[l], c->c_params + c->c_off[2 * l + 1], A.h[l + 1], g, ACT_LRELU, masks ? masks[l] : nullptr, st, A.a[l + 1], 1));
     }
-    TRY(ew_dense_score(A.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A.score, B, (int)critic_act_elems(c, 4), st));
+    {   // the score only feeds the reported loss mean(-D(G(z))) (wasserstein_loss with target -1, :408, :452): off the chain
+        SideStream s0{c, st, 0};
+        TRY(s0.init()); TRY(s0.fork());
+        TRY(ew_dense_score(A.h[4], c->c_params + c->c_off[8], c->c_params + c->c_off[9], A.score, B, (int)critic_act_elems(c, 4), s0.aux()));
+        TRY(ew_score_losses(A.score, B, 1, -1.f, 0.f, loss_dev, s0.aux()));       // joined with the filter gradients below
+    }
     {   // t1 / t0 alternate as the cotangents of the pre-activations a_4 .. a_1 (LeakyReLU backward fused into the transposed convs);
-        // the first launch also forms the loss mean(-D(G(z))) (wasserstein_loss with target -1, :408, :452) and its cotangent -1/B
+        // the first launch forms the cotangent -1/B of the scores and da_4
         float* cur = t1; float* nxt = t0;
         const float cot3[3] = {-1.f / (float)B, 0.f, 0.f}, sign2[2] = {-1.f, 0.f};
-        TRY(ew_critic_tail(A.score, c->c_params + c->c_off[8], A.a[4], masks ? masks[3] : nullptr, ms, B, 1, (int)critic_act_elems(c, 4), cot3, sign2,
-                           1, loss_dev, dscore, cur, st));
+        TRY(ew_critic_tail(nullptr, c->c_params + c->c_off[8], A.a[4], masks ? masks[3] : nullptr, ms, B, 1, (int)critic_act_elems(c, 4), cot3, sign2,
+                           0, nullptr, dscore, cur, st));
         for (int l = 4; l >= 1; --l) {
             ConvGeom g = rdg_critic_conv_geom(c, l - 1, B);
             if (l > 1 && tc_layer_ok(g)) {
